@@ -1,0 +1,856 @@
+// rate_loop_core.h — Layer III rate loop for ONE stream, executed by ONE warp.
+//
+// Replaces iteration_loop()/outer_loop()/inner_loop()/bin_search_StepSize()/quantize()/count_bits()
+// and helpers of /root/reference/src/loop.c (+ the reservoir recurrence of reservoir.c) for the batched
+// C-ABI entry point mp3gpu_iteration_loop_batch().  One warp owns one stream and walks its
+// (frame, granule, channel) sequence in order, because max_bits of a granule depends on the
+// reservoir left by the previous one (reservoir.c:101-145).  Inside a granule all 576 lines are
+// processed in parallel: each lane keeps 9 coefficient PAIRS in registers, and every bit count,
+// maximum and table choice is a warp reduction.
+//
+// Layouts (k = 0..8, lane = 0..31, slot s = lane + 32 k in [0,288)):
+//   long / start / stop blocks: slot s holds elements (2s, 2s+1)            -> Huffman pair s
+//   short blocks (type 2):      slot s = 3 m + w holds elements (6m+w, 6m+3+w), i.e. lines 2m and
+//                               2m+1 of window w (the [192][3] view of loop.c:1375-1376)
+// Per-band quantities (xmin, distortion, scalefactors) are held "band per lane": band b lives in
+// lane b&31 of register b>>5.  long: b = sfb (0..20); short: b = 3*sfb + window (0..35).
+//
+// Decisions are bit-exact restatements of the reference (same probe sequence, same tie rules); the
+// only relaxation is the ORDER of FP64 additions inside per-band energy/noise sums (documented in
+// changes a compare only if two doubles agree to ~1e-16).
+#pragma once
+#include "simt.h"
+
+namespace mp3gpu {
+
+using simt::PerThread;
+using simt::WarpCtx;
+
+// ---- constant tables (host-built with the reference's libm expressions; see tables.cpp) ---------
+struct RateTables {
+    double pow_nint_tab[2049];  // [p] = (p - 0.4054)^(4/3), p = 1..2048 (pow_nint.c:13-19); [0] unused
+    double pow43[2048];         // p^(4/3) (loop.c:1017-1021)
+    double step[512];           // 2^(q/4), q = -256..255 (loop.c:1020,1386); index q + 256
+    double ostep[512];          // 1 / step
+    double pre1[4], pre2[4];    // pow(sqrt 2, n), pow(sqrt 2, 2n)  (loop.c:1205-1210)
+    double ifqstep, ifqstep2;   // sqrt(2), sqrt(2)*sqrt(2)          (loop.c:1252,1293)
+    double log2c;               // log(2.0)                           (loop.c:632)
+    short sfb_l[23], sfb_s[14]; // Table B.8 for this sample rate
+    unsigned char hlen[1412];   // Table B.7 code lengths, flat
+    unsigned short hoff[34];    // offset of each table in hlen
+    unsigned char hxlen[34], hlinbits[34];
+    unsigned short hlinmax[34];
+    unsigned char band_long[288];   // sfb of long pair s (21 = above last band)
+    unsigned char band_short[288];  // 3*sfb + w of short slot s (>= 36 = above last band)
+    unsigned char subdiv[289][2];   // region0/1_count for big_values (long blocks, loop.c:1596-1690)
+    unsigned char pretab[24];
+};
+
+struct GrInfoOut {  // 20 ints, same order as the reference dump (oracle GR_FIELDS)
+    int part2_3_length, big_values, count1, global_gain, scalefac_compress;
+    int window_switching_flag, block_type, mixed_block_flag;
+    int table_select[3];
+    int region0_count, region1_count, preflag, scalefac_scale, count1table_select;
+    int part2_length, address1, address2, address3;
+};
+
+// per-stream state that survives between frames (reference statics: reservoir.c:36-37, loop.c:618-621)
+struct LoopStreamState {
+    int resv_size;
+    int xrmax[4];      // [gr*2+ch]
+    int en_tot[4];
+    int en[4][32];     // [gr*2+ch][sfb] (int-typed log2 energies, sic)
+    int xm[4][32];
+    int addr[4][3];    // address1..3 of each (gr,ch): subdivide() leaves them stale when big_values == 0
+};
+
+struct FrameGeom {
+    int n_ch, mean_bits, bits_per_frame;
+};
+
+// ---- small helpers --------------------------------------------------------------------------------
+SIMT_FN int quant1(const double *tab, double x)
+{
+    // largest p in [0,2047] with x >= tab[p] (tab[0] := -inf): identical to pow_nint()'s gallop +
+    // binary search (pow_nint.h:16-50) because tab is strictly increasing.  Float estimate + exact fix-up.
+    float xf = (float)x;
+    float e = sqrtf(xf);
+    e = e * sqrtf(e);
+    e = fminf(e, 3000.0f);
+    int p = (int)(e + 0.4054f);
+    if (p > 2047) p = 2047;
+    while (p > 0 && x < tab[p]) p--;
+    while (p < 2047 && x >= tab[p + 1]) p++;
+    return p;
+}
+
+SIMT_FN int nint_ref(double in) { return (in < 0) ? (int)(in - 0.5) : (int)(in + 0.5); }
+
+SIMT_FN int popc4(int v) { return (v & 1) + ((v >> 1) & 1) + ((v >> 2) & 1) + ((v >> 3) & 1); }
+
+// bits of one (x,y) pair in table t (count_bit, loop.c:172-225 / HuffmanCode count mode)
+SIMT_FN int pair_bits(const RateTables &T, int t, int x, int y)
+{
+    int s = (x != 0) + (y != 0);
+    if (t > 15) {
+        int lb = T.hlinbits[t];
+        if (x > 14) { x = 15; s += lb; }
+        if (y > 14) { y = 15; s += lb; }
+    }
+    return s + T.hlen[T.hoff[t] + x * T.hxlen[t] + y];
+}
+
+// first table whose range covers max (loop.c:1813-1818 / 1921-1928): max in 1..14
+SIMT_FN int table_for_small_max(int max)
+{
+    return (max == 1) ? 1 : (max == 2) ? 2 : (max == 3) ? 5 : (max <= 5) ? 7 : (max <= 7) ? 10 : 13;
+}
+
+SIMT_FN int esc_table(const RateTables &T, int lo, int hi, int m15)
+{
+    for (int i = lo; i < hi; i++)
+        if ((int)T.hlinmax[i] >= m15) return i;
+    return 0;
+}
+
+// ---- the per-granule working set ------------------------------------------------------------------
+struct GcRegs {
+    PerThread<double> xa[9], xb[9];  // |xr| of the slot's two elements (amplified in place)
+    PerThread<int> ia[9], ib[9];     // quantised values
+    PerThread<int> band[9];          // band id of slot
+};
+
+struct BandRegs {
+    PerThread<double> xmin[2], xfsf[2];
+    PerThread<int> sf[2];
+};
+
+struct CountResult {
+    int bits, big_values, count1, count1table_select;
+    int region0_count, region1_count, address1, address2, address3;
+    int table_select[3];
+};
+
+SIMT_FN int slot_e0(bool is_short, int s)
+{
+    if (!is_short) return 2 * s;
+    int m = s / 3;
+    return 6 * m + (s - 3 * m);
+}
+
+// quantize(): loop.c:1360-1428 with subblock_gain == 0 and mixed_block_flag == 0 (always, l3psy.c:739)
+SIMT_FN void quantize_all(const WarpCtx &w, const RateTables &T, GcRegs &R, int q)
+{
+    const double ostep = T.ostep[q + 256];
+    FOR_THREADS(w)
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        R.ia[k]() = quant1(T.pow_nint_tab, simt::dmul(R.xa[k](), ostep));
+        R.ib[k]() = quant1(T.pow_nint_tab, simt::dmul(R.xb[k](), ostep));
+    }
+    END_THREADS
+}
+
+// count_bits(): calc_runlen + count1_bitcount + subdivide + bigv_tab_select + bigv_bitcount
+// (loop.c:2099-2113 and 590-594) on the quantised values in registers.
+SIMT_FN void count_all(const WarpCtx &w, const RateTables &T, const GcRegs &R, bool is_short, bool wsf, CountResult &C)
+{
+    C.table_select[0] = C.table_select[1] = C.table_select[2] = 0;
+    if (is_short) {
+        // loop.c:1492-1496, 1667-1674, 1723-1760, 1958-2003
+        PerThread<int> m1, m2;
+        FOR_THREADS(w)
+        int a = 0, b = 0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            int s = lane + 32 * k;
+            int mx = R.ia[k]() > R.ib[k]() ? R.ia[k]() : R.ib[k]();
+            if (s < 18) a = mx > a ? mx : a; else b = mx > b ? mx : b;  // lines < 12 <=> m < 6 <=> s < 18
+        }
+        m1() = a; m2() = b;
+        END_THREADS
+        int max1 = w.reduce_max(m1), max2 = w.reduce_max(m2);
+        int t0 = (max1 == 0) ? 0 : (max1 < 15) ? table_for_small_max(max1) : esc_table(T, 15, 32, max1 - 15);
+        int t1 = (max2 == 0) ? 0 : (max2 < 15) ? table_for_small_max(max2) : esc_table(T, 15, 32, max2 - 15);
+        PerThread<int> sum;
+        FOR_THREADS(w)
+        int acc = 0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            int s = lane + 32 * k;
+            int t = (s < 18) ? t0 : t1;
+            if (t) acc += pair_bits(T, t, R.ia[k](), R.ib[k]());
+        }
+        sum() = acc;
+        END_THREADS
+        C.bits = w.reduce_add(sum);
+        C.big_values = 288; C.count1 = 0; C.count1table_select = 1;
+        C.region0_count = 8; C.region1_count = 36;
+        C.address1 = 36; C.address2 = 576; C.address3 = 0;
+        C.table_select[0] = t0; C.table_select[1] = t1;
+        return;
+    }
+    // ---- calc_runlen, loop.c:1498-1517 ----
+    PerThread<int> nzmax, bigmax;
+    FOR_THREADS(w)
+    int nz = -1, bg = -1;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        int s = lane + 32 * k;
+        if ((R.ia[k]() | R.ib[k]()) != 0) nz = s;
+        if (R.ia[k]() > 1 || R.ib[k]() > 1) bg = s;
+    }
+    nzmax() = nz; bigmax() = bg;
+    END_THREADS
+    const int n = w.reduce_max(nzmax) + 1;
+    const int B = w.reduce_max(bigmax);
+    const int count1 = (n - 1 - B) >> 1;
+    const int bv = n - 2 * count1;
+    C.big_values = bv; C.count1 = count1;
+    // ---- count1_bitcount, loop.c:1531-1590: quads = slot pairs (bv+2t, bv+2t+1) ----
+    int c1bits = 0;
+    C.count1table_select = 1;
+    if (count1 > 0) {
+        PerThread<int> code[10], s0, s1;
+        FOR_THREADS(w)
+#pragma unroll
+        for (int k = 0; k < 9; k++) code[k]() = (R.ia[k]() & 1) | ((R.ib[k]() & 1) << 1);
+        code[9]() = 0;
+        END_THREADS
+        PerThread<int> nxt[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) w.shift_down1(nxt[k], code[k], code[k + 1]);
+        FOR_THREADS(w)
+        int a0 = 0, a1 = 0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            int s = lane + 32 * k;
+            int rel = s - bv;
+            if (rel >= 0 && rel < 2 * count1 && (rel & 1) == 0) {
+                int p = code[k]() | (nxt[k]() << 2);
+                int sg = popc4(p);
+                a0 += sg + T.hlen[T.hoff[32] + p];
+                a1 += sg + T.hlen[T.hoff[33] + p];
+            }
+        }
+        s0() = a0; s1() = a1;
+        END_THREADS
+        int sum0 = w.reduce_add(s0), sum1 = w.reduce_add(s1);
+        if (sum0 < sum1) { c1bits = sum0; C.count1table_select = 0; }
+        else { c1bits = sum1; C.count1table_select = 1; }
+    }
+    // ---- subdivide, loop.c:1638-1704 ----
+    const int bvr = 2 * bv;
+    if (bv == 0) {
+        // subdivide() leaves address1..3 untouched (stale values from the previous probe / frame) and
+        // bigv_tab_select()/bigv_bitcount() then still walk them (loop.c:1642-1647,1764-1772)
+        C.region0_count = 0; C.region1_count = 0;
+    } else if (!wsf) {
+        C.region0_count = T.subdiv[bv][0];
+        C.region1_count = T.subdiv[bv][1];
+        C.address1 = T.sfb_l[C.region0_count + 1];
+        C.address2 = T.sfb_l[C.region0_count + C.region1_count + 2];
+        C.address3 = bvr;
+    } else {
+        C.region0_count = 7; C.region1_count = 13;
+        C.address1 = T.sfb_l[8]; C.address2 = bvr; C.address3 = 0;
+    }
+    C.bits = c1bits;
+}
+
+// bigv_tab_select + bigv_bitcount for long/start/stop blocks (loop.c:1762-1775, 1793-1900, 2005-2015)
+SIMT_FN int count_regions(const WarpCtx &w, const RateTables &T, const GcRegs &R, int a1, int a2, int a3, int bvr, int tsel[3])
+{
+    // region of element e: R0 = [0,a1), R1 = [a1,a2) if a2 > a1, R2 = [a2,bvr) if bvr > a2
+    const bool has1 = a2 > a1, has2 = bvr > a2;
+    PerThread<int> mx[3];
+    FOR_THREADS(w)
+    int m0 = 0, m1 = 0, m2 = 0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        int e = 2 * (lane + 32 * k);
+        int v = R.ia[k]() > R.ib[k]() ? R.ia[k]() : R.ib[k]();
+        if (e < a1) m0 = v > m0 ? v : m0;
+        else if (e < a2) m1 = v > m1 ? v : m1;
+        else if (e < bvr) m2 = v > m2 ? v : m2;
+    }
+    mx[0]() = m0; mx[1]() = m1; mx[2]() = m2;
+    END_THREADS
+    int cand[3][3], ncand[3];
+    for (int r = 0; r < 3; r++) {
+        ncand[r] = 0;
+        cand[r][0] = cand[r][1] = cand[r][2] = 0;
+        bool present = (r == 0) ? (a1 > 0) : (r == 1) ? has1 : has2;
+        if (!present) continue;
+        int max = w.reduce_max(mx[r]);
+        if (max == 0) continue;
+        if (max < 15) {
+            int c0 = table_for_small_max(max);
+            cand[r][0] = c0; ncand[r] = 1;
+            if (c0 == 2) { cand[r][1] = 3; ncand[r] = 2; }
+            else if (c0 == 5) { cand[r][1] = 6; ncand[r] = 2; }
+            else if (c0 == 7) { cand[r][1] = 8; cand[r][2] = 9; ncand[r] = 3; }
+            else if (c0 == 10) { cand[r][1] = 11; cand[r][2] = 12; ncand[r] = 3; }
+            else if (c0 == 13) { cand[r][1] = 15; ncand[r] = 2; }
+        } else {
+            cand[r][0] = esc_table(T, 15, 24, max - 15);
+            cand[r][1] = esc_table(T, 24, 32, max - 15);
+            ncand[r] = 2;
+        }
+    }
+    // bits of every candidate, all regions in one sweep
+    PerThread<int> acc[3][3];
+    FOR_THREADS(w)
+    int s[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        int e = 2 * (lane + 32 * k);
+        int x = R.ia[k](), y = R.ib[k]();
+        // region-2 counting in the reference runs over [a2, a3): a3 == bvr for plain long blocks and 0
+        // for start/stop blocks (where region 2 is never selected), so [a2,bvr) covers both
+        int r = (e < a1) ? 0 : (e < a2) ? 1 : (e < bvr) ? 2 : 3;
+        if (r < 3) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                int t = (r == 0) ? cand[0][c] : (r == 1) ? cand[1][c] : cand[2][c];
+                if (t) {
+                    int b = pair_bits(T, t, x, y);
+                    if (r == 0) s[0][c] += b; else if (r == 1) s[1][c] += b; else s[2][c] += b;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) acc[r][c]() = s[r][c];
+    END_THREADS
+    int bits = 0;
+    for (int r = 0; r < 3; r++) {
+        tsel[r] = 0;
+        if (ncand[r] == 0) continue;
+        int s0 = w.reduce_add(acc[r][0]);
+        int choice = cand[r][0];
+        if (cand[r][0] >= 15 && ncand[r] == 2 && cand[r][1] >= 24) {       // ESC pair: strict '<' (loop.c:1896)
+            int s1 = w.reduce_add(acc[r][1]);
+            if (s1 < s0) { choice = cand[r][1]; s0 = s1; }
+        } else {
+            for (int c = 1; c < ncand[r]; c++) {                            // '<=' chains (loop.c:1826-1868)
+                int s1 = w.reduce_add(acc[r][c]);
+                if (s1 <= s0) { choice = cand[r][c]; s0 = s1; }
+            }
+        }
+        tsel[r] = choice;
+        bits += s0;
+    }
+    (void)a3;
+    return bits;
+}
+
+// one quantize + count_bits probe at step q.  `C` carries address1..3 across probes exactly like the
+// reference's cod_info does (subdivide leaves them untouched when big_values == 0).
+SIMT_FN int probe(const WarpCtx &w, const RateTables &T, GcRegs &R, bool is_short, bool wsf, int q, CountResult &C)
+{
+    quantize_all(w, T, R, q);
+    count_all(w, T, R, is_short, wsf, C);
+    if (is_short) return C.bits;
+    int tsel[3];
+    int bb = count_regions(w, T, R, C.address1, C.address2, C.address3, 2 * C.big_values, tsel);
+    C.table_select[0] = tsel[0]; C.table_select[1] = tsel[1]; C.table_select[2] = tsel[2];
+    C.bits += bb;
+    return C.bits;
+}
+
+// sum over the slots of each band of the per-slot values in scr[288]; result band-per-lane.
+// long: band b = pairs [sfb_l[b]/2, sfb_l[b+1]/2), b < 21; short: b = 3 sfb + w -> slots 3m+w, m in
+// [sfb_s[sfb]/2, sfb_s[sfb+1]/2), sfb < 12.
+SIMT_FN void band_sums(const WarpCtx &w, const RateTables &T, const double *scr, bool is_short, PerThread<double> out[2])
+{
+    FOR_THREADS(w)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        int b = lane + 32 * h;
+        double a0 = 0.0, a1 = 0.0;
+        if (!is_short) {
+            if (b < 21) {
+                int lo = T.sfb_l[b] >> 1, hi = T.sfb_l[b + 1] >> 1, s = lo;
+                for (; s + 1 < hi; s += 2) { a0 = simt::dadd(a0, scr[s]); a1 = simt::dadd(a1, scr[s + 1]); }
+                if (s < hi) a0 = simt::dadd(a0, scr[s]);
+            }
+        } else if (b < 36) {
+            int sfb = b / 3, wi = b - 3 * sfb;
+            int lo = T.sfb_s[sfb] >> 1, hi = T.sfb_s[sfb + 1] >> 1, m = lo;
+            for (; m + 1 < hi; m += 2) { a0 = simt::dadd(a0, scr[3 * m + wi]); a1 = simt::dadd(a1, scr[3 * m + 3 + wi]); }
+            if (m < hi) a0 = simt::dadd(a0, scr[3 * m + wi]);
+        }
+        out[h]() = simt::dadd(a0, a1);
+    }
+    END_THREADS
+}
+
+SIMT_FN double band_width(const RateTables &T, bool is_short, int b)
+{
+    if (!is_short) return (double)(T.sfb_l[b + 1] - T.sfb_l[b]);
+    int sfb = b / 3;
+    return (double)(T.sfb_s[sfb + 1] - T.sfb_s[sfb]);
+}
+
+SIMT_FN int part2_length_of(bool is_short, int gr, int compress, const int scfsi[4])
+{
+    // loop.c:731-784 (MPEG-1)
+    const int s1t = (0x4433322211130000ull >> (4 * compress)) & 15;  // slen1_tab
+    const int s2t = (0x3232132132103210ull >> (4 * compress)) & 15;  // slen2_tab
+    if (is_short) return 18 * s1t + 18 * s2t;
+    int bits = 0;
+    if (gr == 0 || scfsi[0] == 0) bits += 6 * s1t;
+    if (gr == 0 || scfsi[1] == 0) bits += 5 * s1t;
+    if (gr == 0 || scfsi[2] == 0) bits += 5 * s2t;
+    if (gr == 0 || scfsi[3] == 0) bits += 5 * s2t;
+    return bits;
+}
+
+struct Gr0Carry {             // what granule 1 may need from granule 0 of the same channel
+    PerThread<int> sf0;       // long scalefactors of gr 0 (band per lane)
+    int preflag, scalefac_scale;
+};
+
+// Encode one granule-channel.  xr: 576 doubles (mdct_sub output).  ratio: 21 (long) or 36 ([sfb][win])
+// doubles.  Writes ix (signed, sign of xr applied as l3bitstream.c:115-125 does), gi, scalefac bytes.
+// Returns part2_3_length (before ResvFrameEnd stuffing).
+SIMT_FN int encode_gc(const WarpCtx &w, const RateTables &T, double *scr, const FrameGeom &G, LoopStreamState &S,
+                      PerThread<int> st_en[4], PerThread<int> st_xm[4],
+                      int gr, int ch, const double *xr, const double *ratio_l, const double *ratio_s, double pe,
+                      int block_type, int scfsi[4], Gr0Carry &g0, short *ix_out, GrInfoOut &gi, unsigned char *sf_out,
+                      int *max_bits_out)
+{
+    const bool is_short = (block_type == 2);
+    const bool wsf = (block_type != 0);
+    const int nb_l = is_short ? 0 : 21;   // sfb_lmax (gr_deco, loop.c:2063-2081)
+    GcRegs R;
+    BandRegs Bd;
+    PerThread<int> sign;      // bit 2k / 2k+1: sign of the slot's elements
+    PerThread<double> t0, t1;
+
+    // ---- load xr into registers -----------------------------------------------------------------
+    FOR_THREADS(w)
+    int sg = 0;
+    double mx = 0.0, e2 = 0.0, lg = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        int s = lane + 32 * k;
+        int e0 = slot_e0(is_short, s);
+        int e1 = is_short ? e0 + 3 : e0 + 1;
+        double a = xr[e0], b = xr[e1];
+        if (a < 0) sg |= 1 << (2 * k);
+        if (b < 0) sg |= 2 << (2 * k);
+        a = fabs(a); b = fabs(b);
+        R.xa[k]() = a; R.xb[k]() = b;
+        R.band[k]() = is_short ? T.band_short[s] : T.band_long[s];
+        mx = fmax(mx, fmax(a, b));
+        double a2 = simt::dmul(a, a), b2 = simt::dmul(b, b);
+        scr[s] = simt::dadd(a2, b2);
+        e2 = simt::dadd(e2, simt::dadd(a2, b2));
+        if (a != 0) lg = simt::dadd(lg, log(a2));
+        if (b != 0) lg = simt::dadd(lg, log(b2));
+        R.ia[k]() = 0; R.ib[k]() = 0;
+    }
+    sign() = sg; t0() = mx; t1() = e2;
+    Bd.xfsf[0]() = lg;  // borrowed as scratch for the log sum
+    END_THREADS
+    w.sync();
+    const double xrmax = w.reduce_max(t0);
+    const double sum2 = w.reduce_add(t1);
+    const double sum1 = w.reduce_add(Bd.xfsf[0]);
+
+    // ---- calc_xmin, loop.c:1085-1119 ------------------------------------------------------------
+    PerThread<double> en[2];
+    band_sums(w, T, scr, is_short, en);
+    FOR_THREADS(w)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        int b = lane + 32 * h;
+        double v = 0.0;
+        if (!is_short) { if (b < 21) v = simt::dmul(ratio_l[b], en[h]()) / band_width(T, false, b); }
+        else if (b < 36) v = simt::dmul(ratio_s[b], en[h]()) / band_width(T, true, b);
+        Bd.xmin[h]() = v;
+        Bd.xfsf[h]() = 0.0;
+        Bd.sf[h]() = 0;
+    }
+    END_THREADS
+
+    // ---- calc_scfsi, loop.c:615-722 (int-typed statics and swapped [ch][gr] indices kept) ----------
+    {
+        const int cur = gr * 2 + ch;
+        S.xrmax[cur] = (int)xrmax;
+        S.en_tot[cur] = (sum2 == 0.0) ? 0 : (int)(log(sum2) / T.log2c);
+        if (!is_short) {
+            FOR_THREADS(w)
+            if (lane < 21) {
+                double e = en[0](), xm = Bd.xmin[0]();
+                int ev = (e == 0.0) ? 0 : (int)(log(e) / T.log2c);
+                int xv = (xm == 0.0) ? 0 : (int)(log(xm) / T.log2c);
+#pragma unroll
+                for (int i = 0; i < 4; i++) if (i == cur) { st_en[i]() = ev; st_xm[i]() = xv; }
+            }
+            END_THREADS
+        }
+        if (gr == 1) {
+            int condition = 0;
+            for (int gr2 = 0; gr2 < 2; gr2++) {
+                if (S.xrmax[ch * 2 + gr2] != 0) condition++;
+                if (!is_short) condition++;
+            }
+            condition++;  // loop.c:683 compares a pointer difference (== 2) against 10: always true
+            PerThread<int> d_en, d_xm;
+            FOR_THREADS(w)
+            int a = 0, b = 0, c = 0, d = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (i == ch * 2) { a = st_en[i](); c = st_xm[i](); }
+                if (i == ch * 2 + 1) { b = st_en[i](); d = st_xm[i](); }
+            }
+            d_en() = (lane < 21) ? (a > b ? a - b : b - a) : 0;
+            d_xm() = (lane < 21) ? (c > d ? c - d : d - c) : 0;
+            END_THREADS
+            if (w.reduce_add(d_en) < 100) condition++;
+            if (condition == 6) {
+                for (int band = 0; band < 4; band++) {
+                    const int lo = (band == 0) ? 0 : (band == 1) ? 6 : (band == 2) ? 11 : 16;
+                    const int hi = (band == 0) ? 6 : (band == 1) ? 11 : (band == 2) ? 16 : 21;
+                    PerThread<int> p0, p1;
+                    FOR_THREADS(w)
+                    bool in = lane >= lo && lane < hi;
+                    p0() = in ? d_en() : 0; p1() = in ? d_xm() : 0;
+                    END_THREADS
+                    scfsi[band] = (w.reduce_add(p0) < 10 && w.reduce_add(p1) < 10) ? 1 : 0;
+                }
+            } else scfsi[0] = scfsi[1] = scfsi[2] = scfsi[3] = 0;
+        }
+    }
+
+    // ---- ResvMaxBits, reservoir.c:101-134 -------------------------------------------------------
+    int max_bits;
+    {
+        const int mean = G.mean_bits / G.n_ch;
+        const int resv_max = (G.bits_per_frame > 7680) ? 0 : ((7680 - G.bits_per_frame > 4088) ? 4088 : 7680 - G.bits_per_frame);
+        max_bits = mean > 4095 ? 4095 : mean;
+        if (resv_max != 0) {
+            int more_bits = (int)(pe * 3.1 - mean), add_bits = 0;
+            if (more_bits > 100) {
+                int frac = (S.resv_size * 6) / 10;
+                add_bits = frac < more_bits ? frac : more_bits;
+            }
+            int over_bits = S.resv_size - ((resv_max * 8) / 10) - add_bits;
+            if (over_bits > 0) add_bits += over_bits;
+            max_bits += add_bits;
+            if (max_bits > 4095) max_bits = 4095;
+        }
+    }
+    if (max_bits_out) *max_bits_out = max_bits;
+
+    // ---- iteration variables, loop.c:319-346 ------------------------------------------------------
+    CountResult C;
+    C.bits = 0; C.big_values = 0; C.count1 = 0; C.count1table_select = 0;
+    C.region0_count = C.region1_count = 0;
+    C.address1 = S.addr[gr * 2 + ch][0]; C.address2 = S.addr[gr * 2 + ch][1]; C.address3 = S.addr[gr * 2 + ch][2];
+    C.table_select[0] = C.table_select[1] = C.table_select[2] = 0;
+    int preflag = 0, compress = 0, part2 = 0, part23 = 0, q = 0, bits = 0;
+
+    if (xrmax != 0.0) {
+        // quantanf_init, loop.c:369-402
+        {
+            int tp = 0;
+            if (sum2 != 0.0) {
+                double sfm = exp(sum1 / 576.0) / (sum2 / 576.0);
+                tp = nint_ref(8.0 * log(sfm));
+                if (tp < -100) tp = -100;
+            }
+            q = tp - 70;
+        }
+        // outer_loop, loop.c:415-558
+        int save_preflag = 0, save_compress = 0, iteration = 0, status, over;
+        PerThread<int> save_sf[2];
+        do {
+            iteration++;
+            part2 = part2_length_of(is_short, gr, compress, scfsi);
+            const int huff_bits = max_bits - part2;
+            if (iteration == 1) {  // bin_search_StepSize(max_bits, ...), loop.c:2119-2140
+                int top = q, bot = 200, next = q, last, bit;
+                do {
+                    last = next;
+                    next = (top + bot) / 2;  // aint((top+bot)/2.0): truncation toward zero, like C int division
+                    q = next;
+                    bit = probe(w, T, R, is_short, wsf, q, C);
+                    if (bit > max_bits) top = next; else bot = next;
+                } while (bit != max_bits && (last - next > 1 || next - last > 1));
+            }
+            // inner_loop, loop.c:569-606
+            q -= 1;
+            do {
+                q += 1;
+                bits = probe(w, T, R, is_short, wsf, q, C);
+            } while (bits > huff_bits);
+
+            // calc_noise, loop.c:1007-1069
+            {
+                const double step = T.step[q + 256];
+                FOR_THREADS(w)
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    double da = simt::dsub(R.xa[k](), simt::dmul(T.pow43[R.ia[k]()], step));
+                    double db = simt::dsub(R.xb[k](), simt::dmul(T.pow43[R.ib[k]()], step));
+                    scr[lane + 32 * k] = simt::dadd(simt::dmul(da, da), simt::dmul(db, db));
+                }
+                END_THREADS
+                w.sync();
+                PerThread<double> ns[2];
+                band_sums(w, T, scr, is_short, ns);
+                FOR_THREADS(w)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    int b = lane + 32 * h;
+                    bool valid = is_short ? (b < 36) : (b < 21);
+                    Bd.xfsf[h]() = valid ? ns[h]() / band_width(T, is_short, b) : 0.0;
+                    save_sf[h]() = Bd.sf[h]();
+                }
+                END_THREADS
+                w.sync();
+            }
+            save_preflag = preflag;
+            save_compress = compress;
+
+            // over-threshold mask (xfsf > xmin), band per lane -> 64-bit uniform mask
+            PerThread<int> ov0, ov1;
+            FOR_THREADS(w)
+            ov0() = Bd.xfsf[0]() > Bd.xmin[0]();
+            ov1() = Bd.xfsf[1]() > Bd.xmin[1]();
+            END_THREADS
+            unsigned m0 = w.ballot(ov0), m1 = w.ballot(ov1);
+            if (!is_short) { m0 &= (1u << 21) - 1; m1 = 0; } else m1 &= 15u;
+
+            // preemphasis, loop.c:1161-1216
+            bool scfsi_any = (gr == 1) && (scfsi[0] | scfsi[1] | scfsi[2] | scfsi[3]);
+            if (scfsi_any) preflag = g0.preflag;
+            else if (block_type != 2 && preflag == 0 && ((m0 >> 17) & 15u) == 15u) {
+                preflag = 1;
+                FOR_THREADS(w)
+                if (lane < nb_l) Bd.xmin[0]() = simt::dmul(Bd.xmin[0](), T.pre2[T.pretab[lane]]);
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    int b = R.band[k]();
+                    if (b < nb_l) {
+                        double f = T.pre1[T.pretab[b]];
+                        R.xa[k]() = simt::dmul(R.xa[k](), f);
+                        R.xb[k]() = simt::dmul(R.xb[k](), f);
+                    }
+                }
+                END_THREADS
+                // NB the reference re-tests xfsf > xmin in amp_scalefac_bands AFTER xmin was scaled
+                FOR_THREADS(w)
+                ov0() = Bd.xfsf[0]() > Bd.xmin[0]();
+                END_THREADS
+                m0 = w.ballot(ov0) & ((1u << 21) - 1);
+            }
+
+            // amp_scalefac_bands, loop.c:1225-1349
+            {
+                unsigned skip = 0;  // long bands frozen by scfsi
+                bool copySF = false;
+                if (scfsi_any) {
+                    if (iteration == 1) copySF = true;
+                    for (int band = 0; band < 4; band++)
+                        if (scfsi[band]) {
+                            const int lo = (band == 0) ? 0 : (band == 1) ? 6 : (band == 2) ? 11 : 16;
+                            const int hi = (band == 0) ? 6 : (band == 1) ? 11 : (band == 2) ? 16 : 21;
+                            skip |= ((1u << hi) - 1) & ~((1u << lo) - 1);
+                        }
+                    if (is_short) skip = 0;  // loop over sfb < sfb_lmax == 0 never runs
+                }
+                const unsigned amp0 = m0 & ~skip, amp1 = m1;
+                over = simt::popc(amp0) + simt::popc(amp1);
+                const unsigned long long amp = (unsigned long long)amp0 | ((unsigned long long)amp1 << 32);
+                FOR_THREADS(w)
+                if (copySF && !is_short && ((skip >> lane) & 1)) Bd.sf[0]() = g0.sf0();
+                if ((amp0 >> lane) & 1) { Bd.xmin[0]() = simt::dmul(Bd.xmin[0](), T.ifqstep2); Bd.sf[0]()++; }
+                if ((amp1 >> lane) & 1) { Bd.xmin[1]() = simt::dmul(Bd.xmin[1](), T.ifqstep2); Bd.sf[1]()++; }
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    int b = R.band[k]();
+                    if (b < 36 && ((amp >> b) & 1)) {
+                        R.xa[k]() = simt::dmul(R.xa[k](), T.ifqstep);
+                        R.xb[k]() = simt::dmul(R.xb[k](), T.ifqstep);
+                    }
+                }
+                END_THREADS
+            }
+            // loop_break, loop.c:1131-1150; scale_bitcount, loop.c:792-857
+            {
+                PerThread<int> z0, z1, s1m, s2m;
+                FOR_THREADS(w)
+                bool v0 = is_short ? true : (lane < 21);
+                bool v1 = is_short ? (lane < 4) : false;
+                z0() = v0 && Bd.sf[0]() == 0;
+                z1() = v1 && Bd.sf[1]() == 0;
+                int a = 0, b = 0;
+                if (!is_short) {
+                    if (lane < 11) a = Bd.sf[0](); else if (lane < 21) b = Bd.sf[0]();
+                } else {  // bands 3*sfb+w: sfb < 6 <=> b < 18
+                    if (lane < 18) a = Bd.sf[0](); else b = Bd.sf[0]();
+                    if (lane < 4) b = b > Bd.sf[1]() ? b : Bd.sf[1]();
+                }
+                s1m() = a; s2m() = b;
+                END_THREADS
+                status = (w.ballot(z0) | w.ballot(z1)) ? 0 : 1;
+                if (status == 0) {
+                    const int ms1 = w.reduce_max(s1m), ms2 = w.reduce_max(s2m);
+                    int ep = 2, k;
+                    for (k = 0; k < 16; k++) {
+                        const int l1 = (0x4433322211130000ull >> (4 * k)) & 15, l2 = (0x3232132132103210ull >> (4 * k)) & 15;
+                        if (ms1 < (1 << l1) && ms2 < (1 << l2)) { ep = 0; break; }
+                    }
+                    if (ep == 0) compress = k;
+                    status = ep;
+                }
+            }
+        } while (status == 0 && over > 0);
+        preflag = save_preflag;
+        compress = save_compress;
+        FOR_THREADS(w)
+        Bd.sf[0]() = save_sf[0]();
+        Bd.sf[1]() = save_sf[1]();
+        END_THREADS
+        part2 = part2_length_of(is_short, gr, compress, scfsi);
+        part23 = part2 + bits;
+    }
+
+    // ---- ResvAdjust + global_gain, loop.c:355-358 -------------------------------------------------
+    S.resv_size += G.mean_bits / G.n_ch - part23;
+    gi.part2_3_length = part23;
+    gi.big_values = C.big_values; gi.count1 = C.count1;
+    gi.global_gain = nint_ref((double)q + 210.0);
+    gi.scalefac_compress = compress;
+    gi.window_switching_flag = wsf; gi.block_type = block_type; gi.mixed_block_flag = 0;
+    gi.table_select[0] = C.table_select[0]; gi.table_select[1] = C.table_select[1]; gi.table_select[2] = C.table_select[2];
+    gi.region0_count = C.region0_count; gi.region1_count = C.region1_count;
+    gi.preflag = preflag; gi.scalefac_scale = 0; gi.count1table_select = C.count1table_select;
+    gi.part2_length = part2; gi.address1 = C.address1; gi.address2 = C.address2; gi.address3 = C.address3;
+    S.addr[gr * 2 + ch][0] = C.address1; S.addr[gr * 2 + ch][1] = C.address2; S.addr[gr * 2 + ch][2] = C.address3;
+
+    // ---- outputs ------------------------------------------------------------------------------------
+    FOR_THREADS(w)
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        int s = lane + 32 * k;
+        int e0 = slot_e0(is_short, s);
+        int e1 = is_short ? e0 + 3 : e0 + 1;
+        int a = R.ia[k](), b = R.ib[k]();
+        if ((sign() >> (2 * k)) & 1) a = -a;
+        if ((sign() >> (2 * k + 1)) & 1) b = -b;
+        ix_out[e0] = (short)a;
+        ix_out[e1] = (short)b;
+    }
+    if (!is_short) { if (lane < 22) sf_out[lane] = (unsigned char)((lane < 21) ? Bd.sf[0]() : 0); }
+    else { sf_out[lane] = (unsigned char)Bd.sf[0](); if (lane < 4) sf_out[32 + lane] = (unsigned char)Bd.sf[1](); }
+    END_THREADS
+    if (gr == 0) {
+        FOR_THREADS(w)
+        g0.sf0() = is_short ? 0 : Bd.sf[0]();
+        END_THREADS
+        g0.preflag = preflag; g0.scalefac_scale = 0;
+    }
+    w.sync();
+    return part23;
+}
+
+// ResvFrameEnd, reservoir.c:155-226: trims the reservoir and pushes stuffing bits into part2_3_length.
+SIMT_FN void resv_frame_end(const FrameGeom &G, LoopStreamState &S, int p23[4], int *resv_drain)
+{
+    const int resv_max = (G.bits_per_frame > 7680) ? 0 : ((7680 - G.bits_per_frame > 4088) ? 4088 : 7680 - G.bits_per_frame);
+    if (G.n_ch == 2 && (G.mean_bits & 1)) S.resv_size += 1;
+    int over_bits = S.resv_size - resv_max;
+    if (over_bits < 0) over_bits = 0;
+    S.resv_size -= over_bits;
+    int stuffing = over_bits;
+    if ((over_bits = S.resv_size % 8)) { stuffing += over_bits; S.resv_size -= over_bits; }
+    *resv_drain = 0;
+    if (stuffing) {
+        if (p23[0] + stuffing < 4095) p23[0] += stuffing;
+        else {
+            for (int gr = 0; gr < 2; gr++)
+                for (int ch = 0; ch < G.n_ch; ch++) {
+                    if (stuffing == 0) break;
+                    int extra = 4095 - p23[gr * 2 + ch];
+                    int take = extra < stuffing ? extra : stuffing;
+                    p23[gr * 2 + ch] += take;
+                    stuffing -= take;
+                }
+            *resv_drain = stuffing;
+        }
+    }
+}
+
+}  // namespace mp3gpu
+
+// ---------------------------------------------------------------------------------------------------
+// stream driver: one warp, one stream, n_frames frames in order
+// ---------------------------------------------------------------------------------------------------
+namespace mp3gpu {
+
+// what the psychoacoustic scan hands to the rate loop for one granule-channel
+// (L3psycho_anal outputs: ratio_d[21], ratio_ds[12][3], *pe, cod_info->block_type; l3psy.h:32-34)
+struct PsyOut {
+    double pe;
+    double ratio_l[21];
+    double ratio_s[36];  // [sfb][window]
+    int block_type;
+    int pad;
+};
+
+struct FrameOut {
+    int resv_drain;          // l3_side->resvDrain
+    int main_data_begin;     // back pointer of THIS frame in bytes = reservoir size before the frame / 8
+    unsigned char scfsi[2][4];
+};
+
+// gc index inside a stream chunk: g = (frame*2 + gr)*n_ch + ch
+SIMT_FN void rate_loop_stream(const WarpCtx &w, const RateTables &T, double *scr, const FrameGeom &G, LoopStreamState &S,
+                              PerThread<int> st_en[4], PerThread<int> st_xm[4], int n_frames,
+                              const double *xr, const PsyOut *psy, short *ix, GrInfoOut *gi, unsigned char *sf,
+                              FrameOut *fo, int *max_bits_dbg)
+{
+    for (int f = 0; f < n_frames; f++) {
+        int scfsi[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+        int p23[4] = {0, 0, 0, 0};
+        Gr0Carry g0[2];
+        g0[0].preflag = g0[1].preflag = 0;
+        g0[0].scalefac_scale = g0[1].scalefac_scale = 0;
+        const int mdb = S.resv_size / 8;
+        GrInfoOut gout[4];
+        for (int gr = 0; gr < 2; gr++)
+            for (int ch = 0; ch < G.n_ch; ch++) {
+                const int g = (f * 2 + gr) * G.n_ch + ch;
+                const PsyOut &po = psy[g];
+                p23[gr * 2 + ch] = encode_gc(w, T, scr, G, S, st_en, st_xm, gr, ch, xr + (size_t)g * 576, po.ratio_l, po.ratio_s,
+                                             po.pe, po.block_type, scfsi[ch], g0[ch], ix + (size_t)g * 576, gout[gr * 2 + ch],
+                                             sf + (size_t)g * 40, max_bits_dbg ? max_bits_dbg + g : nullptr);
+            }
+        int drain = 0;
+        resv_frame_end(G, S, p23, &drain);
+        FOR_THREADS(w)
+        if (lane == 0) {
+            for (int gr = 0; gr < 2; gr++)
+                for (int ch = 0; ch < G.n_ch; ch++) {
+                    const int g = (f * 2 + gr) * G.n_ch + ch;
+                    gout[gr * 2 + ch].part2_3_length = p23[gr * 2 + ch];
+                    gi[g] = gout[gr * 2 + ch];
+                }
+            fo[f].resv_drain = drain;
+            fo[f].main_data_begin = mdb;
+            for (int ch = 0; ch < 2; ch++)
+                for (int b = 0; b < 4; b++) fo[f].scfsi[ch][b] = (unsigned char)scfsi[ch][b];
+        }
+        END_THREADS
+    }
+}
+
+}  // namespace mp3gpu

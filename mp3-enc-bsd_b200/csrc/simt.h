@@ -1,0 +1,142 @@
+// simt.h — one source, two compilations.
+//
+// The kernels in this directory are written in a phase-structured SIMT style: per-thread code lives
+// inside FOR_THREADS(ctx) { ... } END_THREADS blocks, cross-thread communication happens only
+// through shared memory + ctx.sync() or through the explicit warp collectives of the context.
+//
+//  * nvcc (device): PerThread<T> is a plain register, FOR_THREADS runs the body once for the calling
+//    thread, collectives map to redux.sync / shfl.sync / bar.sync.  Zero overhead.
+//  * g++ -DMP3GPU_HOST_EMUL (tests only, tests/emul): PerThread<T> is an array over the threads of
+//    the group, FOR_THREADS is a loop, collectives are loops.  This lets `pytest -m "not gpu"` run
+//    the *identical kernel logic* against the oracle on a machine without a GPU.  It is a test
+//    harness, never a product fallback: libmp3gpu.so contains no host-emulated path.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(MP3GPU_HOST_EMUL)
+#define SIMT_DEV 1
+#define SIMT_FN __device__ __forceinline__
+#define SIMT_HD __host__ __device__ __forceinline__
+#else
+#define SIMT_DEV 0
+#define SIMT_FN inline
+#define SIMT_HD inline
+#include <cmath>
+#include <cstring>
+#endif
+
+namespace simt {
+
+#if SIMT_DEV
+// ------------------------------------------------------------------------------------------------
+// device
+// ------------------------------------------------------------------------------------------------
+template <class T, int N = 32>
+struct PerThread {
+    T v;
+    SIMT_FN T &operator()() { return v; }
+    SIMT_FN const T &operator()() const { return v; }
+};
+
+struct WarpCtx {  // one warp == one group
+    int lane;
+    static constexpr int kThreads = 32;
+    SIMT_FN WarpCtx() : lane(threadIdx.x & 31) {}
+    SIMT_FN void sync() const { __syncwarp(); }
+    SIMT_FN int reduce_max(const PerThread<int> &x) const { return __reduce_max_sync(0xffffffffu, x.v); }
+    SIMT_FN int reduce_add(const PerThread<int> &x) const { return __reduce_add_sync(0xffffffffu, x.v); }
+    SIMT_FN unsigned ballot(const PerThread<int> &x) const { return __ballot_sync(0xffffffffu, x.v != 0); }
+    SIMT_FN double reduce_max(const PerThread<double> &x) const {
+        double v = x.v;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+    // fixed butterfly order: deterministic, identical in the host emulation
+    SIMT_FN double reduce_add(const PerThread<double> &x) const {
+        double v = x.v;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+    // dst(lane) = src(lane + 1), lane 31 gets `wrap`(lane 0 of the next row, supplied by caller)
+    SIMT_FN void shift_down1(PerThread<int> &dst, const PerThread<int> &src, const PerThread<int> &next_row) const {
+        int a = __shfl_down_sync(0xffffffffu, src.v, 1);
+        int b = __shfl_sync(0xffffffffu, next_row.v, 0);
+        dst.v = (lane == 31) ? b : a;
+    }
+    template <class T>
+    SIMT_FN T broadcast(const PerThread<T> &x, int src_lane) const { return __shfl_sync(0xffffffffu, x.v, src_lane); }
+};
+
+struct BlockCtx {  // a whole CTA
+    int tid, nthreads;
+    SIMT_FN BlockCtx() : tid(threadIdx.x), nthreads(blockDim.x) {}
+    SIMT_FN void sync() const { __syncthreads(); }
+};
+
+#define FOR_THREADS(ctx) { const int lane = (ctx).lane; (void)lane;
+#define END_THREADS }
+#define FOR_BLOCK_THREADS(ctx) { const int tid = (ctx).tid; (void)tid;
+#define END_BLOCK_THREADS }
+
+SIMT_FN double dmul(double a, double b) { return __dmul_rn(a, b); }
+SIMT_FN double dadd(double a, double b) { return __dadd_rn(a, b); }
+SIMT_FN double dsub(double a, double b) { return __dsub_rn(a, b); }
+SIMT_FN float fmul(float a, float b) { return __fmul_rn(a, b); }
+SIMT_FN float fadd(float a, float b) { return __fadd_rn(a, b); }
+SIMT_FN float fsub(float a, float b) { return __fsub_rn(a, b); }
+SIMT_FN int popc(unsigned v) { return __popc(v); }
+
+#else
+// ------------------------------------------------------------------------------------------------
+// host emulation (tests only)
+// ------------------------------------------------------------------------------------------------
+extern thread_local int g_tid;  // defined in tests/emul
+
+template <class T, int N = 32>
+struct PerThread {
+    T v[N];
+    T &operator()() { return v[g_tid]; }
+    const T &operator()() const { return v[g_tid]; }
+};
+
+struct WarpCtx {
+    int lane;  // unused on host (loop variable shadows it)
+    static constexpr int kThreads = 32;
+    WarpCtx() : lane(0) {}
+    void sync() const {}
+    int reduce_max(const PerThread<int> &x) const { int m = x.v[0]; for (int i = 1; i < 32; i++) if (x.v[i] > m) m = x.v[i]; return m; }
+    int reduce_add(const PerThread<int> &x) const { int s = 0; for (int i = 0; i < 32; i++) s += x.v[i]; return s; }
+    unsigned ballot(const PerThread<int> &x) const { unsigned b = 0; for (int i = 0; i < 32; i++) if (x.v[i]) b |= 1u << i; return b; }
+    double reduce_max(const PerThread<double> &x) const {
+        double t[32]; for (int i = 0; i < 32; i++) t[i] = x.v[i];
+        for (int o = 16; o > 0; o >>= 1) { double u[32]; for (int i = 0; i < 32; i++) u[i] = std::fmax(t[i], t[i ^ o]); std::memcpy(t, u, sizeof(t)); }
+        return t[0];
+    }
+    double reduce_add(const PerThread<double> &x) const {
+        double t[32]; for (int i = 0; i < 32; i++) t[i] = x.v[i];
+        for (int o = 16; o > 0; o >>= 1) { double u[32]; for (int i = 0; i < 32; i++) u[i] = t[i] + t[i ^ o]; std::memcpy(t, u, sizeof(t)); }
+        return t[0];
+    }
+    void shift_down1(PerThread<int> &dst, const PerThread<int> &src, const PerThread<int> &next_row) const {
+        for (int i = 0; i < 31; i++) dst.v[i] = src.v[i + 1];
+        dst.v[31] = next_row.v[0];
+    }
+    template <class T>
+    T broadcast(const PerThread<T> &x, int src_lane) const { return x.v[src_lane]; }
+};
+
+#define FOR_THREADS(ctx) for (int lane = 0; lane < 32; ++lane) { simt::g_tid = lane;
+#define END_THREADS }
+
+inline double dmul(double a, double b) { return a * b; }
+inline double dadd(double a, double b) { return a + b; }
+inline double dsub(double a, double b) { return a - b; }
+inline float fmul(float a, float b) { return a * b; }
+inline float fadd(float a, float b) { return a + b; }
+inline float fsub(float a, float b) { return a - b; }
+inline int popc(unsigned v) { return __builtin_popcount(v); }
+#endif
+
+}  // namespace simt

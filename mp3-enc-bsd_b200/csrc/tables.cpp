@@ -1,0 +1,371 @@
+// tables.cpp — host-side builders for the constant tables (see tables.h).
+// Every expression that the reference evaluates with libm at start-up is evaluated here with the
+// same libm, in the same association order, so that the uploaded tables are bit-identical to the
+// reference's (citations: /root/reference/src/<file>:<line>).
+#include "tables.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "iso_tables.h"
+
+namespace mp3gpu {
+
+static const double kRefPi = 3.14159265358979;   // common.h:199 — the reference's PI, not M_PI
+static const double kLnToLog10 = 0.2302585093;   // common.h:204
+static const double kTwoPi = 6.28318530717958647692;  // subs.c:25
+
+int sr_index(int sfreq_hz)
+{
+    return sfreq_hz == 32000 ? 0 : sfreq_hz == 44100 ? 1 : sfreq_hz == 48000 ? 2 : -1;
+}
+
+void frame_geometry(int sfreq_hz, int n_ch, int bitrate_kbps, FrameGeom *G)
+{
+    double avg_slots = (1152.0 / ((double)sfreq_hz / 1000.0)) * ((double)bitrate_kbps / 8.0);
+    int whole = (int)avg_slots;
+    G->n_ch = n_ch;
+    G->bits_per_frame = 8 * whole;
+    int sideinfo_len = 32 + (n_ch == 1 ? 136 : 256);
+    G->mean_bits = (G->bits_per_frame - sideinfo_len) / 2;
+}
+
+void build_front_tables(FrontTables *F)
+{
+    memset(F, 0, sizeof(*F));
+    for (int i = 0; i < 512; i++) F->window[i] = MP3T_ANA_WINDOW[i];
+    // create_ana_filter, encode.c:331-345: cos rounded to 9 decimals through modf
+    for (int sb = 0; sb < 32; sb++) {
+        double row[64];
+        for (int k = 0; k < 64; k++) {
+            double v = 1e9 * cos((double)((2 * sb + 1) * (16 - k) * kRefPi / 64)), ip;
+            if (v >= 0) modf(v + 0.5, &ip); else modf(v - 0.5, &ip);
+            row[k] = ip * 1e-9;
+        }
+        for (int j = 0; j < 16; j++) F->am[sb][j] = row[j];           // pairs with ysum[j], encode.c:403
+        for (int j = 0; j < 15; j++) F->am[sb][16 + j] = row[33 + j]; // pairs with ysub[j], encode.c:404-406
+    }
+    static const double c[8] = {-0.6, -0.535, -0.33, -0.185, -0.095, -0.041, -0.0142, -0.0037};  // Table B.9
+    for (int k = 0; k < 8; k++) {
+        double sq = sqrt(1.0 + c[k] * c[k]);
+        F->ca[k] = c[k] / sq;
+        F->cs[k] = 1.0 / sq;
+    }
+    // mdct.c:132-156
+    for (int i = 0; i < 36; i++) F->win[0][i] = sin(kRefPi / 36 * (i + 0.5));
+    for (int i = 0; i < 18; i++) F->win[1][i] = sin(kRefPi / 36 * (i + 0.5));
+    for (int i = 18; i < 24; i++) F->win[1][i] = 1.0;
+    for (int i = 24; i < 30; i++) F->win[1][i] = sin(kRefPi / 12 * (i + 0.5 - 18));
+    for (int i = 30; i < 36; i++) F->win[1][i] = 0.0;
+    for (int i = 0; i < 6; i++) F->win[3][i] = 0.0;
+    for (int i = 6; i < 12; i++) F->win[3][i] = sin(kRefPi / 12 * (i + 0.5 - 6));
+    for (int i = 12; i < 18; i++) F->win[3][i] = 1.0;
+    for (int i = 18; i < 36; i++) F->win[3][i] = sin(kRefPi / 36 * (i + 0.5));
+    for (int i = 0; i < 12; i++) F->win[2][i] = sin(kRefPi / 12 * (i + 0.5));
+    // mdct.c:158-168
+    int N = 12;
+    for (int m = 0; m < N / 2; m++)
+        for (int k = 0; k < N; k++)
+            F->cos_s[m][k] = cos((kRefPi / (2 * N)) * (2 * k + 1 + N / 2) * (2 * m + 1)) / (N / 4);
+    N = 36;
+    for (int m = 0; m < N / 2; m++)
+        for (int k = 0; k < N; k++)
+            F->cos_l[m][k] = cos((kRefPi / (2 * N)) * (2 * k + 1 + N / 2) * (2 * m + 1)) / (N / 4);
+}
+
+void build_rate_tables(int sr, RateTables *R)
+{
+    memset(R, 0, sizeof(*R));
+    for (int i = 1; i <= 2048; i++) R->pow_nint_tab[i] = pow((double)i - 0.4054, 4.0 / 3.0);
+    for (int i = 0; i < 2048; i++) R->pow43[i] = pow((double)i, 4.0 / 3.0);
+    for (int q = -256; q < 256; q++) {
+        double step = (q == 0) ? 1.0 : pow(2.0, (double)q * 0.25);
+        R->step[q + 256] = step;
+        R->ostep[q + 256] = 1.0 / step;
+    }
+    const double ifq = sqrt(2.);
+    for (int n = 0; n < 4; n++) {
+        R->pre1[n] = pow(ifq, (double)n);
+        R->pre2[n] = pow(ifq, 2.0 * (double)n);
+    }
+    R->ifqstep = sqrt(2.0);
+    R->ifqstep2 = R->ifqstep * R->ifqstep;
+    R->log2c = log(2.0);
+    for (int i = 0; i < 23; i++) R->sfb_l[i] = MP3T_SFB_LONG[sr][i];
+    for (int i = 0; i < 14; i++) R->sfb_s[i] = MP3T_SFB_SHORT[sr][i];
+    for (int i = 0; i < MP3T_HUFF_FLAT; i++) R->hlen[i] = MP3T_HLEN[i];
+    for (int t = 0; t < 34; t++) {
+        R->hoff[t] = MP3T_HUFF[t].off;
+        R->hxlen[t] = (t >= 32) ? 0 : MP3T_HUFF[t].ylen;   // count1 tables are indexed by p alone
+        R->hlinbits[t] = MP3T_HUFF[t].linbits;
+        R->hlinmax[t] = MP3T_HUFF[t].linmax;
+    }
+    for (int s = 0; s < 288; s++) {
+        int e = 2 * s, b = 21;
+        for (int sfb = 0; sfb < 21; sfb++)
+            if (e >= R->sfb_l[sfb] && e < R->sfb_l[sfb + 1]) b = sfb;
+        R->band_long[s] = (unsigned char)b;
+        int m = s / 3, w = s % 3, line = 2 * m;
+        b = 36 + w;
+        for (int sfb = 0; sfb < 12; sfb++)
+            if (line >= R->sfb_s[sfb] && line < R->sfb_s[sfb + 1]) b = 3 * sfb + w;
+        R->band_short[s] = (unsigned char)b;
+    }
+    // subdivide() for plain long blocks, loop.c:1596-1690, tabulated over big_values
+    static const unsigned char subdv[23][2] = {{0,0},{0,0},{0,0},{0,0},{0,0},{0,1},{1,1},{1,1},{1,2},{2,2},{2,3},{2,3},
+        {3,4},{3,4},{3,4},{4,5},{4,5},{4,6},{5,6},{5,6},{5,7},{6,7},{6,7}};
+    for (int bv = 1; bv <= 288; bv++) {
+        int bvr = 2 * bv, n = 0;
+        while (R->sfb_l[n] < bvr) n++;
+        int r0 = subdv[n][0], index = r0 + 1;
+        while (r0 && R->sfb_l[index] > bvr) { r0--; index--; }
+        int r1 = subdv[n][1];
+        index = r0 + r1 + 2;
+        while (r1 && R->sfb_l[index] > bvr) { r1--; index--; }
+        R->subdiv[bv][0] = (unsigned char)r0;
+        R->subdiv[bv][1] = (unsigned char)r1;
+    }
+    static const unsigned char pretab[21] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 2};  // Table B.6
+    for (int i = 0; i < 21; i++) R->pretab[i] = pretab[i];
+}
+
+static double spread_value(double bi, double bj, bool j_ge_i)
+{
+    // l3psy.c:823-842
+    double tempx = j_ge_i ? (bi - bj) * 3.0 : (bi - bj) * 1.5, x, tempy;
+    if (tempx >= 0.5 && tempx <= 2.5) {
+        double temp = tempx - 0.5;
+        x = 8.0 * (temp * temp - 2.0 * temp);
+    } else x = 0.0;
+    tempx += 0.474;
+    tempy = 15.811389 + 7.5 * tempx - 17.5 * sqrt(1.0 + tempx * tempx);
+    if (tempy <= -60.0) return 0.0;
+    return exp((x + tempy) * kLnToLog10);
+}
+
+void build_psy_tables(int sr, PsyTables *P)
+{
+    memset(P, 0, sizeof(*P));
+    const mp3t_part_long &L = MP3T_PART_LONG[sr];
+    const mp3t_part_short &S = MP3T_PART_SHORT[sr];
+    const mp3t_sfb_map &ML = MP3T_SFBMAP_LONG[sr], &MS = MP3T_SFBMAP_SHORT[sr];
+    P->sr_idx = sr; P->n_l = L.n; P->n_s = S.n;
+    for (int i = 0; i < 1024; i++) P->hann_l[i] = (float)(0.5 * (1 - cos(2.0 * kRefPi * (i - 0.5) / 1024)));  // l3psy.c:194
+    for (int i = 0; i < 256; i++) P->hann_s[i] = (float)(0.5 * (1 - cos(2.0 * kRefPi * (i - 0.5) / 256)));    // l3psy.c:195
+    int k2 = 0;
+    for (int i = 0; i < L.n; i++) {
+        P->numlines_pe[i] = L.lines[i];
+        P->minval[i] = L.minval[i]; P->qthr_l[i] = L.qthr[i]; P->norm_l[i] = L.norm[i];
+        P->lo_l[i] = (short)k2;
+        for (int k = 0; k < L.lines[i]; k++) P->part_l[k2++] = (short)i;
+        P->hi_l[i] = (short)k2;
+    }
+    P->tail_l = k2;  // lines k2..512 keep the zero-initialised partition 0 (l3psy.c:93,805-806)
+    for (int i = 0; i < L.n; i++)
+        for (int j = 0; j < L.n; j++) P->s3_l[i * 64 + j] = spread_value(L.bval[i], L.bval[j], j >= i);
+    k2 = 0;
+    for (int i = 0; i < S.n; i++) {
+        P->numlines_pe[i] = S.lines[i];  // l3psy.c:868 overwrites the long counts read at :796
+        P->qthr_s[i] = S.qthr[i]; P->norm_s[i] = S.norm[i];
+        P->snr_s_exp[i] = exp((double)S.snr[i] * kLnToLog10);
+        P->lo_s[i] = (short)k2;
+        for (int k = 0; k < S.lines[i]; k++) P->part_s[k2++] = (short)i;
+        P->hi_s[i] = (short)k2;
+    }
+    for (int i = S.n; i < 42; i++) P->snr_s_exp[i] = exp(0.0 * kLnToLog10);
+    P->tail_s = k2;
+    P->sparse = (sr == 1);
+    // sprdngf1/2 row ranges for 44.1 kHz, l3psy.c:996-1060
+    static const unsigned char lo441[63] = {0,0,0,0,0,0,0,0,0,0,0,1,1,2,3,5,6,7,9,10,11,12,14,15,15,16,16,17,18,19,19,20,
+        21,22,22,23,24,25,26,27,28,29,30,31,32,33,34,35,36,37,37,38,39,40,41,42,43,44,45,46,47,48,48};
+    static const unsigned char hi441[63] = {2,3,4,5,6,7,8,9,10,11,12,14,14,15,15,16,17,19,20,21,22,23,24,25,27,28,28,29,30,31,32,34,
+        35,36,36,37,38,39,41,42,43,44,45,46,47,48,49,50,51,52,53,54,55,56,57,58,59,60,61,62,62,62,62};
+    for (int b = 0; b < 63; b++) {
+        P->spr_lo[b] = P->sparse ? lo441[b] : 0;
+        P->spr_hi[b] = P->sparse ? hi441[b] : 62;
+    }
+    for (int i = 0; i < 21; i++) { P->bu_l[i] = ML.bu[i]; P->bo_l[i] = ML.bo[i]; P->w1_l[i] = ML.w1[i]; P->w2_l[i] = ML.w2[i]; }
+    for (int i = 0; i < 12; i++) { P->bu_s[i] = MS.bu[i]; P->bo_s[i] = MS.bo[i]; P->w1_s[i] = MS.w1[i]; P->w2_s[i] = MS.w2[i]; }
+    P->n_hist_part = P->part_l[5] + 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FFT program builder
+// ---------------------------------------------------------------------------------------------------
+void build_fft_twiddles(std::vector<FftTwiddle> *tw, std::vector<int> *tw_base)
+{
+    // subs.c:255-279 / 446-460: `ang` is a float, cos/sin are evaluated in double on it, results are
+    // stored as float; -(s+c) and s-c are float operations.  Layout here: per logm >= 4, first the
+    // (cn,spcn,smcn) triples for n = 1..m/4-1 (n != m/8), then the (c3n,spc3n,smc3n) triples.
+    tw->clear();
+    tw_base->assign(11, -1);
+    for (int logm = 4; logm <= 10; logm++) {
+        int m = 1 << logm, m4 = m / 4, m8 = m / 8;
+        (*tw_base)[logm] = (int)tw->size();
+        for (int pass = 0; pass < 2; pass++)
+            for (int n = 1; n < m4; n++) {
+                if (n == m8) continue;
+                float ang = (float)((pass ? 3 * n : n) * kTwoPi / m);
+                float c = (float)cos((double)ang), s = (float)sin((double)ang);  // double libm on the float angle
+                FftTwiddle t;
+                t.cn = c; t.spcn = -(s + c); t.smcn = s - c; t.pad = 0.f;
+                tw->push_back(t);
+            }
+    }
+}
+
+namespace {
+struct Builder {
+    std::vector<int> phys;      // logical position -> physical slot
+    std::vector<uint8_t> neg;   // logical position currently stored negated
+    std::vector<FftOp> ops;
+    const std::vector<int> *tw_base;
+
+    void emit(uint8_t type, int a, int b, int c, int d, int tw)
+    {
+        FftOp o;
+        memset(&o, 0, sizeof(o));
+        o.type = type; o.tw = (uint16_t)tw;
+        int idx[4] = {a, b, c, d};
+        uint16_t *dst[4] = {&o.a, &o.b, &o.c, &o.d};
+        for (int i = 0; i < 4; i++)
+            if (idx[i] >= 0) {
+                *dst[i] = (uint16_t)phys[idx[i]];
+                if (neg[idx[i]]) o.neg |= 1 << i;
+                neg[idx[i]] = 0;  // results are stored with their true sign
+            } else *dst[i] = 0xffff;
+        ops.push_back(o);
+    }
+    void flip(int i) { neg[i] ^= 1; }
+    void swap_pos(int i, int j) { std::swap(phys[i], phys[j]); std::swap(neg[i], neg[j]); }
+
+    // complex split-radix node on logical positions xr[0..m), xi[0..m)  (srrec, subs.c:185-362)
+    void cplx(int xr, int xi, int logm)
+    {
+        if (logm <= 0) return;
+        if (logm == 1) { emit(FFT_BFLY, xr, xr + 1, -1, -1, 0); emit(FFT_BFLY, xi, xi + 1, -1, -1, 0); return; }
+        if (logm == 2) {  // subs.c:202-238
+            emit(FFT_BFLY, xr, xr + 2, -1, -1, 0); emit(FFT_BFLY, xi, xi + 2, -1, -1, 0);
+            emit(FFT_BFLY, xr + 1, xr + 3, -1, -1, 0); emit(FFT_BFLY, xi + 1, xi + 3, -1, -1, 0);
+            emit(FFT_BFLY, xr, xr + 1, -1, -1, 0); emit(FFT_BFLY, xi, xi + 1, -1, -1, 0);
+            emit(FFT_CROSS, xr + 2, xr + 3, xi + 2, xi + 3, 0);
+            return;
+        }
+        int m = 1 << logm, m2 = m / 2, m4 = m / 4, m8 = m / 8;
+        for (int n = 0; n < m2; n++) { emit(FFT_BFLY, xr + n, xr + n + m2, -1, -1, 0); emit(FFT_BFLY, xi + n, xi + n + m2, -1, -1, 0); }
+        for (int n = 0; n < m4; n++) emit(FFT_CROSS, xr + m2 + n, xr + m2 + m4 + n, xi + m2 + n, xi + m2 + m4 + n, 0);
+        int nel = m4 - 2, k = 0;
+        for (int n = 1; n < m4; n++) {
+            int a = xr + m2 + n, b = xr + m2 + m4 + n, c = xi + m2 + n, d = xi + m2 + m4 + n;
+            if (n == m8) {
+                emit(FFT_ROT8A, a, -1, c, -1, 0);
+                emit(FFT_ROT8B, b, -1, d, -1, 0);
+            } else {
+                int base = (*tw_base)[logm];
+                emit(FFT_ROT, a, -1, c, -1, base + k);
+                emit(FFT_ROT, b, -1, d, -1, base + nel + k);
+                k++;
+            }
+        }
+        cplx(xr, xi, logm - 1);
+        cplx(xr + m2, xi + m2, logm - 2);
+        cplx(xr + 3 * m4, xi + 3 * m4, logm - 2);
+    }
+
+    // real split-radix node on logical positions x[0..m)  (rsrec, subs.c:412-523)
+    void real(int x, int logm)
+    {
+        if (logm <= 0) return;
+        if (logm == 1) { emit(FFT_BFLY, x, x + 1, -1, -1, 0); return; }
+        int m = 1 << logm, m2 = m / 2, m4 = m / 4, m8 = m / 8;
+        for (int n = 0; n < m2; n++) emit(FFT_BFLY, x + n, x + n + m2, -1, -1, 0);
+        for (int n = 0; n < m4; n++) flip(x + m2 + m4 + n);
+        int k = 0;
+        for (int n = 1; n < m4; n++) {
+            int a = x + m2 + n, c = x + m2 + m4 + n;
+            if (n == m8) emit(FFT_ROT8A, a, -1, c, -1, 0);
+            else { emit(FFT_ROT, a, -1, c, -1, (*tw_base)[logm] + k); k++; }
+        }
+        real(x, logm - 1);
+        cplx(x + m2, x + 3 * m4, logm - 2);
+        {   // step 5, subs.c:501-521: new p = -old q, new q = -old p ; then new p = -old q, new q = old p
+            int p = x + m2 + m4, q = x + m - 1;
+            for (int n = 0; n < m8; n++) { swap_pos(p, q); flip(p); flip(q); p++; q--; }
+            p = x + m2 + 1; q = x + m - 2;
+            for (int n = 0; n < m8; n++) { swap_pos(p, q); flip(p); p += 2; q -= 2; }
+        }
+        if (logm == 2) flip(x + 3);
+    }
+};
+}  // namespace
+
+void build_fft_program(int logm, const std::vector<int> &tw_base, FftProgram *P)
+{
+    const int n = 1 << logm;
+    Builder B;
+    B.phys.resize(n); B.neg.assign(n, 0); B.tw_base = &tw_base;
+    for (int i = 0; i < n; i++) B.phys[i] = i;
+    B.real(0, logm);
+    // BR_permute, subs.c:136-177 (Evans' algorithm == full bit reversal for even logm)
+    for (int i = 0; i < n; i++) {
+        int r = 0;
+        for (int b = 0; b < logm; b++) if (i & (1 << b)) r |= 1 << (logm - 1 - b);
+        if (r > i) B.swap_pos(i, r);
+    }
+    // levelise: every op reads and writes all of its slots
+    std::vector<int> last(n, 0), level(B.ops.size());
+    int n_levels = 0;
+    for (size_t i = 0; i < B.ops.size(); i++) {
+        const FftOp &o = B.ops[i];
+        int l = 0;
+        const uint16_t s[4] = {o.a, o.b, o.c, o.d};
+        for (int j = 0; j < 4; j++) if (s[j] != 0xffff) l = std::max(l, last[s[j]]);
+        l += 1;
+        for (int j = 0; j < 4; j++) if (s[j] != 0xffff) last[s[j]] = l;
+        level[i] = l;
+        n_levels = std::max(n_levels, l);
+    }
+    std::vector<int> order(B.ops.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        if (level[x] != level[y]) return level[x] < level[y];
+        return B.ops[x].type < B.ops[y].type;
+    });
+    P->n = n; P->logm = logm;
+    P->ops.clear(); P->level_start.assign(n_levels + 1, 0);
+    for (size_t i = 0; i < order.size(); i++) {
+        P->ops.push_back(B.ops[order[i]]);
+        P->level_start[level[order[i]]] = (int)i + 1;  // running "end of level l"
+    }
+    for (int l = 1; l <= n_levels; l++) if (P->level_start[l] == 0) P->level_start[l] = P->level_start[l - 1];
+    P->out_slot.resize(n); P->out_neg.resize(n);
+    for (int i = 0; i < n; i++) { P->out_slot[i] = (uint16_t)B.phys[i]; P->out_neg[i] = B.neg[i]; }
+}
+
+void run_fft_program_host(const FftProgram &P, const std::vector<FftTwiddle> &tw, float *x)
+{
+    const double SQ = 0.707106781186547524401;  // subs.c:26
+    for (size_t i = 0; i < P.ops.size(); i++) {
+        const FftOp &o = P.ops[i];
+        float a = 0, b = 0, c = 0, d = 0, t1, t2;
+        if (o.a != 0xffff) a = (o.neg & 1) ? -x[o.a] : x[o.a];
+        if (o.b != 0xffff) b = (o.neg & 2) ? -x[o.b] : x[o.b];
+        if (o.c != 0xffff) c = (o.neg & 4) ? -x[o.c] : x[o.c];
+        if (o.d != 0xffff) d = (o.neg & 8) ? -x[o.d] : x[o.d];
+        switch (o.type) {
+        case FFT_BFLY: t1 = a + b; b = a - b; a = t1; x[o.a] = a; x[o.b] = b; break;
+        case FFT_CROSS: t1 = a + d; t2 = c + b; c = c - b; b = a - d; a = t1; d = t2;
+            x[o.a] = a; x[o.b] = b; x[o.c] = c; x[o.d] = d; break;
+        case FFT_ROT: {
+            const FftTwiddle &w = tw[o.tw];
+            t2 = w.cn * (a + c); t1 = w.spcn * a + t2; a = w.smcn * c + t2; c = t1;
+            x[o.a] = a; x[o.c] = c; break; }
+        case FFT_ROT8A: t1 = (float)(SQ * (a + c)); c = (float)(SQ * (c - a)); a = t1; x[o.a] = a; x[o.c] = c; break;
+        case FFT_ROT8B: t2 = (float)(SQ * (c - a)); c = (float)(-SQ * (a + c)); a = t2; x[o.a] = a; x[o.c] = c; break;
+        }
+    }
+}
+
+}  // namespace mp3gpu

@@ -1,0 +1,89 @@
+// tables.h — constant tables of the hot path, built ON THE HOST with the same libm expressions the
+// reference uses and uploaded once per context.  Nothing here is recomputed
+// with device intrinsics.
+#pragma once
+#include <stdint.h>
+
+#include <vector>
+
+#include "rate_loop_core.h"
+
+namespace mp3gpu {
+
+// ---- polyphase filterbank + MDCT (encode.c:287-409, mdct.c:25-198) ------------------------------
+struct FrontTables {
+    double window[512];      // Table C.1
+    double am[32][32];       // am[sb][j<16] = m[sb][j], am[sb][16+j] = m[sb][33+j] (j<15); [31] unused
+    double win[4][36];       // MDCT windows by block type
+    double cos_l[18][36];
+    double cos_s[6][12];
+    double ca[8], cs[8];     // alias butterflies
+};
+
+// ---- FFT as a levelised straight-line program (subs.c:185-534) ------------------------------------
+// The reference's recursive split-radix real FFT is a fixed dataflow graph.  To get bit-identical
+// FP32 results on a GPU we flatten the recursion ONCE on the host into elementary in-place ops,
+// schedule them into dependency levels, and let a warp execute one level per __syncwarp().
+// Sign changes and data reorders (rsrec step 2/5, BR_permute) are folded into the operand maps.
+enum FftOpType : uint8_t {
+    FFT_BFLY = 0,   // t=a+b; b=a-b; a=t
+    FFT_CROSS = 1,  // t1=a+d; t2=c+b; c=c-b; b=a-d; a=t1; d=t2
+    FFT_ROT = 2,    // t2=cn*(a+c); t1=spcn*a+t2; a=smcn*c+t2; c=t1
+    FFT_ROT8A = 3,  // t1=SQ*(a+c); c=SQ*(c-a); a=t1        (double multiply, rounded to float)
+    FFT_ROT8B = 4,  // t2=SQ*(d-b); d=-SQ*(b+d); b=t2       (operands passed as a:=b, c:=d)
+};
+
+struct FftOp {
+    uint16_t a, b, c, d;  // physical slots
+    uint16_t tw;          // twiddle triple index (FFT_ROT)
+    uint8_t type;
+    uint8_t neg;          // bit0..3: operand a,b,c,d is stored negated
+    uint32_t pad;
+};
+
+struct FftProgram {
+    int n, logm;
+    std::vector<FftOp> ops;            // sorted by level
+    std::vector<int> level_start;      // size n_levels+1
+    std::vector<uint16_t> out_slot;    // logical output index -> physical slot (after bit reversal)
+    std::vector<uint8_t> out_neg;      // ... stored negated?
+};
+
+struct FftTwiddle { float cn, spcn, smcn, pad; };
+
+void build_fft_program(int logm, const std::vector<int> &tw_base, FftProgram *P);
+void build_fft_twiddles(std::vector<FftTwiddle> *tw, std::vector<int> *tw_base);  // tw_base[logm]
+// host interpreter (used by the emulation tests and to self-check the builder at context creation)
+void run_fft_program_host(const FftProgram &P, const std::vector<FftTwiddle> &tw, float *x);
+
+// ---- psychoacoustic model tables (l3psy.c:770-994 + :194-195) -------------------------------------
+struct PsyTables {
+    int sr_idx, n_l, n_s;
+    float hann_l[1024], hann_s[256];
+    int numlines_pe[64];          // quirk: short-table counts overwrite long ones (l3psy.c:796/868)
+    short part_l[513 + 3];
+    short part_s[129 + 3];
+    short lo_l[64], hi_l[64];     // first line / one past last line of long partition b in [0,Σlines)
+    short lo_s[64], hi_s[64];
+    int tail_l, tail_s;           // lines >= tail map to partition 0 (zero-initialised statics)
+    double minval[64], qthr_l[64], norm_l[64];
+    double qthr_s[64], norm_s[64];
+    double snr_s_exp[64];         // exp(SNR_s[b] * LN_TO_LOG10), host libm (l3psy.c:712)
+    double s3_l[63 * 64];         // [b*64 + k]
+    short spr_lo[64], spr_hi[64]; // spreading row range actually summed (44.1 kHz sparse, else dense+skip)
+    int sparse;                   // 1 for 44.1 kHz (sprdngf1/2), 0 otherwise (dense with != 1.0 test)
+    short bu_l[24], bo_l[24], bu_s[12], bo_s[12];
+    double w1_l[24], w2_l[24], w1_s[12], w2_s[12];
+    int n_hist_part;              // partitions that contain FFT lines 0..5 (history-dependent cw)
+};
+
+void build_front_tables(FrontTables *F);
+void build_rate_tables(int sr_idx, RateTables *R);
+void build_psy_tables(int sr_idx, PsyTables *P);
+
+int sr_index(int sfreq_hz);  // 0:32000 1:44100 2:48000, -1 otherwise
+// frame geometry, musicin.c:562-572 and 729-746 (the reference never pads: frac_SpF is computed
+// after avg_slots_per_frame was truncated)
+void frame_geometry(int sfreq_hz, int n_ch, int bitrate_kbps, FrameGeom *G);
+
+}  // namespace mp3gpu

@@ -545,6 +545,8 @@ typedef struct {
 typedef struct {
     int resv_size, resv_max;
     int en_tot[2][2], en[2][2][21], xm[2][2][21], xrmax[2][2]; /* calc_scfsi statics, loop.c:618-621 */
+    int addr[2][2][3]; /* address1..3 live in main()'s static l3_side and are NOT reset per frame:
+                          subdivide() leaves them stale when big_values == 0 (loop.c:1642-1647) */
 } loop_state;
 
 static const int PRETAB[21] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 2}; /* Table B.6 */
@@ -1121,6 +1123,7 @@ int l3o_encode_frame(l3o_enc *e, const short *pcm, l3o_frame *out)
             memset(w, 0, sizeof(*w));
             memset(&xm, 0, sizeof(xm));
             set_block(&w->g, out->block_type[gr][ch]);
+            w->g.address1 = L->addr[gr][ch][0]; w->g.address2 = L->addr[gr][ch][1]; w->g.address3 = L->addr[gr][ch][2];
             if (is_short(&w->g)) { w->sfb_lmax = 0; w->sfb_smax = 0; } else { w->sfb_lmax = 21; w->sfb_smax = 12; } /* gr_deco */
             memcpy(xr, out->xr[gr][ch], sizeof(xr));
             calc_xmin_ref(xr, out->ratio_l[gr][ch], out->ratio_s[gr][ch], w, sr, &xm);
@@ -1135,6 +1138,7 @@ int l3o_encode_frame(l3o_enc *e, const short *pcm, l3o_frame *out)
             }
             L->resv_size += e->mean_bits / n_ch - w->g.part2_3_length;         /* ResvAdjust */
             w->g.global_gain = nint_ref(w->q + 210.0);
+            L->addr[gr][ch][0] = w->g.address1; L->addr[gr][ch][1] = w->g.address2; L->addr[gr][ch][2] = w->g.address3;
         }
     { /* ResvFrameEnd, reservoir.c:155-226 */
         int over_bits, stuffing;

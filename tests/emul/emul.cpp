@@ -1,0 +1,62 @@
+// TEST HARNESS (host emulation of the SIMT kernels, see csrc/simt.h).  Compiled by tests/emul/Makefile
+// with -DMP3GPU_HOST_EMUL; loaded by tests/test_emul_*.py.  Not part of libmp3gpu.so.
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../mp3-enc-bsd_b200/csrc/rate_loop_core.h"
+#include "../../mp3-enc-bsd_b200/csrc/tables.h"
+
+namespace simt { thread_local int g_tid = 0; }
+using namespace mp3gpu;
+
+extern "C" {
+
+// FFT program vs the oracle FFT: x[n] in, transformed in place into LOGICAL order
+int emul_fft(float *x, int n, int *n_ops, int *n_levels)
+{
+    std::vector<FftTwiddle> tw; std::vector<int> base;
+    build_fft_twiddles(&tw, &base);
+    FftProgram P;
+    build_fft_program(n == 1024 ? 10 : 8, base, &P);
+    std::vector<float> buf(x, x + n);
+    run_fft_program_host(P, tw, buf.data());
+    for (int i = 0; i < n; i++) x[i] = P.out_neg[i] ? -buf[P.out_slot[i]] : buf[P.out_slot[i]];
+    *n_ops = (int)P.ops.size(); *n_levels = (int)P.level_start.size() - 1;
+    // level sanity: ops of one level must touch disjoint slots
+    for (size_t l = 0; l + 1 < P.level_start.size(); l++) {
+        std::vector<char> used(n, 0);
+        for (int i = P.level_start[l]; i < P.level_start[l + 1]; i++) {
+            const FftOp &o = P.ops[i];
+            const uint16_t s[4] = {o.a, o.b, o.c, o.d};
+            for (int j = 0; j < 4; j++) if (s[j] != 0xffff) { if (used[s[j]]) return -1; used[s[j]] = 1; }
+        }
+    }
+    return 0;
+}
+
+// rate loop over one stream. xr [n_frames*2*n_ch][576], psy [same] PsyOut; outputs as the kernel writes them
+int emul_rate_loop_stream(int sfreq, int n_ch, int bitrate, int n_frames, const double *xr, const PsyOut *psy,
+                          short *ix, GrInfoOut *gi, unsigned char *sf, FrameOut *fo, int *max_bits)
+{
+    int sr = sr_index(sfreq);
+    if (sr < 0) return -1;
+    RateTables *T = (RateTables *)calloc(1, sizeof(RateTables));
+    build_rate_tables(sr, T);
+    FrameGeom G;
+    frame_geometry(sfreq, n_ch, bitrate, &G);
+    LoopStreamState S;
+    memset(&S, 0, sizeof(S));
+    PerThread<int> st_en[4], st_xm[4];
+    memset(st_en, 0, sizeof(st_en)); memset(st_xm, 0, sizeof(st_xm));
+    double scr[288];
+    WarpCtx w;
+    rate_loop_stream(w, *T, scr, G, S, st_en, st_xm, n_frames, xr, psy, ix, gi, sf, fo, max_bits);
+    free(T);
+    return 0;
+}
+
+int emul_sizeof_psyout() { return (int)sizeof(PsyOut); }
+int emul_sizeof_frameout() { return (int)sizeof(FrameOut); }
+}
