@@ -1,0 +1,447 @@
+// psy_core.h — psychoacoustic model 2, Layer III branch (replaces L3psycho_anal(),
+// /root/reference/src/l3psy.c:443-740, and fft()/enphinew(), subs.c:38-534).
+//
+// The reference call for granule g of a channel depends on earlier calls only through
+//   (i)   r / phi of FFT lines 0..5 of calls g-1, g-2          (l3psy.c:498-501)
+//   (ii)  nb of calls g-1, g-2 (pre-echo control)              (l3psy.c:632-635)
+//   (iii) blocktype_old and the delayed ratio / ratio_s        (l3psy.c:452-456, 653-733)
+// so the work is split in two kernels:
+//   psy_front : one warp per granule-channel, fully parallel — windows, the 1024- and 3x256-point
+//               FFTs (bit-exact FP32 op program, tables.h), energies, unpredictability of lines
+//               6..205, partition energies, the energy spreading and the complete short-block
+//               threshold path.  Writes a PsyMid record (1.5 KB).
+//   psy_scan  : one warp per (stream, channel), sequential over granules — the few hundred flops
+//               per granule that need history: cw of lines 0..5, tonality, SNR, nb, pre-echo,
+//               PE, long-block ratios, block-type state machine.  Writes PsyOut.
+// Mixed float/double accumulation types and orders follow the reference statement by statement.
+#pragma once
+#include "rate_loop_core.h"  // PsyOut
+#include "simt.h"
+#include "tables.h"
+
+namespace mp3gpu {
+
+using simt::PerThread;
+using simt::WarpCtx;
+
+struct FftDev {
+    const FftOp *ops;
+    const int *level_start;
+    int n_levels;
+    const uint16_t *out;  // logical index -> slot | (neg << 15)
+};
+
+struct PsyDev {
+    const PsyTables *T;
+    const FftTwiddle *tw;
+    FftDev f1024, f256;
+};
+
+struct PsyMid {
+    double eb[64];       // long partition energies (history free)
+    double ratio_s[36];  // short-block ratios this granule WOULD produce, [sfb][window]
+    float ecb[64];       // spread energy
+    float cb[64];        // weighted unpredictability, valid for partitions >= n_hist_part
+    float tail[48];      // energies of lines >= tail_l (they fold into partition 0), line order
+    float e6[8], phi6[8];
+};
+
+struct PsyFrontSmem {
+    float x[1024];
+    float E[520];
+    float Es[3][132];
+    float Ps[3][56];
+    double cwv[52];
+    double eb[64];
+    double thr[64];
+};
+
+struct PsyScanSmem {
+    double eb[64], thr[64], prod[64];
+    double cw6[8];
+    float cb[64];
+    double pe;
+};
+
+struct PsyChanState {  // persistent per (stream, channel)
+    float r1[8], r2[8], p1[8], p2[8];  // r / phi of lines 0..5 after calls g-1 (1) and g-2 (2)
+    float nb1[64], nb2[64];
+    double ratio_l[24];
+    double ratio_s[36];
+    int blocktype_old, pad;
+};
+
+static const double kLn2Log10 = 0.2302585093;  // LN_TO_LOG10, common.h:204
+
+SIMT_FN void fft_exec(const FftOp &o, const FftTwiddle *tw, float *x)
+{
+    const double SQ = 0.707106781186547524401;  // SQHALF, subs.c:26
+    float a = x[o.a], c, b, d, t1, t2;
+    if (o.neg & 1) a = -a;
+    switch (o.type) {
+    case FFT_BFLY:
+        b = x[o.b]; if (o.neg & 2) b = -b;
+        t1 = simt::fadd(a, b); b = simt::fsub(a, b);
+        x[o.a] = t1; x[o.b] = b;
+        break;
+    case FFT_CROSS:
+        b = x[o.b]; c = x[o.c]; d = x[o.d];
+        if (o.neg & 2) b = -b;
+        if (o.neg & 4) c = -c;
+        if (o.neg & 8) d = -d;
+        t1 = simt::fadd(a, d); t2 = simt::fadd(c, b);
+        x[o.c] = simt::fsub(c, b); x[o.b] = simt::fsub(a, d);
+        x[o.a] = t1; x[o.d] = t2;
+        break;
+    case FFT_ROT: {
+        c = x[o.c]; if (o.neg & 4) c = -c;
+        const FftTwiddle w = tw[o.tw];
+        t2 = simt::fmul(w.cn, simt::fadd(a, c));
+        t1 = simt::fadd(simt::fmul(w.spcn, a), t2);
+        x[o.a] = simt::fadd(simt::fmul(w.smcn, c), t2);
+        x[o.c] = t1;
+        break; }
+    case FFT_ROT8A:
+        c = x[o.c]; if (o.neg & 4) c = -c;
+        t1 = (float)simt::dmul(SQ, (double)simt::fadd(a, c));
+        x[o.c] = (float)simt::dmul(SQ, (double)simt::fsub(c, a));
+        x[o.a] = t1;
+        break;
+    default:  // FFT_ROT8B
+        c = x[o.c]; if (o.neg & 4) c = -c;
+        t2 = (float)simt::dmul(SQ, (double)simt::fsub(c, a));
+        x[o.c] = (float)simt::dmul(-SQ, (double)simt::fadd(a, c));
+        x[o.a] = t2;
+        break;
+    }
+}
+
+SIMT_FN void fft_run(const WarpCtx &w, const FftDev &P, const FftTwiddle *tw, float *x)
+{
+    for (int l = 0; l < P.n_levels; l++) {
+        const int lo = P.level_start[l], hi = P.level_start[l + 1];
+        FOR_THREADS(w)
+        for (int i = lo + lane; i < hi; i += 32) fft_exec(P.ops[i], tw, x);
+        END_THREADS
+        w.sync();
+    }
+}
+
+SIMT_FN float fft_logical(const FftDev &P, const float *x, int i)
+{
+    unsigned s = P.out[i];
+    float v = x[s & 0x7fff];
+    return (s & 0x8000) ? -v : v;
+}
+
+// energy + phase of bin i (enphinew, subs.c:53-123); n = transform length
+SIMT_FN void bin_energy_phase(const FftDev &P, const float *x, int n, int i, bool want_phi, float *e_out, float *phi_out)
+{
+    float re = fft_logical(P, x, i);
+    if (i == 0 || i == n / 2) {
+        *e_out = simt::fmul(re, re);
+        if (want_phi) *phi_out = (float)atan2(0.0, (double)re);
+        return;
+    }
+    float im = fft_logical(P, x, n - i);
+    float e = simt::fadd(simt::fmul(re, re), simt::fmul(im, im));
+    if ((double)e < 0.0005) { *e_out = (float)0.0005; if (want_phi) *phi_out = 0.0f; }
+    else { *e_out = e; if (want_phi) *phi_out = (float)atan2(-(double)im, (double)re); }
+}
+
+SIMT_FN double unpredictability(double r_new, double phi_new, double r_prime, double phi_prime)
+{
+    // l3psy.c:503-511 / 540-547
+    double t1 = simt::dsub(simt::dmul(r_new, cos(phi_new)), simt::dmul(r_prime, cos(phi_prime)));
+    double t2 = simt::dsub(simt::dmul(r_new, sin(phi_new)), simt::dmul(r_prime, sin(phi_prime)));
+    double t3 = simt::dadd(r_new, fabs(r_prime));
+    if (t3 != 0.0) return sqrt(simt::dadd(simt::dmul(t1, t1), simt::dmul(t2, t2))) / t3;
+    return 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// psy_front: history-free part, one warp per granule-channel.
+// pcm points at the first NEW sample of the granule (sample 576 g); pcm[-768 ..  575] are read.
+// ---------------------------------------------------------------------------------------------------
+SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &M, const short *pcm, PsyMid *out)
+{
+    const PsyTables &T = *D.T;
+    // long window + FFT, l3psy.c:483-494
+    FOR_THREADS(w)
+    for (int j = lane; j < 1024; j += 32) M.x[j] = simt::fmul(T.hann_l[j], (float)(int)pcm[j - 768]);
+    END_THREADS
+    w.sync();
+    fft_run(w, D.f1024, D.tw, M.x);
+    FOR_THREADS(w)
+    for (int i = lane; i <= 512; i += 32) {
+        float e, ph = 0.f;
+        bin_energy_phase(D.f1024, M.x, 1024, i, i < 6, &e, &ph);
+        M.E[i] = e;
+        if (i < 6) { out->e6[i] = e; out->phi6[i] = ph; }
+    }
+    END_THREADS
+    w.sync();
+    // three short FFTs, l3psy.c:518-527
+    for (int sb = 0; sb < 3; sb++) {
+        FOR_THREADS(w)
+        for (int j = lane; j < 256; j += 32) M.x[j] = simt::fmul(T.hann_s[j], (float)(int)pcm[j - 768 + 128 * (2 + sb)]);
+        END_THREADS
+        w.sync();
+        fft_run(w, D.f256, D.tw, M.x);
+        FOR_THREADS(w)
+        for (int i = lane; i <= 128; i += 32) {
+            float e, ph = 0.f;
+            bool wp = (i >= 2 && i < 52);
+            bin_energy_phase(D.f256, M.x, 256, i, wp, &e, &ph);
+            M.Es[sb][i] = e;
+            if (wp) M.Ps[sb][i] = ph;
+        }
+        END_THREADS
+        w.sync();
+    }
+    // unpredictability of lines 6..205 in groups of four, l3psy.c:531-549
+    FOR_THREADS(w)
+    for (int i = lane; i < 50; i += 32) {
+        const int k = i + 2;
+        double r_prime = simt::dsub(simt::dmul(2.0, sqrt((double)M.Es[0][k])), sqrt((double)M.Es[2][k]));
+        double phi_prime = simt::dsub(simt::dmul(2.0, (double)M.Ps[0][k]), (double)M.Ps[2][k]);
+        double r2 = sqrt((double)M.Es[1][k]);
+        M.cwv[i] = unpredictability(r2, (double)M.Ps[1][k], r_prime, phi_prime);
+    }
+    for (int j = T.tail_l + lane; j <= 512; j += 32) out->tail[j - T.tail_l] = M.E[j];
+    END_THREADS
+    w.sync();
+    // partition energy / weighted unpredictability, l3psy.c:565-578
+    FOR_THREADS(w)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int p = lane + 32 * h;
+        double eb = 0.0;
+        float cb = 0.0f;
+        if (p < T.n_l) {
+            for (int j = T.lo_l[p]; j < T.hi_l[p]; j++) {
+                eb = simt::dadd(eb, (double)M.E[j]);
+                if (p >= T.n_hist_part) {
+                    double cw = (j < 206) ? M.cwv[(j - 6) >> 2] : 0.4;
+                    cb = (float)simt::dadd((double)cb, simt::dmul(cw, (double)M.E[j]));
+                }
+            }
+            if (p == 0)
+                for (int j = T.tail_l; j <= 512; j++) eb = simt::dadd(eb, (double)M.E[j]);
+        }
+        M.eb[p] = eb;
+        out->eb[p] = eb;
+        out->cb[p] = cb;
+    }
+    END_THREADS
+    w.sync();
+    // energy spreading, l3psy.c:586-605 (ecb is a float accumulator)
+    FOR_THREADS(w)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int b = lane + 32 * h;
+        float ecb = 0.0f;
+        if (b < 63) {
+            for (int k = T.spr_lo[b]; k <= T.spr_hi[b]; k++) {
+                double s = T.s3_l[b * 64 + k];
+                if (T.sparse || s != 1.0) ecb = (float)simt::dadd((double)ecb, simt::dmul(s, M.eb[k]));
+            }
+        }
+        out->ecb[b] = ecb;
+    }
+    END_THREADS
+    w.sync();
+    // short-block thresholds, l3psy.c:698-729 (uses the LONG spreading matrix and norm_l, sic)
+    for (int sb = 0; sb < 3; sb++) {
+        FOR_THREADS(w)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int p = lane + 32 * h;
+            if (p < 42) {
+                double eb = 0.0;
+                if (p < T.n_s) for (int j = T.lo_s[p]; j < T.hi_s[p]; j++) eb = simt::dadd(eb, (double)M.Es[sb][j]);
+                if (p == 0) for (int j = T.tail_s; j <= 128; j++) eb = simt::dadd(eb, (double)M.Es[sb][j]);
+                M.eb[p] = eb;
+            }
+        }
+        END_THREADS
+        w.sync();
+        FOR_THREADS(w)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int b = lane + 32 * h;
+            if (b < 42) {
+                float ecb = 0.0f;
+                for (int k = 0; k < 42; k++) ecb = (float)simt::dadd((double)ecb, simt::dmul(T.s3_l[b * 64 + k], M.eb[k]));
+                float nb = (float)simt::dmul(simt::dmul((double)ecb, T.norm_l[b]), T.snr_s_exp[b]);
+                M.thr[b] = (T.qthr_s[b] > (double)nb) ? T.qthr_s[b] : (double)nb;
+            }
+        }
+        END_THREADS
+        w.sync();
+        FOR_THREADS(w)
+        if (lane < 12) {
+            const int bu = T.bu_s[lane], bo = T.bo_s[lane];
+            double en = simt::dadd(simt::dmul(T.w1_s[lane], M.eb[bu]), simt::dmul(T.w2_s[lane], M.eb[bo]));
+            double thm = simt::dadd(simt::dmul(T.w1_s[lane], M.thr[bu]), simt::dmul(T.w2_s[lane], M.thr[bo]));
+            for (int b = bu + 1; b < bo; b++) { en = simt::dadd(en, M.eb[b]); thm = simt::dadd(thm, M.thr[b]); }
+            out->ratio_s[lane * 3 + sb] = (en != 0.0) ? thm / en : 0.0;
+        }
+        END_THREADS
+        w.sync();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// psy_scan: history-dependent part, one warp per (stream, channel), granules in order.
+// ---------------------------------------------------------------------------------------------------
+struct PsyScanRegs {
+    PerThread<float> r1, r2, p1, p2;  // lane = FFT line (< 6)
+    PerThread<float> nb1[2], nb2[2];  // partition lane + 32 h
+    PerThread<double> rl;             // long ratio, lane = sfb (< 21)
+    PerThread<double> rs[2];          // short ratio, index lane + 32 h (< 36)
+    int blocktype_old;
+};
+
+SIMT_FN void psy_scan_load(const WarpCtx &w, const PsyChanState &S, PsyScanRegs &R)
+{
+    FOR_THREADS(w)
+    R.r1() = (lane < 6) ? S.r1[lane] : 0.f; R.r2() = (lane < 6) ? S.r2[lane] : 0.f;
+    R.p1() = (lane < 6) ? S.p1[lane] : 0.f; R.p2() = (lane < 6) ? S.p2[lane] : 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; h++) { R.nb1[h]() = S.nb1[lane + 32 * h]; R.nb2[h]() = S.nb2[lane + 32 * h]; }
+    R.rl() = (lane < 21) ? S.ratio_l[lane] : 0.0;
+    R.rs[0]() = S.ratio_s[lane];
+    R.rs[1]() = (lane < 4) ? S.ratio_s[32 + lane] : 0.0;
+    END_THREADS
+    R.blocktype_old = S.blocktype_old;
+}
+
+SIMT_FN void psy_scan_store(const WarpCtx &w, PsyChanState &S, const PsyScanRegs &R)
+{
+    FOR_THREADS(w)
+    if (lane < 6) { S.r1[lane] = R.r1(); S.r2[lane] = R.r2(); S.p1[lane] = R.p1(); S.p2[lane] = R.p2(); }
+#pragma unroll
+    for (int h = 0; h < 2; h++) { S.nb1[lane + 32 * h] = R.nb1[h](); S.nb2[lane + 32 * h] = R.nb2[h](); }
+    if (lane < 21) S.ratio_l[lane] = R.rl();
+    S.ratio_s[lane] = R.rs[0]();
+    if (lane < 4) S.ratio_s[32 + lane] = R.rs[1]();
+    if (lane == 0) S.blocktype_old = R.blocktype_old;
+    END_THREADS
+}
+
+SIMT_FN void psy_scan_step(const WarpCtx &w, const PsyTables &T, PsyScanSmem &M, const PsyMid &mid, PsyScanRegs &R, PsyOut *out)
+{
+    // delayed outputs first: the caller gets the ratios left by the PREVIOUS call (l3psy.c:452-456)
+    FOR_THREADS(w)
+    if (lane < 21) out->ratio_l[lane] = R.rl();
+    out->ratio_s[lane] = R.rs[0]();
+    if (lane < 4) out->ratio_s[32 + lane] = R.rs[1]();
+    END_THREADS
+    // unpredictability of lines 0..5, l3psy.c:496-512
+    FOR_THREADS(w)
+    if (lane < 6) {
+        double r_prime = simt::dsub(simt::dmul(2.0, (double)R.r1()), (double)R.r2());
+        double phi_prime = simt::dsub(simt::dmul(2.0, (double)R.p1()), (double)R.p2());
+        float rn = (float)sqrt((double)mid.e6[lane]);
+        float pn = mid.phi6[lane];
+        M.cw6[lane] = unpredictability((double)rn, (double)pn, r_prime, phi_prime);
+        R.r2() = R.r1(); R.r1() = rn;
+        R.p2() = R.p1(); R.p1() = pn;
+    }
+    END_THREADS
+    w.sync();
+    // cb of the partitions that hold lines 0..5 (+ the partition-0 tail), l3psy.c:570-578
+    FOR_THREADS(w)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int p = lane + 32 * h;
+        float cb = mid.cb[p];
+        if (p < T.n_hist_part) {
+            cb = 0.0f;
+            for (int j = T.lo_l[p]; j < T.hi_l[p]; j++) cb = (float)simt::dadd((double)cb, simt::dmul(M.cw6[j], (double)mid.e6[j]));
+            if (p == 0)
+                for (int j = T.tail_l; j <= 512; j++) cb = (float)simt::dadd((double)cb, simt::dmul(0.4, (double)mid.tail[j - T.tail_l]));
+        }
+        M.cb[p] = cb;
+    }
+    END_THREADS
+    w.sync();
+    // spreading of cb, tonality, SNR, nb, pre-echo, PE terms: l3psy.c:586-645
+    FOR_THREADS(w)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int b = lane + 32 * h;
+        if (b < 63) {
+            double ctb = 0.0;
+            for (int k = T.spr_lo[b]; k <= T.spr_hi[b]; k++) {
+                double s = T.s3_l[b * 64 + k];
+                if (T.sparse || s != 1.0) ctb = simt::dadd(ctb, simt::dmul(s, (double)M.cb[k]));
+            }
+            const float ecb = mid.ecb[b];
+            double cbb;
+            if ((double)ecb != 0.0) {
+                cbb = ctb / (double)ecb;
+                if (cbb < 0.01) cbb = 0.01;
+                cbb = log(cbb);
+            } else cbb = 0.0;
+            double tbb = simt::dsub(-0.299, simt::dmul(0.43, cbb));
+            tbb = (0.0 > tbb) ? 0.0 : tbb;
+            tbb = (1.0 < tbb) ? 1.0 : tbb;
+            double v = simt::dadd(simt::dmul(29.0, tbb), simt::dmul(6.0, simt::dsub(1.0, tbb)));
+            double snr = (T.minval[b] > v) ? T.minval[b] : v;
+            float nb = (float)simt::dmul(simt::dmul((double)ecb, T.norm_l[b]), exp(simt::dmul(-snr, kLn2Log10)));
+            double a = simt::dmul(2.0, (double)R.nb1[h]()), c = simt::dmul(16.0, (double)R.nb2[h]());
+            double mn = (a < c) ? a : c;
+            double t = ((double)nb < mn) ? (double)nb : mn;
+            double thr = (T.qthr_l[b] > t) ? T.qthr_l[b] : t;
+            R.nb2[h]() = R.nb1[h]();
+            R.nb1[h]() = nb;
+            const double eb = mid.eb[b];
+            double l = log(simt::dadd(thr, 1.0) / simt::dadd(eb, 1.0));
+            double tp = (0.0 < l) ? 0.0 : l;
+            M.prod[b] = simt::dmul((double)T.numlines_pe[b], tp);
+            M.thr[b] = thr;
+            M.eb[b] = eb;
+        }
+    }
+    END_THREADS
+    w.sync();
+    FOR_THREADS(w)
+    if (lane == 0) {
+        double pe = 0.0;
+        for (int b = 0; b < 63; b++) pe = simt::dsub(pe, M.prod[b]);
+        M.pe = pe;
+    }
+    END_THREADS
+    w.sync();
+    const double pe = M.pe;
+    int blocktype;
+    if (pe < 1800) {  // l3psy.c:651-685
+        blocktype = (R.blocktype_old == 2) ? 3 : 0;
+        FOR_THREADS(w)
+        if (lane < 21) {
+            const int bu = T.bu_l[lane], bo = T.bo_l[lane];
+            double en = simt::dadd(simt::dmul(T.w1_l[lane], M.eb[bu]), simt::dmul(T.w2_l[lane], M.eb[bo]));
+            double thm = simt::dadd(simt::dmul(T.w1_l[lane], M.thr[bu]), simt::dmul(T.w2_l[lane], M.thr[bo]));
+            for (int b = bu + 1; b < bo; b++) { en = simt::dadd(en, M.eb[b]); thm = simt::dadd(thm, M.thr[b]); }
+            R.rl() = (en != 0.0) ? thm / en : 0.0;
+        }
+        END_THREADS
+    } else {          // l3psy.c:686-730
+        blocktype = 2;
+        if (R.blocktype_old == 0) R.blocktype_old = 1;
+        if (R.blocktype_old == 3) R.blocktype_old = 2;
+        FOR_THREADS(w)
+        R.rs[0]() = mid.ratio_s[lane];
+        if (lane < 4) R.rs[1]() = mid.ratio_s[32 + lane];
+        END_THREADS
+    }
+    FOR_THREADS(w)
+    if (lane == 0) { out->pe = pe; out->block_type = R.blocktype_old; out->pad = 0; }
+    END_THREADS
+    R.blocktype_old = blocktype;  // l3psy.c:732-733
+    w.sync();
+}
+
+}  // namespace mp3gpu

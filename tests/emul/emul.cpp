@@ -5,6 +5,8 @@
 
 #include <vector>
 
+#include "../../mp3-enc-bsd_b200/csrc/front_core.h"
+#include "../../mp3-enc-bsd_b200/csrc/psy_core.h"
 #include "../../mp3-enc-bsd_b200/csrc/rate_loop_core.h"
 #include "../../mp3-enc-bsd_b200/csrc/tables.h"
 
@@ -54,6 +56,58 @@ int emul_rate_loop_stream(int sfreq, int n_ch, int bitrate, int n_frames, const 
     WarpCtx w;
     rate_loop_stream(w, *T, scr, G, S, st_en, st_xm, n_frames, xr, psy, ix, gi, sf, fo, max_bits);
     free(T);
+    return 0;
+}
+
+// whole pipeline for one stream, kernel by kernel, exactly as the CUDA launch sequence does it.
+// pcm: planar [n_ch][hist + n_frames*1152] with hist = 1056 leading zeros (history before the stream)
+int emul_encode_stream(int sfreq, int n_ch, int bitrate, int n_frames, const short *pcm, long ch_stride, int hist,
+                       double *sb /*[gc][18][32]*/, double *xr /*[gc][576]*/, PsyOut *psy /*[gc]*/, short *ix,
+                       GrInfoOut *gi, unsigned char *sf, FrameOut *fo, int *max_bits)
+{
+    int sr = sr_index(sfreq);
+    if (sr < 0) return -1;
+    static FrontTables F; static PsyTables PT; static RateTables RT;
+    build_front_tables(&F); build_psy_tables(sr, &PT); build_rate_tables(sr, &RT);
+    std::vector<FftTwiddle> tw; std::vector<int> base;
+    build_fft_twiddles(&tw, &base);
+    FftProgram P10, P8;
+    build_fft_program(10, base, &P10); build_fft_program(8, base, &P8);
+    auto mkdev = [](const FftProgram &P, std::vector<uint16_t> &outmap) {
+        outmap.resize(P.n);
+        for (int i = 0; i < P.n; i++) outmap[i] = (uint16_t)(P.out_slot[i] | (P.out_neg[i] ? 0x8000 : 0));
+        FftDev d; d.ops = P.ops.data(); d.level_start = P.level_start.data(); d.n_levels = (int)P.level_start.size() - 1; d.out = outmap.data();
+        return d;
+    };
+    std::vector<uint16_t> o10, o8;
+    PsyDev D; D.T = &PT; D.tw = tw.data(); D.f1024 = mkdev(P10, o10); D.f256 = mkdev(P8, o8);
+    const int n_gran = 2 * n_frames;
+    WarpCtx w;
+    std::vector<PsyMid> mid((size_t)n_gran * n_ch);
+    static PsyFrontSmem PF;
+    for (int ch = 0; ch < n_ch; ch++)
+        for (int g = 0; g < n_gran; g++) {
+            memset(&mid[(size_t)g * n_ch + ch], 0, sizeof(PsyMid));
+            psy_front(w, D, PF, pcm + ch * ch_stride + hist + 576L * g, &mid[(size_t)g * n_ch + ch]);
+        }
+    static PsyScanSmem PS;
+    for (int ch = 0; ch < n_ch; ch++) {
+        PsyChanState st; memset(&st, 0, sizeof(st));
+        PsyScanRegs R;
+        psy_scan_load(w, st, R);
+        for (int g = 0; g < n_gran; g++) psy_scan_step(w, PT, PS, mid[(size_t)g * n_ch + ch], R, &psy[(size_t)g * n_ch + ch]);
+        psy_scan_store(w, st, R);
+    }
+    static FrontWarpSmem FM;
+    for (int ch = 0; ch < n_ch; ch++)
+        front_walk(w, F, FM, pcm + ch * ch_stride + hist, 0, n_gran, &psy[ch].block_type, (long)(sizeof(PsyOut) / sizeof(int)) * n_ch,
+                   xr + 576L * ch, 576L * n_ch, sb ? sb + 576L * ch : nullptr, 576L * n_ch);
+    FrameGeom G; frame_geometry(sfreq, n_ch, bitrate, &G);
+    LoopStreamState S; memset(&S, 0, sizeof(S));
+    PerThread<int> st_en[4], st_xm[4];
+    memset(st_en, 0, sizeof(st_en)); memset(st_xm, 0, sizeof(st_xm));
+    double scr[288];
+    rate_loop_stream(w, RT, scr, G, S, st_en, st_xm, n_frames, xr, psy, ix, gi, sf, fo, max_bits);
     return 0;
 }
 
