@@ -1,0 +1,133 @@
+/* mp3gpu.h — C ABI of libmp3gpu.so: the Layer III front end + rate loop of lieff/mp3-enc-bsd,
+ * batched over many streams on one B200 (hand-written sm_100a CUDA, no CPU fallback).
+ *
+ * Drop-in boundary: the reference is a monolithic C program; what its frame loop
+ * calls for the hot path are five plain C symbols (musicin.c:754,767,768,774,779).  This library
+ * exports, for each of them, a BATCHED variant over n_streams x n_frames with the reference's
+ * hidden function statics turned into per-stream state owned by an mp3gpu_ctx:
+ *
+ *   reference entry point (file:line)                        batched replacement
+ *   -------------------------------------------------------  ------------------------------------
+ *   window_subband  encode.c:287 / filter_subband encode.c:361  mp3gpu_filter_subband_batch
+ *   mdct_sub        mdct.c:25                                 mp3gpu_mdct_sub_batch
+ *   L3psycho_anal   l3psy.c:53                                mp3gpu_L3psycho_anal_batch
+ *   iteration_loop  loop.c:232 (outer_loop, inner_loop,       mp3gpu_iteration_loop_batch
+ *                   bin_search_StepSize, reservoir.c)
+ *   quantize loop.c:1360 + count_bits loop.c:2099             mp3gpu_quantize_count_batch
+ *     (calc_runlen, count1_bitcount, subdivide,
+ *      bigv_tab_select/new_choose_table, bigv_bitcount)
+ *   the four calls of one frame, musicin.c:751-779            mp3gpu_encode_frames[_dev]
+ *
+ * The single-frame legacy signatures themselves are declared in mp3gpu_legacy.h.
+ *
+ * Conventions: every function returns 0 on success, a negative MP3GPU_E* code otherwise (the
+ * reference exit()s/abort()s instead; a library must not).  mp3gpu_last_error() gives the text.
+ * All pointers are plain host or device pointers as documented; `stream` is a cudaStream_t passed
+ * as void* (NULL = default stream).  A ctx is bound to one device and is not thread safe.
+ *
+ * Data layouts (gc = granule-channel; n_gran = 2*n_frames; per stream g = granule*n_ch + ch):
+ *   pcm   int16  [n_streams][n_ch][n_frames*1152]   planar (de-interleaved, as get_audio() does)
+ *   sb    double [n_streams][n_gran*n_ch][18][32]    raw filter_subband output (before mdct sign fix)
+ *   xr    double [n_streams][n_gran*n_ch][576]       mdct_sub output, band major, short = [192][3]
+ *   psy   mp3gpu_psy_out [n_streams][n_gran*n_ch]
+ *   ix    int16  [n_streams][n_gran*n_ch][576]       quantised spectrum WITH sign (what the reference
+ *                                                    has after l3bitstream.c:115-125)
+ *   gi    mp3gpu_gr_info [n_streams][n_gran*n_ch]
+ *   sf    uint8  [n_streams][n_gran*n_ch][40]        long: l[0..21]; short: s[sfb][window] at 3*sfb+w
+ *   fo    mp3gpu_frame_out [n_streams][n_frames]
+ */
+#ifndef MP3GPU_H
+#define MP3GPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MP3GPU_OK 0
+#define MP3GPU_EINVAL (-1)   /* bad argument / unsupported configuration */
+#define MP3GPU_ECUDA (-2)    /* CUDA runtime error (no device, launch failure, ...) */
+#define MP3GPU_ENOMEM (-3)
+#define MP3GPU_ESTATE (-4)   /* call sequence error (e.g. more streams than the ctx was created for) */
+
+typedef struct mp3gpu_ctx mp3gpu_ctx;
+
+typedef struct {
+    int sfreq_hz;        /* 32000 | 44100 | 48000 (MPEG-1; the reference refuses LSF rates for Layer III) */
+    int n_ch;            /* 1 | 2 (plain stereo; the reference refuses joint stereo for Layer III) */
+    int bitrate_kbps;    /* MPEG-1 Layer III table value, total for all channels */
+    int max_streams;     /* capacity: streams per call */
+    int max_frames;      /* capacity: frames per stream per call */
+    int device;          /* CUDA device ordinal */
+} mp3gpu_config;
+
+/* side info of one granule-channel (subset of gr_info, l3side.h:41-72), 20 ints */
+typedef struct {
+    int part2_3_length, big_values, count1, global_gain, scalefac_compress;
+    int window_switching_flag, block_type, mixed_block_flag;
+    int table_select[3];
+    int region0_count, region1_count, preflag, scalefac_scale, count1table_select;
+    int part2_length, address1, address2, address3;
+} mp3gpu_gr_info;
+
+/* L3psycho_anal outputs of one call (l3psy.h:32-34) */
+typedef struct {
+    double pe;
+    double ratio_l[21];
+    double ratio_s[36];   /* [sfb][window] */
+    int block_type;
+    int pad;
+} mp3gpu_psy_out;
+
+typedef struct {
+    int resv_drain;        /* III_side_info_t.resvDrain */
+    int main_data_begin;   /* back pointer of this frame, bytes */
+    unsigned char scfsi[2][4];
+} mp3gpu_frame_out;
+
+const char *mp3gpu_last_error(void);
+const char *mp3gpu_version(void);
+
+int mp3gpu_create(const mp3gpu_config *cfg, mp3gpu_ctx **out);
+void mp3gpu_destroy(mp3gpu_ctx *ctx);
+/* forget all per-stream state (filterbank/MDCT history, psy history, reservoir): start of new streams */
+int mp3gpu_reset(mp3gpu_ctx *ctx);
+/* frame geometry the reference derives in musicin.c:562-572,729-746 */
+int mp3gpu_frame_geometry(const mp3gpu_ctx *ctx, int *bits_per_frame, int *mean_bits);
+
+/* ---- whole hot path: psy -> filterbank -> MDCT -> rate loop, continuing the ctx's streams ---------
+ * Host variant: pcm and outputs are HOST pointers (pinned for async copies); H2D and D2H copies are
+ * issued on `stream` and the call returns after they were enqueued; synchronise the stream (or call
+ * mp3gpu_sync) before reading outputs.  Any output pointer may be NULL to skip that copy. */
+int mp3gpu_encode_frames(mp3gpu_ctx *ctx, const int16_t *pcm, int n_streams, int n_frames,
+                         int16_t *ix, mp3gpu_gr_info *gi, uint8_t *sf, mp3gpu_frame_out *fo, void *stream);
+/* Device variant: same, all pointers are DEVICE pointers (e.g. torch tensors' data_ptr()). */
+int mp3gpu_encode_frames_dev(mp3gpu_ctx *ctx, const int16_t *pcm, int n_streams, int n_frames,
+                             int16_t *ix, mp3gpu_gr_info *gi, uint8_t *sf, mp3gpu_frame_out *fo, void *stream);
+int mp3gpu_sync(mp3gpu_ctx *ctx, void *stream);
+
+/* ---- stage entry points (DEVICE pointers; each continues the ctx's per-stream state of that stage) */
+/* window_subband + filter_subband for every slot of n_frames frames */
+int mp3gpu_filter_subband_batch(mp3gpu_ctx *ctx, const int16_t *pcm, int n_streams, int n_frames, double *sb, void *stream);
+/* mdct_sub: sb (raw) + block types (from psy) -> xr.  The previous granule of each channel is ctx state. */
+int mp3gpu_mdct_sub_batch(mp3gpu_ctx *ctx, const double *sb, const mp3gpu_psy_out *psy, int n_streams, int n_frames,
+                          double *xr, void *stream);
+/* fused filter_subband + mdct_sub (the production path: subband samples never touch HBM) */
+int mp3gpu_subband_mdct_batch(mp3gpu_ctx *ctx, const int16_t *pcm, const mp3gpu_psy_out *psy, int n_streams, int n_frames,
+                              double *xr, void *stream);
+int mp3gpu_L3psycho_anal_batch(mp3gpu_ctx *ctx, const int16_t *pcm, int n_streams, int n_frames, mp3gpu_psy_out *psy, void *stream);
+int mp3gpu_iteration_loop_batch(mp3gpu_ctx *ctx, const double *xr, const mp3gpu_psy_out *psy, int n_streams, int n_frames,
+                                int16_t *ix, mp3gpu_gr_info *gi, uint8_t *sf, mp3gpu_frame_out *fo, void *stream);
+/* quantize() at step q[i] followed by count_bits(), n independent granules (no ctx stream state):
+ * xr_abs [n][576] magnitudes, q [n], block_type [n]; writes ix [n][576] (unsigned values), gi [n]
+ * (big_values,count1,count1table_select,region0/1_count,table_select,address1-3), bits [n]. */
+int mp3gpu_quantize_count_batch(mp3gpu_ctx *ctx, const double *xr_abs, const int *q, const int *block_type, int n,
+                                int16_t *ix, mp3gpu_gr_info *gi, int *bits, void *stream);
+
+/* last launch statistics: number of kernels this library launched since ctx creation */
+long mp3gpu_kernel_launches(const mp3gpu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -26,7 +26,7 @@ struct FrontWarpSmem {
 };
 
 // one polyphase slot: 32 new samples (time t0..t0+31) -> s (one subband sample per lane)
-SIMT_FN void polyphase_slot(const WarpCtx &w, const FrontTables &F, FrontWarpSmem &M, const PerThread<double> am[31],
+SIMT_FN void polyphase_slot(const WarpCtx &w, const double *window, FrontWarpSmem &M, const PerThread<double> am[31],
                             const short *pcm32, long t0, PerThread<double> &s_out)
 {
     FOR_THREADS(w)
@@ -39,10 +39,10 @@ SIMT_FN void polyphase_slot(const WarpCtx &w, const FrontTables &F, FrontWarpSme
     for (int h = 0; h < 2; h++) {
         const int i = lane + 32 * h;
         // z[i+64j] = x * enwindow (encode.c:310-311); y[i] = z[i] + z[i+64] + ... (encode.c:392-396)
-        double acc = simt::dmul(M.ring[(tnew - i) & 511], F.window[i]);
+        double acc = simt::dmul(M.ring[(tnew - i) & 511], window[i]);
 #pragma unroll
         for (int j = 1; j < 8; j++)
-            acc = simt::dadd(acc, simt::dmul(M.ring[(tnew - i - 64 * j) & 511], F.window[i + 64 * j]));
+            acc = simt::dadd(acc, simt::dmul(M.ring[(tnew - i - 64 * j) & 511], window[i + 64 * j]));
         M.y[i] = acc;
     }
     END_THREADS
@@ -89,13 +89,51 @@ SIMT_FN void mdct_lane(const FrontTables &F, const double in[36], int bt, double
     }
 }
 
+// MDCT of all 32 bands (lane == band) + alias reduction + coalesced store; prev <- cur afterwards.
+SIMT_FN void mdct_store(const WarpCtx &w, const FrontTables &F, FrontWarpSmem &M, PerThread<double> prev[18],
+                        const PerThread<double> cur[18], int bt, double *xr_out)
+{
+    FOR_THREADS(w)
+    double in[36], out[18];
+#pragma unroll
+    for (int k = 0; k < 18; k++) { in[k] = prev[k](); in[k + 18] = cur[k](); }
+    mdct_lane(F, in, bt, out);
+#pragma unroll
+    for (int m = 0; m < 18; m++) M.xr[lane * 18 + m] = out[m];
+#pragma unroll
+    for (int k = 0; k < 18; k++) prev[k]() = cur[k]();
+    END_THREADS
+    w.sync();
+    if (bt != 2) {                                                                  // mdct.c:83-91
+        FOR_THREADS(w)
+        if (lane < 31) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                double a = M.xr[lane * 18 + 17 - k], b = M.xr[(lane + 1) * 18 + k];
+                double bu = simt::dadd(simt::dmul(a, F.cs[k]), simt::dmul(b, F.ca[k]));
+                double bd = simt::dsub(simt::dmul(b, F.cs[k]), simt::dmul(a, F.ca[k]));
+                M.xr[lane * 18 + 17 - k] = bu;
+                M.xr[(lane + 1) * 18 + k] = bd;
+            }
+        }
+        END_THREADS
+        w.sync();
+    }
+    FOR_THREADS(w)
+    for (int i = lane; i < 576; i += 32) xr_out[i] = M.xr[i];
+    END_THREADS
+    w.sync();
+}
+
 // Walk granules [g_first, g_first + n_gran) of one channel.
 //  pcm        : channel samples; pcm[t] valid for t >= -hist (zeros before the stream started)
 //  block_type : per granule (stride bt_stride ints), produced by the psy scan
 //  xr         : output, 576 doubles per granule (stride xr_stride doubles)
 //  sb_out     : optional raw subband samples [granule][18][32] (parity tests), stride sb_stride
-SIMT_FN void front_walk(const WarpCtx &w, const FrontTables &F, FrontWarpSmem &M, const short *pcm, long g_first, int n_gran,
-                        const int *block_type, long bt_stride, double *xr, long xr_stride, double *sb_out, long sb_stride)
+// window: the 512 analysis-window taps (shared memory copy on the device: lane-varying index)
+SIMT_FN void front_walk(const WarpCtx &w, const FrontTables &F, const double *window, FrontWarpSmem &M, const short *pcm, long g_first, int n_gran,
+                        const int *block_type, long bt_stride, double *xr, long xr_stride, double *sb_out, long sb_stride,
+                        bool do_mdct = true)
 {
     PerThread<double> am[31];
     FOR_THREADS(w)
@@ -115,7 +153,8 @@ SIMT_FN void front_walk(const WarpCtx &w, const FrontTables &F, FrontWarpSmem &M
     // previous granule's subband samples (mdct.c:68-72 reads slot gr, saved at :99-102)
     for (int k = 0; k < 18; k++) {
         PerThread<double> s;
-        polyphase_slot(w, F, M, am, pcm + t_begin + 32 * k, t_begin + 32 * k, s);
+        if (!do_mdct) { FOR_THREADS(w) M.ring[(t_begin + 32 * k + lane) & 511] = (double)pcm[t_begin + 32 * k + lane] / 32768; END_THREADS w.sync(); continue; }
+        polyphase_slot(w, window, M, am, pcm + t_begin + 32 * k, t_begin + 32 * k, s);
         FOR_THREADS(w)
         prev[k]() = ((lane & 1) && (k & 1)) ? simt::dmul(s(), -1.0) : s();          // mdct.c:57-60
         END_THREADS
@@ -124,43 +163,13 @@ SIMT_FN void front_walk(const WarpCtx &w, const FrontTables &F, FrontWarpSmem &M
         const long t0 = 576 * (g_first + g);
         for (int k = 0; k < 18; k++) {
             PerThread<double> s;
-            polyphase_slot(w, F, M, am, pcm + t0 + 32 * k, t0 + 32 * k, s);
+            polyphase_slot(w, window, M, am, pcm + t0 + 32 * k, t0 + 32 * k, s);
             FOR_THREADS(w)
             if (sb_out) sb_out[g * sb_stride + k * 32 + lane] = s();
             cur[k]() = ((lane & 1) && (k & 1)) ? simt::dmul(s(), -1.0) : s();
             END_THREADS
         }
-        const int bt = block_type[g * bt_stride];
-        FOR_THREADS(w)
-        double in[36], out[18];
-#pragma unroll
-        for (int k = 0; k < 18; k++) { in[k] = prev[k](); in[k + 18] = cur[k](); }
-        mdct_lane(F, in, bt, out);
-#pragma unroll
-        for (int m = 0; m < 18; m++) M.xr[lane * 18 + m] = out[m];
-#pragma unroll
-        for (int k = 0; k < 18; k++) prev[k]() = cur[k]();
-        END_THREADS
-        w.sync();
-        if (bt != 2) {                                                              // mdct.c:83-91
-            FOR_THREADS(w)
-            if (lane < 31) {
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    double a = M.xr[lane * 18 + 17 - k], b = M.xr[(lane + 1) * 18 + k];
-                    double bu = simt::dadd(simt::dmul(a, F.cs[k]), simt::dmul(b, F.ca[k]));
-                    double bd = simt::dsub(simt::dmul(b, F.cs[k]), simt::dmul(a, F.ca[k]));
-                    M.xr[lane * 18 + 17 - k] = bu;
-                    M.xr[(lane + 1) * 18 + k] = bd;
-                }
-            }
-            END_THREADS
-            w.sync();
-        }
-        FOR_THREADS(w)
-        for (int i = lane; i < 576; i += 32) xr[g * xr_stride + i] = M.xr[i];
-        END_THREADS
-        w.sync();
+        if (do_mdct) mdct_store(w, F, M, prev, cur, block_type[g * bt_stride], xr + g * xr_stride);
     }
 }
 

@@ -1,0 +1,610 @@
+// mp3gpu.cu — sm_100a kernels and the C ABI of libmp3gpu.so (include/mp3gpu.h).
+//
+// Kernels (all warp-centric; the per-warp algorithms live in *_core.h and are shared verbatim with
+// the host-emulation test harness):
+//   k_psy_front   one warp per granule-channel        FFTs + history-free psy          (psy_core.h)
+//   k_psy_scan    one warp per (stream, channel)      history-dependent psy scan       (psy_core.h)
+//   k_front       one warp per (stream, channel, tile) polyphase + MDCT + alias, fused (front_core.h)
+//   k_rate_loop   one warp per stream                 rate loop + reservoir            (rate_loop_core.h)
+//   k_mdct / k_quantize_count / k_roll_history        stage entry points and plumbing
+// There is no CPU fallback: every entry point fails with MP3GPU_ECUDA if no device is usable.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mp3gpu.h"
+#include "front_core.h"
+#include "psy_core.h"
+#include "rate_loop_core.h"
+#include "tables.h"
+
+using namespace mp3gpu;
+
+static_assert(sizeof(mp3gpu_gr_info) == sizeof(GrInfoOut), "gr_info layout");
+static_assert(sizeof(mp3gpu_psy_out) == sizeof(PsyOut), "psy_out layout");
+static_assert(sizeof(mp3gpu_frame_out) == sizeof(FrameOut), "frame_out layout");
+static_assert(sizeof(RateTables) % 16 == 0, "RateTables must be int4-copyable");
+
+#define HIST 1056  // PCM samples of history kept per channel: 576 (previous granule) + 480 (filterbank)
+
+__constant__ FrontTables c_front;
+
+// ---------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------
+#define FRONT_WARPS 4
+__global__ void __launch_bounds__(FRONT_WARPS * 32)
+k_front(const short *pcm, long stream_stride, long ch_stride, int n_streams, int n_ch, int n_gran, int tile,
+        const PsyOut *psy, double *xr, double *sb, int do_mdct)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *window = reinterpret_cast<double *>(smem_raw);
+    FrontWarpSmem *Ms = reinterpret_cast<FrontWarpSmem *>(window + 512);
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) window[i] = c_front.window[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    const int n_tiles = (n_gran + tile - 1) / tile;
+    const long wid = (long)blockIdx.x * FRONT_WARPS + warp;
+    if (wid >= (long)n_streams * n_ch * n_tiles) return;
+    const int t = (int)(wid % n_tiles);
+    const int ch = (int)((wid / n_tiles) % n_ch);
+    const long s = wid / ((long)n_tiles * n_ch);
+    const int g_first = t * tile;
+    const int ng = min(tile, n_gran - g_first);
+    const long gc0 = (s * n_gran + g_first) * n_ch + ch;  // first granule-channel of this warp
+    WarpCtx w;
+    front_walk(w, c_front, window, Ms[warp], pcm + s * stream_stride + ch * ch_stride + HIST, g_first, ng,
+               psy ? &psy[gc0].block_type : nullptr, (long)(sizeof(PsyOut) / sizeof(int)) * n_ch,
+               xr ? xr + gc0 * 576 : nullptr, 576L * n_ch, sb ? sb + gc0 * 576 : nullptr, 576L * n_ch, do_mdct != 0);
+}
+
+// stage entry point mdct_sub: subband samples come from HBM, previous granule from ctx state
+__global__ void __launch_bounds__(FRONT_WARPS * 32)
+k_mdct(const double *sb, const PsyOut *psy, double *sb_prev, int n_streams, int n_ch, int n_gran, double *xr)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FrontWarpSmem *Ms = reinterpret_cast<FrontWarpSmem *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long wid = (long)blockIdx.x * FRONT_WARPS + warp;
+    if (wid >= (long)n_streams * n_ch) return;
+    const int ch = (int)(wid % n_ch);
+    const long s = wid / n_ch;
+    WarpCtx w;
+    PerThread<double> prev[18], cur[18];
+    double *pv = sb_prev + wid * 576;
+#pragma unroll
+    for (int k = 0; k < 18; k++) prev[k].v = pv[k * 32 + lane];
+    for (int g = 0; g < n_gran; g++) {
+        const long gc = (s * n_gran + g) * n_ch + ch;
+#pragma unroll
+        for (int k = 0; k < 18; k++) {
+            double v = sb[gc * 576 + k * 32 + lane];
+            cur[k].v = ((lane & 1) && (k & 1)) ? __dmul_rn(v, -1.0) : v;  // mdct.c:57-60
+        }
+        mdct_store(w, c_front, Ms[warp], prev, cur, psy[gc].block_type, xr + gc * 576);
+    }
+#pragma unroll
+    for (int k = 0; k < 18; k++) pv[k * 32 + lane] = prev[k].v;
+}
+
+#define PSYF_WARPS 8
+__global__ void __launch_bounds__(PSYF_WARPS * 32)
+k_psy_front(PsyDev D, const short *pcm, long stream_stride, long ch_stride, int n_streams, int n_ch, int n_gran, PsyMid *mid)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PsyFrontSmem *Ms = reinterpret_cast<PsyFrontSmem *>(smem_raw);
+    const int warp = threadIdx.x >> 5;
+    const long gc = (long)blockIdx.x * PSYF_WARPS + warp;
+    if (gc >= (long)n_streams * n_gran * n_ch) return;
+    const int ch = (int)(gc % n_ch);
+    const int g = (int)((gc / n_ch) % n_gran);
+    const long s = gc / ((long)n_ch * n_gran);
+    WarpCtx w;
+    psy_front(w, D, Ms[warp], pcm + s * stream_stride + ch * ch_stride + HIST + 576L * g, &mid[gc]);
+}
+
+#define PSYS_WARPS 4
+__global__ void __launch_bounds__(PSYS_WARPS * 32)
+k_psy_scan(const PsyTables *T, const PsyMid *mid, PsyChanState *states, int n_streams, int n_ch, int n_gran, PsyOut *psy)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PsyScanSmem *Ms = reinterpret_cast<PsyScanSmem *>(smem_raw);
+    const int warp = threadIdx.x >> 5;
+    const long wid = (long)blockIdx.x * PSYS_WARPS + warp;
+    if (wid >= (long)n_streams * n_ch) return;
+    const int ch = (int)(wid % n_ch);
+    const long s = wid / n_ch;
+    WarpCtx w;
+    PsyScanRegs R;
+    psy_scan_load(w, states[wid], R);
+    for (int g = 0; g < n_gran; g++) {
+        const long gc = (s * n_gran + g) * n_ch + ch;
+        psy_scan_step(w, *T, Ms[warp], mid[gc], R, &psy[gc]);
+    }
+    psy_scan_store(w, states[wid], R);
+}
+
+#define RL_WARPS 4
+#define RL_TABLE_BYTES ((sizeof(RateTables) + 15) & ~(size_t)15)
+__global__ void __launch_bounds__(RL_WARPS * 32)
+k_rate_loop(const RateTables *gT, FrameGeom G, LoopStreamState *states, LoopLaneState *lane_states, int n_streams, int n_frames,
+            const double *xr, const PsyOut *psy, short *ix, GrInfoOut *gi, unsigned char *sf, FrameOut *fo)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(gT);
+        int4 *dst = reinterpret_cast<int4 *>(smem_raw);
+        for (int i = threadIdx.x; i < (int)(sizeof(RateTables) / 16); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const RateTables &T = *reinterpret_cast<const RateTables *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *scr = reinterpret_cast<double *>(smem_raw + RL_TABLE_BYTES) + warp * 288;
+    const long s = (long)blockIdx.x * RL_WARPS + warp;
+    if (s >= n_streams) return;
+    WarpCtx w;
+    LoopStreamState S = states[s];
+    PerThread<int> st_en[4], st_xm[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { st_en[i].v = lane_states[s].en[i][lane]; st_xm[i].v = lane_states[s].xm[i][lane]; }
+    const long gcs = (long)n_frames * 2 * G.n_ch;
+    rate_loop_stream(w, T, scr, G, S, st_en, st_xm, n_frames, xr + s * gcs * 576, psy + s * gcs, ix + s * gcs * 576,
+                     gi + s * gcs, sf + s * gcs * 40, fo + s * (long)n_frames, nullptr);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { lane_states[s].en[i][lane] = st_en[i].v; lane_states[s].xm[i][lane] = st_xm[i].v; }
+    if (lane == 0) states[s] = S;
+}
+
+// quantize + count_bits on n independent granules
+__global__ void __launch_bounds__(RL_WARPS * 32)
+k_quantize_count(const RateTables *gT, const double *xr_abs, const int *q, const int *block_type, int n, short *ix,
+                 GrInfoOut *gi, int *bits)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(gT);
+        int4 *dst = reinterpret_cast<int4 *>(smem_raw);
+        for (int i = threadIdx.x; i < (int)(sizeof(RateTables) / 16); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const RateTables &T = *reinterpret_cast<const RateTables *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long i = (long)blockIdx.x * RL_WARPS + warp;
+    if (i >= n) return;
+    WarpCtx w;
+    const int bt = block_type[i];
+    const bool is_short = (bt == 2), wsf = (bt != 0);
+    GcRegs R;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        const int s = lane + 32 * k;
+        const int e0 = slot_e0(is_short, s), e1 = is_short ? e0 + 3 : e0 + 1;
+        R.xa[k].v = xr_abs[i * 576 + e0];
+        R.xb[k].v = xr_abs[i * 576 + e1];
+        R.band[k].v = 0;
+    }
+    CountResult C;
+    memset(&C, 0, sizeof(C));
+    int qq = q[i];
+    qq = qq < -256 ? -256 : (qq > 255 ? 255 : qq);
+    const int b = probe(w, T, R, is_short, wsf, qq, C);
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        const int s = lane + 32 * k;
+        const int e0 = slot_e0(is_short, s), e1 = is_short ? e0 + 3 : e0 + 1;
+        ix[i * 576 + e0] = (short)R.ia[k].v;
+        ix[i * 576 + e1] = (short)R.ib[k].v;
+    }
+    if (lane == 0) {
+        GrInfoOut g;
+        memset(&g, 0, sizeof(g));
+        g.big_values = C.big_values; g.count1 = C.count1; g.count1table_select = C.count1table_select;
+        g.region0_count = C.region0_count; g.region1_count = C.region1_count;
+        g.table_select[0] = C.table_select[0]; g.table_select[1] = C.table_select[1]; g.table_select[2] = C.table_select[2];
+        g.address1 = C.address1; g.address2 = C.address2; g.address3 = C.address3;
+        g.block_type = bt; g.window_switching_flag = wsf;
+        gi[i] = g;
+        bits[i] = b;
+    }
+}
+
+// keep the last HIST samples of every channel in front of the next call's samples
+__global__ void k_roll_history(short *pcm, long row_stride, long n_rows, int n_new)
+{
+    const long row = blockIdx.x;
+    if (row >= n_rows) return;
+    short *p = pcm + row * row_stride;
+    for (int i = threadIdx.x; i < HIST; i += blockDim.x) p[i] = p[n_new + i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, const char *a = "", const char *b = "")
+{
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+#define CU(call)                                                                            \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) return fail(MP3GPU_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct PcmStage {
+    short *buf = nullptr;  // [max_streams*n_ch][HIST + max_frames*1152]
+};
+
+struct mp3gpu_ctx {
+    mp3gpu_config cfg;
+    int sr;
+    FrameGeom geom;
+    long row;  // samples per PCM row = HIST + max_frames*1152
+    // tables
+    PsyTables *d_psy_tab = nullptr;
+    RateTables *d_rate_tab = nullptr;
+    FftOp *d_ops1024 = nullptr, *d_ops256 = nullptr;
+    int *d_lv1024 = nullptr, *d_lv256 = nullptr;
+    uint16_t *d_out1024 = nullptr, *d_out256 = nullptr;
+    FftTwiddle *d_tw = nullptr;
+    PsyDev psy_dev;
+    // state
+    PcmStage pcm_main, pcm_fb, pcm_psy;
+    PsyChanState *d_psy_state = nullptr;
+    LoopStreamState *d_loop_state = nullptr;
+    LoopLaneState *d_lane_state = nullptr;
+    double *d_sb_prev = nullptr;
+    // workspace
+    PsyMid *d_mid = nullptr;
+    PsyOut *d_psyout = nullptr;
+    double *d_xr = nullptr;
+    short *d_ix = nullptr;
+    GrInfoOut *d_gi = nullptr;
+    unsigned char *d_sf = nullptr;
+    FrameOut *d_fo = nullptr;
+    long launches = 0;
+};
+
+extern "C" const char *mp3gpu_last_error(void) { return g_err; }
+extern "C" const char *mp3gpu_version(void) { return "mp3gpu 0.1 (sm_100a)"; }
+extern "C" long mp3gpu_kernel_launches(const mp3gpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+template <class T>
+static int dalloc(T **p, size_t n)
+{
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e != cudaSuccess) return fail(MP3GPU_ENOMEM, "cudaMalloc(%s bytes): %s", std::to_string(n * sizeof(T)).c_str(), cudaGetErrorString(e));
+    return 0;
+}
+
+static int upload_fft(const FftProgram &P, FftOp **ops, int **lv, uint16_t **out, FftDev *dev)
+{
+    int rc;
+    if ((rc = dalloc(ops, P.ops.size()))) return rc;
+    if ((rc = dalloc(lv, P.level_start.size()))) return rc;
+    if ((rc = dalloc(out, (size_t)P.n))) return rc;
+    std::vector<uint16_t> o(P.n);
+    for (int i = 0; i < P.n; i++) o[i] = (uint16_t)(P.out_slot[i] | (P.out_neg[i] ? 0x8000 : 0));
+    CU(cudaMemcpy(*ops, P.ops.data(), P.ops.size() * sizeof(FftOp), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(*lv, P.level_start.data(), P.level_start.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(*out, o.data(), o.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    dev->ops = *ops; dev->level_start = *lv; dev->n_levels = (int)P.level_start.size() - 1; dev->out = *out;
+    return 0;
+}
+
+extern "C" int mp3gpu_create(const mp3gpu_config *cfg, mp3gpu_ctx **out)
+{
+    if (!cfg || !out) return fail(MP3GPU_EINVAL, "null argument");
+    *out = nullptr;
+    const int sr = sr_index(cfg->sfreq_hz);
+    if (sr < 0) return fail(MP3GPU_EINVAL, "unsupported sampling frequency (MPEG-1 Layer III: 32000/44100/48000)");
+    if (cfg->n_ch < 1 || cfg->n_ch > 2) return fail(MP3GPU_EINVAL, "n_ch must be 1 or 2");
+    static const int rates[] = {32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320};
+    bool ok = false;
+    for (int r : rates) ok |= (r == cfg->bitrate_kbps);
+    if (!ok) return fail(MP3GPU_EINVAL, "bitrate not in the MPEG-1 Layer III table");
+    if (cfg->max_streams < 1 || cfg->max_frames < 1) return fail(MP3GPU_EINVAL, "max_streams/max_frames must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(MP3GPU_ECUDA, "no CUDA device: libmp3gpu has no CPU fallback");
+    CU(cudaSetDevice(cfg->device));
+    mp3gpu_ctx *c = new (std::nothrow) mp3gpu_ctx();
+    if (!c) return fail(MP3GPU_ENOMEM, "out of host memory");
+    c->cfg = *cfg; c->sr = sr;
+    frame_geometry(cfg->sfreq_hz, cfg->n_ch, cfg->bitrate_kbps, &c->geom);
+    c->row = HIST + (long)cfg->max_frames * 1152;
+    int rc = 0;
+    // ---- tables ----
+    {
+        FrontTables *F = new FrontTables;
+        build_front_tables(F);
+        cudaError_t e = cudaMemcpyToSymbol(c_front, F, sizeof(FrontTables));
+        delete F;
+        if (e != cudaSuccess) { delete c; return fail(MP3GPU_ECUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString(e)); }
+        PsyTables *P = new PsyTables;
+        build_psy_tables(sr, P);
+        if (!(rc = dalloc(&c->d_psy_tab, 1))) cudaMemcpy(c->d_psy_tab, P, sizeof(PsyTables), cudaMemcpyHostToDevice);
+        delete P;
+        RateTables *R = new RateTables;
+        build_rate_tables(sr, R);
+        if (!rc && !(rc = dalloc(&c->d_rate_tab, 1))) cudaMemcpy(c->d_rate_tab, R, sizeof(RateTables), cudaMemcpyHostToDevice);
+        delete R;
+        std::vector<FftTwiddle> tw; std::vector<int> base;
+        build_fft_twiddles(&tw, &base);
+        FftProgram P10, P8;
+        build_fft_program(10, base, &P10);
+        build_fft_program(8, base, &P8);
+        if (!rc && !(rc = dalloc(&c->d_tw, tw.size()))) cudaMemcpy(c->d_tw, tw.data(), tw.size() * sizeof(FftTwiddle), cudaMemcpyHostToDevice);
+        if (!rc) rc = upload_fft(P10, &c->d_ops1024, &c->d_lv1024, &c->d_out1024, &c->psy_dev.f1024);
+        if (!rc) rc = upload_fft(P8, &c->d_ops256, &c->d_lv256, &c->d_out256, &c->psy_dev.f256);
+        c->psy_dev.T = c->d_psy_tab; c->psy_dev.tw = c->d_tw;
+    }
+    // ---- state + workspace ----
+    const size_t S = cfg->max_streams, NCH = cfg->n_ch, GC = (size_t)cfg->max_frames * 2 * NCH;
+    if (!rc) rc = dalloc(&c->pcm_main.buf, S * NCH * c->row);
+    if (!rc) rc = dalloc(&c->d_psy_state, S * NCH);
+    if (!rc) rc = dalloc(&c->d_loop_state, S);
+    if (!rc) rc = dalloc(&c->d_lane_state, S);
+    if (!rc) rc = dalloc(&c->d_mid, S * GC);
+    if (!rc) rc = dalloc(&c->d_psyout, S * GC);
+    if (!rc) rc = dalloc(&c->d_xr, S * GC * 576);
+    if (!rc) rc = dalloc(&c->d_ix, S * GC * 576);
+    if (!rc) rc = dalloc(&c->d_gi, S * GC);
+    if (!rc) rc = dalloc(&c->d_sf, S * GC * 40);
+    if (!rc) rc = dalloc(&c->d_fo, S * (size_t)cfg->max_frames);
+    if (rc) { mp3gpu_destroy(c); return rc; }
+    // opt in to large dynamic shared memory
+    cudaFuncSetAttribute(k_psy_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PSYF_WARPS * sizeof(PsyFrontSmem)));
+    cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(512 * 8 + FRONT_WARPS * sizeof(FrontWarpSmem)));
+    cudaFuncSetAttribute(k_mdct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FRONT_WARPS * sizeof(FrontWarpSmem)));
+    cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RL_TABLE_BYTES + RL_WARPS * 288 * 8));
+    cudaFuncSetAttribute(k_quantize_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RL_TABLE_BYTES));
+    *out = c;
+    rc = mp3gpu_reset(c);
+    if (rc) { mp3gpu_destroy(c); *out = nullptr; return rc; }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { mp3gpu_destroy(c); *out = nullptr; return fail(MP3GPU_ECUDA, "context init: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
+extern "C" void mp3gpu_destroy(mp3gpu_ctx *c)
+{
+    if (!c) return;
+    void *ptrs[] = {c->d_psy_tab, c->d_rate_tab, c->d_ops1024, c->d_ops256, c->d_lv1024, c->d_lv256, c->d_out1024, c->d_out256,
+                    c->d_tw, c->pcm_main.buf, c->pcm_fb.buf, c->pcm_psy.buf, c->d_psy_state, c->d_loop_state, c->d_lane_state,
+                    c->d_sb_prev, c->d_mid, c->d_psyout, c->d_xr, c->d_ix, c->d_gi, c->d_sf, c->d_fo};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    delete c;
+}
+
+extern "C" int mp3gpu_reset(mp3gpu_ctx *c)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    const size_t S = c->cfg.max_streams, NCH = c->cfg.n_ch;
+    CU(cudaMemset(c->pcm_main.buf, 0, S * NCH * c->row * sizeof(short)));
+    if (c->pcm_fb.buf) CU(cudaMemset(c->pcm_fb.buf, 0, S * NCH * c->row * sizeof(short)));
+    if (c->pcm_psy.buf) CU(cudaMemset(c->pcm_psy.buf, 0, S * NCH * c->row * sizeof(short)));
+    if (c->d_sb_prev) CU(cudaMemset(c->d_sb_prev, 0, S * NCH * 576 * sizeof(double)));
+    CU(cudaMemset(c->d_psy_state, 0, S * NCH * sizeof(PsyChanState)));
+    CU(cudaMemset(c->d_loop_state, 0, S * sizeof(LoopStreamState)));
+    CU(cudaMemset(c->d_lane_state, 0, S * sizeof(LoopLaneState)));
+    return 0;
+}
+
+extern "C" int mp3gpu_frame_geometry(const mp3gpu_ctx *c, int *bits_per_frame, int *mean_bits)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    if (bits_per_frame) *bits_per_frame = c->geom.bits_per_frame;
+    if (mean_bits) *mean_bits = c->geom.mean_bits;
+    return 0;
+}
+
+extern "C" int mp3gpu_sync(mp3gpu_ctx *c, void *stream)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+static int check_shape(mp3gpu_ctx *c, int n_streams, int n_frames)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    if (n_streams < 1 || n_frames < 1) return fail(MP3GPU_EINVAL, "n_streams and n_frames must be >= 1");
+    if (n_streams > c->cfg.max_streams || n_frames > c->cfg.max_frames)
+        return fail(MP3GPU_ESTATE, "batch exceeds the capacity the ctx was created with");
+    return 0;
+}
+
+// copy the call's PCM ([n_streams*n_ch][n_frames*1152], dense) behind the history of each row
+static int stage_pcm(mp3gpu_ctx *c, PcmStage &st, const int16_t *pcm, int n_streams, int n_frames, cudaMemcpyKind kind, cudaStream_t q)
+{
+    if (!st.buf) {
+        int rc = dalloc(&st.buf, (size_t)c->cfg.max_streams * c->cfg.n_ch * c->row);
+        if (rc) return rc;
+        CU(cudaMemsetAsync(st.buf, 0, (size_t)c->cfg.max_streams * c->cfg.n_ch * c->row * sizeof(short), q));
+    }
+    const size_t w = (size_t)n_frames * 1152 * sizeof(short);
+    CU(cudaMemcpy2DAsync(st.buf + HIST, c->row * sizeof(short), pcm, w, w, (size_t)n_streams * c->cfg.n_ch, kind, q));
+    return 0;
+}
+
+static int roll_pcm(mp3gpu_ctx *c, PcmStage &st, int n_streams, int n_frames, cudaStream_t q)
+{
+    k_roll_history<<<(unsigned)(n_streams * c->cfg.n_ch), 256, 0, q>>>(st.buf, c->row, (long)n_streams * c->cfg.n_ch, n_frames * 1152);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int pick_tile(int n_streams, int n_ch, int n_gran)
+{
+    // enough warps to fill 148 SMs several times over, but tiles as long as possible (1 granule of
+    // polyphase is recomputed per tile for the MDCT overlap)
+    long total = (long)n_streams * n_ch * n_gran;
+    long want = 148L * 16 * 4;
+    long tile = total / want;
+    if (tile < 1) tile = 1;
+    if (tile > n_gran) tile = n_gran;
+    return (int)tile;
+}
+
+static int launch_front(mp3gpu_ctx *c, const short *pcm_rows, const PsyOut *psy, int n_streams, int n_frames, double *xr, double *sb,
+                        bool do_mdct, cudaStream_t q)
+{
+    const int n_gran = 2 * n_frames, n_ch = c->cfg.n_ch;
+    const int tile = pick_tile(n_streams, n_ch, n_gran);
+    const long n_tiles = (n_gran + tile - 1) / tile;
+    const long warps = (long)n_streams * n_ch * n_tiles;
+    const unsigned grid = (unsigned)((warps + FRONT_WARPS - 1) / FRONT_WARPS);
+    const size_t smem = 512 * 8 + FRONT_WARPS * sizeof(FrontWarpSmem);
+    k_front<<<grid, FRONT_WARPS * 32, smem, q>>>(pcm_rows, c->row * n_ch, c->row, n_streams, n_ch, n_gran, tile, psy, xr, sb, do_mdct ? 1 : 0);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int launch_psy(mp3gpu_ctx *c, const short *pcm_rows, int n_streams, int n_frames, PsyOut *psy, cudaStream_t q)
+{
+    const int n_gran = 2 * n_frames, n_ch = c->cfg.n_ch;
+    const long gcs = (long)n_streams * n_gran * n_ch;
+    k_psy_front<<<(unsigned)((gcs + PSYF_WARPS - 1) / PSYF_WARPS), PSYF_WARPS * 32, PSYF_WARPS * sizeof(PsyFrontSmem), q>>>(
+        c->psy_dev, pcm_rows, c->row * n_ch, c->row, n_streams, n_ch, n_gran, c->d_mid);
+    c->launches++;
+    CU(cudaGetLastError());
+    const long chans = (long)n_streams * n_ch;
+    k_psy_scan<<<(unsigned)((chans + PSYS_WARPS - 1) / PSYS_WARPS), PSYS_WARPS * 32, PSYS_WARPS * sizeof(PsyScanSmem), q>>>(
+        c->d_psy_tab, c->d_mid, c->d_psy_state, n_streams, n_ch, n_gran, psy);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int launch_rate_loop(mp3gpu_ctx *c, const double *xr, const PsyOut *psy, int n_streams, int n_frames, short *ix, GrInfoOut *gi,
+                            unsigned char *sf, FrameOut *fo, cudaStream_t q)
+{
+    const unsigned grid = (unsigned)((n_streams + RL_WARPS - 1) / RL_WARPS);
+    k_rate_loop<<<grid, RL_WARPS * 32, RL_TABLE_BYTES + RL_WARPS * 288 * 8, q>>>(c->d_rate_tab, c->geom, c->d_loop_state, c->d_lane_state,
+                                                                                n_streams, n_frames, xr, psy, ix, gi, sf, fo);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int encode_common(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, int16_t *ix, mp3gpu_gr_info *gi, uint8_t *sf,
+                         mp3gpu_frame_out *fo, void *stream, bool host)
+{
+    int rc = check_shape(c, n_streams, n_frames);
+    if (rc) return rc;
+    if (!pcm) return fail(MP3GPU_EINVAL, "null pcm");
+    cudaStream_t q = (cudaStream_t)stream;
+    const size_t gcs = (size_t)n_streams * n_frames * 2 * c->cfg.n_ch;
+    if ((rc = stage_pcm(c, c->pcm_main, pcm, n_streams, n_frames, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, q))) return rc;
+    // musicin.c:751-779 order: psy first (it decides block_type), then filterbank + MDCT, then the rate loop
+    if ((rc = launch_psy(c, c->pcm_main.buf, n_streams, n_frames, c->d_psyout, q))) return rc;
+    if ((rc = launch_front(c, c->pcm_main.buf, c->d_psyout, n_streams, n_frames, c->d_xr, nullptr, true, q))) return rc;
+    short *o_ix = host ? c->d_ix : (ix ? ix : c->d_ix);
+    GrInfoOut *o_gi = host ? c->d_gi : (gi ? (GrInfoOut *)gi : c->d_gi);
+    unsigned char *o_sf = host ? c->d_sf : (sf ? sf : c->d_sf);
+    FrameOut *o_fo = host ? c->d_fo : (fo ? (FrameOut *)fo : c->d_fo);
+    if ((rc = launch_rate_loop(c, c->d_xr, c->d_psyout, n_streams, n_frames, o_ix, o_gi, o_sf, o_fo, q))) return rc;
+    if ((rc = roll_pcm(c, c->pcm_main, n_streams, n_frames, q))) return rc;
+    if (host) {
+        if (ix) CU(cudaMemcpyAsync(ix, c->d_ix, gcs * 576 * sizeof(short), cudaMemcpyDeviceToHost, q));
+        if (gi) CU(cudaMemcpyAsync(gi, c->d_gi, gcs * sizeof(GrInfoOut), cudaMemcpyDeviceToHost, q));
+        if (sf) CU(cudaMemcpyAsync(sf, c->d_sf, gcs * 40, cudaMemcpyDeviceToHost, q));
+        if (fo) CU(cudaMemcpyAsync(fo, c->d_fo, (size_t)n_streams * n_frames * sizeof(FrameOut), cudaMemcpyDeviceToHost, q));
+    }
+    return 0;
+}
+
+extern "C" int mp3gpu_encode_frames(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, int16_t *ix, mp3gpu_gr_info *gi,
+                                    uint8_t *sf, mp3gpu_frame_out *fo, void *stream)
+{
+    return encode_common(c, pcm, n_streams, n_frames, ix, gi, sf, fo, stream, true);
+}
+
+extern "C" int mp3gpu_encode_frames_dev(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, int16_t *ix, mp3gpu_gr_info *gi,
+                                        uint8_t *sf, mp3gpu_frame_out *fo, void *stream)
+{
+    return encode_common(c, pcm, n_streams, n_frames, ix, gi, sf, fo, stream, false);
+}
+
+extern "C" int mp3gpu_filter_subband_batch(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, double *sb, void *stream)
+{
+    int rc = check_shape(c, n_streams, n_frames);
+    if (rc) return rc;
+    if (!pcm || !sb) return fail(MP3GPU_EINVAL, "null pointer");
+    cudaStream_t q = (cudaStream_t)stream;
+    if ((rc = stage_pcm(c, c->pcm_fb, pcm, n_streams, n_frames, cudaMemcpyDeviceToDevice, q))) return rc;
+    if ((rc = launch_front(c, c->pcm_fb.buf, nullptr, n_streams, n_frames, nullptr, sb, false, q))) return rc;
+    return roll_pcm(c, c->pcm_fb, n_streams, n_frames, q);
+}
+
+extern "C" int mp3gpu_subband_mdct_batch(mp3gpu_ctx *c, const int16_t *pcm, const mp3gpu_psy_out *psy, int n_streams, int n_frames,
+                                         double *xr, void *stream)
+{
+    int rc = check_shape(c, n_streams, n_frames);
+    if (rc) return rc;
+    if (!pcm || !psy || !xr) return fail(MP3GPU_EINVAL, "null pointer");
+    cudaStream_t q = (cudaStream_t)stream;
+    if ((rc = stage_pcm(c, c->pcm_fb, pcm, n_streams, n_frames, cudaMemcpyDeviceToDevice, q))) return rc;
+    if ((rc = launch_front(c, c->pcm_fb.buf, (const PsyOut *)psy, n_streams, n_frames, xr, nullptr, true, q))) return rc;
+    return roll_pcm(c, c->pcm_fb, n_streams, n_frames, q);
+}
+
+extern "C" int mp3gpu_mdct_sub_batch(mp3gpu_ctx *c, const double *sb, const mp3gpu_psy_out *psy, int n_streams, int n_frames, double *xr,
+                                     void *stream)
+{
+    int rc = check_shape(c, n_streams, n_frames);
+    if (rc) return rc;
+    if (!sb || !psy || !xr) return fail(MP3GPU_EINVAL, "null pointer");
+    cudaStream_t q = (cudaStream_t)stream;
+    if (!c->d_sb_prev) {
+        const size_t n = (size_t)c->cfg.max_streams * c->cfg.n_ch * 576;
+        if ((rc = dalloc(&c->d_sb_prev, n))) return rc;
+        CU(cudaMemsetAsync(c->d_sb_prev, 0, n * sizeof(double), q));
+    }
+    const long chans = (long)n_streams * c->cfg.n_ch;
+    k_mdct<<<(unsigned)((chans + FRONT_WARPS - 1) / FRONT_WARPS), FRONT_WARPS * 32, FRONT_WARPS * sizeof(FrontWarpSmem), q>>>(
+        sb, (const PsyOut *)psy, c->d_sb_prev, n_streams, c->cfg.n_ch, 2 * n_frames, xr);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mp3gpu_L3psycho_anal_batch(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, mp3gpu_psy_out *psy, void *stream)
+{
+    int rc = check_shape(c, n_streams, n_frames);
+    if (rc) return rc;
+    if (!pcm || !psy) return fail(MP3GPU_EINVAL, "null pointer");
+    cudaStream_t q = (cudaStream_t)stream;
+    if ((rc = stage_pcm(c, c->pcm_psy, pcm, n_streams, n_frames, cudaMemcpyDeviceToDevice, q))) return rc;
+    if ((rc = launch_psy(c, c->pcm_psy.buf, n_streams, n_frames, (PsyOut *)psy, q))) return rc;
+    return roll_pcm(c, c->pcm_psy, n_streams, n_frames, q);
+}
+
+extern "C" int mp3gpu_iteration_loop_batch(mp3gpu_ctx *c, const double *xr, const mp3gpu_psy_out *psy, int n_streams, int n_frames,
+                                           int16_t *ix, mp3gpu_gr_info *gi, uint8_t *sf, mp3gpu_frame_out *fo, void *stream)
+{
+    int rc = check_shape(c, n_streams, n_frames);
+    if (rc) return rc;
+    if (!xr || !psy || !ix || !gi || !sf || !fo) return fail(MP3GPU_EINVAL, "null pointer");
+    return launch_rate_loop(c, xr, (const PsyOut *)psy, n_streams, n_frames, ix, (GrInfoOut *)gi, sf, (FrameOut *)fo, (cudaStream_t)stream);
+}
+
+extern "C" int mp3gpu_quantize_count_batch(mp3gpu_ctx *c, const double *xr_abs, const int *q, const int *block_type, int n, int16_t *ix,
+                                           mp3gpu_gr_info *gi, int *bits, void *stream)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    if (n < 1 || !xr_abs || !q || !block_type || !ix || !gi || !bits) return fail(MP3GPU_EINVAL, "bad argument");
+    k_quantize_count<<<(unsigned)((n + RL_WARPS - 1) / RL_WARPS), RL_WARPS * 32, RL_TABLE_BYTES, (cudaStream_t)stream>>>(
+        c->d_rate_tab, xr_abs, q, block_type, n, ix, (GrInfoOut *)gi, bits);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}

@@ -27,7 +27,7 @@ using simt::PerThread;
 using simt::WarpCtx;
 
 // ---- constant tables (host-built with the reference's libm expressions; see tables.cpp) ---------
-struct RateTables {
+struct alignas(16) RateTables {
     double pow_nint_tab[2049];  // [p] = (p - 0.4054)^(4/3), p = 1..2048 (pow_nint.c:13-19); [0] unused
     double pow43[2048];         // p^(4/3) (loop.c:1017-1021)
     double step[512];           // 2^(q/4), q = -256..255 (loop.c:1020,1386); index q + 256
@@ -59,9 +59,15 @@ struct LoopStreamState {
     int resv_size;
     int xrmax[4];      // [gr*2+ch]
     int en_tot[4];
-    int en[4][32];     // [gr*2+ch][sfb] (int-typed log2 energies, sic)
-    int xm[4][32];
     int addr[4][3];    // address1..3 of each (gr,ch): subdivide() leaves them stale when big_values == 0
+    int pad[3];
+};
+
+// band-per-lane part of the state: calc_scfsi's `en` and `xm` statics, [gr*2+ch][sfb]
+// (int-typed log2 energies, sic — loop.c:619-620)
+struct LoopLaneState {
+    int en[4][32];
+    int xm[4][32];
 };
 
 struct FrameGeom {
@@ -141,7 +147,7 @@ SIMT_FN int slot_e0(bool is_short, int s)
 // quantize(): loop.c:1360-1428 with subblock_gain == 0 and mixed_block_flag == 0 (always, l3psy.c:739)
 SIMT_FN void quantize_all(const WarpCtx &w, const RateTables &T, GcRegs &R, int q)
 {
-    const double ostep = T.ostep[q + 256];
+    const double ostep = T.ostep[(q > 255 ? 255 : q) + 256];
     FOR_THREADS(w)
 #pragma unroll
     for (int k = 0; k < 9; k++) {
@@ -589,11 +595,11 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateTables &T, double *scr, const 
             do {
                 q += 1;
                 bits = probe(w, T, R, is_short, wsf, q, C);
-            } while (bits > huff_bits);
+            } while (bits > huff_bits && q < 1024);  // q guard: the reference assert()s huff_bits >= 0 (loop.c:579)
 
             // calc_noise, loop.c:1007-1069
             {
-                const double step = T.step[q + 256];
+                const double step = T.step[(q > 255 ? 255 : q) + 256];
                 FOR_THREADS(w)
 #pragma unroll
                 for (int k = 0; k < 9; k++) {

@@ -1,0 +1,242 @@
+"""Python host side above the C ABI (include/mp3gpu.h): a thin ctypes mirror of libmp3gpu.so.
+
+The reference has no plugin/operator API — its boundary is the five C symbols its frame loop calls
+(musicin.c:754-779).  This module gives each batched replacement a method with the same name and
+argument meaning, so the parity tests read like a batched version of the reference's frame loop:
+
+    enc = Encoder(sfreq=44100, n_ch=2, bitrate=128, max_streams=S, max_frames=F)
+    psy = enc.L3psycho_anal_batch(pcm)             # l3psy.c:53
+    sb  = enc.filter_subband_batch(pcm)            # encode.c:287,361
+    xr  = enc.mdct_sub_batch(sb, psy)              # mdct.c:25
+    out = enc.iteration_loop_batch(xr, psy)        # loop.c:232
+    out = enc.encode_frames(pcm)                   # all four, fused pipeline, host buffers
+
+torch is used only for device memory and streams (plumbing).  There is NO CPU fallback: if the
+shared library is missing or no GPU is present, constructing an Encoder raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmp3gpu.so")
+
+PSY_DT = np.dtype([("pe", "f8"), ("ratio_l", "f8", 21), ("ratio_s", "f8", 36), ("block_type", "i4"), ("pad", "i4")])
+FO_DT = np.dtype([("resv_drain", "i4"), ("main_data_begin", "i4"), ("scfsi", "u1", (2, 4))])
+GI_FIELDS = ["part2_3_length", "big_values", "count1", "global_gain", "scalefac_compress", "window_switching_flag",
+             "block_type", "mixed_block_flag", "table_select0", "table_select1", "table_select2", "region0_count",
+             "region1_count", "preflag", "scalefac_scale", "count1table_select", "part2_length", "address1",
+             "address2", "address3"]
+
+EXPORTS = ["mp3gpu_last_error", "mp3gpu_version", "mp3gpu_create", "mp3gpu_destroy", "mp3gpu_reset",
+           "mp3gpu_frame_geometry", "mp3gpu_encode_frames", "mp3gpu_encode_frames_dev", "mp3gpu_sync",
+           "mp3gpu_filter_subband_batch", "mp3gpu_mdct_sub_batch", "mp3gpu_subband_mdct_batch",
+           "mp3gpu_L3psycho_anal_batch", "mp3gpu_iteration_loop_batch", "mp3gpu_quantize_count_batch",
+           "mp3gpu_kernel_launches"]
+
+
+class Config(C.Structure):
+    _fields_ = [("sfreq_hz", C.c_int), ("n_ch", C.c_int), ("bitrate_kbps", C.c_int), ("max_streams", C.c_int),
+                ("max_frames", C.c_int), ("device", C.c_int)]
+
+
+class Mp3GpuError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libmp3gpu.so (built in-tree by __graft_entry__.build()). Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Mp3GpuError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback for the hot path)")
+        lib = C.CDLL(LIB_PATH)
+        lib.mp3gpu_last_error.restype = C.c_char_p
+        lib.mp3gpu_version.restype = C.c_char_p
+        lib.mp3gpu_kernel_launches.restype = C.c_long
+        lib.mp3gpu_kernel_launches.argtypes = [C.c_void_p]
+        lib.mp3gpu_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+        lib.mp3gpu_destroy.argtypes = [C.c_void_p]
+        lib.mp3gpu_reset.argtypes = [C.c_void_p]
+        lib.mp3gpu_sync.argtypes = [C.c_void_p, C.c_void_p]
+        lib.mp3gpu_frame_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        vp = C.c_void_p
+        for name in ("mp3gpu_encode_frames", "mp3gpu_encode_frames_dev"):
+            getattr(lib, name).argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+        lib.mp3gpu_filter_subband_batch.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+        lib.mp3gpu_mdct_sub_batch.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp]
+        lib.mp3gpu_subband_mdct_batch.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp]
+        lib.mp3gpu_L3psycho_anal_batch.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+        lib.mp3gpu_iteration_loop_batch.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+        lib.mp3gpu_quantize_count_batch.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
+        _lib = lib
+    return _lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Encoder:
+    """One mp3gpu_ctx: S streams of identical format, state carried from call to call."""
+
+    def __init__(self, sfreq=44100, n_ch=2, bitrate=128, max_streams=1, max_frames=2, device=0):
+        self.lib = load_library()
+        self.cfg = Config(sfreq, n_ch, bitrate, max_streams, max_frames, device)
+        self.ctx = C.c_void_p()
+        self.n_ch, self.device = n_ch, device
+        rc = self.lib.mp3gpu_create(C.byref(self.cfg), C.byref(self.ctx))
+        if rc != 0:
+            raise Mp3GpuError(f"mp3gpu_create failed ({rc}): {self.lib.mp3gpu_last_error().decode()}")
+        bpf, mb = C.c_int(), C.c_int()
+        self.lib.mp3gpu_frame_geometry(self.ctx, C.byref(bpf), C.byref(mb))
+        self.bits_per_frame, self.mean_bits = bpf.value, mb.value
+
+    def close(self):
+        if self.ctx:
+            self.lib.mp3gpu_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise Mp3GpuError(f"{what} failed ({rc}): {self.lib.mp3gpu_last_error().decode()}")
+
+    def reset(self):
+        self._check(self.lib.mp3gpu_reset(self.ctx), "mp3gpu_reset")
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.mp3gpu_kernel_launches(self.ctx))
+
+    def sync(self, stream=None):
+        self._check(self.lib.mp3gpu_sync(self.ctx, C.c_void_p(stream or 0)), "mp3gpu_sync")
+
+    # ---- helpers -------------------------------------------------------------------------------
+    def _shape(self, pcm_shape):
+        S, n_ch, n = pcm_shape
+        assert n_ch == self.n_ch and n % 1152 == 0, (pcm_shape, self.n_ch)
+        return S, n // 1152
+
+    def _dev(self):
+        return _torch().device("cuda", self.device)
+
+    def _empty(self, shape, dtype):
+        return _torch().empty(shape, dtype=dtype, device=self._dev())
+
+    # ---- whole hot path, HOST buffers (numpy, ideally pinned via torch) ---------------------------
+    def encode_frames(self, pcm, out=None, stream=None, sync=True):
+        """pcm: int16 [S][n_ch][n_frames*1152] numpy array (or pinned torch CPU tensor).
+        Returns dict(ix [S][gc][576] int16, gi [S][gc][20] int32, sf [S][gc][40] uint8, fo [S][frames] FO_DT)."""
+        pcm_np = pcm if isinstance(pcm, np.ndarray) else pcm.numpy()
+        assert pcm_np.dtype == np.int16 and pcm_np.flags["C_CONTIGUOUS"]
+        S, F = self._shape(pcm_np.shape)
+        gcs = F * 2 * self.n_ch
+        if out is None:
+            out = dict(ix=np.empty((S, gcs, 576), np.int16), gi=np.empty((S, gcs, 20), np.int32),
+                       sf=np.empty((S, gcs, 40), np.uint8), fo=np.empty((S, F), FO_DT))
+        p = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
+        rc = self.lib.mp3gpu_encode_frames(self.ctx, p(pcm_np), S, F, p(out.get("ix")), p(out.get("gi")), p(out.get("sf")),
+                                           p(out.get("fo")), C.c_void_p(stream or 0))
+        self._check(rc, "mp3gpu_encode_frames")
+        if sync:
+            self.sync(stream)
+        return out
+
+    # ---- whole hot path, DEVICE buffers (torch tensors) -------------------------------------------
+    def encode_frames_dev(self, pcm, out=None, stream=None):
+        torch = _torch()
+        S, F = self._shape(tuple(pcm.shape))
+        gcs = F * 2 * self.n_ch
+        if out is None:
+            out = dict(ix=self._empty((S, gcs, 576), torch.int16), gi=self._empty((S, gcs, 20), torch.int32),
+                       sf=self._empty((S, gcs, 40), torch.uint8), fo=self._empty((S, F, FO_DT.itemsize), torch.uint8))
+        rc = self.lib.mp3gpu_encode_frames_dev(self.ctx, pcm.data_ptr(), S, F, out["ix"].data_ptr(), out["gi"].data_ptr(),
+                                               out["sf"].data_ptr(), out["fo"].data_ptr(), C.c_void_p(stream or 0))
+        self._check(rc, "mp3gpu_encode_frames_dev")
+        return out
+
+    # ---- stage entry points (torch device tensors in, torch device tensors out) -------------------
+    def filter_subband_batch(self, pcm, stream=None):
+        torch = _torch()
+        S, F = self._shape(tuple(pcm.shape))
+        sb = self._empty((S, F * 2 * self.n_ch, 18, 32), torch.float64)
+        self._check(self.lib.mp3gpu_filter_subband_batch(self.ctx, pcm.data_ptr(), S, F, sb.data_ptr(), C.c_void_p(stream or 0)),
+                    "mp3gpu_filter_subband_batch")
+        return sb
+
+    def L3psycho_anal_batch(self, pcm, stream=None):
+        torch = _torch()
+        S, F = self._shape(tuple(pcm.shape))
+        psy = self._empty((S, F * 2 * self.n_ch, PSY_DT.itemsize), torch.uint8)
+        self._check(self.lib.mp3gpu_L3psycho_anal_batch(self.ctx, pcm.data_ptr(), S, F, psy.data_ptr(), C.c_void_p(stream or 0)),
+                    "mp3gpu_L3psycho_anal_batch")
+        return psy
+
+    def mdct_sub_batch(self, sb, psy, stream=None):
+        torch = _torch()
+        S, gcs = sb.shape[0], sb.shape[1]
+        F = gcs // (2 * self.n_ch)
+        xr = self._empty((S, gcs, 576), torch.float64)
+        self._check(self.lib.mp3gpu_mdct_sub_batch(self.ctx, sb.data_ptr(), psy.data_ptr(), S, F, xr.data_ptr(), C.c_void_p(stream or 0)),
+                    "mp3gpu_mdct_sub_batch")
+        return xr
+
+    def subband_mdct_batch(self, pcm, psy, stream=None):
+        torch = _torch()
+        S, F = self._shape(tuple(pcm.shape))
+        xr = self._empty((S, F * 2 * self.n_ch, 576), torch.float64)
+        self._check(self.lib.mp3gpu_subband_mdct_batch(self.ctx, pcm.data_ptr(), psy.data_ptr(), S, F, xr.data_ptr(),
+                                                       C.c_void_p(stream or 0)), "mp3gpu_subband_mdct_batch")
+        return xr
+
+    def iteration_loop_batch(self, xr, psy, stream=None):
+        torch = _torch()
+        S, gcs = xr.shape[0], xr.shape[1]
+        F = gcs // (2 * self.n_ch)
+        out = dict(ix=self._empty((S, gcs, 576), torch.int16), gi=self._empty((S, gcs, 20), torch.int32),
+                   sf=self._empty((S, gcs, 40), torch.uint8), fo=self._empty((S, F, FO_DT.itemsize), torch.uint8))
+        rc = self.lib.mp3gpu_iteration_loop_batch(self.ctx, xr.data_ptr(), psy.data_ptr(), S, F, out["ix"].data_ptr(),
+                                                  out["gi"].data_ptr(), out["sf"].data_ptr(), out["fo"].data_ptr(),
+                                                  C.c_void_p(stream or 0))
+        self._check(rc, "mp3gpu_iteration_loop_batch")
+        return out
+
+    def quantize_count_batch(self, xr_abs, q, block_type, stream=None):
+        torch = _torch()
+        n = xr_abs.shape[0]
+        ix = self._empty((n, 576), torch.int16)
+        gi = self._empty((n, 20), torch.int32)
+        bits = self._empty((n,), torch.int32)
+        rc = self.lib.mp3gpu_quantize_count_batch(self.ctx, xr_abs.data_ptr(), q.data_ptr(), block_type.data_ptr(), n,
+                                                  ix.data_ptr(), gi.data_ptr(), bits.data_ptr(), C.c_void_p(stream or 0))
+        self._check(rc, "mp3gpu_quantize_count_batch")
+        return ix, gi, bits
+
+
+def psy_to_numpy(psy_tensor):
+    """uint8 device tensor [..., sizeof(psy_out)] -> numpy structured array PSY_DT."""
+    a = psy_tensor.cpu().numpy()
+    return a.view(PSY_DT).reshape(a.shape[:-1])
+
+
+def psy_from_numpy(psy_np, device):
+    torch = _torch()
+    raw = np.ascontiguousarray(psy_np).view(np.uint8).reshape(psy_np.shape + (PSY_DT.itemsize,))
+    return torch.from_numpy(raw.copy()).to(device)
+
+
+def fo_to_numpy(fo_tensor):
+    a = fo_tensor.cpu().numpy()
+    return a.view(FO_DT).reshape(a.shape[:-1])

@@ -67,3 +67,27 @@ def config3(seconds=30.0, fs=48000, seeds=(4, 5)):
 def clip_batch(n_clips, seconds=10.0, fs=44100, first=0):
     """Config 4: n_clips x stereo clips, config-1 recipe with seed = clip index. [n_clips][2][n]."""
     return np.stack([config1(seconds, fs, (2 * (first + c) + 1, 2 * (first + c) + 2)) for c in range(n_clips)])
+
+
+def loud_sweep(seconds=1.0, fs=44100, seed=7):
+    """Full-scale stereo test signal: loud low-frequency tone + sweep + clipped noise bursts. Drives
+    |xr| >= 1 (so calc_scfsi's int-typed statistics become non-trivial) and large ix / ESC tables."""
+    rng = np.random.default_rng(seed)
+    n = int(round(seconds * fs))
+    t = np.arange(n, dtype=np.float64) / fs
+    f = 60.0 + (8000.0 - 60.0) * t / max(seconds, 1e-9)
+    sweep = np.sin(2 * np.pi * np.cumsum(f) / fs)
+    l = 0.98 * np.sin(2 * np.pi * 110.0 * t) * 0.6 + 0.5 * sweep
+    r = 0.98 * np.sin(2 * np.pi * 110.0 * t + 0.3) * 0.6 + 0.45 * sweep
+    burst = (np.floor(t / 0.1) % 4 == 3)
+    l = np.where(burst, l + 0.9 * rng.uniform(-1, 1, n), l)
+    r = np.where(burst, r + 0.9 * rng.uniform(-1, 1, n), r)
+    return _to_i16(np.stack([l, r]))
+
+
+def full_scale_tone(seconds=1.0, fs=44100, freq=1000.0, n_ch=2):
+    """Full-scale sine on every channel: |xr| >= 1, so the reference's int-typed calc_scfsi statistics
+    (loop.c:615-722) become non-zero and scfsi gets set; also saturates pow_nint at 2047 in the bin search."""
+    n = int(round(seconds * fs))
+    t = np.arange(n, dtype=np.float64) / fs
+    return _to_i16(np.stack([np.sin(2 * np.pi * freq * t)] * n_ch))

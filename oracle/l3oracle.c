@@ -972,7 +972,7 @@ static int outer_loop_ref(double *xr, int max_bits, xmin_t *xm, int *ix, work_gi
             w->q += 1.0;
             quantize_ref(xr, ix, w->q);
             bits = count_bits_ref(ix, &w->g, sr);
-        } while (bits > huff_bits);
+        } while (bits > huff_bits && w->q < 1024); /* guard: the reference assert()s huff_bits >= 0, loop.c:579 */
 
         calc_noise_ref(xr, ix, w, sr, xfsf);
         for (sfb = 0; sfb < 21; sfb++) save_l[sfb] = sf_l[sfb];

@@ -220,8 +220,23 @@ def run_ref_stream(pcm, sfreq=44100, bitrate=128, keys=None):
     parent, child = ctx.Pipe()
     p = ctx.Process(target=_child, args=(child, pcm, sfreq, n_ch, bitrate, keys))
     p.start()
-    res = parent.recv()
-    p.join()
+    child.close()
+    res = None
+    try:
+        # the reference abort()s / exit()s on conditions it cannot handle (e.g. loop.c:358): never block on it
+        while True:
+            if parent.poll(0.2):
+                res = parent.recv()
+                break
+            if not p.is_alive():
+                if parent.poll(0.2):
+                    res = parent.recv()
+                break
+    except EOFError:
+        res = None
+    p.join(timeout=5)
+    if res is None:
+        raise RuntimeError("reference process died (exit code %s) - it abort()s on inputs it cannot encode" % p.exitcode)
     if isinstance(res, Exception):
         raise res
     return res

@@ -50,7 +50,7 @@ int emul_rate_loop_stream(int sfreq, int n_ch, int bitrate, int n_frames, const 
     frame_geometry(sfreq, n_ch, bitrate, &G);
     LoopStreamState S;
     memset(&S, 0, sizeof(S));
-    PerThread<int> st_en[4], st_xm[4];
+    static PerThread<int> st_en[4], st_xm[4];
     memset(st_en, 0, sizeof(st_en)); memset(st_xm, 0, sizeof(st_xm));
     double scr[288];
     WarpCtx w;
@@ -100,7 +100,7 @@ int emul_encode_stream(int sfreq, int n_ch, int bitrate, int n_frames, const sho
     }
     static FrontWarpSmem FM;
     for (int ch = 0; ch < n_ch; ch++)
-        front_walk(w, F, FM, pcm + ch * ch_stride + hist, 0, n_gran, &psy[ch].block_type, (long)(sizeof(PsyOut) / sizeof(int)) * n_ch,
+        front_walk(w, F, F.window, FM, pcm + ch * ch_stride + hist, 0, n_gran, &psy[ch].block_type, (long)(sizeof(PsyOut) / sizeof(int)) * n_ch,
                    xr + 576L * ch, 576L * n_ch, sb ? sb + 576L * ch : nullptr, 576L * n_ch);
     FrameGeom G; frame_geometry(sfreq, n_ch, bitrate, &G);
     LoopStreamState S; memset(&S, 0, sizeof(S));

@@ -1,0 +1,75 @@
+"""CPU: the CUDA kernel cores (csrc/*_core.h), compiled for the host through csrc/simt.h, against the oracle.
+With glibc's libm on both sides everything must be BIT-IDENTICAL, which validates the parallel
+restructuring (pair/slot layouts, warp reductions, count1 closed form, FFT op program, psy front/scan split)
+independently of GPU arithmetic."""
+import numpy as np
+import pytest
+
+import oracle
+from util import Emul, expected_sf, oracle_flat, sf_mask
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return Emul()
+
+
+@pytest.mark.parametrize("n", [1024, 256])
+def test_fft_program_bit_exact(emul, n):
+    rng = np.random.default_rng(n)
+    for scale in (1.0, 3000.0, 1e-3):
+        x = (rng.standard_normal(n) * scale).astype(np.float32)
+        rc, y, nops, nlev = emul.fft(x)
+        assert rc == 0, "two ops of one level touch the same slot"
+        e_ref, _ = oracle.fft(x.copy())
+        h = n // 2
+        e = np.empty(h + 1, np.float32)
+        e[0], e[h] = y[0] * y[0], y[h] * y[h]
+        e[1:h] = y[1:h] * y[1:h] + y[n - 1:h:-1] * y[n - 1:h:-1]
+        e[1:h] = np.where(e[1:h].astype(np.float64) < 0.0005, np.float32(0.0005), e[1:h])
+        assert np.array_equal(e, e_ref)
+        assert nlev <= 16
+
+
+@pytest.mark.parametrize("name", ["cfg1_44k_stereo_128", "cfg2_32k_mono_64", "cfg3_48k_stereo_320", "loud_44k_stereo_128",
+                                  "scfsi_44k_stereo_128"])
+def test_pipeline_bit_exact_vs_oracle(emul, golden, name):
+    g = golden[name]
+    pcm, fs, br = g["pcm"], int(g["sfreq"]), int(g["bitrate"])
+    n_ch = pcm.shape[0]
+    o = oracle_flat(oracle.encode_stream(pcm, fs, br), n_ch)
+    r = emul.encode_stream(pcm, fs, br)
+    assert np.array_equal(r["sb"], o["sb"])
+    assert np.array_equal(r["xr"], o["xr"])
+    assert np.array_equal(r["psy"]["pe"], o["pe"])
+    assert np.array_equal(r["psy"]["ratio_l"], o["ratio_l"])
+    assert np.array_equal(r["psy"]["ratio_s"], o["ratio_s"])
+    assert np.array_equal(r["psy"]["block_type"], o["block_type"])
+    assert np.array_equal(r["max_bits"], o["max_bits"])
+    assert np.array_equal(np.abs(r["ix"].astype(np.int32)), o["ix"])
+    assert np.array_equal(np.sign(r["ix"]), (np.sign(o["xr"]) * (o["ix"] > 0)).astype(np.int16))  # l3bitstream.c:115-125
+    assert np.array_equal(r["gi"], o["gi"])
+    m = sf_mask(o["block_type"])
+    assert np.array_equal(r["sf"][m], expected_sf(o)[m])
+    assert np.array_equal(r["fo"]["scfsi"][:, :n_ch], o["scfsi"][:, :n_ch])
+    assert np.array_equal(r["fo"]["resv_drain"], o["resv_drain"])
+    assert np.array_equal(r["fo"]["main_data_begin"][1:] * 8, o["resv_size"][:-1])
+
+
+def test_pipeline_edge_inputs(emul):
+    fs = 44100
+    t = np.arange(fs // 2) / fs
+    cases = {
+        "silence": np.zeros((2, 3000), np.int16),
+        "dc": np.full((1, 9000), -12000, np.int16),
+        "square": (np.stack([np.sign(np.sin(2 * np.pi * 200 * t))] * 2) * 32000).astype(np.int16),
+        "clipped": np.clip(np.random.default_rng(5).normal(0, 30000, (2, 12000)), -32768, 32767).astype(np.int16),
+    }
+    for name, pcm in cases.items():
+        n_ch = pcm.shape[0]
+        o = oracle_flat(oracle.encode_stream(pcm, fs, 128), n_ch)
+        r = emul.encode_stream(pcm, fs, 128)
+        assert np.array_equal(r["xr"], o["xr"]), name
+        assert np.array_equal(r["psy"]["pe"], o["pe"]), name
+        assert np.array_equal(np.abs(r["ix"].astype(np.int32)), o["ix"]), name
+        assert np.array_equal(r["gi"], o["gi"]), name
