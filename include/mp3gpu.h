@@ -127,6 +127,16 @@ int mp3gpu_quantize_count_batch(mp3gpu_ctx *ctx, const double *xr_abs, const int
 /* last launch statistics: number of kernels this library launched since ctx creation */
 long mp3gpu_kernel_launches(const mp3gpu_ctx *ctx);
 
+/* per-kernel device time of the four hot kernels, measured with CUDA events on the launching stream
+ * (used by bench.py for the live roofline figure).  collect() synchronises the device. */
+#define MP3GPU_K_PSY_FRONT 0   /* FFTs + history-free psychoacoustics */
+#define MP3GPU_K_PSY_SCAN 1    /* history-dependent psychoacoustic scan */
+#define MP3GPU_K_FRONT 2       /* fused polyphase filterbank + MDCT + alias reduction */
+#define MP3GPU_K_RATE_LOOP 3   /* rate loop + reservoir */
+#define MP3GPU_N_KERNELS 4
+int mp3gpu_profile_enable(mp3gpu_ctx *ctx, int on);
+int mp3gpu_profile_collect(mp3gpu_ctx *ctx, double ms[MP3GPU_N_KERNELS], long launches[MP3GPU_N_KERNELS], int reset);
+
 #ifdef __cplusplus
 }
 #endif

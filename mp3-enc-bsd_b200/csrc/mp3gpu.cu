@@ -268,7 +268,28 @@ struct mp3gpu_ctx {
     unsigned char *d_sf = nullptr;
     FrameOut *d_fo = nullptr;
     long launches = 0;
+    // per-kernel timing (mp3gpu_profile_*): events bracket every launch of the four hot kernels
+    int prof_on = 0;
+    std::vector<cudaEvent_t> prof_ev;     // pairs (start, stop)
+    std::vector<int> prof_kind;           // kernel id of each pair
+    double prof_ms[MP3GPU_N_KERNELS] = {0, 0, 0, 0};
+    long prof_n[MP3GPU_N_KERNELS] = {0, 0, 0, 0};
 };
+
+static void prof_begin(mp3gpu_ctx *c, int kind, cudaStream_t q)
+{
+    if (!c->prof_on) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, q);
+    c->prof_ev.push_back(a); c->prof_ev.push_back(b);
+    c->prof_kind.push_back(kind);
+}
+static void prof_end(mp3gpu_ctx *c, cudaStream_t q)
+{
+    if (!c->prof_on) return;
+    cudaEventRecord(c->prof_ev.back(), q);
+}
 
 extern "C" const char *mp3gpu_last_error(void) { return g_err; }
 extern "C" const char *mp3gpu_version(void) { return "mp3gpu 0.1 (sm_100a)"; }
@@ -396,6 +417,35 @@ extern "C" int mp3gpu_reset(mp3gpu_ctx *c)
     return 0;
 }
 
+extern "C" int mp3gpu_profile_enable(mp3gpu_ctx *c, int on)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    c->prof_on = on;
+    return 0;
+}
+
+// Synchronises the device, folds all recorded event pairs into per-kernel totals and returns them.
+extern "C" int mp3gpu_profile_collect(mp3gpu_ctx *c, double ms[MP3GPU_N_KERNELS], long launches[MP3GPU_N_KERNELS], int reset)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    CU(cudaDeviceSynchronize());
+    for (size_t i = 0; i < c->prof_kind.size(); i++) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]) == cudaSuccess) {
+            c->prof_ms[c->prof_kind[i]] += t;
+            c->prof_n[c->prof_kind[i]]++;
+        }
+        cudaEventDestroy(c->prof_ev[2 * i]); cudaEventDestroy(c->prof_ev[2 * i + 1]);
+    }
+    c->prof_ev.clear(); c->prof_kind.clear();
+    for (int k = 0; k < MP3GPU_N_KERNELS; k++) {
+        if (ms) ms[k] = c->prof_ms[k];
+        if (launches) launches[k] = c->prof_n[k];
+        if (reset) { c->prof_ms[k] = 0; c->prof_n[k] = 0; }
+    }
+    return 0;
+}
+
 extern "C" int mp3gpu_frame_geometry(const mp3gpu_ctx *c, int *bits_per_frame, int *mean_bits)
 {
     if (!c) return fail(MP3GPU_EINVAL, "null ctx");
@@ -462,7 +512,9 @@ static int launch_front(mp3gpu_ctx *c, const short *pcm_rows, const PsyOut *psy,
     const long warps = (long)n_streams * n_ch * n_tiles;
     const unsigned grid = (unsigned)((warps + FRONT_WARPS - 1) / FRONT_WARPS);
     const size_t smem = 512 * 8 + FRONT_WARPS * sizeof(FrontWarpSmem);
+    prof_begin(c, MP3GPU_K_FRONT, q);
     k_front<<<grid, FRONT_WARPS * 32, smem, q>>>(pcm_rows, c->row * n_ch, c->row, n_streams, n_ch, n_gran, tile, psy, xr, sb, do_mdct ? 1 : 0);
+    prof_end(c, q);
     c->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -472,13 +524,17 @@ static int launch_psy(mp3gpu_ctx *c, const short *pcm_rows, int n_streams, int n
 {
     const int n_gran = 2 * n_frames, n_ch = c->cfg.n_ch;
     const long gcs = (long)n_streams * n_gran * n_ch;
+    prof_begin(c, MP3GPU_K_PSY_FRONT, q);
     k_psy_front<<<(unsigned)((gcs + PSYF_WARPS - 1) / PSYF_WARPS), PSYF_WARPS * 32, PSYF_WARPS * sizeof(PsyFrontSmem), q>>>(
         c->psy_dev, pcm_rows, c->row * n_ch, c->row, n_streams, n_ch, n_gran, c->d_mid);
+    prof_end(c, q);
     c->launches++;
     CU(cudaGetLastError());
     const long chans = (long)n_streams * n_ch;
+    prof_begin(c, MP3GPU_K_PSY_SCAN, q);
     k_psy_scan<<<(unsigned)((chans + PSYS_WARPS - 1) / PSYS_WARPS), PSYS_WARPS * 32, PSYS_WARPS * sizeof(PsyScanSmem), q>>>(
         c->d_psy_tab, c->d_mid, c->d_psy_state, n_streams, n_ch, n_gran, psy);
+    prof_end(c, q);
     c->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -488,8 +544,10 @@ static int launch_rate_loop(mp3gpu_ctx *c, const double *xr, const PsyOut *psy, 
                             unsigned char *sf, FrameOut *fo, cudaStream_t q)
 {
     const unsigned grid = (unsigned)((n_streams + RL_WARPS - 1) / RL_WARPS);
+    prof_begin(c, MP3GPU_K_RATE_LOOP, q);
     k_rate_loop<<<grid, RL_WARPS * 32, RL_TABLE_BYTES + RL_WARPS * 288 * 8, q>>>(c->d_rate_tab, c->geom, c->d_loop_state, c->d_lane_state,
                                                                                 n_streams, n_frames, xr, psy, ix, gi, sf, fo);
+    prof_end(c, q);
     c->launches++;
     CU(cudaGetLastError());
     return 0;

@@ -33,7 +33,8 @@ EXPORTS = ["mp3gpu_last_error", "mp3gpu_version", "mp3gpu_create", "mp3gpu_destr
            "mp3gpu_frame_geometry", "mp3gpu_encode_frames", "mp3gpu_encode_frames_dev", "mp3gpu_sync",
            "mp3gpu_filter_subband_batch", "mp3gpu_mdct_sub_batch", "mp3gpu_subband_mdct_batch",
            "mp3gpu_L3psycho_anal_batch", "mp3gpu_iteration_loop_batch", "mp3gpu_quantize_count_batch",
-           "mp3gpu_kernel_launches"]
+           "mp3gpu_kernel_launches", "mp3gpu_profile_enable", "mp3gpu_profile_collect"]
+KERNEL_NAMES = ["psy_front", "psy_scan", "front_polyphase_mdct", "rate_loop"]
 
 
 class Config(C.Structure):
@@ -60,6 +61,8 @@ def load_library():
         lib.mp3gpu_version.restype = C.c_char_p
         lib.mp3gpu_kernel_launches.restype = C.c_long
         lib.mp3gpu_kernel_launches.argtypes = [C.c_void_p]
+        lib.mp3gpu_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        lib.mp3gpu_profile_collect.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_int]
         lib.mp3gpu_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
         lib.mp3gpu_destroy.argtypes = [C.c_void_p]
         lib.mp3gpu_reset.argtypes = [C.c_void_p]
@@ -119,6 +122,15 @@ class Encoder:
     @property
     def kernel_launches(self):
         return int(self.lib.mp3gpu_kernel_launches(self.ctx))
+
+    def profile_enable(self, on=True):
+        self._check(self.lib.mp3gpu_profile_enable(self.ctx, 1 if on else 0), "mp3gpu_profile_enable")
+
+    def profile_collect(self, reset=True):
+        """-> {kernel name: (total ms, launches)} measured with CUDA events on the launching stream"""
+        ms, n = (C.c_double * 4)(), (C.c_long * 4)()
+        self._check(self.lib.mp3gpu_profile_collect(self.ctx, ms, n, 1 if reset else 0), "mp3gpu_profile_collect")
+        return {KERNEL_NAMES[i]: (ms[i], n[i]) for i in range(4)}
 
     def sync(self, stream=None):
         self._check(self.lib.mp3gpu_sync(self.ctx, C.c_void_p(stream or 0)), "mp3gpu_sync")

@@ -1,0 +1,115 @@
+"""GPU: the fused hot path (mp3gpu_encode_frames, host buffers) against the oracle and the reference's
+golden outputs: multi-stream batches, chunked streaming (state carried between calls), mixed lengths."""
+import numpy as np
+import pytest
+
+import oracle
+from util import expected_sf, oracle_flat, pad_frames, sf_mask
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def check_stream(out_s, o, n_ch, exact_psy_required=True):
+    ix_ok = (np.abs(out_s["ix"].astype(np.int32)) == o["ix"]).all(axis=1)
+    gi_ok = (out_s["gi"] == o["gi"]).all(axis=1)
+    return ix_ok, gi_ok
+
+
+@pytest.mark.parametrize("name", ["cfg1_44k_stereo_128", "cfg2_32k_mono_64", "cfg3_48k_stereo_320", "loud_44k_stereo_128",
+                                  "scfsi_44k_stereo_128"])
+def test_encode_frames_vs_reference_golden(pkg, golden, name):
+    """whole pipeline vs what the UNMODIFIED reference produced (tests/golden)"""
+    g = golden[name]
+    pcm, fs, br = g["pcm"], int(g["sfreq"]), int(g["bitrate"])
+    n_ch = pcm.shape[0]
+    padded, nf = pad_frames(pcm)
+    enc = pkg.Encoder(fs, n_ch, br, max_streams=1, max_frames=nf)
+    out = enc.encode_frames(np.ascontiguousarray(padded[None]))
+    ngc = nf * 2 * n_ch
+    ref_ix = np.ascontiguousarray(g["ix"][:, :, :n_ch]).reshape(ngc, 576).astype(np.int32)
+    ref_gi = np.ascontiguousarray(g["gi"][:, :, :n_ch]).reshape(ngc, 20)
+    ix_ok = (out["ix"][0].astype(np.int32) == ref_ix).all(axis=1)   # golden ix carries the sign already
+    gi_ok = (out["gi"][0] == ref_gi).all(axis=1)
+    frac = (ix_ok & gi_ok).mean()
+    print(f"{name}: {100 * frac:.2f}% of granule-channels identical to the reference (ix with sign + all side info)")
+    assert frac >= 0.98
+    assert enc.kernel_launches == 5
+
+
+def test_batch_and_chunked_streaming(pkg):
+    """8 different streams in one batch, fed in chunks of 3,1,5,... frames: state (PCM history, psy history,
+    reservoir, stale addresses) must carry exactly -> identical to the oracle's one-shot encode."""
+    S, F = 8, 14
+    s = pkg.synth
+    pcm = np.stack([s.config1(F * 1152 / 44100.0 + 0.01, seeds=(100 + 2 * i, 101 + 2 * i))[:, :F * 1152] for i in range(S)])
+    pcm[3] = 0                                  # a silent stream
+    pcm[5, :, 4000:] = 0                        # a stream that goes silent
+    enc = pkg.Encoder(44100, 2, 128, max_streams=S, max_frames=5)
+    chunks = [3, 1, 5, 2, 3]
+    assert sum(chunks) == F
+    outs, f0 = [], 0
+    for c in chunks:
+        outs.append(enc.encode_frames(np.ascontiguousarray(pcm[:, :, f0 * 1152:(f0 + c) * 1152])))
+        f0 += c
+    ix = np.concatenate([o["ix"] for o in outs], axis=1)
+    gi = np.concatenate([o["gi"] for o in outs], axis=1)
+    sf = np.concatenate([o["sf"] for o in outs], axis=1)
+    bad = 0
+    for i in range(S):
+        o = oracle_flat(oracle.encode_stream(pcm[i], 44100, 128), 2)
+        ok = (np.abs(ix[i].astype(np.int32)) == o["ix"]).all(axis=1) & (gi[i] == o["gi"]).all(axis=1)
+        m = sf_mask(o["block_type"])
+        ok &= ((sf[i] == expected_sf(o)) | ~m).all(axis=1)
+        bad += (~ok).sum()
+    total = S * F * 4
+    print(f"chunked batch: {total - bad}/{total} granule-channels identical to the oracle")
+    assert bad <= total // 100
+
+
+def test_reset_and_determinism(pkg):
+    s = pkg.synth
+    pcm = np.ascontiguousarray(s.clip_batch(3, seconds=4 * 1152 / 44100.0)[:, :, :4 * 1152])
+    enc = pkg.Encoder(44100, 2, 128, max_streams=3, max_frames=4)
+    a = enc.encode_frames(pcm)
+    enc.reset()
+    b = enc.encode_frames(pcm)
+    for k in ("ix", "gi", "sf"):
+        assert np.array_equal(a[k], b[k]), k
+    c = enc.encode_frames(pcm)                  # continuing the streams is different from restarting them
+    assert not np.array_equal(a["gi"], c["gi"])
+
+
+def test_capacity_errors(pkg):
+    enc = pkg.Encoder(44100, 2, 128, max_streams=2, max_frames=2)
+    with pytest.raises(pkg.Mp3GpuError):
+        enc.encode_frames(np.zeros((3, 2, 1152), np.int16))
+    with pytest.raises(pkg.Mp3GpuError):
+        enc.encode_frames(np.zeros((1, 2, 3 * 1152), np.int16))
+
+
+def test_full_size_properties(pkg):
+    """BASELINE-size batch slice (512 streams x 20 frames): size-independent properties —
+    bit budget conservation (sum part2_3_length + reservoir == frames * mean bits), reservoir bounds,
+    replicated streams give replicated outputs, silence gives empty granules."""
+    S, F = 512, 20
+    s = pkg.synth
+    base = s.clip_batch(16, seconds=F * 1152 / 44100.0 + 0.01)[:, :, :F * 1152]
+    pcm = np.ascontiguousarray(np.tile(base, (S // 16, 1, 1)))
+    pcm[7] = 0
+    enc = pkg.Encoder(44100, 2, 128, max_streams=S, max_frames=F)
+    out = enc.encode_frames(pcm)
+    gi, fo = out["gi"], out["fo"]
+    for r in range(2, S // 16):                                # replicated streams -> replicated outputs
+        assert np.array_equal(out["ix"][16 * r:16 * r + 16], out["ix"][16:32])
+        assert np.array_equal(gi[16 * r:16 * r + 16], gi[16:32])
+    assert out["ix"][7].max() == 0 and (gi[7][:, 1] == 0).all()
+    mean_bits = enc.mean_bits
+    p23 = gi[:, :, 0].reshape(S, F, 4).sum(axis=2)            # bits used per frame (incl. stuffing)
+    resv_after = np.concatenate([fo["main_data_begin"][:, 1:] * 8, np.zeros((S, 1), np.int64)], axis=1)
+    resv_before = fo["main_data_begin"] * 8
+    # frame f: resv_before + 2*mean_bits - used == resv_after  (ResvAdjust/ResvFrameEnd conservation)
+    lhs = resv_before[:, :-1] + 2 * mean_bits - p23[:, :-1] - fo["resv_drain"][:, :-1]
+    assert np.array_equal(lhs, resv_after[:, :-1])
+    assert (fo["main_data_begin"] * 8 <= 4088).all() and (fo["main_data_begin"] >= 0).all()
+    assert (gi[:, :, 0] <= 4095).all() and (gi[:, :, 1] <= 288).all() and (gi[:, :, 3] < 256).all()

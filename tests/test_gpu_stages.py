@@ -1,0 +1,118 @@
+"""GPU: every batched C-ABI stage entry point against the oracle on identical synthetic PCM.
+
+Tolerances (BASELINE.json north_star): FP64 path <= 1e-12 relative (normalised by the per-granule max);
+integer work (ix, Huffman bit counts, table selection, side info) bit-exact.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from util import PSY_DT, expected_sf, oracle_flat, pad_frames, psy_array, sf_mask
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+CASES = ["cfg1_44k_stereo_128", "cfg2_32k_mono_64", "cfg3_48k_stereo_320", "loud_44k_stereo_128", "scfsi_44k_stereo_128"]
+
+
+def setup_case(pkg, golden, name):
+    g = golden[name]
+    pcm, fs, br = g["pcm"], int(g["sfreq"]), int(g["bitrate"])
+    n_ch = pcm.shape[0]
+    padded, nf = pad_frames(pcm)
+    o = oracle_flat(oracle.encode_stream(pcm, fs, br), n_ch)
+    enc = pkg.Encoder(fs, n_ch, br, max_streams=1, max_frames=nf)
+    dev = torch.device("cuda", 0)
+    return g, o, enc, torch.from_numpy(padded[None].copy()).to(dev), nf, n_ch, dev
+
+
+def rel_err(a, b):
+    scale = np.maximum(np.abs(b).max(axis=-1, keepdims=True), 1e-300)
+    return (np.abs(a - b) / scale).max()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_filter_subband_batch(pkg, golden, name):
+    g, o, enc, pcm, nf, n_ch, dev = setup_case(pkg, golden, name)
+    sb = enc.filter_subband_batch(pcm).cpu().numpy()[0]
+    assert np.array_equal(sb, o["sb"]), "subband samples must be bit-identical (same operation order)"
+    # and against the reference's own dump
+    nh = len(g["sb_head"])
+    ref = np.ascontiguousarray(g["sb_head"][:, :, :n_ch]).reshape(nh * 2 * n_ch, 18, 32)
+    assert np.array_equal(sb[:len(ref)], ref)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_mdct_sub_batch_and_fused(pkg, golden, name):
+    g, o, enc, pcm, nf, n_ch, dev = setup_case(pkg, golden, name)
+    psy = pkg.host.psy_from_numpy(psy_array(o)[None], dev)
+    sb = torch.from_numpy(o["sb"][None].copy()).to(dev)
+    xr = enc.mdct_sub_batch(sb, psy).cpu().numpy()[0]
+    assert rel_err(xr, o["xr"]) <= 1e-12
+    assert np.array_equal(xr, o["xr"]), "same dot-product order as the oracle -> bit-identical"
+    xr2 = enc.subband_mdct_batch(pcm, psy).cpu().numpy()[0]
+    assert np.array_equal(xr2, xr), "fused filterbank+MDCT must equal the two-stage path"
+    nh = len(g["xr_head"])
+    ref = np.ascontiguousarray(g["xr_head"][:, :, :n_ch]).reshape(nh * 2 * n_ch, 576)
+    assert rel_err(xr[:len(ref)], ref) <= 1e-12        # vs the reference (type-0 summation order differs)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_L3psycho_anal_batch(pkg, golden, name):
+    g, o, enc, pcm, nf, n_ch, dev = setup_case(pkg, golden, name)
+    psy = pkg.host.psy_to_numpy(enc.L3psycho_anal_batch(pcm))[0]
+    assert np.array_equal(psy["block_type"], o["block_type"])
+    # FP32 FFT is bit-exact by construction; device libm (atan2/sin/cos/log/exp) is within 1-2 ulp of glibc
+    assert np.abs(psy["pe"] - o["pe"]).max() <= 1e-5 * max(1.0, np.abs(o["pe"]).max())
+    assert rel_err(psy["ratio_l"], o["ratio_l"]) <= 1e-5
+    assert rel_err(psy["ratio_s"], o["ratio_s"]) <= 1e-5
+    exact = (psy["pe"] == o["pe"]).mean()
+    print(f"{name}: pe bit-identical in {100 * exact:.1f}% of granules, max |dpe| {np.abs(psy['pe'] - o['pe']).max():.3e}")
+    assert exact >= 0.5
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_iteration_loop_batch(pkg, golden, name):
+    g, o, enc, pcm, nf, n_ch, dev = setup_case(pkg, golden, name)
+    psy = pkg.host.psy_from_numpy(psy_array(o)[None], dev)
+    xr = torch.from_numpy(o["xr"][None].copy()).to(dev)
+    out = enc.iteration_loop_batch(xr, psy)
+    ix = out["ix"].cpu().numpy()[0]
+    gi = out["gi"].cpu().numpy()[0]
+    sf = out["sf"].cpu().numpy()[0]
+    fo = pkg.host.fo_to_numpy(out["fo"])[0]
+    assert np.array_equal(np.abs(ix.astype(np.int32)), o["ix"])
+    assert np.array_equal(np.sign(ix), (np.sign(o["xr"]) * (o["ix"] > 0)).astype(np.int16))
+    assert np.array_equal(gi, o["gi"])
+    m = sf_mask(o["block_type"])
+    assert np.array_equal(sf[m], expected_sf(o)[m])
+    assert np.array_equal(fo["scfsi"][:, :n_ch], o["scfsi"][:, :n_ch])
+    assert np.array_equal(fo["resv_drain"], o["resv_drain"])
+    assert np.array_equal(fo["main_data_begin"][1:] * 8, o["resv_size"][:-1])
+
+
+def test_quantize_count_batch_bit_exact(pkg, golden):
+    """quantize + count_bits + table selection on thousands of (granule, step) probes: integer-exact."""
+    g = golden["cfg1_44k_stereo_128"]
+    o = oracle_flat(oracle.encode_stream(g["pcm"], 44100, 128), 2)
+    rng = np.random.default_rng(0)
+    n = 600
+    sel = rng.integers(0, len(o["xr"]), n)
+    xr_abs = np.abs(o["xr"][sel]) * rng.choice([1.0, 8.0, 200.0], n)[:, None]
+    q = rng.integers(-60, 40, n).astype(np.int32)
+    bt = rng.choice([0, 0, 0, 1, 2, 3], n).astype(np.int32)
+    # edge cases: all zero, single line, saturating values
+    xr_abs[0] = 0.0
+    xr_abs[1] = 0.0; xr_abs[1, 575] = 1.0
+    xr_abs[2] = 1e6
+    xr_abs[3] = 0.0; xr_abs[3, :2] = 0.3
+    enc = pkg.Encoder(44100, 2, 128)
+    dev = torch.device("cuda", 0)
+    ix, gi, bits = enc.quantize_count_batch(torch.from_numpy(xr_abs).to(dev), torch.from_numpy(q).to(dev), torch.from_numpy(bt).to(dev))
+    ix, gi, bits = ix.cpu().numpy(), gi.cpu().numpy(), bits.cpu().numpy()
+    cols = [1, 2, 8, 9, 10, 11, 12, 15, 17, 18, 19]  # big_values,count1,table_select[3],region0/1,count1table,address1-3
+    for i in range(n):
+        b_ref, ix_ref, gi_ref = oracle.quantize_count(xr_abs[i], q[i], bt[i], 1)
+        assert np.array_equal(ix[i].astype(np.int32), ix_ref), i
+        assert bits[i] == b_ref, (i, bits[i], b_ref)
+        assert np.array_equal(gi[i][cols], gi_ref[cols]), (i, gi[i], gi_ref)
