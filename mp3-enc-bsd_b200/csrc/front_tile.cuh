@@ -1,0 +1,237 @@
+// front_tile.cuh — production kernel for the fused polyphase filterbank + MDCT + alias reduction
+// (replaces window_subband()/filter_subband(), /root/reference/src/encode.c:287-409, and
+// mdct_sub()/mdct(), mdct.c:25-198, for mp3gpu_encode_frames / mp3gpu_subband_mdct_batch).
+//
+// One CTA of 288 threads encodes a TILE of up to 15 consecutive granules of one (stream, channel),
+// plus one warm-up granule in front (the MDCT needs the previous granule's subband samples).
+// 16 granules = 288 polyphase slots = 9 warps x 32 slots, so every stage runs with full warps:
+//
+//   stage 0  PCM tile (int16) HBM -> shared memory, 16-byte coalesced loads
+//   stage A  windowing + 8-fold (encode.c:310-311,392-398).  lane = tap index i: each thread runs two
+//            8-tap FIRs (i, i+32) with the window taps in registers and a register sliding window of
+//            samples (1 shared load per output instead of 8); the fold to ysum/ysub is two shuffles.
+//   stage B  32x31 matrixing (encode.c:399-408).  thread = SLOT: the 31 folded inputs live in
+//            registers, the cosine matrix is read as immediate constant-bank operands of fully
+//            unrolled DMUL/DADD (no loads in the inner loop), results overwrite the thread's own row.
+//   stage C  MDCT (mdct.c:171-198), warp = granule, lane = band, cosine tables again as immediates.
+//   stage D  alias butterflies (mdct.c:83-91) in shared memory, then coalesced 128-bit stores of xr.
+//
+// Arithmetic: every sum is evaluated in the reference's order with unfused IEEE mul/add, so subband
+// samples are bit-identical to the reference and xr is bit-identical to the oracle (the reference's
+// hand-unrolled type-0 MDCT differs only in summation order, <= 2e-14 relative).
+// The bound of this kernel is the FP64 pipe (about 100 k FP64 instructions per granule-channel against
+// 5764 algorithmic bytes), see DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "tables.h"
+
+namespace mp3gpu {
+
+#define FT_G 15                         // output granules per tile
+#define FT_SLOTS (18 * (FT_G + 1))      // 288
+#define FT_THREADS FT_SLOTS
+#define FT_WARPS (FT_THREADS / 32)      // 9
+#define FT_ROW 33                       // doubles per slot row (odd: conflict-free for lane = slot)
+#define FT_PCM (480 + 32 * FT_SLOTS)    // 9696 samples
+
+struct FrontTileSmem {
+    double rows[FT_SLOTS * FT_ROW];     // stage A: ysum/ysub/y16; stage B: subband samples (in place);
+                                        // stage D: xr staging in the rows of the previous granule
+    double window[512];
+    short pcm[FT_PCM];
+};
+
+__constant__ FrontTables c_front;  // defined here: this header is included by exactly one translation unit (mp3gpu.cu)
+
+// ---- stage B: s[sb] = y16 + sum_j am[sb][j] * ys[j], j ascending (encode.c:399-408) ----------------
+template <int SB>
+__device__ __forceinline__ double ft_matrix_row(const double (&ys)[32])
+{
+    double s = ys[31];
+#pragma unroll
+    for (int j = 0; j < 31; j++) s = __dadd_rn(s, __dmul_rn(c_front.am[SB][j], ys[j]));
+    return s;
+}
+
+template <int SB0>
+__device__ __forceinline__ void ft_matrix_rows8(const double (&ys)[32], double *row, bool odd_slot)
+{
+    double s[8];
+    s[0] = ft_matrix_row<SB0 + 0>(ys); s[1] = ft_matrix_row<SB0 + 1>(ys);
+    s[2] = ft_matrix_row<SB0 + 2>(ys); s[3] = ft_matrix_row<SB0 + 3>(ys);
+    s[4] = ft_matrix_row<SB0 + 4>(ys); s[5] = ft_matrix_row<SB0 + 5>(ys);
+    s[6] = ft_matrix_row<SB0 + 6>(ys); s[7] = ft_matrix_row<SB0 + 7>(ys);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        // mdct.c:57-60: odd band, odd time slot -> * -1 (applied here, the raw value is never needed)
+        const double v = (((SB0 + k) & 1) && odd_slot) ? __dmul_rn(s[k], -1.0) : s[k];
+        row[SB0 + k] = v;
+    }
+}
+
+// ---- stage C: MDCT of one band held in registers ---------------------------------------------------
+__device__ __forceinline__ void ft_mdct_long(double (&fin)[36], int bt, double (&out)[18])
+{
+    // fin[k] = win[bt][k] * in[k] (mdct.c:190-192): the window is selected with a switch so that every
+    // table read has a compile-time address (a register-indexed __constant__ read goes through the ADU)
+    if (bt == 0) {
+#pragma unroll
+        for (int k = 0; k < 36; k++) fin[k] = __dmul_rn(c_front.win[0][k], fin[k]);
+    } else if (bt == 1) {
+#pragma unroll
+        for (int k = 0; k < 36; k++) fin[k] = __dmul_rn(c_front.win[1][k], fin[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 36; k++) fin[k] = __dmul_rn(c_front.win[3][k], fin[k]);
+    }
+#pragma unroll
+    for (int m = 0; m < 18; m++) {                                                  // mdct.c:193-198
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < 36; k++) sum = __dadd_rn(sum, __dmul_rn(fin[k], c_front.cos_l[m][k]));
+        out[m] = sum;
+    }
+}
+
+__device__ __forceinline__ void ft_mdct_short(const double (&in)[36], double (&out)[18])
+{
+#pragma unroll
+    for (int l = 0; l < 3; l++)                                                     // mdct.c:171-185
+#pragma unroll
+        for (int m = 0; m < 6; m++) {
+            double sum = 0.0;
+#pragma unroll
+            for (int k = 0; k < 12; k++)
+                sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(c_front.win[2][k], in[k + 6 * l + 6]), c_front.cos_s[m][k]));
+            out[3 * m + l] = sum;
+        }
+}
+
+// pcm_rows: [n_streams*n_ch] rows of `row` samples, HIST samples of history first (see mp3gpu.cu)
+__global__ void __launch_bounds__(FT_THREADS, 1)
+k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_stride, int hist, int n_streams, int n_ch, int n_gran,
+             const PsyOut *__restrict__ psy, double *__restrict__ xr)
+{
+    extern __shared__ __align__(16) unsigned char ft_smem_raw[];
+    FrontTileSmem &M = *reinterpret_cast<FrontTileSmem *>(ft_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_tiles = (n_gran + FT_G - 1) / FT_G;
+    const long bid = blockIdx.x;
+    const int t = (int)(bid % n_tiles);
+    const int ch = (int)((bid / n_tiles) % n_ch);
+    const long s = bid / ((long)n_tiles * n_ch);
+    const int g_first = t * FT_G;
+    const int ng = min(FT_G, n_gran - g_first);
+    const int n_slots = 18 * (ng + 1);
+    const int n_chunks = (n_slots + 31) >> 5;
+
+    // ---- stage 0: PCM tile.  smem sample j <-> stream time 576*(g_first-1) - 480 + j ---------------
+    {
+        const short *src = pcm_rows + s * stream_stride + ch * ch_stride + hist + 576L * (g_first - 1) - 480;
+        const int n_valid = 480 + 32 * n_slots;           // multiple of 8
+        const uint4 *src4 = reinterpret_cast<const uint4 *>(src);
+        uint4 *dst4 = reinterpret_cast<uint4 *>(M.pcm);
+        for (int i = tid; i < FT_PCM / 8; i += FT_THREADS)
+            dst4[i] = (i < n_valid / 8) ? src4[i] : make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < 512; i += FT_THREADS) M.window[i] = c_front.window[i];
+    }
+    __syncthreads();
+
+    // ---- stage A: lane = tap i (and i+32); slots of one parity form a sliding 8-tap FIR -------------
+    for (int c = warp; c < n_chunks; c += FT_WARPS) {
+        double w0[8], w1[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { w0[j] = M.window[lane + 64 * j]; w1[j] = M.window[lane + 32 + 64 * j]; }
+        const int src_lane = (32 - lane) & 31;
+#pragma unroll 1
+        for (int p = 0; p < 2; p++) {
+            // slot n = 32c + 2k + p; newest sample of tap i: pcm[480 + 32n + 31 - i]
+            const int base0 = 480 + 32 * (32 * c + p) + 31 - lane;      // k = 0, i = lane
+            double h0[8], h1[8];                                         // h[j] = sample for tap j of the CURRENT slot
+#pragma unroll
+            for (int j = 1; j < 8; j++) {
+                h0[j] = __dmul_rn((double)M.pcm[base0 - 64 * j], 1.0 / 32768);       // encode.c:306 (/SCALE, exact)
+                h1[j] = __dmul_rn((double)M.pcm[base0 - 32 - 64 * j], 1.0 / 32768);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                h0[0] = __dmul_rn((double)M.pcm[base0 + 64 * k], 1.0 / 32768);
+                h1[0] = __dmul_rn((double)M.pcm[base0 - 32 + 64 * k], 1.0 / 32768);
+                double y0 = __dmul_rn(h0[0], w0[0]), y1 = __dmul_rn(h1[0], w1[0]);   // encode.c:310-311,392-396
+#pragma unroll
+                for (int j = 1; j < 8; j++) {
+                    y0 = __dadd_rn(y0, __dmul_rn(h0[j], w0[j]));
+                    y1 = __dadd_rn(y1, __dmul_rn(h1[j], w1[j]));
+                }
+#pragma unroll
+                for (int j = 7; j > 0; j--) { h0[j] = h0[j - 1]; h1[j] = h1[j - 1]; }
+                const double a0 = __shfl_sync(0xffffffffu, y0, src_lane);            // y[32 - i]
+                const double a1 = __shfl_sync(0xffffffffu, y1, src_lane);            // y[64 - i]
+                double *row = M.rows + (size_t)(32 * c + 2 * k + p) * FT_ROW;
+                if (lane == 0) row[0] = __dadd_rn(y0, y1);                            // ysum[0] = y[0] + y[32]
+                else if (lane < 16) {
+                    row[lane] = __dadd_rn(y0, a0);                                    // ysum[i] = y[i] + y[32-i]
+                    row[15 + lane] = __dsub_rn(y1, a1);                               // ysub[i-1] = y[32+i] - y[64-i]
+                } else if (lane == 16) row[31] = y0;                                  // y[16]
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- stage B: thread = slot ---------------------------------------------------------------------
+    if (tid < n_chunks * 32) {
+        double *row = M.rows + (size_t)tid * FT_ROW;
+        double ys[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) ys[j] = row[j];
+        const bool odd_slot = ((tid % 18) & 1) != 0;
+        ft_matrix_rows8<0>(ys, row, odd_slot);
+        ft_matrix_rows8<8>(ys, row, odd_slot);
+        ft_matrix_rows8<16>(ys, row, odd_slot);
+        ft_matrix_rows8<24>(ys, row, odd_slot);
+    }
+    __syncthreads();
+
+    // ---- stage C + D: warp = granule, lane = band ---------------------------------------------------
+    const long gc_stride = n_ch;
+    for (int r = 0; r * FT_WARPS < ng; r++) {
+        const int gl = 1 + r * FT_WARPS + warp;            // local granule index, 1..ng (0 is the warm-up granule)
+        const bool active = gl <= ng;
+        double in[36], out[18];
+        int bt = 0;
+        if (active) {
+            const double *p = M.rows + (size_t)(18 * (gl - 1)) * FT_ROW + lane;
+#pragma unroll
+            for (int k = 0; k < 36; k++) in[k] = p[k * FT_ROW];
+            bt = psy[((s * n_gran + g_first + gl - 1) * gc_stride + ch)].block_type;
+        }
+        __syncthreads();                                    // every warp has its inputs: previous granules' rows are free
+        if (active) {
+            if (bt == 2) ft_mdct_short(in, out);
+            else ft_mdct_long(in, bt, out);
+            double *st = M.rows + (size_t)(18 * (gl - 1)) * FT_ROW;   // 594 doubles of the previous granule's rows
+#pragma unroll
+            for (int m = 0; m < 18; m++) st[lane * 18 + m] = out[m];
+            __syncwarp();
+            if (bt != 2 && lane < 31) {                                                 // mdct.c:83-91
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const double a = st[lane * 18 + 17 - k], b = st[(lane + 1) * 18 + k];
+                    const double bu = __dadd_rn(__dmul_rn(a, c_front.cs[k]), __dmul_rn(b, c_front.ca[k]));
+                    const double bd = __dsub_rn(__dmul_rn(b, c_front.cs[k]), __dmul_rn(a, c_front.ca[k]));
+                    st[lane * 18 + 17 - k] = bu;
+                    st[(lane + 1) * 18 + k] = bd;
+                }
+            }
+            __syncwarp();
+            double2 *dst = reinterpret_cast<double2 *>(xr + ((s * n_gran + g_first + gl - 1) * gc_stride + ch) * 576);
+            const double2 *src = reinterpret_cast<const double2 *>(st);
+#pragma unroll
+            for (int i = 0; i < 9; i++) dst[lane + 32 * i] = src[lane + 32 * i];
+        }
+        __syncthreads();                                    // staging rows are reused as inputs of nobody, but keep rounds ordered
+    }
+}
+
+}  // namespace mp3gpu

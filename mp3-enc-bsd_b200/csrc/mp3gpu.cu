@@ -18,6 +18,7 @@
 
 #include "../../include/mp3gpu.h"
 #include "front_core.h"
+#include "front_tile.cuh"
 #include "psy_core.h"
 #include "rate_loop_core.h"
 #include "tables.h"
@@ -31,7 +32,7 @@ static_assert(sizeof(RateTables) % 16 == 0, "RateTables must be int4-copyable");
 
 #define HIST 1056  // PCM samples of history kept per channel: 576 (previous granule) + 480 (filterbank)
 
-__constant__ FrontTables c_front;
+
 
 // ---------------------------------------------------------------------------------------------------
 // kernels
@@ -382,6 +383,7 @@ extern "C" int mp3gpu_create(const mp3gpu_config *cfg, mp3gpu_ctx **out)
     // opt in to large dynamic shared memory
     cudaFuncSetAttribute(k_psy_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PSYF_WARPS * sizeof(PsyFrontSmem)));
     cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(512 * 8 + FRONT_WARPS * sizeof(FrontWarpSmem)));
+    cudaFuncSetAttribute(k_front_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontTileSmem));
     cudaFuncSetAttribute(k_mdct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FRONT_WARPS * sizeof(FrontWarpSmem)));
     cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RL_TABLE_BYTES + RL_WARPS * 288 * 8));
     cudaFuncSetAttribute(k_quantize_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RL_TABLE_BYTES));
@@ -507,6 +509,16 @@ static int launch_front(mp3gpu_ctx *c, const short *pcm_rows, const PsyOut *psy,
                         bool do_mdct, cudaStream_t q)
 {
     const int n_gran = 2 * n_frames, n_ch = c->cfg.n_ch;
+    if (do_mdct && !sb) {  // production path: tiled kernel (front_tile.cuh)
+        const long n_tiles = (n_gran + FT_G - 1) / FT_G;
+        const long ctas = (long)n_streams * n_ch * n_tiles;
+        prof_begin(c, MP3GPU_K_FRONT, q);
+        k_front_tile<<<(unsigned)ctas, FT_THREADS, sizeof(FrontTileSmem), q>>>(pcm_rows, c->row * n_ch, c->row, HIST, n_streams, n_ch, n_gran, psy, xr);
+        prof_end(c, q);
+        c->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
     const int tile = pick_tile(n_streams, n_ch, n_gran);
     const long n_tiles = (n_gran + tile - 1) / tile;
     const long warps = (long)n_streams * n_ch * n_tiles;
