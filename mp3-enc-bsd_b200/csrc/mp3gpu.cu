@@ -28,7 +28,6 @@ using namespace mp3gpu;
 static_assert(sizeof(mp3gpu_gr_info) == sizeof(GrInfoOut), "gr_info layout");
 static_assert(sizeof(mp3gpu_psy_out) == sizeof(PsyOut), "psy_out layout");
 static_assert(sizeof(mp3gpu_frame_out) == sizeof(FrameOut), "frame_out layout");
-static_assert(sizeof(RateTables) % 16 == 0, "RateTables must be int4-copyable");
 
 #define HIST 1056  // PCM samples of history kept per channel: 576 (previous granule) + 480 (filterbank)
 
@@ -129,22 +128,29 @@ k_psy_scan(const PsyTables *T, const PsyMid *mid, PsyChanState *states, int n_st
     psy_scan_store(w, states[wid], R);
 }
 
-#define RL_WARPS 4
-#define RL_TABLE_BYTES ((sizeof(RateTables) + 15) & ~(size_t)15)
-__global__ void __launch_bounds__(RL_WARPS * 32)
-k_rate_loop(const RateTables *gT, FrameGeom G, LoopStreamState *states, LoopLaneState *lane_states, int n_streams, int n_frames,
-            const double *xr, const PsyOut *psy, short *ix, GrInfoOut *gi, unsigned char *sf, FrameOut *fo)
+#define RL_WARPS 8
+#define RL_HOT_BYTES ((sizeof(RateHot) + 15) & ~(size_t)15)
+#define RL_SMEM_BYTES (RL_HOT_BYTES + RL_WARPS * sizeof(RateWarpSmem))
+static_assert(sizeof(RateHot) % 16 == 0, "RateHot must be int4-copyable");
+static_assert(sizeof(RateWarpSmem) % 16 == 0, "RateWarpSmem alignment");
+
+__device__ __forceinline__ const RateHot &load_rate_hot(const RateTables *gT, unsigned char *smem_raw)
+{
+    const int4 *src = reinterpret_cast<const int4 *>(&gT->hot);
+    int4 *dst = reinterpret_cast<int4 *>(smem_raw);
+    for (int i = threadIdx.x; i < (int)(sizeof(RateHot) / 16); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    return *reinterpret_cast<const RateHot *>(smem_raw);
+}
+
+__global__ void __launch_bounds__(RL_WARPS * 32, 2)
+k_rate_loop(const RateTables *__restrict__ gT, FrameGeom G, LoopStreamState *states, LoopLaneState *lane_states, int n_streams, int n_frames,
+            const double *__restrict__ xr, const PsyOut *__restrict__ psy, short *ix, GrInfoOut *gi, unsigned char *sf, FrameOut *fo)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    {
-        const int4 *src = reinterpret_cast<const int4 *>(gT);
-        int4 *dst = reinterpret_cast<int4 *>(smem_raw);
-        for (int i = threadIdx.x; i < (int)(sizeof(RateTables) / 16); i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-    const RateTables &T = *reinterpret_cast<const RateTables *>(smem_raw);
+    const RateHot &H = load_rate_hot(gT, smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *scr = reinterpret_cast<double *>(smem_raw + RL_TABLE_BYTES) + warp * 288;
+    RateWarpSmem &M = reinterpret_cast<RateWarpSmem *>(smem_raw + RL_HOT_BYTES)[warp];
     const long s = (long)blockIdx.x * RL_WARPS + warp;
     if (s >= n_streams) return;
     WarpCtx w;
@@ -153,7 +159,7 @@ k_rate_loop(const RateTables *gT, FrameGeom G, LoopStreamState *states, LoopLane
 #pragma unroll
     for (int i = 0; i < 4; i++) { st_en[i].v = lane_states[s].en[i][lane]; st_xm[i].v = lane_states[s].xm[i][lane]; }
     const long gcs = (long)n_frames * 2 * G.n_ch;
-    rate_loop_stream(w, T, scr, G, S, st_en, st_xm, n_frames, xr + s * gcs * 576, psy + s * gcs, ix + s * gcs * 576,
+    rate_loop_stream(w, H, *gT, M, G, S, st_en, st_xm, n_frames, xr + s * gcs * 576, psy + s * gcs, ix + s * gcs * 576,
                      gi + s * gcs, sf + s * gcs * 40, fo + s * (long)n_frames, nullptr);
 #pragma unroll
     for (int i = 0; i < 4; i++) { lane_states[s].en[i][lane] = st_en[i].v; lane_states[s].xm[i][lane] = st_xm[i].v; }
@@ -162,43 +168,37 @@ k_rate_loop(const RateTables *gT, FrameGeom G, LoopStreamState *states, LoopLane
 
 // quantize + count_bits on n independent granules
 __global__ void __launch_bounds__(RL_WARPS * 32)
-k_quantize_count(const RateTables *gT, const double *xr_abs, const int *q, const int *block_type, int n, short *ix,
+k_quantize_count(const RateTables *__restrict__ gT, const double *xr_abs, const int *q, const int *block_type, int n, short *ix,
                  GrInfoOut *gi, int *bits)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    {
-        const int4 *src = reinterpret_cast<const int4 *>(gT);
-        int4 *dst = reinterpret_cast<int4 *>(smem_raw);
-        for (int i = threadIdx.x; i < (int)(sizeof(RateTables) / 16); i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-    const RateTables &T = *reinterpret_cast<const RateTables *>(smem_raw);
+    const RateHot &H = load_rate_hot(gT, smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    RateWarpSmem &M = reinterpret_cast<RateWarpSmem *>(smem_raw + RL_HOT_BYTES)[warp];
     const long i = (long)blockIdx.x * RL_WARPS + warp;
     if (i >= n) return;
     WarpCtx w;
     const int bt = block_type[i];
     const bool is_short = (bt == 2), wsf = (bt != 0);
-    GcRegs R;
-#pragma unroll
     for (int k = 0; k < 9; k++) {
         const int s = lane + 32 * k;
         const int e0 = slot_e0(is_short, s), e1 = is_short ? e0 + 3 : e0 + 1;
-        R.xa[k].v = xr_abs[i * 576 + e0];
-        R.xb[k].v = xr_abs[i * 576 + e1];
-        R.band[k].v = 0;
+        D2 x; x.x = xr_abs[i * 576 + e0]; x.y = xr_abs[i * 576 + e1];
+        M.xs[s] = x;
     }
+    __syncwarp();
     CountResult C;
     memset(&C, 0, sizeof(C));
     int qq = q[i];
     qq = qq < -256 ? -256 : (qq > 255 ? 255 : qq);
-    const int b = probe(w, T, R, is_short, wsf, qq, C);
-#pragma unroll
+    const int b = probe(w, H, *gT, M, is_short, wsf, qq, C);
+    __syncwarp();
     for (int k = 0; k < 9; k++) {
         const int s = lane + 32 * k;
         const int e0 = slot_e0(is_short, s), e1 = is_short ? e0 + 3 : e0 + 1;
-        ix[i * 576 + e0] = (short)R.ia[k].v;
-        ix[i * 576 + e1] = (short)R.ib[k].v;
+        const U2 v = M.ix[s];
+        ix[i * 576 + e0] = (short)v.x;
+        ix[i * 576 + e1] = (short)v.y;
     }
     if (lane == 0) {
         GrInfoOut g;
@@ -385,8 +385,8 @@ extern "C" int mp3gpu_create(const mp3gpu_config *cfg, mp3gpu_ctx **out)
     cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(512 * 8 + FRONT_WARPS * sizeof(FrontWarpSmem)));
     cudaFuncSetAttribute(k_front_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontTileSmem));
     cudaFuncSetAttribute(k_mdct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FRONT_WARPS * sizeof(FrontWarpSmem)));
-    cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RL_TABLE_BYTES + RL_WARPS * 288 * 8));
-    cudaFuncSetAttribute(k_quantize_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RL_TABLE_BYTES));
+    cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES);
+    cudaFuncSetAttribute(k_quantize_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES);
     *out = c;
     rc = mp3gpu_reset(c);
     if (rc) { mp3gpu_destroy(c); *out = nullptr; return rc; }
@@ -557,7 +557,7 @@ static int launch_rate_loop(mp3gpu_ctx *c, const double *xr, const PsyOut *psy, 
 {
     const unsigned grid = (unsigned)((n_streams + RL_WARPS - 1) / RL_WARPS);
     prof_begin(c, MP3GPU_K_RATE_LOOP, q);
-    k_rate_loop<<<grid, RL_WARPS * 32, RL_TABLE_BYTES + RL_WARPS * 288 * 8, q>>>(c->d_rate_tab, c->geom, c->d_loop_state, c->d_lane_state,
+    k_rate_loop<<<grid, RL_WARPS * 32, RL_SMEM_BYTES, q>>>(c->d_rate_tab, c->geom, c->d_loop_state, c->d_lane_state,
                                                                                 n_streams, n_frames, xr, psy, ix, gi, sf, fo);
     prof_end(c, q);
     c->launches++;
@@ -672,7 +672,7 @@ extern "C" int mp3gpu_quantize_count_batch(mp3gpu_ctx *c, const double *xr_abs, 
 {
     if (!c) return fail(MP3GPU_EINVAL, "null ctx");
     if (n < 1 || !xr_abs || !q || !block_type || !ix || !gi || !bits) return fail(MP3GPU_EINVAL, "bad argument");
-    k_quantize_count<<<(unsigned)((n + RL_WARPS - 1) / RL_WARPS), RL_WARPS * 32, RL_TABLE_BYTES, (cudaStream_t)stream>>>(
+    k_quantize_count<<<(unsigned)((n + RL_WARPS - 1) / RL_WARPS), RL_WARPS * 32, RL_SMEM_BYTES, (cudaStream_t)stream>>>(
         c->d_rate_tab, xr_abs, q, block_type, n, ix, (GrInfoOut *)gi, bits);
     c->launches++;
     CU(cudaGetLastError());

@@ -27,23 +27,40 @@ using simt::PerThread;
 using simt::WarpCtx;
 
 // ---- constant tables (host-built with the reference's libm expressions; see tables.cpp) ---------
+// Hot part: copied to shared memory by every CTA.
+// glut[g][16 x + y]: code length + sign bits of the pair (x, y) in every candidate table of group g,
+// three 10-bit fields, so ONE shared load per pair prices all sibling tables new_choose_table()
+// compares (loop.c:1793-1900):
+//   g0 {1}   g1 {2,3}   g2 {5,6}   g3 {7,8,9}   g4 {10,11,12}   g5 {13,15}
+//   g6 {16..23, 24..31, #escapes}   g7 {15, 24, #escapes}   (x, y clamped to 15; linbits added per escape)
+struct alignas(16) RateHot {
+    unsigned int glut[8][256];
+    unsigned int c1lut[16];         // count1 quad p: (hlen32 + signs) | (hlen33 + signs) << 16
+    double pre1[4], pre2[4];        // pow(sqrt 2, n), pow(sqrt 2, 2n)  (loop.c:1205-1210)
+    double ifqstep, ifqstep2;       // sqrt(2), sqrt(2)*sqrt(2)          (loop.c:1252,1293)
+    double log2c, pad0;             // log(2.0)                           (loop.c:632)
+    short sfb_l[24], sfb_s[16];     // Table B.8 for this sample rate
+    unsigned short hlinmax[36];
+    unsigned char hlinbits[36];
+    unsigned char band_long[288];   // sfb of long pair s (21 = above last band)
+    unsigned char band_short[288];  // 3*sfb + w of short slot s (>= 36 = above last band)
+    unsigned char subdiv[290][2];   // region0/1_count for big_values (long blocks, loop.c:1596-1690)
+    unsigned char pretab[24];
+    unsigned char pad1[8];
+};
+
+// Cold part: stays in global memory (L1/L2 resident; touched rarely or with warp-uniform addresses)
 struct alignas(16) RateTables {
-    double pow_nint_tab[2049];  // [p] = (p - 0.4054)^(4/3), p = 1..2048 (pow_nint.c:13-19); [0] unused
+    RateHot hot;
+    double pow_nint_tab[2050];  // [p] = (p - 0.4054)^(4/3), p = 1..2048 (pow_nint.c:13-19); [0] unused
     double pow43[2048];         // p^(4/3) (loop.c:1017-1021)
     double step[512];           // 2^(q/4), q = -256..255 (loop.c:1020,1386); index q + 256
     double ostep[512];          // 1 / step
-    double pre1[4], pre2[4];    // pow(sqrt 2, n), pow(sqrt 2, 2n)  (loop.c:1205-1210)
-    double ifqstep, ifqstep2;   // sqrt(2), sqrt(2)*sqrt(2)          (loop.c:1252,1293)
-    double log2c;               // log(2.0)                           (loop.c:632)
-    short sfb_l[23], sfb_s[14]; // Table B.8 for this sample rate
-    unsigned char hlen[1412];   // Table B.7 code lengths, flat
-    unsigned short hoff[34];    // offset of each table in hlen
+    unsigned char hlen[1412];   // Table B.7 code lengths, flat (table builders / diagnostics)
+    unsigned short hoff[34];
     unsigned char hxlen[34], hlinbits[34];
     unsigned short hlinmax[34];
-    unsigned char band_long[288];   // sfb of long pair s (21 = above last band)
-    unsigned char band_short[288];  // 3*sfb + w of short slot s (>= 36 = above last band)
-    unsigned char subdiv[289][2];   // region0/1_count for big_values (long blocks, loop.c:1596-1690)
-    unsigned char pretab[24];
+    unsigned char pad[6];
 };
 
 struct GrInfoOut {  // 20 ints, same order as the reference dump (oracle GR_FIELDS)
@@ -74,37 +91,58 @@ struct FrameGeom {
     int n_ch, mean_bits, bits_per_frame;
 };
 
+// ---- per-warp working set in shared memory ---------------------------------------------------------
+// Slot order (k = 0..8, lane = 0..31, slot s = lane + 32 k in [0,288)):
+//   long / start / stop blocks: slot s holds elements (2s, 2s+1)            -> Huffman pair s
+//   short blocks (type 2):      slot s = 3 m + w holds elements (6m+w, 6m+3+w), i.e. lines 2m and
+//                               2m+1 of window w (the [192][3] view of loop.c:1375-1376)
+struct alignas(16) D2 { double x, y; };
+struct U2 { unsigned short x, y; };
+struct alignas(16) RateWarpSmem {
+    D2 xs[288];        // |xr| of the slot's two elements (amplified in place by the outer loop)
+    double scr[288];   // per-slot energies / noise for the band sums
+    U2 ix[288];        // quantised values of the slot
+};
+
 // ---- small helpers --------------------------------------------------------------------------------
-SIMT_FN int quant1(const double *tab, double x)
+SIMT_FN float pow075_estimate(float x)
 {
-    // largest p in [0,2047] with x >= tab[p] (tab[0] := -inf): identical to pow_nint()'s gallop +
-    // binary search (pow_nint.h:16-50) because tab is strictly increasing.  Float estimate + exact fix-up.
-    float xf = (float)x;
-    float e = sqrtf(xf);
-    e = e * sqrtf(e);
-    e = fminf(e, 3000.0f);
-    int p = (int)(e + 0.4054f);
-    if (p > 2047) p = 2047;
+#if SIMT_DEV
+    return __powf(x, 0.75f);   // 2 MUFU; relative error ~1.3e-6, only ever used inside a verified margin
+#else
+    return powf(x, 0.75f);
+#endif
+}
+
+// pow_nint(): largest p in [0,2047] with x >= tab[p] (tab strictly increasing, tab[0] := -inf) — the
+// value the reference finds with gallop + binary search (pow_nint.h:16-50).  x^(3/4) + 0.4054 is
+// estimated in FP32; unless the estimate lies within a conservative error margin of an integer the
+// truncation is already exact, otherwise the exact FP64 comparison against the table decides.
+SIMT_NOINLINE int quant1_exact(const double *tab, double x, int p)
+{
+    if (p < 0) p = 0;
     while (p > 0 && x < tab[p]) p--;
     while (p < 2047 && x >= tab[p + 1]) p++;
     return p;
 }
 
-SIMT_FN int nint_ref(double in) { return (in < 0) ? (int)(in - 0.5) : (int)(in + 0.5); }
-
-SIMT_FN int popc4(int v) { return (v & 1) + ((v >> 1) & 1) + ((v >> 2) & 1) + ((v >> 3) & 1); }
-
-// bits of one (x,y) pair in table t (count_bit, loop.c:172-225 / HuffmanCode count mode)
-SIMT_FN int pair_bits(const RateTables &T, int t, int x, int y)
+SIMT_FN int quant1(const double *tab, double x)
 {
-    int s = (x != 0) + (y != 0);
-    if (t > 15) {
-        int lb = T.hlinbits[t];
-        if (x > 14) { x = 15; s += lb; }
-        if (y > 14) { y = 15; s += lb; }
-    }
-    return s + T.hlen[T.hoff[t] + x * T.hxlen[t] + y];
+    const float e = pow075_estimate((float)x);
+    const float t = e + 0.4054f;
+    const int p0 = (t < 2047.0f) ? (int)t : 2047;   // also catches inf / nan estimates
+    const float d = t - (float)p0;
+    const float margin = 1e-5f * t + 1e-6f;
+    if (t < 2040.0f && d > margin && d < 1.0f - margin) return p0;
+    return quant1_exact(tab, x, p0);
 }
+
+// libm calls that sit outside the hot loop are kept out of line: the kernel's working set of
+// instructions must fit the instruction cache (see profiles/r01_a_baseline.md)
+SIMT_NOINLINE double ref_log(double x) { return log(x); }
+SIMT_NOINLINE double ref_exp(double x) { return exp(x); }
+
+SIMT_FN int nint_ref(double in) { return (in < 0) ? (int)(in - 0.5) : (int)(in + 0.5); }
 
 // first table whose range covers max (loop.c:1813-1818 / 1921-1928): max in 1..14
 SIMT_FN int table_for_small_max(int max)
@@ -112,21 +150,20 @@ SIMT_FN int table_for_small_max(int max)
     return (max == 1) ? 1 : (max == 2) ? 2 : (max == 3) ? 5 : (max <= 5) ? 7 : (max <= 7) ? 10 : 13;
 }
 
-SIMT_FN int esc_table(const RateTables &T, int lo, int hi, int m15)
+SIMT_FN int esc_table(const RateHot &H, int lo, int hi, int m15)
 {
     for (int i = lo; i < hi; i++)
-        if ((int)T.hlinmax[i] >= m15) return i;
+        if ((int)H.hlinmax[i] >= m15) return i;
     return 0;
 }
 
-// ---- the per-granule working set ------------------------------------------------------------------
-struct GcRegs {
-    PerThread<double> xa[9], xb[9];  // |xr| of the slot's two elements (amplified in place)
-    PerThread<int> ia[9], ib[9];     // quantised values
-    PerThread<int> band[9];          // band id of slot
-};
+// glut group of a region whose largest value is max (> 0)
+SIMT_FN int group_for_max(int max)
+{
+    return (max == 1) ? 0 : (max == 2) ? 1 : (max == 3) ? 2 : (max <= 5) ? 3 : (max <= 7) ? 4 : (max < 15) ? 5 : (max == 15) ? 7 : 6;
+}
 
-struct BandRegs {
+struct BandRegs {   // band per lane: band b lives in lane b & 31 of register b >> 5
     PerThread<double> xmin[2], xfsf[2];
     PerThread<int> sf[2];
 };
@@ -144,257 +181,218 @@ SIMT_FN int slot_e0(bool is_short, int s)
     return 6 * m + (s - 3 * m);
 }
 
-// quantize(): loop.c:1360-1428 with subblock_gain == 0 and mixed_block_flag == 0 (always, l3psy.c:739)
-SIMT_FN void quantize_all(const WarpCtx &w, const RateTables &T, GcRegs &R, int q)
+// quantize(): loop.c:1360-1428 with subblock_gain == 0 and mixed_block_flag == 0 (always, l3psy.c:739).
+// Also returns, per lane, the last slot holding a non-zero value and the last slot holding a value
+// > 1 (calc_runlen's scan, loop.c:1498-1517) since the values are at hand.
+SIMT_FN void quantize_all(const WarpCtx &w, const RateTables &T, RateWarpSmem &M, int q, PerThread<int> &nzmax, PerThread<int> &bigmax)
 {
     const double ostep = T.ostep[(q > 255 ? 255 : q) + 256];
     FOR_THREADS(w)
-#pragma unroll
-    for (int k = 0; k < 9; k++) {
-        R.ia[k]() = quant1(T.pow_nint_tab, simt::dmul(R.xa[k](), ostep));
-        R.ib[k]() = quant1(T.pow_nint_tab, simt::dmul(R.xb[k](), ostep));
-    }
-    END_THREADS
-}
-
-// count_bits(): calc_runlen + count1_bitcount + subdivide + bigv_tab_select + bigv_bitcount
-// (loop.c:2099-2113 and 590-594) on the quantised values in registers.
-SIMT_FN void count_all(const WarpCtx &w, const RateTables &T, const GcRegs &R, bool is_short, bool wsf, CountResult &C)
-{
-    C.table_select[0] = C.table_select[1] = C.table_select[2] = 0;
-    if (is_short) {
-        // loop.c:1492-1496, 1667-1674, 1723-1760, 1958-2003
-        PerThread<int> m1, m2;
-        FOR_THREADS(w)
-        int a = 0, b = 0;
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-            int s = lane + 32 * k;
-            int mx = R.ia[k]() > R.ib[k]() ? R.ia[k]() : R.ib[k]();
-            if (s < 18) a = mx > a ? mx : a; else b = mx > b ? mx : b;  // lines < 12 <=> m < 6 <=> s < 18
-        }
-        m1() = a; m2() = b;
-        END_THREADS
-        int max1 = w.reduce_max(m1), max2 = w.reduce_max(m2);
-        int t0 = (max1 == 0) ? 0 : (max1 < 15) ? table_for_small_max(max1) : esc_table(T, 15, 32, max1 - 15);
-        int t1 = (max2 == 0) ? 0 : (max2 < 15) ? table_for_small_max(max2) : esc_table(T, 15, 32, max2 - 15);
-        PerThread<int> sum;
-        FOR_THREADS(w)
-        int acc = 0;
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-            int s = lane + 32 * k;
-            int t = (s < 18) ? t0 : t1;
-            if (t) acc += pair_bits(T, t, R.ia[k](), R.ib[k]());
-        }
-        sum() = acc;
-        END_THREADS
-        C.bits = w.reduce_add(sum);
-        C.big_values = 288; C.count1 = 0; C.count1table_select = 1;
-        C.region0_count = 8; C.region1_count = 36;
-        C.address1 = 36; C.address2 = 576; C.address3 = 0;
-        C.table_select[0] = t0; C.table_select[1] = t1;
-        return;
-    }
-    // ---- calc_runlen, loop.c:1498-1517 ----
-    PerThread<int> nzmax, bigmax;
-    FOR_THREADS(w)
     int nz = -1, bg = -1;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 9; k++) {
-        int s = lane + 32 * k;
-        if ((R.ia[k]() | R.ib[k]()) != 0) nz = s;
-        if (R.ia[k]() > 1 || R.ib[k]() > 1) bg = s;
+        const int s = lane + 32 * k;
+        const D2 x = M.xs[s];
+        const int a = quant1(T.pow_nint_tab, simt::dmul(x.x, ostep));
+        const int b = quant1(T.pow_nint_tab, simt::dmul(x.y, ostep));
+        U2 v; v.x = (unsigned short)a; v.y = (unsigned short)b;
+        M.ix[s] = v;
+        if ((a | b) != 0) nz = s;
+        if (a > 1 || b > 1) bg = s;
     }
     nzmax() = nz; bigmax() = bg;
     END_THREADS
-    const int n = w.reduce_max(nzmax) + 1;
-    const int B = w.reduce_max(bigmax);
-    const int count1 = (n - 1 - B) >> 1;
-    const int bv = n - 2 * count1;
-    C.big_values = bv; C.count1 = count1;
-    // ---- count1_bitcount, loop.c:1531-1590: quads = slot pairs (bv+2t, bv+2t+1) ----
-    int c1bits = 0;
-    C.count1table_select = 1;
-    if (count1 > 0) {
-        PerThread<int> code[10], s0, s1;
-        FOR_THREADS(w)
-#pragma unroll
-        for (int k = 0; k < 9; k++) code[k]() = (R.ia[k]() & 1) | ((R.ib[k]() & 1) << 1);
-        code[9]() = 0;
-        END_THREADS
-        PerThread<int> nxt[9];
-#pragma unroll
-        for (int k = 0; k < 9; k++) w.shift_down1(nxt[k], code[k], code[k + 1]);
-        FOR_THREADS(w)
-        int a0 = 0, a1 = 0;
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-            int s = lane + 32 * k;
-            int rel = s - bv;
-            if (rel >= 0 && rel < 2 * count1 && (rel & 1) == 0) {
-                int p = code[k]() | (nxt[k]() << 2);
-                int sg = popc4(p);
-                a0 += sg + T.hlen[T.hoff[32] + p];
-                a1 += sg + T.hlen[T.hoff[33] + p];
-            }
-        }
-        s0() = a0; s1() = a1;
-        END_THREADS
-        int sum0 = w.reduce_add(s0), sum1 = w.reduce_add(s1);
-        if (sum0 < sum1) { c1bits = sum0; C.count1table_select = 0; }
-        else { c1bits = sum1; C.count1table_select = 1; }
-    }
-    // ---- subdivide, loop.c:1638-1704 ----
-    const int bvr = 2 * bv;
-    if (bv == 0) {
-        // subdivide() leaves address1..3 untouched (stale values from the previous probe / frame) and
-        // bigv_tab_select()/bigv_bitcount() then still walk them (loop.c:1642-1647,1764-1772)
-        C.region0_count = 0; C.region1_count = 0;
-    } else if (!wsf) {
-        C.region0_count = T.subdiv[bv][0];
-        C.region1_count = T.subdiv[bv][1];
-        C.address1 = T.sfb_l[C.region0_count + 1];
-        C.address2 = T.sfb_l[C.region0_count + C.region1_count + 2];
-        C.address3 = bvr;
-    } else {
-        C.region0_count = 7; C.region1_count = 13;
-        C.address1 = T.sfb_l[8]; C.address2 = bvr; C.address3 = 0;
-    }
-    C.bits = c1bits;
+    w.sync();
 }
 
-// bigv_tab_select + bigv_bitcount for long/start/stop blocks (loop.c:1762-1775, 1793-1900, 2005-2015)
-SIMT_FN int count_regions(const WarpCtx &w, const RateTables &T, const GcRegs &R, int a1, int a2, int a3, int bvr, int tsel[3])
+// count_bits() = calc_runlen + count1_bitcount + subdivide + bigv_tab_select + bigv_bitcount
+// (loop.c:2099-2113 and 590-594) on the quantised values in shared memory.  `C` carries address1..3
+// across probes exactly like the reference's cod_info does (subdivide() leaves them untouched when
+// big_values == 0, and bigv_tab_select()/bigv_bitcount() then still walk them, loop.c:1642-1647,1764-1772).
+SIMT_FN int count_all(const WarpCtx &w, const RateHot &H, const RateWarpSmem &M, bool is_short, bool wsf,
+                      const PerThread<int> &nzmax, const PerThread<int> &bigmax, CountResult &C)
 {
-    // region of element e: R0 = [0,a1), R1 = [a1,a2) if a2 > a1, R2 = [a2,bvr) if bvr > a2
-    const bool has1 = a2 > a1, has2 = bvr > a2;
-    PerThread<int> mx[3];
+    int c1bits = 0, bvr;
+    C.table_select[0] = C.table_select[1] = C.table_select[2] = 0;
+    if (is_short) {
+        // loop.c:1492-1496, 1667-1674: fixed partition, lines < 12 (slots < 18) form region 0
+        C.big_values = 288; C.count1 = 0; C.count1table_select = 1;
+        C.region0_count = 8; C.region1_count = 36;
+        C.address1 = 36; C.address2 = 576; C.address3 = 0;
+        bvr = 576;
+    } else {
+        // ---- calc_runlen, loop.c:1498-1517 ----
+        const int n = w.reduce_max(nzmax) + 1;
+        const int B = w.reduce_max(bigmax);
+        const int count1 = (n - 1 - B) >> 1;
+        const int bv = n - 2 * count1;
+        C.big_values = bv; C.count1 = count1;
+        // ---- count1_bitcount, loop.c:1531-1590: quad t = slots (bv+2t, bv+2t+1) ----
+        C.count1table_select = 1;
+        if (count1 > 0) {
+            PerThread<int> acc;
+            FOR_THREADS(w)
+            int a = 0;
+            for (int t = lane; t < count1; t += 32) {
+                const U2 u = M.ix[bv + 2 * t], v = M.ix[bv + 2 * t + 1];
+                const int p = (u.x & 1) | ((u.y & 1) << 1) | ((v.x & 1) << 2) | ((v.y & 1) << 3);
+                a += (int)H.c1lut[p];
+            }
+            acc() = a;
+            END_THREADS
+            const int both = w.reduce_add(acc);
+            const int sum0 = both & 0xffff, sum1 = both >> 16;
+            if (sum0 < sum1) { c1bits = sum0; C.count1table_select = 0; }
+            else c1bits = sum1;
+        }
+        // ---- subdivide, loop.c:1638-1704 ----
+        bvr = 2 * bv;
+        if (bv == 0) {
+            C.region0_count = 0; C.region1_count = 0;   // address1..3 stay stale
+        } else if (!wsf) {
+            C.region0_count = H.subdiv[bv][0];
+            C.region1_count = H.subdiv[bv][1];
+            C.address1 = H.sfb_l[C.region0_count + 1];
+            C.address2 = H.sfb_l[C.region0_count + C.region1_count + 2];
+            C.address3 = bvr;
+        } else {
+            C.region0_count = 7; C.region1_count = 13;
+            C.address1 = H.sfb_l[8]; C.address2 = bvr; C.address3 = 0;
+        }
+    }
+    // ---- bigv_tab_select + bigv_bitcount (loop.c:1717-1775, 1793-1943, 1954-2016) ----
+    // region of element e: R0 = [0,a1), R1 = [a1,a2) if a2 > a1, R2 = [a2,bvr) if bvr > a2.  (Region-2
+    // counting in the reference runs over [a2, a3): a3 == bvr for plain long blocks and 0 for
+    // start/stop/short blocks, where region 2 is never selected, so [a2,bvr) covers both.)
+    const int a1 = C.address1, a2 = C.address2;
+    const bool has0 = a1 > 0, has1 = a2 > a1, has2 = !is_short && bvr > a2;
+    int e_end = has0 ? a1 : 0;
+    if (has1) e_end = a2;
+    if (has2) e_end = bvr;
+    if (e_end > 576) e_end = 576;
+    const int k_end = (e_end + 63) >> 6;     // slots s = lane + 32 k hold elements 2 s, 2 s + 1
+    PerThread<int> mx0, mx1, mx2;
     FOR_THREADS(w)
     int m0 = 0, m1 = 0, m2 = 0;
-#pragma unroll
-    for (int k = 0; k < 9; k++) {
-        int e = 2 * (lane + 32 * k);
-        int v = R.ia[k]() > R.ib[k]() ? R.ia[k]() : R.ib[k]();
+    for (int k = 0; k < k_end; k++) {
+        const int e = 2 * (lane + 32 * k);
+        const U2 u = M.ix[lane + 32 * k];
+        const int v = u.x > u.y ? u.x : u.y;
         if (e < a1) m0 = v > m0 ? v : m0;
         else if (e < a2) m1 = v > m1 ? v : m1;
         else if (e < bvr) m2 = v > m2 ? v : m2;
     }
-    mx[0]() = m0; mx[1]() = m1; mx[2]() = m2;
+    mx0() = m0; mx1() = m1; mx2() = m2;
     END_THREADS
-    int cand[3][3], ncand[3];
-    for (int r = 0; r < 3; r++) {
-        ncand[r] = 0;
-        cand[r][0] = cand[r][1] = cand[r][2] = 0;
-        bool present = (r == 0) ? (a1 > 0) : (r == 1) ? has1 : has2;
-        if (!present) continue;
-        int max = w.reduce_max(mx[r]);
-        if (max == 0) continue;
-        if (max < 15) {
-            int c0 = table_for_small_max(max);
-            cand[r][0] = c0; ncand[r] = 1;
-            if (c0 == 2) { cand[r][1] = 3; ncand[r] = 2; }
-            else if (c0 == 5) { cand[r][1] = 6; ncand[r] = 2; }
-            else if (c0 == 7) { cand[r][1] = 8; cand[r][2] = 9; ncand[r] = 3; }
-            else if (c0 == 10) { cand[r][1] = 11; cand[r][2] = 12; ncand[r] = 3; }
-            else if (c0 == 13) { cand[r][1] = 15; ncand[r] = 2; }
-        } else {
-            cand[r][0] = esc_table(T, 15, 24, max - 15);
-            cand[r][1] = esc_table(T, 24, 32, max - 15);
-            ncand[r] = 2;
-        }
-    }
-    // bits of every candidate, all regions in one sweep
-    PerThread<int> acc[3][3];
-    FOR_THREADS(w)
-    int s[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-#pragma unroll
-    for (int k = 0; k < 9; k++) {
-        int e = 2 * (lane + 32 * k);
-        int x = R.ia[k](), y = R.ib[k]();
-        // region-2 counting in the reference runs over [a2, a3): a3 == bvr for plain long blocks and 0
-        // for start/stop blocks (where region 2 is never selected), so [a2,bvr) covers both
-        int r = (e < a1) ? 0 : (e < a2) ? 1 : (e < bvr) ? 2 : 3;
-        if (r < 3) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                int t = (r == 0) ? cand[0][c] : (r == 1) ? cand[1][c] : cand[2][c];
-                if (t) {
-                    int b = pair_bits(T, t, x, y);
-                    if (r == 0) s[0][c] += b; else if (r == 1) s[1][c] += b; else s[2][c] += b;
-                }
-            }
-        }
-    }
+    int grp[3] = {-1, -1, -1}, rmax[3] = {0, 0, 0};
+    if (has0) rmax[0] = w.reduce_max(mx0);
+    if (has1) rmax[1] = w.reduce_max(mx1);
+    if (has2) rmax[2] = w.reduce_max(mx2);
+    bool any = false;
 #pragma unroll
     for (int r = 0; r < 3; r++)
-#pragma unroll
-        for (int c = 0; c < 3; c++) acc[r][c]() = s[r][c];
-    END_THREADS
-    int bits = 0;
-    for (int r = 0; r < 3; r++) {
-        tsel[r] = 0;
-        if (ncand[r] == 0) continue;
-        int s0 = w.reduce_add(acc[r][0]);
-        int choice = cand[r][0];
-        if (cand[r][0] >= 15 && ncand[r] == 2 && cand[r][1] >= 24) {       // ESC pair: strict '<' (loop.c:1896)
-            int s1 = w.reduce_add(acc[r][1]);
-            if (s1 < s0) { choice = cand[r][1]; s0 = s1; }
-        } else {
-            for (int c = 1; c < ncand[r]; c++) {                            // '<=' chains (loop.c:1826-1868)
-                int s1 = w.reduce_add(acc[r][c]);
-                if (s1 <= s0) { choice = cand[r][c]; s0 = s1; }
-            }
+        if (rmax[r] > 0) { grp[r] = group_for_max(rmax[r]); any = true; }
+    int bits = c1bits;
+    if (any) {
+        PerThread<int> lo[3], hi[3];
+        const int g0 = grp[0], g1 = grp[1], g2 = grp[2];
+        FOR_THREADS(w)
+        unsigned acc0 = 0, acc1 = 0, acc2 = 0;
+        for (int k = 0; k < k_end; k++) {
+            const int e = 2 * (lane + 32 * k);
+            const U2 u = M.ix[lane + 32 * k];
+            const int x = u.x > 15 ? 15 : u.x, y = u.y > 15 ? 15 : u.y;
+            const int r = (e < a1) ? 0 : (e < a2) ? 1 : (e < bvr) ? 2 : 3;
+            const int g = (r == 0) ? g0 : (r == 1) ? g1 : (r == 2) ? g2 : -1;
+            const unsigned wv = (g >= 0) ? H.glut[g][16 * x + y] : 0u;
+            if (r == 0) acc0 += wv; else if (r == 1) acc1 += wv; else acc2 += wv;
         }
-        tsel[r] = choice;
-        bits += s0;
+        // per lane <= 9 pairs x <= 63 per field: no carry between the 10-bit fields
+        lo[0]() = (int)((acc0 & 1023u) | (((acc0 >> 10) & 1023u) << 16)); hi[0]() = (int)(acc0 >> 20);
+        lo[1]() = (int)((acc1 & 1023u) | (((acc1 >> 10) & 1023u) << 16)); hi[1]() = (int)(acc1 >> 20);
+        lo[2]() = (int)((acc2 & 1023u) | (((acc2 >> 10) & 1023u) << 16)); hi[2]() = (int)(acc2 >> 20);
+        END_THREADS
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            if (grp[r] < 0) continue;
+            const int g = grp[r], max = rmax[r];
+            const int both = w.reduce_add(lo[r]);
+            int s0 = both & 0xffff, s1 = both >> 16, choice;
+            if (is_short) {
+                // choose_table (by max alone), loop.c:1908-1943: first table covering max; 15 -> table 15
+                if (g == 7) { choice = 15; }                               // glut g7 field 0 = table 15
+                else if (g == 6) { choice = esc_table(H, 16, 24, max - 15); s0 += (int)H.hlinbits[choice] * w.reduce_add(hi[r]); }
+                else choice = table_for_small_max(max);
+            } else if (g >= 6) {
+                // ESC pair, strict '<' (loop.c:1870-1898)
+                const int nesc = w.reduce_add(hi[r]);
+                const int c0 = esc_table(H, 15, 24, max - 15), c1 = esc_table(H, 24, 32, max - 15);
+                s0 += (int)H.hlinbits[c0] * nesc;
+                s1 += (int)H.hlinbits[c1] * nesc;
+                choice = c0;
+                if (s1 < s0) { choice = c1; s0 = s1; }
+            } else {
+                // sibling tables, '<=' chains (loop.c:1826-1868)
+                choice = table_for_small_max(max);
+                if (g >= 1) {
+                    const int c1 = (g == 1) ? 3 : (g == 2) ? 6 : (g == 3) ? 8 : (g == 4) ? 11 : 15;
+                    if (s1 <= s0) { choice = c1; s0 = s1; }
+                    if (g == 3 || g == 4) {
+                        const int s2 = w.reduce_add(hi[r]);
+                        if (s2 <= s0) { choice = (g == 3) ? 9 : 12; s0 = s2; }
+                    }
+                }
+            }
+            C.table_select[r] = choice;
+            bits += s0;
+        }
     }
-    (void)a3;
+    C.bits = bits;
     return bits;
 }
 
-// one quantize + count_bits probe at step q.  `C` carries address1..3 across probes exactly like the
-// reference's cod_info does (subdivide leaves them untouched when big_values == 0).
-SIMT_FN int probe(const WarpCtx &w, const RateTables &T, GcRegs &R, bool is_short, bool wsf, int q, CountResult &C)
+// one quantize + count_bits probe at step q
+SIMT_FN int probe(const WarpCtx &w, const RateHot &H, const RateTables &T, RateWarpSmem &M, bool is_short, bool wsf, int q, CountResult &C)
 {
-    quantize_all(w, T, R, q);
-    count_all(w, T, R, is_short, wsf, C);
-    if (is_short) return C.bits;
-    int tsel[3];
-    int bb = count_regions(w, T, R, C.address1, C.address2, C.address3, 2 * C.big_values, tsel);
-    C.table_select[0] = tsel[0]; C.table_select[1] = tsel[1]; C.table_select[2] = tsel[2];
-    C.bits += bb;
-    return C.bits;
+    PerThread<int> nzmax, bigmax;
+    quantize_all(w, T, M, q, nzmax, bigmax);
+    return count_all(w, H, M, is_short, wsf, nzmax, bigmax, C);
 }
 
 // sum over the slots of each band of the per-slot values in scr[288]; result band-per-lane.
 // long: band b = pairs [sfb_l[b]/2, sfb_l[b+1]/2), b < 21; short: b = 3 sfb + w -> slots 3m+w, m in
 // [sfb_s[sfb]/2, sfb_s[sfb+1]/2), sfb < 12.
-SIMT_FN void band_sums(const WarpCtx &w, const RateTables &T, const double *scr, bool is_short, PerThread<double> out[2])
+SIMT_FN double band_sum_one(const RateHot &T, const double *scr, bool is_short, int b)
+{
+    // slots of band b: start, stride, count (two interleaved accumulators, even/odd slot of the band)
+    int st, stride, n;
+    if (!is_short) {
+        if (b >= 21) return 0.0;
+        st = T.sfb_l[b] >> 1; stride = 1; n = (T.sfb_l[b + 1] >> 1) - st;
+    } else {
+        if (b >= 36) return 0.0;
+        const int sfb = b / 3, wi = b - 3 * sfb;
+        const int lo = T.sfb_s[sfb] >> 1;
+        st = 3 * lo + wi; stride = 3; n = (T.sfb_s[sfb + 1] >> 1) - lo;
+    }
+    double a0 = 0.0, a1 = 0.0;
+    const double *p = scr + st;
+    int i = 0;
+#pragma unroll 1
+    for (; i + 1 < n; i += 2) { a0 = simt::dadd(a0, p[0]); a1 = simt::dadd(a1, p[stride]); p += 2 * stride; }
+    if (i < n) a0 = simt::dadd(a0, p[0]);
+    return simt::dadd(a0, a1);
+}
+
+SIMT_FN void band_sums(const WarpCtx &w, const RateHot &T, const double *scr, bool is_short, PerThread<double> out[2])
 {
     FOR_THREADS(w)
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        int b = lane + 32 * h;
-        double a0 = 0.0, a1 = 0.0;
-        if (!is_short) {
-            if (b < 21) {
-                int lo = T.sfb_l[b] >> 1, hi = T.sfb_l[b + 1] >> 1, s = lo;
-                for (; s + 1 < hi; s += 2) { a0 = simt::dadd(a0, scr[s]); a1 = simt::dadd(a1, scr[s + 1]); }
-                if (s < hi) a0 = simt::dadd(a0, scr[s]);
-            }
-        } else if (b < 36) {
-            int sfb = b / 3, wi = b - 3 * sfb;
-            int lo = T.sfb_s[sfb] >> 1, hi = T.sfb_s[sfb + 1] >> 1, m = lo;
-            for (; m + 1 < hi; m += 2) { a0 = simt::dadd(a0, scr[3 * m + wi]); a1 = simt::dadd(a1, scr[3 * m + 3 + wi]); }
-            if (m < hi) a0 = simt::dadd(a0, scr[3 * m + wi]);
-        }
-        out[h]() = simt::dadd(a0, a1);
-    }
+    out[0]() = band_sum_one(T, scr, is_short, lane);
+    out[1]() = is_short ? band_sum_one(T, scr, true, lane + 32) : 0.0;
     END_THREADS
 }
 
-SIMT_FN double band_width(const RateTables &T, bool is_short, int b)
+SIMT_FN double band_width(const RateHot &T, bool is_short, int b)
 {
     if (!is_short) return (double)(T.sfb_l[b + 1] - T.sfb_l[b]);
     int sfb = b / 3;
@@ -423,16 +421,16 @@ struct Gr0Carry {             // what granule 1 may need from granule 0 of the s
 // Encode one granule-channel.  xr: 576 doubles (mdct_sub output).  ratio: 21 (long) or 36 ([sfb][win])
 // doubles.  Writes ix (signed, sign of xr applied as l3bitstream.c:115-125 does), gi, scalefac bytes.
 // Returns part2_3_length (before ResvFrameEnd stuffing).
-SIMT_FN int encode_gc(const WarpCtx &w, const RateTables &T, double *scr, const FrameGeom &G, LoopStreamState &S,
+SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, RateWarpSmem &M, const FrameGeom &G, LoopStreamState &S,
                       PerThread<int> st_en[4], PerThread<int> st_xm[4],
                       int gr, int ch, const double *xr, const double *ratio_l, const double *ratio_s, double pe,
-                      int block_type, int scfsi[4], Gr0Carry &g0, short *ix_out, GrInfoOut &gi, unsigned char *sf_out,
+                      int block_type, int scfsi[4], Gr0Carry &g0, short *ix_out, GrInfoOut *gi_out, unsigned char *sf_out,
                       int *max_bits_out)
 {
     const bool is_short = (block_type == 2);
     const bool wsf = (block_type != 0);
     const int nb_l = is_short ? 0 : 21;   // sfb_lmax (gr_deco, loop.c:2063-2081)
-    GcRegs R;
+    double *scr = M.scr;
     BandRegs Bd;
     PerThread<int> sign;      // bit 2k / 2k+1: sign of the slot's elements
     PerThread<double> t0, t1;
@@ -441,7 +439,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateTables &T, double *scr, const 
     FOR_THREADS(w)
     int sg = 0;
     double mx = 0.0, e2 = 0.0, lg = 0.0;
-#pragma unroll
+#pragma unroll 3
     for (int k = 0; k < 9; k++) {
         int s = lane + 32 * k;
         int e0 = slot_e0(is_short, s);
@@ -450,15 +448,16 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateTables &T, double *scr, const 
         if (a < 0) sg |= 1 << (2 * k);
         if (b < 0) sg |= 2 << (2 * k);
         a = fabs(a); b = fabs(b);
-        R.xa[k]() = a; R.xb[k]() = b;
-        R.band[k]() = is_short ? T.band_short[s] : T.band_long[s];
+        D2 x2; x2.x = a; x2.y = b;
+        M.xs[s] = x2;
+        U2 z; z.x = 0; z.y = 0;
+        M.ix[s] = z;
         mx = fmax(mx, fmax(a, b));
         double a2 = simt::dmul(a, a), b2 = simt::dmul(b, b);
         scr[s] = simt::dadd(a2, b2);
         e2 = simt::dadd(e2, simt::dadd(a2, b2));
-        if (a != 0) lg = simt::dadd(lg, log(a2));
-        if (b != 0) lg = simt::dadd(lg, log(b2));
-        R.ia[k]() = 0; R.ib[k]() = 0;
+        if (a != 0) lg = simt::dadd(lg, ref_log(a2));
+        if (b != 0) lg = simt::dadd(lg, ref_log(b2));
     }
     sign() = sg; t0() = mx; t1() = e2;
     Bd.xfsf[0]() = lg;  // borrowed as scratch for the log sum
@@ -470,14 +469,14 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateTables &T, double *scr, const 
 
     // ---- calc_xmin, loop.c:1085-1119 ------------------------------------------------------------
     PerThread<double> en[2];
-    band_sums(w, T, scr, is_short, en);
+    band_sums(w, H, scr, is_short, en);
     FOR_THREADS(w)
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         int b = lane + 32 * h;
         double v = 0.0;
-        if (!is_short) { if (b < 21) v = simt::dmul(ratio_l[b], en[h]()) / band_width(T, false, b); }
-        else if (b < 36) v = simt::dmul(ratio_s[b], en[h]()) / band_width(T, true, b);
+        if (!is_short) { if (b < 21) v = simt::dmul(ratio_l[b], en[h]()) / band_width(H, false, b); }
+        else if (b < 36) v = simt::dmul(ratio_s[b], en[h]()) / band_width(H, true, b);
         Bd.xmin[h]() = v;
         Bd.xfsf[h]() = 0.0;
         Bd.sf[h]() = 0;
@@ -488,13 +487,13 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateTables &T, double *scr, const 
     {
         const int cur = gr * 2 + ch;
         S.xrmax[cur] = (int)xrmax;
-        S.en_tot[cur] = (sum2 == 0.0) ? 0 : (int)(log(sum2) / T.log2c);
+        S.en_tot[cur] = (sum2 == 0.0) ? 0 : (int)(ref_log(sum2) / H.log2c);
         if (!is_short) {
             FOR_THREADS(w)
             if (lane < 21) {
                 double e = en[0](), xm = Bd.xmin[0]();
-                int ev = (e == 0.0) ? 0 : (int)(log(e) / T.log2c);
-                int xv = (xm == 0.0) ? 0 : (int)(log(xm) / T.log2c);
+                int ev = (e == 0.0) ? 0 : (int)(ref_log(e) / H.log2c);
+                int xv = (xm == 0.0) ? 0 : (int)(ref_log(xm) / H.log2c);
 #pragma unroll
                 for (int i = 0; i < 4; i++) if (i == cur) { st_en[i]() = ev; st_xm[i]() = xv; }
             }
@@ -567,8 +566,8 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateTables &T, double *scr, const 
         {
             int tp = 0;
             if (sum2 != 0.0) {
-                double sfm = exp(sum1 / 576.0) / (sum2 / 576.0);
-                tp = nint_ref(8.0 * log(sfm));
+                double sfm = ref_exp(sum1 / 576.0) / (sum2 / 576.0);
+                tp = nint_ref(8.0 * ref_log(sfm));
                 if (tp < -100) tp = -100;
             }
             q = tp - 70;
@@ -580,43 +579,49 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateTables &T, double *scr, const 
             iteration++;
             part2 = part2_length_of(is_short, gr, compress, scfsi);
             const int huff_bits = max_bits - part2;
-            if (iteration == 1) {  // bin_search_StepSize(max_bits, ...), loop.c:2119-2140
-                int top = q, bot = 200, next = q, last, bit;
-                do {
-                    last = next;
-                    next = (top + bot) / 2;  // aint((top+bot)/2.0): truncation toward zero, like C int division
-                    q = next;
-                    bit = probe(w, T, R, is_short, wsf, q, C);
-                    if (bit > max_bits) top = next; else bot = next;
-                } while (bit != max_bits && (last - next > 1 || next - last > 1));
+            // bin_search_StepSize(max_bits, ...) on the first iteration (loop.c:2119-2140), then inner_loop
+            // (loop.c:569-606), as ONE probe site (code size: the probe is the hot loop of the kernel).
+            // inner_loop starts by re-quantising at the step the binary search stopped at; that probe is
+            // a pure function of (xr, q, stale addresses) and therefore equal to the one just made, so
+            // its result is reused instead of recomputed.
+            {
+                bool searching = (iteration == 1);
+                int top = q, bot = 200, next = q, last = q;
+                for (;;) {
+                    if (searching) { last = next; next = (top + bot) / 2; q = next; }  // aint((top+bot)/2.0)
+                    bits = probe(w, H, T, M, is_short, wsf, q, C);
+                    if (searching) {
+                        if (bits > max_bits) top = next; else bot = next;
+                        if (bits != max_bits && (last - next > 1 || next - last > 1)) continue;
+                        searching = false;
+                    }
+                    if (!(bits > huff_bits && q < 1024)) break;  // q guard: the reference assert()s huff_bits >= 0 (loop.c:579)
+                    q += 1;
+                }
             }
-            // inner_loop, loop.c:569-606
-            q -= 1;
-            do {
-                q += 1;
-                bits = probe(w, T, R, is_short, wsf, q, C);
-            } while (bits > huff_bits && q < 1024);  // q guard: the reference assert()s huff_bits >= 0 (loop.c:579)
 
             // calc_noise, loop.c:1007-1069
             {
                 const double step = T.step[(q > 255 ? 255 : q) + 256];
                 FOR_THREADS(w)
-#pragma unroll
+#pragma unroll 3
                 for (int k = 0; k < 9; k++) {
-                    double da = simt::dsub(R.xa[k](), simt::dmul(T.pow43[R.ia[k]()], step));
-                    double db = simt::dsub(R.xb[k](), simt::dmul(T.pow43[R.ib[k]()], step));
+                    const D2 x = M.xs[lane + 32 * k];
+                    const U2 v = M.ix[lane + 32 * k];
+                    double da = simt::dsub(x.x, simt::dmul(T.pow43[v.x], step));
+                    double db = simt::dsub(x.y, simt::dmul(T.pow43[v.y], step));
                     scr[lane + 32 * k] = simt::dadd(simt::dmul(da, da), simt::dmul(db, db));
                 }
                 END_THREADS
                 w.sync();
                 PerThread<double> ns[2];
-                band_sums(w, T, scr, is_short, ns);
+                band_sums(w, H, scr, is_short, ns);
                 FOR_THREADS(w)
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     int b = lane + 32 * h;
                     bool valid = is_short ? (b < 36) : (b < 21);
-                    Bd.xfsf[h]() = valid ? ns[h]() / band_width(T, is_short, b) : 0.0;
+                    Bd.xfsf[h]() = valid ? ns[h]() / band_width(H, is_short, b) : 0.0;
                     save_sf[h]() = Bd.sf[h]();
                 }
                 END_THREADS
@@ -640,14 +645,16 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateTables &T, double *scr, const 
             else if (block_type != 2 && preflag == 0 && ((m0 >> 17) & 15u) == 15u) {
                 preflag = 1;
                 FOR_THREADS(w)
-                if (lane < nb_l) Bd.xmin[0]() = simt::dmul(Bd.xmin[0](), T.pre2[T.pretab[lane]]);
-#pragma unroll
+                if (lane < nb_l) Bd.xmin[0]() = simt::dmul(Bd.xmin[0](), H.pre2[H.pretab[lane]]);
+#pragma unroll 3
                 for (int k = 0; k < 9; k++) {
-                    int b = R.band[k]();
+                    const int s = lane + 32 * k;
+                    const int b = H.band_long[s];        // preemphasis never runs for short blocks
                     if (b < nb_l) {
-                        double f = T.pre1[T.pretab[b]];
-                        R.xa[k]() = simt::dmul(R.xa[k](), f);
-                        R.xb[k]() = simt::dmul(R.xb[k](), f);
+                        const double f = H.pre1[H.pretab[b]];
+                        D2 x = M.xs[s];
+                        x.x = simt::dmul(x.x, f); x.y = simt::dmul(x.y, f);
+                        M.xs[s] = x;
                     }
                 }
                 END_THREADS
@@ -677,14 +684,18 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateTables &T, double *scr, const 
                 const unsigned long long amp = (unsigned long long)amp0 | ((unsigned long long)amp1 << 32);
                 FOR_THREADS(w)
                 if (copySF && !is_short && ((skip >> lane) & 1)) Bd.sf[0]() = g0.sf0();
-                if ((amp0 >> lane) & 1) { Bd.xmin[0]() = simt::dmul(Bd.xmin[0](), T.ifqstep2); Bd.sf[0]()++; }
-                if ((amp1 >> lane) & 1) { Bd.xmin[1]() = simt::dmul(Bd.xmin[1](), T.ifqstep2); Bd.sf[1]()++; }
-#pragma unroll
-                for (int k = 0; k < 9; k++) {
-                    int b = R.band[k]();
-                    if (b < 36 && ((amp >> b) & 1)) {
-                        R.xa[k]() = simt::dmul(R.xa[k](), T.ifqstep);
-                        R.xb[k]() = simt::dmul(R.xb[k](), T.ifqstep);
+                if ((amp0 >> lane) & 1) { Bd.xmin[0]() = simt::dmul(Bd.xmin[0](), H.ifqstep2); Bd.sf[0]()++; }
+                if ((amp1 >> lane) & 1) { Bd.xmin[1]() = simt::dmul(Bd.xmin[1](), H.ifqstep2); Bd.sf[1]()++; }
+                if (amp != 0) {
+#pragma unroll 3
+                    for (int k = 0; k < 9; k++) {
+                        const int s = lane + 32 * k;
+                        const int b = is_short ? H.band_short[s] : H.band_long[s];
+                        if (b < 36 && ((amp >> b) & 1)) {
+                            D2 x = M.xs[s];
+                            x.x = simt::dmul(x.x, H.ifqstep); x.y = simt::dmul(x.y, H.ifqstep);
+                            M.xs[s] = x;
+                        }
                     }
                 }
                 END_THREADS
@@ -731,15 +742,21 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateTables &T, double *scr, const 
 
     // ---- ResvAdjust + global_gain, loop.c:355-358 -------------------------------------------------
     S.resv_size += G.mean_bits / G.n_ch - part23;
-    gi.part2_3_length = part23;
-    gi.big_values = C.big_values; gi.count1 = C.count1;
-    gi.global_gain = nint_ref((double)q + 210.0);
-    gi.scalefac_compress = compress;
-    gi.window_switching_flag = wsf; gi.block_type = block_type; gi.mixed_block_flag = 0;
-    gi.table_select[0] = C.table_select[0]; gi.table_select[1] = C.table_select[1]; gi.table_select[2] = C.table_select[2];
-    gi.region0_count = C.region0_count; gi.region1_count = C.region1_count;
-    gi.preflag = preflag; gi.scalefac_scale = 0; gi.count1table_select = C.count1table_select;
-    gi.part2_length = part2; gi.address1 = C.address1; gi.address2 = C.address2; gi.address3 = C.address3;
+    FOR_THREADS(w)
+    if (lane == 0) {   // part2_3_length is rewritten after ResvFrameEnd (stuffing bits)
+        GrInfoOut gi;
+        gi.part2_3_length = part23;
+        gi.big_values = C.big_values; gi.count1 = C.count1;
+        gi.global_gain = nint_ref((double)q + 210.0);
+        gi.scalefac_compress = compress;
+        gi.window_switching_flag = wsf; gi.block_type = block_type; gi.mixed_block_flag = 0;
+        gi.table_select[0] = C.table_select[0]; gi.table_select[1] = C.table_select[1]; gi.table_select[2] = C.table_select[2];
+        gi.region0_count = C.region0_count; gi.region1_count = C.region1_count;
+        gi.preflag = preflag; gi.scalefac_scale = 0; gi.count1table_select = C.count1table_select;
+        gi.part2_length = part2; gi.address1 = C.address1; gi.address2 = C.address2; gi.address3 = C.address3;
+        *gi_out = gi;
+    }
+    END_THREADS
     S.addr[gr * 2 + ch][0] = C.address1; S.addr[gr * 2 + ch][1] = C.address2; S.addr[gr * 2 + ch][2] = C.address3;
 
     // ---- outputs ------------------------------------------------------------------------------------
@@ -749,7 +766,8 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateTables &T, double *scr, const 
         int s = lane + 32 * k;
         int e0 = slot_e0(is_short, s);
         int e1 = is_short ? e0 + 3 : e0 + 1;
-        int a = R.ia[k](), b = R.ib[k]();
+        const U2 v = M.ix[s];
+        int a = v.x, b = v.y;
         if ((sign() >> (2 * k)) & 1) a = -a;
         if ((sign() >> (2 * k + 1)) & 1) b = -b;
         ix_out[e0] = (short)a;
@@ -819,7 +837,7 @@ struct FrameOut {
 };
 
 // gc index inside a stream chunk: g = (frame*2 + gr)*n_ch + ch
-SIMT_FN void rate_loop_stream(const WarpCtx &w, const RateTables &T, double *scr, const FrameGeom &G, LoopStreamState &S,
+SIMT_FN void rate_loop_stream(const WarpCtx &w, const RateHot &H, const RateTables &T, RateWarpSmem &M, const FrameGeom &G, LoopStreamState &S,
                               PerThread<int> st_en[4], PerThread<int> st_xm[4], int n_frames,
                               const double *xr, const PsyOut *psy, short *ix, GrInfoOut *gi, unsigned char *sf,
                               FrameOut *fo, int *max_bits_dbg)
@@ -831,13 +849,12 @@ SIMT_FN void rate_loop_stream(const WarpCtx &w, const RateTables &T, double *scr
         g0[0].preflag = g0[1].preflag = 0;
         g0[0].scalefac_scale = g0[1].scalefac_scale = 0;
         const int mdb = S.resv_size / 8;
-        GrInfoOut gout[4];
         for (int gr = 0; gr < 2; gr++)
             for (int ch = 0; ch < G.n_ch; ch++) {
                 const int g = (f * 2 + gr) * G.n_ch + ch;
                 const PsyOut &po = psy[g];
-                p23[gr * 2 + ch] = encode_gc(w, T, scr, G, S, st_en, st_xm, gr, ch, xr + (size_t)g * 576, po.ratio_l, po.ratio_s,
-                                             po.pe, po.block_type, scfsi[ch], g0[ch], ix + (size_t)g * 576, gout[gr * 2 + ch],
+                p23[gr * 2 + ch] = encode_gc(w, H, T, M, G, S, st_en, st_xm, gr, ch, xr + (size_t)g * 576, po.ratio_l, po.ratio_s,
+                                             po.pe, po.block_type, scfsi[ch], g0[ch], ix + (size_t)g * 576, gi + g,
                                              sf + (size_t)g * 40, max_bits_dbg ? max_bits_dbg + g : nullptr);
             }
         int drain = 0;
@@ -847,8 +864,7 @@ SIMT_FN void rate_loop_stream(const WarpCtx &w, const RateTables &T, double *scr
             for (int gr = 0; gr < 2; gr++)
                 for (int ch = 0; ch < G.n_ch; ch++) {
                     const int g = (f * 2 + gr) * G.n_ch + ch;
-                    gout[gr * 2 + ch].part2_3_length = p23[gr * 2 + ch];
-                    gi[g] = gout[gr * 2 + ch];
+                    gi[g].part2_3_length = p23[gr * 2 + ch];
                 }
             fo[f].resv_drain = drain;
             fo[f].main_data_begin = mdb;

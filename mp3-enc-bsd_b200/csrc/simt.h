@@ -17,10 +17,12 @@
 #define SIMT_DEV 1
 #define SIMT_FN __device__ __forceinline__
 #define SIMT_HD __host__ __device__ __forceinline__
+#define SIMT_NOINLINE static __device__ __noinline__
 #else
 #define SIMT_DEV 0
 #define SIMT_FN inline
 #define SIMT_HD inline
+#define SIMT_NOINLINE static inline
 #include <cmath>
 #include <cstring>
 #endif

@@ -85,50 +85,75 @@ void build_rate_tables(int sr, RateTables *R)
         R->step[q + 256] = step;
         R->ostep[q + 256] = 1.0 / step;
     }
+    RateHot &H = R->hot;
     const double ifq = sqrt(2.);
     for (int n = 0; n < 4; n++) {
-        R->pre1[n] = pow(ifq, (double)n);
-        R->pre2[n] = pow(ifq, 2.0 * (double)n);
+        H.pre1[n] = pow(ifq, (double)n);
+        H.pre2[n] = pow(ifq, 2.0 * (double)n);
     }
-    R->ifqstep = sqrt(2.0);
-    R->ifqstep2 = R->ifqstep * R->ifqstep;
-    R->log2c = log(2.0);
-    for (int i = 0; i < 23; i++) R->sfb_l[i] = MP3T_SFB_LONG[sr][i];
-    for (int i = 0; i < 14; i++) R->sfb_s[i] = MP3T_SFB_SHORT[sr][i];
+    H.ifqstep = sqrt(2.0);
+    H.ifqstep2 = H.ifqstep * H.ifqstep;
+    H.log2c = log(2.0);
+    for (int i = 0; i < 23; i++) H.sfb_l[i] = MP3T_SFB_LONG[sr][i];
+    for (int i = 0; i < 14; i++) H.sfb_s[i] = MP3T_SFB_SHORT[sr][i];
     for (int i = 0; i < MP3T_HUFF_FLAT; i++) R->hlen[i] = MP3T_HLEN[i];
     for (int t = 0; t < 34; t++) {
         R->hoff[t] = MP3T_HUFF[t].off;
         R->hxlen[t] = (t >= 32) ? 0 : MP3T_HUFF[t].ylen;   // count1 tables are indexed by p alone
-        R->hlinbits[t] = MP3T_HUFF[t].linbits;
-        R->hlinmax[t] = MP3T_HUFF[t].linmax;
+        R->hlinbits[t] = H.hlinbits[t] = MP3T_HUFF[t].linbits;
+        R->hlinmax[t] = H.hlinmax[t] = MP3T_HUFF[t].linmax;
+    }
+    // glut: code length + sign bits of (x, y) in every candidate table of a group, 10-bit fields
+    // (count_bit, loop.c:172-225: sum += hlen[x][y] + (x != 0) + (y != 0), escapes add linbits)
+    {
+        static const int members[8][3] = {{1, 0, 0}, {2, 3, 0}, {5, 6, 0}, {7, 8, 9}, {10, 11, 12}, {13, 15, 0}, {16, 24, -1}, {15, 24, -1}};
+        for (int g = 0; g < 8; g++)
+            for (int x = 0; x < 16; x++)
+                for (int y = 0; y < 16; y++) {
+                    unsigned v = 0;
+                    for (int c = 0; c < 3; c++) {
+                        const int t = members[g][c];
+                        unsigned f = 0;
+                        if (t > 0) {
+                            const int xl = MP3T_HUFF[t].xlen, yl = MP3T_HUFF[t].ylen;
+                            if (x < xl && y < yl) f = MP3T_HLEN[MP3T_HUFF[t].off + x * yl + y] + (x != 0) + (y != 0);
+                        } else if (t < 0) f = (x > 14) + (y > 14);   // number of escaped values of the pair
+                        v |= f << (10 * c);
+                    }
+                    H.glut[g][16 * x + y] = v;
+                }
+        for (int p = 0; p < 16; p++) {
+            const int sg = (p & 1) + ((p >> 1) & 1) + ((p >> 2) & 1) + ((p >> 3) & 1);
+            H.c1lut[p] = (unsigned)(MP3T_HLEN[MP3T_HUFF[32].off + p] + sg) | ((unsigned)(MP3T_HLEN[MP3T_HUFF[33].off + p] + sg) << 16);
+        }
     }
     for (int s = 0; s < 288; s++) {
         int e = 2 * s, b = 21;
         for (int sfb = 0; sfb < 21; sfb++)
-            if (e >= R->sfb_l[sfb] && e < R->sfb_l[sfb + 1]) b = sfb;
-        R->band_long[s] = (unsigned char)b;
+            if (e >= H.sfb_l[sfb] && e < H.sfb_l[sfb + 1]) b = sfb;
+        H.band_long[s] = (unsigned char)b;
         int m = s / 3, w = s % 3, line = 2 * m;
         b = 36 + w;
         for (int sfb = 0; sfb < 12; sfb++)
-            if (line >= R->sfb_s[sfb] && line < R->sfb_s[sfb + 1]) b = 3 * sfb + w;
-        R->band_short[s] = (unsigned char)b;
+            if (line >= H.sfb_s[sfb] && line < H.sfb_s[sfb + 1]) b = 3 * sfb + w;
+        H.band_short[s] = (unsigned char)b;
     }
     // subdivide() for plain long blocks, loop.c:1596-1690, tabulated over big_values
     static const unsigned char subdv[23][2] = {{0,0},{0,0},{0,0},{0,0},{0,0},{0,1},{1,1},{1,1},{1,2},{2,2},{2,3},{2,3},
         {3,4},{3,4},{3,4},{4,5},{4,5},{4,6},{5,6},{5,6},{5,7},{6,7},{6,7}};
     for (int bv = 1; bv <= 288; bv++) {
         int bvr = 2 * bv, n = 0;
-        while (R->sfb_l[n] < bvr) n++;
+        while (H.sfb_l[n] < bvr) n++;
         int r0 = subdv[n][0], index = r0 + 1;
-        while (r0 && R->sfb_l[index] > bvr) { r0--; index--; }
+        while (r0 && H.sfb_l[index] > bvr) { r0--; index--; }
         int r1 = subdv[n][1];
         index = r0 + r1 + 2;
-        while (r1 && R->sfb_l[index] > bvr) { r1--; index--; }
-        R->subdiv[bv][0] = (unsigned char)r0;
-        R->subdiv[bv][1] = (unsigned char)r1;
+        while (r1 && H.sfb_l[index] > bvr) { r1--; index--; }
+        H.subdiv[bv][0] = (unsigned char)r0;
+        H.subdiv[bv][1] = (unsigned char)r1;
     }
     static const unsigned char pretab[21] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 2};  // Table B.6
-    for (int i = 0; i < 21; i++) R->pretab[i] = pretab[i];
+    for (int i = 0; i < 21; i++) H.pretab[i] = pretab[i];
 }
 
 static double spread_value(double bi, double bj, bool j_ge_i)

@@ -52,9 +52,9 @@ int emul_rate_loop_stream(int sfreq, int n_ch, int bitrate, int n_frames, const 
     memset(&S, 0, sizeof(S));
     static PerThread<int> st_en[4], st_xm[4];
     memset(st_en, 0, sizeof(st_en)); memset(st_xm, 0, sizeof(st_xm));
-    double scr[288];
+    static RateWarpSmem M;
     WarpCtx w;
-    rate_loop_stream(w, *T, scr, G, S, st_en, st_xm, n_frames, xr, psy, ix, gi, sf, fo, max_bits);
+    rate_loop_stream(w, T->hot, *T, M, G, S, st_en, st_xm, n_frames, xr, psy, ix, gi, sf, fo, max_bits);
     free(T);
     return 0;
 }
@@ -106,8 +106,8 @@ int emul_encode_stream(int sfreq, int n_ch, int bitrate, int n_frames, const sho
     LoopStreamState S; memset(&S, 0, sizeof(S));
     PerThread<int> st_en[4], st_xm[4];
     memset(st_en, 0, sizeof(st_en)); memset(st_xm, 0, sizeof(st_xm));
-    double scr[288];
-    rate_loop_stream(w, RT, scr, G, S, st_en, st_xm, n_frames, xr, psy, ix, gi, sf, fo, max_bits);
+    static RateWarpSmem M;
+    rate_loop_stream(w, RT.hot, RT, M, G, S, st_en, st_xm, n_frames, xr, psy, ix, gi, sf, fo, max_bits);
     return 0;
 }
 
