@@ -1,0 +1,349 @@
+// legacy_shim.cuh — the reference's single-frame entry points (include/mp3gpu_legacy.h) on top of the same
+// kernels as the batched API.  Included by mp3gpu.cu only.  Every function cites the reference lines whose
+// caller-visible behaviour it reproduces; the arithmetic itself runs on the device.
+#pragma once
+#include "../../include/mp3gpu_legacy.h"
+
+namespace mp3gpu {
+
+// ---- window_subband / filter_subband, one slot per call (encode.c:287-316, 361-409) ----------------
+__global__ void k_legacy_window(double *ring /*[512]*/, int off, const short *pcm32, double *z)
+{
+    __shared__ double x[512];
+    const int t = threadIdx.x;                      // 512 threads
+    x[t] = ring[t];
+    __syncthreads();
+    if (t < 32) x[31 - t + off] = (double)pcm32[t] / 32768;                  // encode.c:306-307
+    __syncthreads();
+    z[t] = __dmul_rn(x[(t + off) & 511], c_front.window[t]);                  // encode.c:310-311
+    ring[t] = x[t];
+}
+
+__global__ void k_legacy_filter(const double *z, double *s)
+{
+    __shared__ double y[64], ys[32];
+    const int t = threadIdx.x;                      // 64 threads
+    double acc = z[t];                                                        // encode.c:392-396
+#pragma unroll
+    for (int j = 1; j < 8; j++) acc = __dadd_rn(acc, z[t + 64 * j]);
+    y[t] = acc;
+    __syncthreads();
+    if (t < 16) ys[t] = __dadd_rn(y[t], y[32 - t]);                           // encode.c:397
+    else if (t < 31) ys[t] = __dsub_rn(y[33 + t - 16], y[63 - (t - 16)]);     // encode.c:398
+    __syncthreads();
+    if (t < 32) {
+        double si = y[16];                                                    // encode.c:399-408
+        for (int j = 0; j < 31; j++) si = __dadd_rn(si, __dmul_rn(c_front.am[t][j], ys[j]));
+        s[t] = si;
+    }
+}
+
+// ---- mdct_sub for one frame: sb [ch][3][18][32] already sign-fixed, xr [gr][ch][576] ----------------
+__global__ void __launch_bounds__(32)
+k_legacy_mdct(const double *sb, const int *block_type /*[gr*2+ch]*/, int stereo, double *xr)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FrontWarpSmem &M = *reinterpret_cast<FrontWarpSmem *>(smem_raw);
+    const int gr = blockIdx.x / stereo, ch = blockIdx.x % stereo, lane = threadIdx.x;
+    WarpCtx w;
+    PerThread<double> prev[18], cur[18];
+#pragma unroll
+    for (int k = 0; k < 18; k++) {
+        prev[k].v = sb[((ch * 3 + gr) * 18 + k) * 32 + lane];
+        cur[k].v = sb[((ch * 3 + gr + 1) * 18 + k) * 32 + lane];
+    }
+    mdct_store(w, c_front, M, prev, cur, block_type[gr * 2 + ch], xr + (gr * 2 + ch) * 576);
+}
+
+struct LegacyState {
+    bool ready = false;
+    long launches = 0;
+    // filterbank
+    double *d_ring = nullptr;   // [2][512]
+    int off[2] = {0, 0};
+    short *d_pcm32 = nullptr;
+    double *d_z = nullptr, *d_s = nullptr;
+    // mdct
+    double *d_sb = nullptr, *d_xr = nullptr;
+    int *d_bt = nullptr;
+    // psy
+    int psy_sr = -1;
+    PsyTables *d_psy_tab = nullptr;
+    FftOp *ops1024 = nullptr, *ops256 = nullptr;
+    int *lv1024 = nullptr, *lv256 = nullptr;
+    uint16_t *out1024 = nullptr, *out256 = nullptr;
+    FftTwiddle *d_tw = nullptr;
+    PsyDev psy_dev;
+    short *d_save = nullptr;            // [2][1344]
+    PsyMid *d_mid = nullptr;
+    PsyChanState *d_psy_state = nullptr;  // [2]
+    PsyOut *d_psyout = nullptr;           // [4]
+    // rate loop
+    int loop_sr = -1;
+    RateTables *d_rate_tab = nullptr;
+    LoopStreamState *d_loop_state = nullptr;
+    LoopLaneState *d_lane_state = nullptr;
+    short *d_ix = nullptr;
+    GrInfoOut *d_gi = nullptr;
+    unsigned char *d_sf = nullptr;
+    FrameOut *d_fo = nullptr;
+    double *d_xr4 = nullptr;
+};
+static LegacyState g_legacy;
+static unsigned g_legacy_partition_table[4] = {0, 0, 0, 0};
+
+// The legacy entry points return void and the reference's host program cannot check a status, so they keep
+// the reference's own convention for unrecoverable conditions: message + exit(1) (musicin.c:550-557,
+// l3psy.c:174-175).  There is no CPU fallback to fall back to.
+[[noreturn]] static void legacy_fatal(const char *msg)
+{
+    fprintf(stderr, "libmp3gpu (legacy entry point): %s\n", msg);
+    exit(1);
+}
+static int legacy_fail(int code, const char *what, cudaError_t e)
+{
+    fail(code, "legacy %s: %s", what, cudaGetErrorString(e));
+    legacy_fatal(g_err);
+    return code;
+}
+#define LCU(call)                                                                  \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) { legacy_fail(MP3GPU_ECUDA, #call, e_); return; }   \
+    } while (0)
+
+static bool legacy_init()
+{
+    LegacyState &L = g_legacy;
+    if (L.ready) return true;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) legacy_fatal("no CUDA device: libmp3gpu has no CPU fallback");
+    FrontTables *F = new FrontTables;
+    build_front_tables(F);
+    cudaError_t e = cudaMemcpyToSymbol(c_front, F, sizeof(FrontTables));
+    delete F;
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_ring, 2 * 512 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_pcm32, 32 * sizeof(short));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_z, 512 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_s, 32 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_sb, 2 * 3 * 576 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_xr, 4 * 576 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_bt, 4 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_save, 2 * 1344 * sizeof(short));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_mid, sizeof(PsyMid));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_psy_state, 2 * sizeof(PsyChanState));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_psyout, 4 * sizeof(PsyOut));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_loop_state, sizeof(LoopStreamState));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_lane_state, sizeof(LoopLaneState));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_ix, 4 * 576 * sizeof(short));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_gi, 4 * sizeof(GrInfoOut));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_sf, 4 * 40);
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_fo, sizeof(FrameOut));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_xr4, 4 * 576 * sizeof(double));
+    if (e != cudaSuccess) { legacy_fail(MP3GPU_ECUDA, "init", e); return false; }
+    cudaFuncSetAttribute(k_psy_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PSYF_WARPS * sizeof(PsyFrontSmem)));
+    cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES);
+    L.ready = true;
+    mp3gpu_legacy_reset();
+    return true;
+}
+
+}  // namespace mp3gpu
+
+using namespace mp3gpu;
+
+extern "C" long mp3gpu_legacy_kernel_launches(void) { return g_legacy.launches; }
+
+extern "C" void mp3gpu_legacy_reset(void)
+{
+    LegacyState &L = g_legacy;
+    if (!L.ready) return;
+    L.off[0] = L.off[1] = 0;
+    cudaMemset(L.d_ring, 0, 2 * 512 * sizeof(double));
+    cudaMemset(L.d_psy_state, 0, 2 * sizeof(PsyChanState));
+    cudaMemset(L.d_psyout, 0, 4 * sizeof(PsyOut));
+    cudaMemset(L.d_loop_state, 0, sizeof(LoopStreamState));
+    cudaMemset(L.d_lane_state, 0, sizeof(LoopLaneState));
+}
+
+// encode.c:287-316: consumes 32 samples through the caller's pointer (which it advances), updates the
+// per-channel ring, returns the windowed vector z.
+extern "C" void window_subband(short **buffer, double z[512], int k)
+{
+    if (!legacy_init()) return;
+    LegacyState &L = g_legacy;
+    LCU(cudaMemcpy(L.d_pcm32, *buffer, 32 * sizeof(short), cudaMemcpyHostToDevice));
+    *buffer += 32;
+    k_legacy_window<<<1, 512>>>(L.d_ring + 512 * k, L.off[k], L.d_pcm32, L.d_z);
+    L.launches++;
+    LCU(cudaGetLastError());
+    LCU(cudaMemcpy(z, L.d_z, 512 * sizeof(double), cudaMemcpyDeviceToHost));
+    L.off[k] = (L.off[k] + 480) & 511;                                        // encode.c:313-314
+}
+
+// encode.c:361-409
+extern "C" void filter_subband(double z[512], double s[32])
+{
+    if (!legacy_init()) return;
+    LegacyState &L = g_legacy;
+    LCU(cudaMemcpy(L.d_z, z, 512 * sizeof(double), cudaMemcpyHostToDevice));
+    k_legacy_filter<<<1, 64>>>(L.d_z, L.d_s);
+    L.launches++;
+    LCU(cudaGetLastError());
+    LCU(cudaMemcpy(s, L.d_s, 32 * sizeof(double), cudaMemcpyDeviceToHost));
+}
+
+// mdct.c:25-103: sign fix in place (:57-60), MDCT + alias per (gr, ch), slot mode_gr saved to slot 0 (:99-102)
+extern "C" void mdct_sub(mp3gpu_L3SBS *sb_sample, double (*mdct_freq)[2][576], int stereo, III_side_info_t *l3_side, int mode_gr)
+{
+    if (!legacy_init()) return;
+    LegacyState &L = g_legacy;
+    int bt[4] = {0, 0, 0, 0};
+    for (int gr = 0; gr < mode_gr; gr++)
+        for (int ch = 0; ch < stereo; ch++) {
+            bt[gr * 2 + ch] = (int)l3_side->gr[gr].ch[ch].tt.block_type;
+            for (int band = 1; band < 32; band += 2)
+                for (int k = 1; k < 18; k += 2) (*sb_sample)[ch][gr + 1][k][band] *= -1.0;
+        }
+    LCU(cudaMemcpy(L.d_sb, sb_sample, sizeof(mp3gpu_L3SBS), cudaMemcpyHostToDevice));
+    LCU(cudaMemcpy(L.d_bt, bt, sizeof(bt), cudaMemcpyHostToDevice));
+    k_legacy_mdct<<<mode_gr * stereo, 32, sizeof(FrontWarpSmem)>>>(L.d_sb, L.d_bt, stereo, L.d_xr);
+    L.launches++;
+    LCU(cudaGetLastError());
+    double xr[4][576];
+    LCU(cudaMemcpy(xr, L.d_xr, sizeof(xr), cudaMemcpyDeviceToHost));
+    for (int gr = 0; gr < mode_gr; gr++)
+        for (int ch = 0; ch < stereo; ch++) memcpy(mdct_freq[gr][ch], xr[gr * 2 + ch], 576 * sizeof(double));
+    for (int ch = 0; ch < stereo; ch++) memcpy((*sb_sample)[ch][0], (*sb_sample)[ch][mode_gr], 576 * sizeof(double));
+}
+
+// l3psy.c:53-764 (Layer III branch :443-740): one granule of one channel.  `savebuf` is the caller's delay
+// line and is updated exactly as the reference does (:477-481).
+extern "C" void L3psycho_anal(short *buffer, short savebuf[1344], int chn, int lay, float snr32[32], double sfreq,
+                              double ratio_d[21], double ratio_ds[12][3], double *pe, gr_info *cod_info)
+{
+    (void)snr32;
+    if (!legacy_init()) return;
+    LegacyState &L = g_legacy;
+    if (lay != 3) legacy_fatal("L3psycho_anal: only Layer III is implemented");
+    const int sr = sr_index((int)(sfreq + 0.5));
+    if (sr < 0) legacy_fatal("L3psycho_anal: invalid sampling frequency (MPEG-1 rates only)");   // l3psy.c:169-176 exit()s too
+    if (L.psy_sr != sr) {
+        if (L.psy_sr >= 0) legacy_fatal("L3psycho_anal: sampling frequency changed between calls");
+        PsyTables *P = new PsyTables;
+        build_psy_tables(sr, P);
+        cudaError_t e = cudaMalloc(&L.d_psy_tab, sizeof(PsyTables));
+        if (e == cudaSuccess) e = cudaMemcpy(L.d_psy_tab, P, sizeof(PsyTables), cudaMemcpyHostToDevice);
+        delete P;
+        std::vector<FftTwiddle> tw; std::vector<int> base;
+        build_fft_twiddles(&tw, &base);
+        FftProgram P10, P8;
+        build_fft_program(10, base, &P10);
+        build_fft_program(8, base, &P8);
+        if (e == cudaSuccess) e = cudaMalloc(&L.d_tw, tw.size() * sizeof(FftTwiddle));
+        if (e == cudaSuccess) e = cudaMemcpy(L.d_tw, tw.data(), tw.size() * sizeof(FftTwiddle), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { legacy_fail(MP3GPU_ECUDA, "psy tables", e); return; }
+        if (upload_fft(P10, &L.ops1024, &L.lv1024, &L.out1024, &L.psy_dev.f1024) ||
+            upload_fft(P8, &L.ops256, &L.lv256, &L.out256, &L.psy_dev.f256)) legacy_fatal(g_err);
+        L.psy_dev.T = L.d_psy_tab; L.psy_dev.tw = L.d_tw;
+        L.psy_sr = sr;
+    }
+    memmove(savebuf, savebuf + 576, 768 * sizeof(short));                    // l3psy.c:477-478
+    memcpy(savebuf + 768, buffer, 576 * sizeof(short));                      // l3psy.c:480-481
+    short *row = L.d_save + 1344 * chn;
+    LCU(cudaMemcpy(row, savebuf, 1344 * sizeof(short), cudaMemcpyHostToDevice));
+    // the granule's first new sample is savebuf[768]; psy_front reads [-768, 576) around it
+    k_psy_front<<<1, PSYF_WARPS * 32, PSYF_WARPS * sizeof(PsyFrontSmem)>>>(L.psy_dev, row + 768 - HIST, 0, 0, 1, 1, 1, L.d_mid);
+    k_psy_scan<<<1, PSYS_WARPS * 32, PSYS_WARPS * sizeof(PsyScanSmem)>>>(L.d_psy_tab, L.d_mid, L.d_psy_state + chn, 1, 1, 1, L.d_psyout);
+    L.launches += 2;
+    LCU(cudaGetLastError());
+    PsyOut po;
+    LCU(cudaMemcpy(&po, L.d_psyout, sizeof(po), cudaMemcpyDeviceToHost));
+    for (int j = 0; j < 21; j++) ratio_d[j] = po.ratio_l[j];                 // l3psy.c:452-456 (previous call's ratios)
+    for (int j = 0; j < 12; j++)
+        for (int i = 0; i < 3; i++) ratio_ds[j][i] = po.ratio_s[3 * j + i];
+    *pe = po.pe;
+    cod_info->block_type = (unsigned)po.block_type;                          // l3psy.c:732-739
+    cod_info->window_switching_flag = po.block_type != 0;
+    cod_info->mixed_block_flag = 0;
+}
+
+// loop.c:232-362 for one frame; the reservoir recurrence (reservoir.c) runs inside the kernel.
+extern "C" void iteration_loop(double pe[][2], double xr_org[2][2][576], III_psy_ratio *ratio, III_side_info_t *l3_side,
+                               int l3_enc[2][2][576], int mean_bits, int stereo, double xr_dec[2][2][576],
+                               III_scalefac_t *scalefac, frame_params *fr_ps, int ancillary_pad, int bitsPerFrame)
+{
+    (void)xr_dec; (void)ancillary_pad;
+    if (!legacy_init()) return;
+    LegacyState &L = g_legacy;
+    const layer *info = fr_ps->header;
+    if (info->version != 1) legacy_fatal("iteration_loop: MPEG-1 only");
+    static const int idx2sr[3] = {1, 2, 0};   // header index 0:44.1 1:48 2:32 kHz -> table index 0:32 1:44.1 2:48
+    const int sr = idx2sr[info->sampling_frequency % 3];
+    if (L.loop_sr != sr) {
+        RateTables *R = new RateTables;
+        build_rate_tables(sr, R);
+        cudaError_t e = L.d_rate_tab ? cudaSuccess : cudaMalloc(&L.d_rate_tab, sizeof(RateTables));
+        if (e == cudaSuccess) e = cudaMemcpy(L.d_rate_tab, R, sizeof(RateTables), cudaMemcpyHostToDevice);
+        delete R;
+        if (e != cudaSuccess) { legacy_fail(MP3GPU_ECUDA, "rate tables", e); return; }
+        L.loop_sr = sr;
+    }
+    PsyOut po[4];
+    double xr[4][576];
+    memset(po, 0, sizeof(po));
+    for (int gr = 0; gr < 2; gr++)
+        for (int ch = 0; ch < stereo; ch++) {
+            PsyOut &p = po[gr * stereo + ch];
+            p.pe = pe[gr][ch];
+            memcpy(p.ratio_l, ratio->l[gr][ch], 21 * sizeof(double));
+            memcpy(p.ratio_s, ratio->s[gr][ch], 36 * sizeof(double));
+            p.block_type = (int)l3_side->gr[gr].ch[ch].tt.block_type;
+            memcpy(xr[gr * stereo + ch], xr_org[gr][ch], 576 * sizeof(double));
+        }
+    LCU(cudaMemcpy(L.d_psyout, po, sizeof(po), cudaMemcpyHostToDevice));
+    LCU(cudaMemcpy(L.d_xr4, xr, sizeof(xr), cudaMemcpyHostToDevice));
+    FrameGeom G;
+    G.n_ch = stereo; G.mean_bits = mean_bits; G.bits_per_frame = bitsPerFrame;
+    k_rate_loop<<<1, RL_WARPS * 32, RL_SMEM_BYTES>>>(L.d_rate_tab, G, L.d_loop_state, L.d_lane_state, 1, 1, L.d_xr4, L.d_psyout, L.d_ix,
+                                                      L.d_gi, L.d_sf, L.d_fo);
+    L.launches++;
+    LCU(cudaGetLastError());
+    short ix[4][576];
+    GrInfoOut gi[4];
+    unsigned char sf[4][40];
+    FrameOut fo;
+    LCU(cudaMemcpy(ix, L.d_ix, sizeof(ix), cudaMemcpyDeviceToHost));
+    LCU(cudaMemcpy(gi, L.d_gi, sizeof(gi), cudaMemcpyDeviceToHost));
+    LCU(cudaMemcpy(sf, L.d_sf, sizeof(sf), cudaMemcpyDeviceToHost));
+    LCU(cudaMemcpy(&fo, L.d_fo, sizeof(fo), cudaMemcpyDeviceToHost));
+    l3_side->resvDrain = fo.resv_drain;                                       // reservoir.c:223
+    for (int ch = 0; ch < stereo; ch++)
+        for (int b = 0; b < 4; b++) l3_side->scfsi[ch][b] = fo.scfsi[ch][b];  // loop.c:700-716
+    for (int gr = 0; gr < 2; gr++)
+        for (int ch = 0; ch < stereo; ch++) {
+            const int g = gr * stereo + ch;
+            const GrInfoOut &o = gi[g];
+            gr_info *c = &l3_side->gr[gr].ch[ch].tt;
+            for (int i = 0; i < 576; i++) l3_enc[gr][ch][i] = ix[g][i] < 0 ? -ix[g][i] : ix[g][i];   // magnitudes; sign: l3bitstream.c:115-125
+            c->part2_3_length = o.part2_3_length; c->big_values = o.big_values; c->count1 = o.count1;
+            c->global_gain = o.global_gain; c->scalefac_compress = o.scalefac_compress;
+            c->table_select[0] = o.table_select[0]; c->table_select[1] = o.table_select[1]; c->table_select[2] = o.table_select[2];
+            c->subblock_gain[0] = c->subblock_gain[1] = c->subblock_gain[2] = 0;
+            c->region0_count = o.region0_count; c->region1_count = o.region1_count;
+            c->preflag = o.preflag; c->scalefac_scale = o.scalefac_scale; c->count1table_select = o.count1table_select;
+            c->part2_length = o.part2_length;
+            const bool is_short = o.block_type == 2;                          // gr_deco, loop.c:2063-2081
+            c->sfb_lmax = is_short ? 0 : 21; c->sfb_smax = is_short ? 0 : 12;
+            c->address1 = o.address1; c->address2 = o.address2; c->address3 = o.address3;
+            c->quantizerStepSize = (double)(o.global_gain - 210);
+            c->sfb_partition_table = g_legacy_partition_table;
+            c->slen[0] = c->slen[1] = c->slen[2] = c->slen[3] = 0;
+            for (int b = 0; b < 22; b++) scalefac->l[gr][ch][b] = 0;
+            for (int b = 0; b < 13; b++)
+                for (int wdw = 0; wdw < 3; wdw++) scalefac->s[gr][ch][b][wdw] = 0;
+            if (!is_short) for (int b = 0; b < 21; b++) scalefac->l[gr][ch][b] = sf[g][b];
+            else for (int b = 0; b < 12; b++)
+                for (int wdw = 0; wdw < 3; wdw++) scalefac->s[gr][ch][b][wdw] = sf[g][3 * b + wdw];
+        }
+}

@@ -678,3 +678,5 @@ extern "C" int mp3gpu_quantize_count_batch(mp3gpu_ctx *c, const double *xr_abs, 
     CU(cudaGetLastError());
     return 0;
 }
+
+#include "legacy_shim.cuh"

@@ -34,6 +34,8 @@ EXPORTS = ["mp3gpu_last_error", "mp3gpu_version", "mp3gpu_create", "mp3gpu_destr
            "mp3gpu_filter_subband_batch", "mp3gpu_mdct_sub_batch", "mp3gpu_subband_mdct_batch",
            "mp3gpu_L3psycho_anal_batch", "mp3gpu_iteration_loop_batch", "mp3gpu_quantize_count_batch",
            "mp3gpu_kernel_launches", "mp3gpu_profile_enable", "mp3gpu_profile_collect"]
+LEGACY_EXPORTS = ["window_subband", "filter_subband", "mdct_sub", "L3psycho_anal", "iteration_loop",
+                  "mp3gpu_legacy_reset", "mp3gpu_legacy_kernel_launches"]
 KERNEL_NAMES = ["psy_front", "psy_scan", "front_polyphase_mdct", "rate_loop"]
 
 

@@ -31,6 +31,16 @@ def test_every_declared_symbol_is_exported(lib, pkg):
     assert sorted(pkg.host.EXPORTS) == names
 
 
+def test_legacy_entry_points_exported(lib, pkg):
+    """include/mp3gpu_legacy.h: the reference's own five symbols (musicin.c:754-779) + shim control"""
+    src = open(os.path.join(ROOT, "include", "mp3gpu_legacy.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"^(?:void|int|long)\s+([A-Za-z0-9_]+)\s*\(", src, flags=re.M)
+    assert sorted(protos) == sorted(pkg.host.LEGACY_EXPORTS)
+    for n in protos:
+        assert hasattr(lib, n), n
+
+
 def test_struct_layouts(pkg):
     assert pkg.host.PSY_DT.itemsize == 8 + 21 * 8 + 36 * 8 + 8
     assert pkg.host.FO_DT.itemsize == 16

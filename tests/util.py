@@ -87,3 +87,23 @@ class Emul:
         nops, nlev = C.c_int(), C.c_int()
         rc = self.lib.emul_fft(y.ctypes.data_as(C.c_void_p), len(y), C.byref(nops), C.byref(nlev))
         return rc, y, nops.value, nlev.value
+
+
+def write_wav(path, pcm, sfreq):
+    """44-byte-header WAV as the reference sniffs it (musicin.c:352-368): data assumed at 0x2c, little endian"""
+    import struct
+    n_ch = pcm.shape[0]
+    inter = np.ascontiguousarray(pcm.T).reshape(-1).astype("<i2")
+    hdr = b"RIFF" + struct.pack("<I", 36 + inter.nbytes) + b"WAVEfmt " + \
+        struct.pack("<IHHIIHH", 16, 1, n_ch, sfreq, sfreq * 2 * n_ch, 2 * n_ch, 16) + b"data" + struct.pack("<I", inter.nbytes)
+    with open(path, "wb") as f:
+        f.write(hdr + inter.tobytes())
+
+
+def cli_flags(n_ch, sfreq, bitrate):
+    """reference CLI flags (musicin.c:206-296) for a configuration"""
+    return (["-m", "m"] if n_ch == 1 else ["-m", "s"]) + ["-s", {32000: "32", 44100: "44.1", 48000: "48"}[sfreq], "-b", str(bitrate)]
+
+
+def mp3_frames(data, frame_bytes):
+    return [data[i:i + frame_bytes] for i in range(0, len(data), frame_bytes)]
