@@ -249,7 +249,7 @@ struct mp3gpu_ctx {
     // tables
     PsyTables *d_psy_tab = nullptr;
     RateTables *d_rate_tab = nullptr;
-    FftOp *d_ops1024 = nullptr, *d_ops256 = nullptr;
+    FftOpPacked *d_ops1024 = nullptr, *d_ops256 = nullptr;
     int *d_lv1024 = nullptr, *d_lv256 = nullptr;
     uint16_t *d_out1024 = nullptr, *d_out256 = nullptr;
     FftTwiddle *d_tw = nullptr;
@@ -304,15 +304,15 @@ static int dalloc(T **p, size_t n)
     return 0;
 }
 
-static int upload_fft(const FftProgram &P, FftOp **ops, int **lv, uint16_t **out, FftDev *dev)
+static int upload_fft(const FftProgram &P, FftOpPacked **ops, int **lv, uint16_t **out, FftDev *dev)
 {
     int rc;
-    if ((rc = dalloc(ops, P.ops.size()))) return rc;
+    if ((rc = dalloc(ops, P.packed.size()))) return rc;
     if ((rc = dalloc(lv, P.level_start.size()))) return rc;
     if ((rc = dalloc(out, (size_t)P.n))) return rc;
     std::vector<uint16_t> o(P.n);
     for (int i = 0; i < P.n; i++) o[i] = (uint16_t)(P.out_slot[i] | (P.out_neg[i] ? 0x8000 : 0));
-    CU(cudaMemcpy(*ops, P.ops.data(), P.ops.size() * sizeof(FftOp), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(*ops, P.packed.data(), P.packed.size() * sizeof(FftOpPacked), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(*lv, P.level_start.data(), P.level_start.size() * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(*out, o.data(), o.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     dev->ops = *ops; dev->level_start = *lv; dev->n_levels = (int)P.level_start.size() - 1; dev->out = *out;

@@ -25,7 +25,7 @@ using simt::PerThread;
 using simt::WarpCtx;
 
 struct FftDev {
-    const FftOp *ops;
+    const FftOpPacked *ops;
     const int *level_start;
     int n_levels;
     const uint16_t *out;  // logical index -> slot | (neg << 15)
@@ -46,14 +46,25 @@ struct PsyMid {
     float e6[8], phi6[8];
 };
 
+// 6176 B per warp (8 warps per CTA, 4 CTAs per SM).  x[] holds the FFT working set; everything that is
+// produced after a transform and consumed before the next one that needs the space is overlaid on it:
+//   after the LONG FFT only x[0..255] is reused (short transforms), so Es / Ps live in x[256..819];
+//   after the last SHORT FFT x[0..255] is free: cwv and eb live there; thr overlays E[] once the long
+//   partition energies have been formed (E is dead by then).
 struct PsyFrontSmem {
     float x[1024];
     float E[520];
-    float Es[3][132];
-    float Ps[3][56];
-    double cwv[52];
-    double eb[64];
-    double thr[64];
+};
+struct PsyFrontView {
+    float *x, *E;
+    float (*Es)[132];   // [3][132] at x + 256
+    float (*Ps)[56];    // [3][56]  at x + 652
+    double *cwv;        // [52]  at x + 0   (after the short FFTs)
+    double *eb;         // [64]  at x + 104
+    double *thr;        // [64]  at E + 0   (after the long partition energies)
+    SIMT_FN explicit PsyFrontView(PsyFrontSmem &S)
+        : x(S.x), E(S.E), Es(reinterpret_cast<float (*)[132]>(S.x + 256)), Ps(reinterpret_cast<float (*)[56]>(S.x + 652)),
+          cwv(reinterpret_cast<double *>(S.x)), eb(reinterpret_cast<double *>(S.x + 104)), thr(reinterpret_cast<double *>(S.E)) {}
 };
 
 struct PsyScanSmem {
@@ -73,45 +84,48 @@ struct PsyChanState {  // persistent per (stream, channel)
 
 static const double kLn2Log10 = 0.2302585093;  // LN_TO_LOG10, common.h:204
 
-SIMT_FN void fft_exec(const FftOp &o, const FftTwiddle *tw, float *x)
+SIMT_FN void fft_exec(FftOpPacked op, const FftTwiddle *tw, float *x)
 {
     const double SQ = 0.707106781186547524401;  // SQHALF, subs.c:26
-    float a = x[o.a], c, b, d, t1, t2;
-    if (o.neg & 1) a = -a;
-    switch (o.type) {
+    const unsigned lo = (unsigned)op, hi = (unsigned)(op >> 32);
+    const int ia = lo & 1023, ib = (lo >> 10) & 1023, ic = (lo >> 20) & 1023, id = ((lo >> 30) | (hi << 2)) & 1023;
+    const int type = (hi >> 18) & 7, neg = (hi >> 21) & 15;
+    float a = x[ia], c, b, d, t1, t2;
+    if (neg & 1) a = -a;
+    switch (type) {
     case FFT_BFLY:
-        b = x[o.b]; if (o.neg & 2) b = -b;
+        b = x[ib]; if (neg & 2) b = -b;
         t1 = simt::fadd(a, b); b = simt::fsub(a, b);
-        x[o.a] = t1; x[o.b] = b;
+        x[ia] = t1; x[ib] = b;
         break;
     case FFT_CROSS:
-        b = x[o.b]; c = x[o.c]; d = x[o.d];
-        if (o.neg & 2) b = -b;
-        if (o.neg & 4) c = -c;
-        if (o.neg & 8) d = -d;
+        b = x[ib]; c = x[ic]; d = x[id];
+        if (neg & 2) b = -b;
+        if (neg & 4) c = -c;
+        if (neg & 8) d = -d;
         t1 = simt::fadd(a, d); t2 = simt::fadd(c, b);
-        x[o.c] = simt::fsub(c, b); x[o.b] = simt::fsub(a, d);
-        x[o.a] = t1; x[o.d] = t2;
+        x[ic] = simt::fsub(c, b); x[ib] = simt::fsub(a, d);
+        x[ia] = t1; x[id] = t2;
         break;
     case FFT_ROT: {
-        c = x[o.c]; if (o.neg & 4) c = -c;
-        const FftTwiddle w = tw[o.tw];
+        c = x[ic]; if (neg & 4) c = -c;
+        const FftTwiddle w = tw[(hi >> 8) & 1023];
         t2 = simt::fmul(w.cn, simt::fadd(a, c));
         t1 = simt::fadd(simt::fmul(w.spcn, a), t2);
-        x[o.a] = simt::fadd(simt::fmul(w.smcn, c), t2);
-        x[o.c] = t1;
+        x[ia] = simt::fadd(simt::fmul(w.smcn, c), t2);
+        x[ic] = t1;
         break; }
     case FFT_ROT8A:
-        c = x[o.c]; if (o.neg & 4) c = -c;
+        c = x[ic]; if (neg & 4) c = -c;
         t1 = (float)simt::dmul(SQ, (double)simt::fadd(a, c));
-        x[o.c] = (float)simt::dmul(SQ, (double)simt::fsub(c, a));
-        x[o.a] = t1;
+        x[ic] = (float)simt::dmul(SQ, (double)simt::fsub(c, a));
+        x[ia] = t1;
         break;
     default:  // FFT_ROT8B
-        c = x[o.c]; if (o.neg & 4) c = -c;
+        c = x[ic]; if (neg & 4) c = -c;
         t2 = (float)simt::dmul(SQ, (double)simt::fsub(c, a));
-        x[o.c] = (float)simt::dmul(-SQ, (double)simt::fadd(a, c));
-        x[o.a] = t2;
+        x[ic] = (float)simt::dmul(-SQ, (double)simt::fadd(a, c));
+        x[ia] = t2;
         break;
     }
 }
@@ -121,7 +135,18 @@ SIMT_FN void fft_run(const WarpCtx &w, const FftDev &P, const FftTwiddle *tw, fl
     for (int l = 0; l < P.n_levels; l++) {
         const int lo = P.level_start[l], hi = P.level_start[l + 1];
         FOR_THREADS(w)
-        for (int i = lo + lane; i < hi; i += 32) fft_exec(P.ops[i], tw, x);
+        int i = lo + lane;
+        if (i < hi) {
+            FftOpPacked op = P.ops[i];
+            for (;;) {                       // the next op is in flight while this one executes
+                const int nx = i + 32;
+                const bool more = nx < hi;
+                const FftOpPacked nxt = P.ops[more ? nx : i];
+                fft_exec(op, tw, x);
+                if (!more) break;
+                op = nxt; i = nx;
+            }
+        }
         END_THREADS
         w.sync();
     }
@@ -163,9 +188,10 @@ SIMT_FN double unpredictability(double r_new, double phi_new, double r_prime, do
 // psy_front: history-free part, one warp per granule-channel.
 // pcm points at the first NEW sample of the granule (sample 576 g); pcm[-768 ..  575] are read.
 // ---------------------------------------------------------------------------------------------------
-SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &M, const short *pcm, PsyMid *out)
+SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const short *pcm, PsyMid *out)
 {
     const PsyTables &T = *D.T;
+    PsyFrontView M(S);
     // long window + FFT, l3psy.c:483-494
     FOR_THREADS(w)
     for (int j = lane; j < 1024; j += 32) M.x[j] = simt::fmul(T.hann_l[j], (float)(int)pcm[j - 768]);

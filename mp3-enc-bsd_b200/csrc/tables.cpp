@@ -365,6 +365,8 @@ void build_fft_program(int logm, const std::vector<int> &tw_base, FftProgram *P)
         P->level_start[level[order[i]]] = (int)i + 1;  // running "end of level l"
     }
     for (int l = 1; l <= n_levels; l++) if (P->level_start[l] == 0) P->level_start[l] = P->level_start[l - 1];
+    P->packed.clear();
+    for (const FftOp &o : P->ops) P->packed.push_back(fft_pack(o));
     P->out_slot.resize(n); P->out_neg.resize(n);
     for (int i = 0; i < n; i++) { P->out_slot[i] = (uint16_t)B.phys[i]; P->out_neg[i] = B.neg[i]; }
 }

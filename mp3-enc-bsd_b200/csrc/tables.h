@@ -41,9 +41,19 @@ struct FftOp {
     uint32_t pad;
 };
 
+// device encoding of an op, 8 bytes: a | b<<10 | c<<20 | d<<30 | tw<<40 | type<<50 | neg<<53
+typedef unsigned long long FftOpPacked;
+inline FftOpPacked fft_pack(const FftOp &o)
+{
+    return (FftOpPacked)(o.a & 1023) | ((FftOpPacked)(o.b & 1023) << 10) | ((FftOpPacked)(o.c & 1023) << 20) |
+           ((FftOpPacked)(o.d & 1023) << 30) | ((FftOpPacked)(o.tw & 1023) << 40) | ((FftOpPacked)(o.type & 7) << 50) |
+           ((FftOpPacked)(o.neg & 15) << 53);
+}
+
 struct FftProgram {
     int n, logm;
     std::vector<FftOp> ops;            // sorted by level
+    std::vector<FftOpPacked> packed;   // same ops in the device encoding
     std::vector<int> level_start;      // size n_levels+1
     std::vector<uint16_t> out_slot;    // logical output index -> physical slot (after bit reversal)
     std::vector<uint8_t> out_neg;      // ... stored negated?

@@ -76,7 +76,7 @@ int emul_encode_stream(int sfreq, int n_ch, int bitrate, int n_frames, const sho
     auto mkdev = [](const FftProgram &P, std::vector<uint16_t> &outmap) {
         outmap.resize(P.n);
         for (int i = 0; i < P.n; i++) outmap[i] = (uint16_t)(P.out_slot[i] | (P.out_neg[i] ? 0x8000 : 0));
-        FftDev d; d.ops = P.ops.data(); d.level_start = P.level_start.data(); d.n_levels = (int)P.level_start.size() - 1; d.out = outmap.data();
+        FftDev d; d.ops = P.packed.data(); d.level_start = P.level_start.data(); d.n_levels = (int)P.level_start.size() - 1; d.out = outmap.data();
         return d;
     };
     std::vector<uint16_t> o10, o8;
