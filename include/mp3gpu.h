@@ -106,6 +106,31 @@ int mp3gpu_encode_frames_dev(mp3gpu_ctx *ctx, const int16_t *pcm, int n_streams,
                              int16_t *ix, mp3gpu_gr_info *gi, uint8_t *sf, mp3gpu_frame_out *fo, void *stream);
 int mp3gpu_sync(mp3gpu_ctx *ctx, void *stream);
 
+/* ---- hot path + bitstream formatting on the device: PCM in, MPEG-1 Layer III byte stream out ---------------
+ * Replaces musicin.c:751-786 INCLUDING III_format_bitstream (l3bitstream.c:68-163, formatBitstream.c:53-80) for the
+ * batched path: Huffman emission, scalefactors, side info, headers and the back-pointer frame assembly run as
+ * CUDA kernels (the reservoir recurrence already lives in the rate-loop kernel, so nothing sequential is left
+ * for the host).  mp3 is [n_streams][mp3_stride] bytes, ABSOLUTE file positions from the start of each stream:
+ * successive calls continue the same streams and write further along each row (mp3_stride >= total frames x
+ * frame_bytes).  Because main data of a frame may start up to 511 bytes before its header, the bytes of the last
+ * few frames are only final after the NEXT call or after mp3gpu_flush_mp3(); every call delivers the bytes that
+ * became final.  mp3gpu_flush_mp3() delivers the rest and reports, per stream, the length of the stream exactly as
+ * the reference writes it minus the one spurious byte close_bit_stream_w() appends (common.c:968-974): the last
+ * frame is cut short by (reservoir bytes) mod (main-data bytes per frame) (BF_FlushBitstream, formatBitstream.c:87-125).
+ * Host variants take HOST pointers (pinned for asynchronous copies), _dev variants DEVICE pointers; `lengths` is
+ * always a host array of n_streams longs (flush synchronises the stream). */
+int mp3gpu_encode_frames_mp3(mp3gpu_ctx *ctx, const int16_t *pcm, int n_streams, int n_frames, uint8_t *mp3, long mp3_stride, void *stream);
+int mp3gpu_encode_frames_mp3_dev(mp3gpu_ctx *ctx, const int16_t *pcm, int n_streams, int n_frames, uint8_t *mp3, long mp3_stride, void *stream);
+int mp3gpu_flush_mp3(mp3gpu_ctx *ctx, int n_streams, uint8_t *mp3, long mp3_stride, long *lengths, void *stream);
+int mp3gpu_flush_mp3_dev(mp3gpu_ctx *ctx, int n_streams, uint8_t *mp3, long mp3_stride, long *lengths, void *stream);
+/* Segment seam: keep the signal history (filterbank, MDCT overlap, psychoacoustic state) of every stream but empty
+ * its bit reservoir (reservoir.c:36 ResvSize) and restart its byte stream at position 0, so that the next frame has
+ * main_data_begin = 0.  Used when one long stream is cut into segments that are encoded independently after a
+ * pre-roll; the reference has no counterpart (one stream per process). */
+int mp3gpu_begin_segment(mp3gpu_ctx *ctx, void *stream);
+/* bytes per frame (constant: the reference never pads, musicin.c:566-581) and bytes of header + side info */
+int mp3gpu_frame_bytes(const mp3gpu_ctx *ctx, int *frame_bytes, int *sideinfo_bytes);
+
 /* ---- stage entry points (DEVICE pointers; each continues the ctx's per-stream state of that stage) */
 /* window_subband + filter_subband for every slot of n_frames frames */
 int mp3gpu_filter_subband_batch(mp3gpu_ctx *ctx, const int16_t *pcm, int n_streams, int n_frames, double *sb, void *stream);
@@ -123,6 +148,10 @@ int mp3gpu_iteration_loop_batch(mp3gpu_ctx *ctx, const double *xr, const mp3gpu_
  * (big_values,count1,count1table_select,region0/1_count,table_select,address1-3), bits [n]. */
 int mp3gpu_quantize_count_batch(mp3gpu_ctx *ctx, const double *xr_abs, const int *q, const int *block_type, int n,
                                 int16_t *ix, mp3gpu_gr_info *gi, int *bits, void *stream);
+/* III_format_bitstream (l3bitstream.c:68) batched: ix (signed) / gi / sf / fo as produced by the rate loop -> byte
+ * stream, continuing the ctx's streams (same window semantics as mp3gpu_encode_frames_mp3_dev; mp3 may be NULL). */
+int mp3gpu_format_bitstream_batch(mp3gpu_ctx *ctx, const int16_t *ix, const mp3gpu_gr_info *gi, const uint8_t *sf,
+                                  const mp3gpu_frame_out *fo, int n_streams, int n_frames, uint8_t *mp3, long mp3_stride, void *stream);
 
 /* last launch statistics: number of kernels this library launched since ctx creation */
 long mp3gpu_kernel_launches(const mp3gpu_ctx *ctx);
@@ -133,7 +162,8 @@ long mp3gpu_kernel_launches(const mp3gpu_ctx *ctx);
 #define MP3GPU_K_PSY_SCAN 1    /* history-dependent psychoacoustic scan */
 #define MP3GPU_K_FRONT 2       /* fused polyphase filterbank + MDCT + alias reduction */
 #define MP3GPU_K_RATE_LOOP 3   /* rate loop + reservoir */
-#define MP3GPU_N_KERNELS 4
+#define MP3GPU_K_BITSTREAM 4   /* header/side-info + Huffman emission kernels */
+#define MP3GPU_N_KERNELS 5
 int mp3gpu_profile_enable(mp3gpu_ctx *ctx, int on);
 int mp3gpu_profile_collect(mp3gpu_ctx *ctx, double ms[MP3GPU_N_KERNELS], long launches[MP3GPU_N_KERNELS], int reset);
 

@@ -4,5 +4,5 @@ encoder, behind the C ABI of libmp3gpu.so (include/mp3gpu.h).
 The directory name contains '-' and '.', so it is imported through `mp3gpu_pkg.load()` at the repo
 root, which registers it as the module `mp3enc_b200`.
 """
-from . import host, synth  # noqa: F401
+from . import host, segment, synth  # noqa: F401
 from .host import Encoder, Mp3GpuError, load_library  # noqa: F401

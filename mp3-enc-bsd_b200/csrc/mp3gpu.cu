@@ -10,6 +10,7 @@
 // There is no CPU fallback: every entry point fails with MP3GPU_ECUDA if no device is usable.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stddef.h>
 #include <string.h>
 
 #include <new>
@@ -22,6 +23,7 @@
 #include "psy_core.h"
 #include "rate_loop_core.h"
 #include "tables.h"
+#include "bitstream.cuh"
 
 using namespace mp3gpu;
 
@@ -268,13 +270,20 @@ struct mp3gpu_ctx {
     GrInfoOut *d_gi = nullptr;
     unsigned char *d_sf = nullptr;
     FrameOut *d_fo = nullptr;
+    // device bitstream formatter (bitstream.cuh): tables, sliding output window, end-of-stream back pointers
+    BitTables *d_bit_tab = nullptr;
+    unsigned char *d_win = nullptr, *d_win_tmp = nullptr;
+    int *d_next_begin = nullptr;
+    int frame_bytes = 0, si_bytes = 0, tail_frames = 0;
+    long wstride = 0;
+    long frames_done = 0;      // frames already formatted per stream (all streams of a ctx advance in lockstep)
     long launches = 0;
     // per-kernel timing (mp3gpu_profile_*): events bracket every launch of the four hot kernels
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev;     // pairs (start, stop)
     std::vector<int> prof_kind;           // kernel id of each pair
-    double prof_ms[MP3GPU_N_KERNELS] = {0, 0, 0, 0};
-    long prof_n[MP3GPU_N_KERNELS] = {0, 0, 0, 0};
+    double prof_ms[MP3GPU_N_KERNELS] = {0, 0, 0, 0, 0};
+    long prof_n[MP3GPU_N_KERNELS] = {0, 0, 0, 0, 0};
 };
 
 static void prof_begin(mp3gpu_ctx *c, int kind, cudaStream_t q)
@@ -365,6 +374,14 @@ extern "C" int mp3gpu_create(const mp3gpu_config *cfg, mp3gpu_ctx **out)
         if (!rc) rc = upload_fft(P10, &c->d_ops1024, &c->d_lv1024, &c->d_out1024, &c->psy_dev.f1024);
         if (!rc) rc = upload_fft(P8, &c->d_ops256, &c->d_lv256, &c->d_out256, &c->psy_dev.f256);
         c->psy_dev.T = c->d_psy_tab; c->psy_dev.tw = c->d_tw;
+        BitTables *B = new BitTables;
+        build_bit_tables(sr, cfg->sfreq_hz, cfg->n_ch, cfg->bitrate_kbps, B);
+        c->frame_bytes = B->frame_bytes; c->si_bytes = B->si_bytes;
+        if (!rc && !(rc = dalloc(&c->d_bit_tab, 1))) cudaMemcpy(c->d_bit_tab, B, sizeof(BitTables), cudaMemcpyHostToDevice);
+        delete B;
+        // main data reaches back at most 511 main-data bytes (9-bit main_data_begin)
+        c->tail_frames = 511 / (c->frame_bytes - c->si_bytes) + 1;
+        c->wstride = (((long)(c->tail_frames + cfg->max_frames) * c->frame_bytes + 15) / 16) * 16;
     }
     // ---- state + workspace ----
     const size_t S = cfg->max_streams, NCH = cfg->n_ch, GC = (size_t)cfg->max_frames * 2 * NCH;
@@ -379,6 +396,9 @@ extern "C" int mp3gpu_create(const mp3gpu_config *cfg, mp3gpu_ctx **out)
     if (!rc) rc = dalloc(&c->d_gi, S * GC);
     if (!rc) rc = dalloc(&c->d_sf, S * GC * 40);
     if (!rc) rc = dalloc(&c->d_fo, S * (size_t)cfg->max_frames);
+    if (!rc) rc = dalloc(&c->d_win, S * (size_t)c->wstride);
+    if (!rc) rc = dalloc(&c->d_win_tmp, S * (size_t)c->tail_frames * c->frame_bytes);
+    if (!rc) rc = dalloc(&c->d_next_begin, S);
     if (rc) { mp3gpu_destroy(c); return rc; }
     // opt in to large dynamic shared memory
     cudaFuncSetAttribute(k_psy_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PSYF_WARPS * sizeof(PsyFrontSmem)));
@@ -400,7 +420,8 @@ extern "C" void mp3gpu_destroy(mp3gpu_ctx *c)
     if (!c) return;
     void *ptrs[] = {c->d_psy_tab, c->d_rate_tab, c->d_ops1024, c->d_ops256, c->d_lv1024, c->d_lv256, c->d_out1024, c->d_out256,
                     c->d_tw, c->pcm_main.buf, c->pcm_fb.buf, c->pcm_psy.buf, c->d_psy_state, c->d_loop_state, c->d_lane_state,
-                    c->d_sb_prev, c->d_mid, c->d_psyout, c->d_xr, c->d_ix, c->d_gi, c->d_sf, c->d_fo};
+                    c->d_sb_prev, c->d_mid, c->d_psyout, c->d_xr, c->d_ix, c->d_gi, c->d_sf, c->d_fo,
+                    c->d_bit_tab, c->d_win, c->d_win_tmp, c->d_next_begin};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete c;
 }
@@ -416,6 +437,9 @@ extern "C" int mp3gpu_reset(mp3gpu_ctx *c)
     CU(cudaMemset(c->d_psy_state, 0, S * NCH * sizeof(PsyChanState)));
     CU(cudaMemset(c->d_loop_state, 0, S * sizeof(LoopStreamState)));
     CU(cudaMemset(c->d_lane_state, 0, S * sizeof(LoopLaneState)));
+    CU(cudaMemset(c->d_win, 0, S * (size_t)c->wstride));
+    CU(cudaMemset(c->d_next_begin, 0, S * sizeof(int)));
+    c->frames_done = 0;
     return 0;
 }
 
@@ -590,6 +614,123 @@ static int encode_common(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n
         if (fo) CU(cudaMemcpyAsync(fo, c->d_fo, (size_t)n_streams * n_frames * sizeof(FrameOut), cudaMemcpyDeviceToHost, q));
     }
     return 0;
+}
+
+// ---- device bitstream formatter -----------------------------------------------------------------------
+// Formats the call's frames into the sliding window, copies the bytes that are now final to the caller's
+// buffer (absolute file positions), then slides the window.  After the call window byte 0 corresponds to
+// absolute byte (frames_done - tail_frames) * FB.
+static int format_common(mp3gpu_ctx *c, const short *ix, const GrInfoOut *gi, const unsigned char *sf, const FrameOut *fo, int n_streams,
+                         int n_frames, uint8_t *mp3, long stride, bool host, cudaStream_t q)
+{
+    const long FB = c->frame_bytes, T = c->tail_frames;
+    if (mp3 && stride < (c->frames_done + n_frames) * FB) return fail(MP3GPU_EINVAL, "mp3 stride too small for the frames encoded so far");
+    BitsGeom G;
+    G.n_streams = n_streams; G.n_frames = n_frames; G.n_ch = c->cfg.n_ch;
+    G.frame_bytes = c->frame_bytes; G.si_bytes = c->si_bytes;
+    G.frame0 = c->frames_done; G.origin = (c->frames_done - T) * FB; G.wstride = c->wstride;
+    CU(cudaMemset2DAsync(c->d_win + T * FB, c->wstride, 0, (size_t)n_frames * FB, n_streams, q));
+    prof_begin(c, MP3GPU_K_BITSTREAM, q);
+    const long frames = (long)n_streams * n_frames;
+    k_bits_headers<<<(unsigned)((frames + 127) / 128), 128, 0, q>>>(c->d_bit_tab, G, gi, fo, c->d_win, c->d_next_begin);
+    const long gcs = frames * 2 * c->cfg.n_ch;
+    k_bits_emit<<<(unsigned)((gcs + BITS_WARPS - 1) / BITS_WARPS), BITS_WARPS * 32, 0, q>>>(c->d_bit_tab, G, ix, gi, sf, fo, c->d_win);
+    prof_end(c, q);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    const cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (mp3) {  // window bytes [0, n_frames*FB) are final; clip what lies before the start of the stream
+        const long skip = G.origin < 0 ? -G.origin : 0, width = (long)n_frames * FB - skip;
+        if (width > 0)
+            CU(cudaMemcpy2DAsync(mp3 + G.origin + skip, (size_t)stride, c->d_win + skip, (size_t)c->wstride, (size_t)width, n_streams, kind, q));
+    }
+    // slide: the last `tail` frames become the first ones (through a temporary: the ranges may overlap)
+    CU(cudaMemcpy2DAsync(c->d_win_tmp, (size_t)(T * FB), c->d_win + (long)n_frames * FB, (size_t)c->wstride, (size_t)(T * FB), n_streams,
+                         cudaMemcpyDeviceToDevice, q));
+    CU(cudaMemcpy2DAsync(c->d_win, (size_t)c->wstride, c->d_win_tmp, (size_t)(T * FB), (size_t)(T * FB), n_streams, cudaMemcpyDeviceToDevice, q));
+    c->frames_done += n_frames;
+    return 0;
+}
+
+static int flush_common(mp3gpu_ctx *c, int n_streams, uint8_t *mp3, long stride, long *lengths, bool host, cudaStream_t q)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    if (n_streams < 1 || n_streams > c->cfg.max_streams) return fail(MP3GPU_EINVAL, "bad n_streams");
+    const long FB = c->frame_bytes, T = c->tail_frames;
+    const long origin = (c->frames_done - T) * FB, skip = origin < 0 ? -origin : 0, width = T * FB - skip;
+    if (mp3 && stride < c->frames_done * FB) return fail(MP3GPU_EINVAL, "mp3 stride too small");
+    if (mp3 && width > 0)
+        CU(cudaMemcpy2DAsync(mp3 + origin + skip, (size_t)stride, c->d_win + skip, (size_t)c->wstride, (size_t)width, n_streams,
+                             host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, q));
+    if (lengths) {
+        std::vector<int> nb(n_streams);
+        CU(cudaMemcpyAsync(nb.data(), c->d_next_begin, n_streams * sizeof(int), cudaMemcpyDeviceToHost, q));
+        CU(cudaStreamSynchronize(q));
+        // BF_FlushBitstream (formatBitstream.c:87-125) zero-fills main data for every header still queued, i.e. whole
+        // frame capacities: the write position keeps its offset inside the frame, so the last frame ends up short by
+        // (bytes still in the reservoir) mod (main-data bytes per frame)
+        for (int s = 0; s < n_streams; s++) lengths[s] = c->frames_done * FB - nb[s] % (FB - c->si_bytes);
+    }
+    return 0;
+}
+
+// Segment seam (single long stream cut over several GPUs): keep filterbank / MDCT / psy history, empty the bit
+// reservoir of every stream and restart the byte stream, so the next frame has main_data_begin = 0.
+extern "C" int mp3gpu_begin_segment(mp3gpu_ctx *c, void *stream)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    cudaStream_t q = (cudaStream_t)stream;
+    static_assert(offsetof(LoopStreamState, resv_size) == 0, "resv_size must lead LoopStreamState");
+    CU(cudaMemset2DAsync(c->d_loop_state, sizeof(LoopStreamState), 0, sizeof(int), (size_t)c->cfg.max_streams, q));
+    CU(cudaMemsetAsync(c->d_win, 0, (size_t)c->cfg.max_streams * c->wstride, q));
+    CU(cudaMemsetAsync(c->d_next_begin, 0, (size_t)c->cfg.max_streams * sizeof(int), q));
+    c->frames_done = 0;
+    return 0;
+}
+
+extern "C" int mp3gpu_frame_bytes(const mp3gpu_ctx *c, int *frame_bytes, int *sideinfo_bytes)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    if (frame_bytes) *frame_bytes = c->frame_bytes;
+    if (sideinfo_bytes) *sideinfo_bytes = c->si_bytes;
+    return 0;
+}
+
+extern "C" int mp3gpu_format_bitstream_batch(mp3gpu_ctx *c, const int16_t *ix, const mp3gpu_gr_info *gi, const uint8_t *sf,
+                                             const mp3gpu_frame_out *fo, int n_streams, int n_frames, uint8_t *mp3, long mp3_stride, void *stream)
+{
+    int rc = check_shape(c, n_streams, n_frames);
+    if (rc) return rc;
+    if (!ix || !gi || !sf || !fo) return fail(MP3GPU_EINVAL, "null pointer");
+    return format_common(c, ix, (const GrInfoOut *)gi, sf, (const FrameOut *)fo, n_streams, n_frames, mp3, mp3_stride, false, (cudaStream_t)stream);
+}
+
+static int encode_mp3_common(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, uint8_t *mp3, long stride, void *stream, bool host)
+{
+    int rc = encode_common(c, pcm, n_streams, n_frames, nullptr, nullptr, nullptr, nullptr, stream, host);
+    if (rc) return rc;
+    return format_common(c, c->d_ix, c->d_gi, c->d_sf, c->d_fo, n_streams, n_frames, mp3, stride, host, (cudaStream_t)stream);
+}
+
+extern "C" int mp3gpu_encode_frames_mp3(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, uint8_t *mp3, long mp3_stride, void *stream)
+{
+    return encode_mp3_common(c, pcm, n_streams, n_frames, mp3, mp3_stride, stream, true);
+}
+
+extern "C" int mp3gpu_encode_frames_mp3_dev(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, uint8_t *mp3, long mp3_stride,
+                                            void *stream)
+{
+    return encode_mp3_common(c, pcm, n_streams, n_frames, mp3, mp3_stride, stream, false);
+}
+
+extern "C" int mp3gpu_flush_mp3(mp3gpu_ctx *c, int n_streams, uint8_t *mp3, long mp3_stride, long *lengths, void *stream)
+{
+    return flush_common(c, n_streams, mp3, mp3_stride, lengths, true, (cudaStream_t)stream);
+}
+
+extern "C" int mp3gpu_flush_mp3_dev(mp3gpu_ctx *c, int n_streams, uint8_t *mp3, long mp3_stride, long *lengths, void *stream)
+{
+    return flush_common(c, n_streams, mp3, mp3_stride, lengths, false, (cudaStream_t)stream);
 }
 
 extern "C" int mp3gpu_encode_frames(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, int16_t *ix, mp3gpu_gr_info *gi,

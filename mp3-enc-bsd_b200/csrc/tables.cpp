@@ -32,6 +32,38 @@ void frame_geometry(int sfreq_hz, int n_ch, int bitrate_kbps, FrameGeom *G)
     G->mean_bits = (G->bits_per_frame - sideinfo_len) / 2;
 }
 
+// Emit-side Huffman tables + emission order of short blocks + the constant 32 header bits
+// (l3bitstream.c:323-336 with the reference's defaults: no CRC, no padding, not copyrighted, not original, no emphasis;
+// sampling_frequency index order 44.1/48/32 and mode 0 = stereo, 3 = mono as in common.c / musicin.c)
+void build_bit_tables(int sr, int sfreq_hz, int n_ch, int bitrate_kbps, BitTables *B)
+{
+    memset(B, 0, sizeof(*B));
+    for (int i = 0; i < MP3T_HUFF_FLAT; i++) B->hcode[i] = (MP3T_HCODE[i] & 0xffffffu) | ((unsigned)MP3T_HLEN[i] << 24);
+    for (int t = 0; t < 34; t++) {
+        B->hoff[t] = MP3T_HUFF[t].off;
+        B->ylen[t] = MP3T_HUFF[t].ylen;
+        B->linbits[t] = MP3T_HUFF[t].linbits;
+    }
+    int p = 0;
+    for (int sfb = 0; sfb < 13; sfb++)
+        for (int w = 0; w < 3; w++)
+            for (int line = MP3T_SFB_SHORT[sr][sfb]; line < MP3T_SFB_SHORT[sr][sfb + 1]; line += 2) B->short_e0[p++] = (unsigned short)(line * 3 + w);
+    for (int i = 0; i < 23; i++) B->sfb_l[i] = MP3T_SFB_LONG[sr][i];
+    static const int rates[15] = {0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320};
+    int br = 0;
+    for (int i = 1; i < 15; i++) if (rates[i] == bitrate_kbps) br = i;
+    const int sf = (sfreq_hz == 44100) ? 0 : (sfreq_hz == 48000) ? 1 : 2;
+    const unsigned h = (0xfffu << 20) | (1u << 19) | (1u << 17) | (1u << 16) | ((unsigned)br << 12) | ((unsigned)sf << 10) |
+                       ((n_ch == 2 ? 0u : 3u) << 6);
+    B->header[0] = (unsigned char)(h >> 24); B->header[1] = (unsigned char)(h >> 16);
+    B->header[2] = (unsigned char)(h >> 8); B->header[3] = (unsigned char)h;
+    FrameGeom G;
+    frame_geometry(sfreq_hz, n_ch, bitrate_kbps, &G);
+    B->frame_bytes = G.bits_per_frame / 8;
+    B->si_bytes = 4 + (n_ch == 2 ? 32 : 17);
+    B->n_ch = n_ch;
+}
+
 void build_front_tables(FrontTables *F)
 {
     memset(F, 0, sizeof(*F));

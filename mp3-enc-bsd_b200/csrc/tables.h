@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "rate_loop_core.h"
+#include "bitstream_tables.h"
 
 namespace mp3gpu {
 
@@ -90,6 +91,7 @@ struct PsyTables {
 void build_front_tables(FrontTables *F);
 void build_rate_tables(int sr_idx, RateTables *R);
 void build_psy_tables(int sr_idx, PsyTables *P);
+void build_bit_tables(int sr_idx, int sfreq_hz, int n_ch, int bitrate_kbps, BitTables *B);
 
 int sr_index(int sfreq_hz);  // 0:32000 1:44100 2:48000, -1 otherwise
 // frame geometry, musicin.c:562-572 and 729-746 (the reference never pads: frac_SpF is computed

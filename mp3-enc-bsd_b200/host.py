@@ -33,10 +33,12 @@ EXPORTS = ["mp3gpu_last_error", "mp3gpu_version", "mp3gpu_create", "mp3gpu_destr
            "mp3gpu_frame_geometry", "mp3gpu_encode_frames", "mp3gpu_encode_frames_dev", "mp3gpu_sync",
            "mp3gpu_filter_subband_batch", "mp3gpu_mdct_sub_batch", "mp3gpu_subband_mdct_batch",
            "mp3gpu_L3psycho_anal_batch", "mp3gpu_iteration_loop_batch", "mp3gpu_quantize_count_batch",
-           "mp3gpu_kernel_launches", "mp3gpu_profile_enable", "mp3gpu_profile_collect"]
+           "mp3gpu_kernel_launches", "mp3gpu_profile_enable", "mp3gpu_profile_collect",
+           "mp3gpu_encode_frames_mp3", "mp3gpu_encode_frames_mp3_dev", "mp3gpu_flush_mp3", "mp3gpu_flush_mp3_dev",
+           "mp3gpu_frame_bytes", "mp3gpu_format_bitstream_batch", "mp3gpu_begin_segment"]
 LEGACY_EXPORTS = ["window_subband", "filter_subband", "mdct_sub", "L3psycho_anal", "iteration_loop",
                   "mp3gpu_legacy_reset", "mp3gpu_legacy_kernel_launches"]
-KERNEL_NAMES = ["psy_front", "psy_scan", "front_polyphase_mdct", "rate_loop"]
+KERNEL_NAMES = ["psy_front", "psy_scan", "front_polyphase_mdct", "rate_loop", "bitstream"]
 
 
 class Config(C.Structure):
@@ -79,6 +81,13 @@ def load_library():
         lib.mp3gpu_L3psycho_anal_batch.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
         lib.mp3gpu_iteration_loop_batch.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
         lib.mp3gpu_quantize_count_batch.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
+        for name in ("mp3gpu_encode_frames_mp3", "mp3gpu_encode_frames_mp3_dev"):
+            getattr(lib, name).argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_long, vp]
+        for name in ("mp3gpu_flush_mp3", "mp3gpu_flush_mp3_dev"):
+            getattr(lib, name).argtypes = [vp, C.c_int, vp, C.c_long, C.POINTER(C.c_long), vp]
+        lib.mp3gpu_begin_segment.argtypes = [vp, vp]
+        lib.mp3gpu_frame_bytes.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.mp3gpu_format_bitstream_batch.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, C.c_long, vp]
         _lib = lib
     return _lib
 
@@ -102,6 +111,9 @@ class Encoder:
         bpf, mb = C.c_int(), C.c_int()
         self.lib.mp3gpu_frame_geometry(self.ctx, C.byref(bpf), C.byref(mb))
         self.bits_per_frame, self.mean_bits = bpf.value, mb.value
+        fb, sib = C.c_int(), C.c_int()
+        self.lib.mp3gpu_frame_bytes(self.ctx, C.byref(fb), C.byref(sib))
+        self.frame_bytes, self.sideinfo_bytes = fb.value, sib.value
 
     def close(self):
         if self.ctx:
@@ -130,9 +142,10 @@ class Encoder:
 
     def profile_collect(self, reset=True):
         """-> {kernel name: (total ms, launches)} measured with CUDA events on the launching stream"""
-        ms, n = (C.c_double * 4)(), (C.c_long * 4)()
+        k = len(KERNEL_NAMES)
+        ms, n = (C.c_double * k)(), (C.c_long * k)()
         self._check(self.lib.mp3gpu_profile_collect(self.ctx, ms, n, 1 if reset else 0), "mp3gpu_profile_collect")
-        return {KERNEL_NAMES[i]: (ms[i], n[i]) for i in range(4)}
+        return {KERNEL_NAMES[i]: (ms[i], n[i]) for i in range(k)}
 
     def sync(self, stream=None):
         self._check(self.lib.mp3gpu_sync(self.ctx, C.c_void_p(stream or 0)), "mp3gpu_sync")
@@ -180,6 +193,72 @@ class Encoder:
                                                out["sf"].data_ptr(), out["fo"].data_ptr(), C.c_void_p(stream or 0))
         self._check(rc, "mp3gpu_encode_frames_dev")
         return out
+
+    # ---- hot path + device bitstream formatter: PCM in, MP3 bytes out --------------------------------
+    def encode_frames_mp3(self, pcm, mp3, stream=None):
+        """HOST buffers. pcm int16 [S][n_ch][F*1152]; mp3 uint8 [S][stride] (absolute stream positions, see mp3gpu.h).
+        Asynchronous on `stream`: call flush_mp3() (or sync()) before reading."""
+        pcm_np = pcm if isinstance(pcm, np.ndarray) else pcm.numpy()
+        mp3_np = mp3 if isinstance(mp3, np.ndarray) else mp3.numpy()
+        assert pcm_np.dtype == np.int16 and pcm_np.flags["C_CONTIGUOUS"] and mp3_np.dtype == np.uint8 and mp3_np.flags["C_CONTIGUOUS"]
+        S, F = self._shape(pcm_np.shape)
+        assert mp3_np.shape[0] >= S
+        rc = self.lib.mp3gpu_encode_frames_mp3(self.ctx, C.c_void_p(pcm_np.ctypes.data), S, F, C.c_void_p(mp3_np.ctypes.data),
+                                               mp3_np.strides[0], C.c_void_p(stream or 0))
+        self._check(rc, "mp3gpu_encode_frames_mp3")
+
+    def encode_frames_mp3_dev(self, pcm, mp3, stream=None):
+        """DEVICE tensors. mp3 may be None (format only, e.g. for timing)."""
+        S, F = self._shape(tuple(pcm.shape))
+        rc = self.lib.mp3gpu_encode_frames_mp3_dev(self.ctx, pcm.data_ptr(), S, F, mp3.data_ptr() if mp3 is not None else None,
+                                                   mp3.stride(0) if mp3 is not None else 0, C.c_void_p(stream or 0))
+        self._check(rc, "mp3gpu_encode_frames_mp3_dev")
+
+    def flush_mp3(self, mp3, n_streams, stream=None):
+        """deliver the bytes still in the window; returns the per-stream byte counts (numpy int64). Synchronises."""
+        lengths = (C.c_long * n_streams)()
+        if mp3 is None:
+            rc = self.lib.mp3gpu_flush_mp3(self.ctx, n_streams, None, 0, lengths, C.c_void_p(stream or 0))
+        elif isinstance(mp3, np.ndarray) or not mp3.is_cuda:
+            a = mp3 if isinstance(mp3, np.ndarray) else mp3.numpy()
+            rc = self.lib.mp3gpu_flush_mp3(self.ctx, n_streams, C.c_void_p(a.ctypes.data), a.strides[0], lengths, C.c_void_p(stream or 0))
+        else:
+            rc = self.lib.mp3gpu_flush_mp3_dev(self.ctx, n_streams, mp3.data_ptr(), mp3.stride(0), lengths, C.c_void_p(stream or 0))
+        self._check(rc, "mp3gpu_flush_mp3")
+        return np.array(lengths[:], dtype=np.int64)
+
+    def format_bitstream_batch(self, out, mp3, stream=None):
+        """III_format_bitstream batched: `out` = dict(ix, gi, sf, fo) of DEVICE tensors as the rate loop produces them."""
+        S, gcs = out["ix"].shape[0], out["ix"].shape[1]
+        F = gcs // (2 * self.n_ch)
+        rc = self.lib.mp3gpu_format_bitstream_batch(self.ctx, out["ix"].data_ptr(), out["gi"].data_ptr(), out["sf"].data_ptr(),
+                                                    out["fo"].data_ptr(), S, F, mp3.data_ptr() if mp3 is not None else None,
+                                                    mp3.stride(0) if mp3 is not None else 0, C.c_void_p(stream or 0))
+        self._check(rc, "mp3gpu_format_bitstream_batch")
+
+    def begin_segment(self, stream=None):
+        """segment seam: keep the signal history, empty the bit reservoir, restart the byte stream (mp3gpu.h)"""
+        self._check(self.lib.mp3gpu_begin_segment(self.ctx, C.c_void_p(stream or 0)), "mp3gpu_begin_segment")
+
+    def encode_streams(self, pcm, chunk_frames=None):
+        """Whole streams in one go (HOST numpy): pcm int16 [S][n_ch][n] (zero-padded to whole frames like
+        get_audio(), encode.c:162-166) -> list of S `bytes`, each what the reference CLI writes for that stream
+        except the one spurious byte close_bit_stream_w() appends."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        S, n_ch, n = pcm.shape
+        F = (n + 1151) // 1152
+        if F * 1152 != n:
+            pad = np.zeros((S, n_ch, F * 1152), np.int16)
+            pad[:, :, :n] = pcm
+            pcm = pad
+        chunk = min(chunk_frames or self.cfg.max_frames, self.cfg.max_frames)
+        mp3 = np.zeros((S, F * self.frame_bytes), np.uint8)
+        self.reset()
+        for f0 in range(0, F, chunk):
+            f1 = min(F, f0 + chunk)
+            self.encode_frames_mp3(np.ascontiguousarray(pcm[:, :, f0 * 1152:f1 * 1152]), mp3)
+        lengths = self.flush_mp3(mp3, S)
+        return [mp3[s, :lengths[s]].tobytes() for s in range(S)]
 
     # ---- stage entry points (torch device tensors in, torch device tensors out) -------------------
     def filter_subband_batch(self, pcm, stream=None):

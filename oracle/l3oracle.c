@@ -1188,3 +1188,209 @@ int l3o_encode_stream(int sfreq, int n_ch, int bitrate_kbps, const short *pcm, l
     l3o_destroy(e);
     return 0;
 }
+
+/* ======================================================================================================
+ * Bitstream formatter (TEST INFRASTRUCTURE): sequential restatement of III_format_bitstream
+ * (l3bitstream.c:68-163), encodeSideInfo (:314-458), encodeMainData (:179-309), Huffmancodebits (:517-716),
+ * HuffmanCode (:779-906), L3_huffman_coder_count1 (:728-767) and the frame assembler BF_BitstreamFrame /
+ * WriteMainDataBits / BF_FlushBitstream (formatBitstream.c:53-125, 218-247).  Pinned against the byte streams
+ * the unmodified reference CLI writes (tests/golden/cli_*.mp3).
+ * ====================================================================================================== */
+typedef struct {
+    unsigned char *buf; long cap, nbits;          /* output byte stream */
+    /* side-info queue (formatBitstream.c:276-398): each entry is the packed header+SI of one frame */
+    unsigned char (*q)[40]; int q_head, q_tail, q_cap;
+    int si_bits, frame_bits;
+    long bit_count, this_frame, bits_remaining;   /* BitCount, ThisFrameSize, BitsRemaining */
+} fmt_t;
+
+static void fmt_put(fmt_t *F, unsigned val, int n) /* putbits, common.c:1010-1040: MSB first */
+{
+    int i;
+    for (i = n - 1; i >= 0; i--) {
+        if ((F->nbits >> 3) < F->cap && ((val >> i) & 1u)) F->buf[F->nbits >> 3] |= (unsigned char)(0x80 >> (F->nbits & 7));
+        F->nbits++;
+    }
+}
+static int fmt_write_side_info(fmt_t *F) /* formatBitstream.c:249-269 */
+{
+    int i;
+    const unsigned char *e = F->q[F->q_head % F->q_cap];
+    F->q_head++;
+    F->this_frame = F->frame_bits;
+    for (i = 0; i < F->si_bits / 8; i++) fmt_put(F, e[i], 8);
+    return F->si_bits;
+}
+static void fmt_main(fmt_t *F, unsigned val, unsigned nbits) /* WriteMainDataBits, formatBitstream.c:218-247 */
+{
+    if (F->bit_count == F->this_frame) { F->bit_count = fmt_write_side_info(F); F->bits_remaining = F->this_frame - F->bit_count; }
+    if (nbits == 0) return;
+    if ((long)nbits > F->bits_remaining) {
+        unsigned extra = val >> (nbits - F->bits_remaining);
+        nbits -= (unsigned)F->bits_remaining;
+        fmt_put(F, extra, (int)F->bits_remaining);
+        F->bit_count = fmt_write_side_info(F);
+        F->bits_remaining = F->this_frame - F->bit_count;
+        fmt_put(F, val, (int)nbits);
+    } else fmt_put(F, val, (int)nbits);
+    F->bit_count += nbits; F->bits_remaining -= nbits;
+}
+/* bit packer for one side-info entry */
+typedef struct { unsigned char *p; int n; } sip_t;
+static void si_put(sip_t *s, unsigned v, int n) { int i; for (i = n - 1; i >= 0; i--) { if ((v >> i) & 1u) s->p[s->n >> 3] |= (unsigned char)(0x80 >> (s->n & 7)); s->n++; } }
+
+static int fmt_huffman_pair(fmt_t *F, int t, int x, int y) /* HuffmanCode, l3bitstream.c:779-906 */
+{
+    unsigned signx = 0, signy = 0, code, ext = 0, idx, linbitsx = 0, linbitsy = 0;
+    int cbits, xbits = 0;
+    const mp3t_huff_desc *h = &MP3T_HUFF[t];
+    if (t == 0) return 0;
+    if (x < 0) { x = -x; signx = 1; }
+    if (y < 0) { y = -y; signy = 1; }
+    if (t > 15) {
+        if (x > 14) { linbitsx = (unsigned)x - 15; x = 15; }
+        if (y > 14) { linbitsy = (unsigned)y - 15; y = 15; }
+        idx = (unsigned)x * h->ylen + (unsigned)y;
+        code = MP3T_HCODE[h->off + idx]; cbits = MP3T_HLEN[h->off + idx];
+        if (x > 14) { ext |= linbitsx; xbits += h->linbits; }
+        if (x != 0) { ext <<= 1; ext |= signx; xbits += 1; }
+        if (y > 14) { ext <<= h->linbits; ext |= linbitsy; xbits += h->linbits; }
+        if (y != 0) { ext <<= 1; ext |= signy; xbits += 1; }
+    } else {
+        idx = (unsigned)x * h->ylen + (unsigned)y;
+        code = MP3T_HCODE[h->off + idx]; cbits = MP3T_HLEN[h->off + idx];
+        if (x != 0) { code <<= 1; code |= signx; cbits += 1; }
+        if (y != 0) { code <<= 1; code |= signy; cbits += 1; }
+    }
+    if (cbits) fmt_main(F, code, (unsigned)cbits);
+    if (xbits) fmt_main(F, ext, (unsigned)xbits);
+    return cbits + xbits;
+}
+
+static int fmt_count1_quad(fmt_t *F, int t, int v, int w, int x, int y) /* l3bitstream.c:728-767 */
+{
+    unsigned sv = v < 0, sw = w < 0, sx = x < 0, sy = y < 0, p;
+    int len, total;
+    const mp3t_huff_desc *h = &MP3T_HUFF[t];
+    v = abs(v); w = abs(w); x = abs(x); y = abs(y);
+    p = (unsigned)(v + (w << 1) + (x << 2) + (y << 3));
+    len = MP3T_HLEN[h->off + p];
+    fmt_main(F, MP3T_HCODE[h->off + p], (unsigned)len);
+    total = len;
+    if (v) { fmt_main(F, sv, 1); total++; }
+    if (w) { fmt_main(F, sw, 1); total++; }
+    if (x) { fmt_main(F, sx, 1); total++; }
+    if (y) { fmt_main(F, sy, 1); total++; }
+    return total;
+}
+
+static void fmt_granule(fmt_t *F, const l3o_frame *fr, int gr, int ch, int sr)
+{
+    static const unsigned slen1_tab[16] = {0, 0, 0, 0, 3, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4};
+    static const unsigned slen2_tab[16] = {0, 1, 2, 3, 0, 1, 2, 3, 1, 2, 3, 1, 2, 3, 2, 3};
+    const l3o_gr_info *g = &fr->gi[gr][ch];
+    unsigned slen1 = slen1_tab[g->scalefac_compress], slen2 = slen2_tab[g->scalefac_compress];
+    int ix[576], i, sfb, w, bits = 0, bigvalues, count1_end, stuffing;
+    for (i = 0; i < 576; i++) { ix[i] = fr->ix[gr][ch][i]; if (fr->xr[gr][ch][i] < 0 && ix[i] > 0) ix[i] = -ix[i]; } /* :115-125 */
+    /* scalefactors, l3bitstream.c:196-251 (no mixed blocks) */
+    if (g->window_switching_flag == 1 && g->block_type == 2) {
+        for (sfb = 0; sfb < 6; sfb++) for (w = 0; w < 3; w++) fmt_main(F, (unsigned)fr->scalefac_s[gr][ch][sfb][w], slen1);
+        for (sfb = 6; sfb < 12; sfb++) for (w = 0; w < 3; w++) fmt_main(F, (unsigned)fr->scalefac_s[gr][ch][sfb][w], slen2);
+    } else {
+        const int *sc = fr->scfsi[ch];
+        if (gr == 0 || sc[0] == 0) for (sfb = 0; sfb < 6; sfb++) fmt_main(F, (unsigned)fr->scalefac_l[gr][ch][sfb], slen1);
+        if (gr == 0 || sc[1] == 0) for (sfb = 6; sfb < 11; sfb++) fmt_main(F, (unsigned)fr->scalefac_l[gr][ch][sfb], slen1);
+        if (gr == 0 || sc[2] == 0) for (sfb = 11; sfb < 16; sfb++) fmt_main(F, (unsigned)fr->scalefac_l[gr][ch][sfb], slen2);
+        if (gr == 0 || sc[3] == 0) for (sfb = 16; sfb < 21; sfb++) fmt_main(F, (unsigned)fr->scalefac_l[gr][ch][sfb], slen2);
+    }
+    /* Huffmancodebits, l3bitstream.c:517-716 */
+    bigvalues = g->big_values * 2;
+    if (bigvalues) {
+        if (g->window_switching_flag && g->block_type == 2) {
+            const short *sf = MP3T_SFB_SHORT[sr];
+            for (sfb = 0; sfb < 13; sfb++) {
+                int start = sf[sfb], end = sf[sfb + 1], line;
+                int t = (start < 12) ? g->table_select[0] : g->table_select[1];
+                for (w = 0; w < 3; w++)
+                    for (line = start; line < end; line += 2) bits += fmt_huffman_pair(F, t, ix[line * 3 + w], ix[(line + 1) * 3 + w]);
+            }
+        } else {
+            const short *sf = MP3T_SFB_LONG[sr];
+            int r1 = sf[g->region0_count + 1], r2 = sf[g->region0_count + 1 + g->region1_count + 1];
+            for (i = 0; i < bigvalues; i += 2) {
+                int t = (i < r1) ? g->table_select[0] : (i < r2) ? g->table_select[1] : g->table_select[2];
+                if (t) bits += fmt_huffman_pair(F, t, ix[i], ix[i + 1]);
+            }
+        }
+    }
+    count1_end = bigvalues + g->count1 * 4;
+    for (i = bigvalues; i < count1_end; i += 4) bits += fmt_count1_quad(F, 32 + g->count1table_select, ix[i], ix[i + 1], ix[i + 2], ix[i + 3]);
+    stuffing = g->part2_3_length - g->part2_length - bits;
+    if (stuffing > 0) { while (stuffing >= 32) { fmt_main(F, ~0u, 32); stuffing -= 32; } if (stuffing) fmt_main(F, ~0u, (unsigned)stuffing); }
+}
+
+/* Whole stream: frames (from l3o_encode_stream) -> the byte stream the reference CLI writes, INCLUDING the trailing
+ * byte close_bit_stream_w() emits (common.c:968-974 writes buf_byte_idx+1 bytes).  main_data_begin of every frame
+ * is returned in mdb[n_frames] when non-NULL.  Returns the number of bytes, or -1 if `cap` is too small. */
+long l3o_format_stream(int sfreq, int n_ch, int bitrate_kbps, const l3o_frame *frames, long n_frames, unsigned char *out, long cap,
+                       int *mdb)
+{
+    static const int rates[15] = {0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320};
+    fmt_t F;
+    long f, len;
+    int gr, ch, i, br_idx = 0, sr = (sfreq == 32000) ? 0 : (sfreq == 44100) ? 1 : 2;
+    int sf_idx = (sfreq == 44100) ? 0 : (sfreq == 48000) ? 1 : 2;   /* header index, common.c s_freq[] order */
+    int main_data_begin = 0;
+    init_common();
+    for (i = 1; i < 15; i++) if (rates[i] == bitrate_kbps) br_idx = i;
+    memset(&F, 0, sizeof(F));
+    F.buf = out; F.cap = cap; memset(out, 0, (size_t)cap);
+    F.q_cap = 64; F.q = calloc((size_t)F.q_cap, 40);
+    F.si_bits = 32 + (n_ch == 2 ? 256 : 136);
+    F.frame_bits = 8 * (int)((1152.0 / (sfreq / 1000.0)) * ((double)bitrate_kbps / 8.0));
+    for (f = 0; f < n_frames; f++) {
+        const l3o_frame *fr = &frames[f];
+        sip_t s;
+        int elements = 0, fwd_frame = 0, fwd_si = 0;
+        /* encodeSideInfo + store_side_info */
+        if (F.q_tail - F.q_head >= F.q_cap) { free(F.q); return -1; }
+        s.p = F.q[F.q_tail % F.q_cap]; s.n = 0; memset(s.p, 0, 40);
+        si_put(&s, 0xfff, 12); si_put(&s, 1, 1); si_put(&s, 4 - 3, 2); si_put(&s, 1, 1); si_put(&s, (unsigned)br_idx, 4);
+        si_put(&s, (unsigned)sf_idx, 2); si_put(&s, 0, 1); si_put(&s, 0, 1); si_put(&s, n_ch == 2 ? 0 : 3, 2); si_put(&s, 0, 2);
+        si_put(&s, 0, 1); si_put(&s, 0, 1); si_put(&s, 0, 2);
+        si_put(&s, (unsigned)main_data_begin, 9); si_put(&s, 0, n_ch == 2 ? 3 : 5);
+        if (mdb) mdb[f] = main_data_begin;
+        for (ch = 0; ch < n_ch; ch++) for (i = 0; i < 4; i++) si_put(&s, (unsigned)fr->scfsi[ch][i], 1);
+        for (gr = 0; gr < 2; gr++)
+            for (ch = 0; ch < n_ch; ch++) {
+                const l3o_gr_info *g = &fr->gi[gr][ch];
+                si_put(&s, (unsigned)g->part2_3_length, 12); si_put(&s, (unsigned)g->big_values, 9); si_put(&s, (unsigned)g->global_gain, 8);
+                si_put(&s, (unsigned)g->scalefac_compress, 4); si_put(&s, (unsigned)g->window_switching_flag, 1);
+                if (g->window_switching_flag) {
+                    si_put(&s, (unsigned)g->block_type, 2); si_put(&s, (unsigned)g->mixed_block_flag, 1);
+                    si_put(&s, (unsigned)g->table_select[0], 5); si_put(&s, (unsigned)g->table_select[1], 5);
+                    si_put(&s, 0, 3); si_put(&s, 0, 3); si_put(&s, 0, 3);      /* subblock_gain, always 0 */
+                } else {
+                    si_put(&s, (unsigned)g->table_select[0], 5); si_put(&s, (unsigned)g->table_select[1], 5); si_put(&s, (unsigned)g->table_select[2], 5);
+                    si_put(&s, (unsigned)g->region0_count, 4); si_put(&s, (unsigned)g->region1_count, 3);
+                }
+                si_put(&s, (unsigned)g->preflag, 1); si_put(&s, (unsigned)g->scalefac_scale, 1); si_put(&s, (unsigned)g->count1table_select, 1);
+            }
+        F.q_tail++;
+        /* main_data(), formatBitstream.c:187-205 */
+        for (gr = 0; gr < 2; gr++) for (ch = 0; ch < n_ch; ch++) fmt_granule(&F, fr, gr, ch, sr);
+        { int d = fr->resv_drain; while (d >= 32) { fmt_main(&F, 0, 32); d -= 32; } if (d) fmt_main(&F, 0, (unsigned)d); }   /* :497-513 */
+        /* nextBackPtr, formatBitstream.c:76-79 */
+        for (i = F.q_head; i < F.q_tail; i++) { elements++; fwd_frame += F.frame_bits; fwd_si += F.si_bits; }
+        main_data_begin = (int)(F.bits_remaining / 8) + fwd_frame / 8 - fwd_si / 8;
+    }
+    /* BF_FlushBitstream, formatBitstream.c:87-125 */
+    if (F.q_tail > F.q_head) {
+        long rem = (long)(F.q_tail - F.q_head) * (F.frame_bits - F.si_bits);
+        while (rem >= 32) { fmt_main(&F, 0, 32); rem -= 32; }
+        fmt_main(&F, 0, (unsigned)rem);
+    }
+    free(F.q);
+    len = (F.nbits >> 3) + 1;   /* empty_buffer(bs, buf_byte_idx) writes the partially filled byte too */
+    return len <= cap ? len : -1;
+}

@@ -74,6 +74,12 @@ int l3o_quantize_count(const double *xr_abs, int q, int block_type, int sr_idx, 
 /* count_bits on a given ix (bit-exact Huffman bit count + table selection) */
 int l3o_count_bits(const int *ix, int block_type, int sr_idx, l3o_gr_info *gi);
 
+/* Bitstream formatter (l3bitstream.c + formatBitstream.c restated): frames -> the byte stream the reference CLI
+ * writes, including the one trailing byte close_bit_stream_w() adds.  mdb[n_frames] (optional) receives
+ * main_data_begin of each frame.  Returns the byte count, -1 if cap is too small. */
+long l3o_format_stream(int sfreq, int n_ch, int bitrate_kbps, const l3o_frame *frames, long n_frames, unsigned char *out, long cap,
+                       int *mdb);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,8 @@ def lib():
         L.l3o_fft.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.l3o_quantize_count.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.l3o_count_bits.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.l3o_format_stream.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_void_p]
+        L.l3o_format_stream.restype = C.c_long
         _lib = L
     return _lib
 
@@ -117,3 +119,15 @@ def count_bits(ix, block_type, sr_idx):
     g = GrInfo()
     bits = lib().l3o_count_bits(ix.ctypes.data, int(block_type), int(sr_idx), C.byref(g))
     return bits, np.array(gi_row(g), dtype=np.int32)
+
+
+def format_stream(frames, n_ch, sfreq=44100, bitrate=128):
+    """frames: FRAME_DT array from encode_stream -> (bytes the reference CLI writes, main_data_begin per frame)"""
+    frames = np.ascontiguousarray(frames)
+    n = frames.shape[0]
+    cap = n * 1440 + 16
+    out = np.zeros(cap, dtype=np.uint8)
+    mdb = np.zeros(n, dtype=np.int32)
+    ln = lib().l3o_format_stream(sfreq, n_ch, bitrate, frames.ctypes.data, n, out.ctypes.data, cap, mdb.ctypes.data)
+    assert ln >= 0
+    return out[:ln].tobytes(), mdb

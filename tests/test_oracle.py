@@ -11,7 +11,9 @@ import pytest
 
 import oracle
 import ref_harness
-from util import oracle_flat
+import os
+
+from util import ROOT, oracle_flat
 
 XR_TOL = 5e-14   # the oracle uses the plain 36-term dot product for block type 0; the reference's hand-unrolled
                  # form (mdct.c:199-509) only differs in summation order (measured <= 2e-14 at |xr| <= 1.5)
@@ -105,3 +107,17 @@ def test_stage_functions_consistent():
             for col in (1, 2, 8, 9, 10, 11, 12, 15):
                 assert gi[col] == o["gi"][f, 0, 0][col]
             break
+
+
+@pytest.mark.parametrize("name", ["cfg1_44k_stereo_128", "cfg2_32k_mono_64", "cfg3_48k_stereo_320", "loud_44k_stereo_128",
+                                  "scfsi_44k_stereo_128"])
+def test_oracle_formatter_matches_reference_cli_bytes(golden, name):
+    """the oracle's sequential bitstream formatter (l3bitstream.c + formatBitstream.c restated) reproduces the byte
+    stream the unmodified reference CLI wrote (tests/golden/cli_*.mp3 == the npz's `mp3`), incl. the back pointers"""
+    g = golden[name]
+    pcm, fs, br = g["pcm"], int(g["sfreq"]), int(g["bitrate"])
+    fr = oracle.encode_stream(pcm, fs, br)
+    data, mdb = oracle.format_stream(fr, pcm.shape[0], fs, br)
+    ref = open(os.path.join(ROOT, "tests", "golden", "cli_%s.mp3" % name), "rb").read()
+    assert data == ref and data == bytes(g["mp3"])
+    assert np.array_equal(mdb[1:], g["main_data_begin_next"][:-1]) and mdb[0] == 0
