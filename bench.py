@@ -6,9 +6,10 @@ Workload (BASELINE.json configs[3], the configuration the metric is quoted on): 
 seed per clip).  One "step" = one pass of the whole hot path over the rank's batch.  Streams are independent,
 so ranks just take their own batch — no data-path collective, "scaling": "weak" (per-GPU batch fixed).
 
-  value : whole-job throughput with the PCM already resident in HBM (mp3gpu_encode_frames_dev)
-  e2e   : the same through the reference-facing C ABI with HOST buffers (mp3gpu_encode_frames): pinned
-          host PCM -> H2D -> kernels -> D2H of quantised spectra + side info, all inside the timed region
+  value : whole-job throughput with the PCM already resident in HBM (mp3gpu_encode_frames_mp3_dev: psy, filterbank,
+          MDCT, rate loop + reservoir, and the device bitstream formatter; MP3 bytes land in a device buffer)
+  e2e   : the same through the reference-facing C ABI with HOST buffers (mp3gpu_encode_frames_mp3): pinned
+          host PCM -> H2D -> kernels -> D2H of the finished MP3 byte streams, all inside the timed region
   roofline : fused polyphase+MDCT front-end kernel, algorithmic bytes (5764 B per granule-channel,
           FP64 path) / CUDA-event time of that kernel, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline : the unmodified reference CLI encoder (oracle/_ref/encode), one process per host core
@@ -31,7 +32,10 @@ sys.path.insert(0, ROOT)
 
 FS, NCH, KBPS = 44100, 2, 128
 BYTES_PER_GC = {"front_polyphase_mdct": 5764, "psy_front": 1152 + 1568, "psy_scan": 1568 + 472,
-                "rate_loop": 4608 + 472 + 1152 + 80 + 40}
+                "rate_loop": 4608 + 472 + 1152 + 80 + 40, "bitstream": 1152 + 80 + 40 + 417 // 4}
+# DRAM bytes per granule-channel of k_front_tile from the ncu --set full capture profiles/r01_b_capture.md
+# (dram__bytes_read.sum + dram__bytes_write.sum = 173.4 + 547.3 MB for 131 072 gc)
+FRONT_TRAFFIC_PER_GC = (173.369856e6 + 547.285248e6) / 131072
 
 
 def shard_range(n, rank, world):
@@ -223,28 +227,23 @@ def main():
     host_chunks = [torch.empty(c.shape, dtype=torch.int16, pin_memory=True) for c in dev_chunks]
     for h, d in zip(host_chunks, dev_chunks):
         h.copy_(d)
-    gcs = lambda n: n * 2 * NCH
-    dev_out = [dict(ix=torch.empty((S, gcs(n), 576), dtype=torch.int16, device=device),
-                    gi=torch.empty((S, gcs(n), 20), dtype=torch.int32, device=device),
-                    sf=torch.empty((S, gcs(n), 40), dtype=torch.uint8, device=device),
-                    fo=torch.empty((S, n, 16), dtype=torch.uint8, device=device)) for _, n in chunks[:2]]
-    host_out = [dict(ix=torch.empty((S, gcs(n), 576), dtype=torch.int16, pin_memory=True).numpy(),
-                     gi=torch.empty((S, gcs(n), 20), dtype=torch.int32, pin_memory=True).numpy(),
-                     sf=torch.empty((S, gcs(n), 40), dtype=torch.uint8, pin_memory=True).numpy(),
-                     fo=torch.empty((S, n, 16), dtype=torch.uint8, pin_memory=True).numpy()) for _, n in chunks]
+    mp3_bytes = n_frames * enc.frame_bytes
+    mp3_dev = torch.zeros((S, mp3_bytes), dtype=torch.uint8, device=device)
+    mp3_host = torch.zeros((S, mp3_bytes), dtype=torch.uint8, pin_memory=True)
     stream = torch.cuda.current_stream(device)
     sptr = stream.cuda_stream
 
     def step_dev():
         enc.reset()
         for i, (a, n) in enumerate(chunks):
-            o = dev_out[0] if n == chunks[0][1] else dev_out[-1]
-            enc.encode_frames_dev(dev_chunks[i], out=o, stream=sptr)
+            enc.encode_frames_mp3_dev(dev_chunks[i], mp3_dev, stream=sptr)
+        return enc.flush_mp3(mp3_dev, S, stream=sptr)
 
     def step_host():
         enc.reset()
         for i, (a, n) in enumerate(chunks):
-            enc.encode_frames(host_chunks[i].numpy(), out=host_out[i], stream=sptr, sync=False)
+            enc.encode_frames_mp3(host_chunks[i].numpy(), mp3_host.numpy(), stream=sptr)
+        return enc.flush_mp3(mp3_host.numpy(), S, stream=sptr)
 
     def timed(fn, k):
         if world > 1:
@@ -311,11 +310,15 @@ def main():
                    "l2": "inputs larger than L2: %.1f GB PCM and %.1f GB of spectra per step" % (
                        S * n_frames * 1152 * NCH * 2 / 1e9, gc_per_step * 4608 / 1e9)},
         "e2e": {"value": audio_total / t_host_max, "unit": "audio-s/s",
-                "h2d_bytes_per_step": int(S * n_frames * 1152 * NCH * 2), "d2h_bytes_per_step": int(gc_per_step * (1152 + 80 + 40) + S * n_frames * 16)},
+                "h2d_bytes_per_step": int(S * n_frames * 1152 * NCH * 2), "d2h_bytes_per_step": int(S * mp3_bytes + 4 * S),
+                "output": "finished MPEG-1 Layer III byte streams (device bitstream formatter), %d bytes per clip" % mp3_bytes},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_front (fused polyphase filterbank + MDCT + alias reduction, FP64 exact path)",
                      "achieved": fk["achieved_gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": fk["frac_hbm"],
-                     "traffic": None},
+                     "traffic": FRONT_TRAFFIC_PER_GC * S * chunks[0][1] * 2 * NCH,
+                     "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per granule-channel "
+                                       "(profiles/r01_b_capture.md) x granule-channels per launch",
+                     "achieved_per_launch_bytes": 5764 * S * chunks[0][1] * 2 * NCH},
         "kernels": kernels,
         "clocks": clocks,
     }

@@ -277,6 +277,12 @@ struct mp3gpu_ctx {
     int frame_bytes = 0, si_bytes = 0, tail_frames = 0;
     long wstride = 0;
     long frames_done = 0;      // frames already formatted per stream (all streams of a ctx advance in lockstep)
+    // host-PCM ingest: double-buffered dense staging filled on a private copy stream, so that the H2D copy of
+    // call i+1 overlaps the kernels of call i (the caller only ever sees its own stream)
+    cudaStream_t copy_stream = nullptr;
+    short *h2d_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    int h2d_turn = 0;
     long launches = 0;
     // per-kernel timing (mp3gpu_profile_*): events bracket every launch of the four hot kernels
     int prof_on = 0;
@@ -423,6 +429,12 @@ extern "C" void mp3gpu_destroy(mp3gpu_ctx *c)
                     c->d_sb_prev, c->d_mid, c->d_psyout, c->d_xr, c->d_ix, c->d_gi, c->d_sf, c->d_fo,
                     c->d_bit_tab, c->d_win, c->d_win_tmp, c->d_next_begin};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < 2; i++) {
+        if (c->h2d_stage[i]) cudaFree(c->h2d_stage[i]);
+        if (c->ev_ready[i]) cudaEventDestroy(c->ev_ready[i]);
+        if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
 
@@ -506,6 +518,31 @@ static int stage_pcm(mp3gpu_ctx *c, PcmStage &st, const int16_t *pcm, int n_stre
     }
     const size_t w = (size_t)n_frames * 1152 * sizeof(short);
     CU(cudaMemcpy2DAsync(st.buf + HIST, c->row * sizeof(short), pcm, w, w, (size_t)n_streams * c->cfg.n_ch, kind, q));
+    return 0;
+}
+
+// host PCM -> rows of the main staging buffer through the double-buffered copy stream (see mp3gpu_ctx)
+static int stage_pcm_host_overlapped(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, cudaStream_t q)
+{
+    const size_t cap = (size_t)c->cfg.max_streams * c->cfg.n_ch * c->cfg.max_frames * 1152;
+    if (!c->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            int rc = dalloc(&c->h2d_stage[i], cap);
+            if (rc) return rc;
+            CU(cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+        }
+    }
+    const int t = c->h2d_turn;
+    c->h2d_turn ^= 1;
+    const size_t rows = (size_t)n_streams * c->cfg.n_ch, w = (size_t)n_frames * 1152 * sizeof(short);
+    CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[t], 0));       // the D2D that last read this buffer is done
+    CU(cudaMemcpyAsync(c->h2d_stage[t], pcm, rows * w, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaEventRecord(c->ev_ready[t], c->copy_stream));
+    CU(cudaStreamWaitEvent(q, c->ev_ready[t], 0));
+    CU(cudaMemcpy2DAsync(c->pcm_main.buf + HIST, c->row * sizeof(short), c->h2d_stage[t], w, w, rows, cudaMemcpyDeviceToDevice, q));
+    CU(cudaEventRecord(c->ev_free[t], q));
     return 0;
 }
 
@@ -597,7 +634,9 @@ static int encode_common(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n
     if (!pcm) return fail(MP3GPU_EINVAL, "null pcm");
     cudaStream_t q = (cudaStream_t)stream;
     const size_t gcs = (size_t)n_streams * n_frames * 2 * c->cfg.n_ch;
-    if ((rc = stage_pcm(c, c->pcm_main, pcm, n_streams, n_frames, host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, q))) return rc;
+    if (host) rc = stage_pcm_host_overlapped(c, pcm, n_streams, n_frames, q);
+    else rc = stage_pcm(c, c->pcm_main, pcm, n_streams, n_frames, cudaMemcpyDeviceToDevice, q);
+    if (rc) return rc;
     // musicin.c:751-779 order: psy first (it decides block_type), then filterbank + MDCT, then the rate loop
     if ((rc = launch_psy(c, c->pcm_main.buf, n_streams, n_frames, c->d_psyout, q))) return rc;
     if ((rc = launch_front(c, c->pcm_main.buf, c->d_psyout, n_streams, n_frames, c->d_xr, nullptr, true, q))) return rc;
