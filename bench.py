@@ -169,7 +169,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("MP3GPU_BENCH_STREAMS", 4096)), help="clips per GPU")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("MP3GPU_BENCH_STREAMS", 0)),
+                    help="clips per GPU (default: one full wave of the rate loop, mp3gpu_stream_wave(): 3552 on a B200)")
     ap.add_argument("--seconds", type=float, default=10.0, help="clip length")
     ap.add_argument("--chunk-frames", type=int, default=32, help="frames per stream per library call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -180,7 +181,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     n_frames = int(args.seconds * FS) // 1152          # whole frames per clip (383 for 10 s)
     audio_per_stream = n_frames * 1152 / FS
-    workload = "batch of %d x %.0f s synthetic 44.1 kHz stereo clips at 128 kbps per GPU (BASELINE configs[3])" % (args.streams, args.seconds)
+    wl = lambda n: "batch of %d x %.0f s synthetic 44.1 kHz stereo clips at 128 kbps per GPU (BASELINE configs[3])" % (n, args.seconds)
+    workload = wl(args.streams or 3552)
 
     if args.impl == "reference":
         if rank != 0:
@@ -212,6 +214,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
+    if not args.streams:
+        args.streams = mod.host.stream_wave(local_rank)
+        workload = wl(args.streams)
     S, F = args.streams, min(args.chunk_frames, n_frames)
     chunks = []
     f0 = 0

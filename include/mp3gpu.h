@@ -92,6 +92,9 @@ int mp3gpu_create(const mp3gpu_config *cfg, mp3gpu_ctx **out);
 void mp3gpu_destroy(mp3gpu_ctx *ctx);
 /* forget all per-stream state (filterbank/MDCT history, psy history, reservoir): start of new streams */
 int mp3gpu_reset(mp3gpu_ctx *ctx);
+/* number of streams that fills the device exactly once in the rate loop (one warp per stream); batches that are a
+ * multiple of it leave no partially filled last wave.  Negative MP3GPU_E* on error. */
+int mp3gpu_stream_wave(int device);
 /* frame geometry the reference derives in musicin.c:562-572,729-746 */
 int mp3gpu_frame_geometry(const mp3gpu_ctx *ctx, int *bits_per_frame, int *mean_bits);
 

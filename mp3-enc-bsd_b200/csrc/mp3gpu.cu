@@ -145,7 +145,10 @@ __device__ __forceinline__ const RateHot &load_rate_hot(const RateTables *gT, un
     return *reinterpret_cast<const RateHot *>(smem_raw);
 }
 
-__global__ void __launch_bounds__(RL_WARPS * 32, 2)
+#ifndef RL_MIN_CTAS
+#define RL_MIN_CTAS 3     // 80 registers, 24 warps per SM
+#endif
+__global__ void __launch_bounds__(RL_WARPS * 32, RL_MIN_CTAS)
 k_rate_loop(const RateTables *__restrict__ gT, FrameGeom G, LoopStreamState *states, LoopLaneState *lane_states, int n_streams, int n_frames,
             const double *__restrict__ xr, const PsyOut *__restrict__ psy, short *ix, GrInfoOut *gi, unsigned char *sf, FrameOut *fo)
 {
@@ -188,7 +191,7 @@ k_quantize_count(const RateTables *__restrict__ gT, const double *xr_abs, const 
         D2 x; x.x = xr_abs[i * 576 + e0]; x.y = xr_abs[i * 576 + e1];
         M.xs[s] = x;
     }
-    __syncwarp();
+    refresh_pow34(w, M);
     CountResult C;
     memset(&C, 0, sizeof(C));
     int qq = q[i];
@@ -326,7 +329,7 @@ static int upload_fft(const FftProgram &P, FftOpPacked **ops, int **lv, uint16_t
     if ((rc = dalloc(lv, P.level_start.size()))) return rc;
     if ((rc = dalloc(out, (size_t)P.n))) return rc;
     std::vector<uint16_t> o(P.n);
-    for (int i = 0; i < P.n; i++) o[i] = (uint16_t)(P.out_slot[i] | (P.out_neg[i] ? 0x8000 : 0));
+    for (int i = 0; i < P.n; i++) o[i] = (uint16_t)(FFT_SKEW((unsigned)P.out_slot[i]) | (P.out_neg[i] ? 0x8000 : 0));
     CU(cudaMemcpy(*ops, P.packed.data(), P.packed.size() * sizeof(FftOpPacked), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(*lv, P.level_start.data(), P.level_start.size() * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(*out, o.data(), o.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
@@ -725,6 +728,19 @@ extern "C" int mp3gpu_begin_segment(mp3gpu_ctx *c, void *stream)
     CU(cudaMemsetAsync(c->d_next_begin, 0, (size_t)c->cfg.max_streams * sizeof(int), q));
     c->frames_done = 0;
     return 0;
+}
+
+// Streams that fill the GPU exactly once in the rate loop (one warp per stream): SMs x resident CTAs x warps per CTA.
+// Batches that are a multiple of this have no partially filled last wave.
+extern "C" int mp3gpu_stream_wave(int device)
+{
+    int sms = 0, ctas = 0;
+    if (cudaSetDevice(device) != cudaSuccess) return fail(MP3GPU_ECUDA, "cudaSetDevice failed");
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return fail(MP3GPU_ECUDA, "no device attribute");
+    cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_rate_loop, RL_WARPS * 32, RL_SMEM_BYTES) != cudaSuccess || ctas < 1)
+        return fail(MP3GPU_ECUDA, "occupancy query failed");
+    return sms * ctas * RL_WARPS;
 }
 
 extern "C" int mp3gpu_frame_bytes(const mp3gpu_ctx *c, int *frame_bytes, int *sideinfo_bytes)

@@ -46,24 +46,24 @@ struct PsyMid {
     float e6[8], phi6[8];
 };
 
-// 6176 B per warp (8 warps per CTA, 4 CTAs per SM).  x[] holds the FFT working set; everything that is
+// 6304 B per warp (8 warps per CTA, 4 CTAs per SM).  x[] holds the FFT working set; everything that is
 // produced after a transform and consumed before the next one that needs the space is overlaid on it:
 //   after the LONG FFT only x[0..255] is reused (short transforms), so Es / Ps live in x[256..819];
 //   after the last SHORT FFT x[0..255] is free: cwv and eb live there; thr overlays E[] once the long
 //   partition energies have been formed (E is dead by then).
 struct PsyFrontSmem {
-    float x[1024];
+    float x[FFT_X_WORDS];
     float E[520];
 };
 struct PsyFrontView {
     float *x, *E;
-    float (*Es)[132];   // [3][132] at x + 256
-    float (*Ps)[56];    // [3][56]  at x + 652
+    float (*Es)[132];   // [3][132] at x + 272 (the short transforms use skewed x[0..263])
+    float (*Ps)[56];    // [3][56]  at x + 668
     double *cwv;        // [52]  at x + 0   (after the short FFTs)
     double *eb;         // [64]  at x + 104
     double *thr;        // [64]  at E + 0   (after the long partition energies)
     SIMT_FN explicit PsyFrontView(PsyFrontSmem &S)
-        : x(S.x), E(S.E), Es(reinterpret_cast<float (*)[132]>(S.x + 256)), Ps(reinterpret_cast<float (*)[56]>(S.x + 652)),
+        : x(S.x), E(S.E), Es(reinterpret_cast<float (*)[132]>(S.x + 272)), Ps(reinterpret_cast<float (*)[56]>(S.x + 668)),
           cwv(reinterpret_cast<double *>(S.x)), eb(reinterpret_cast<double *>(S.x + 104)), thr(reinterpret_cast<double *>(S.E)) {}
 };
 
@@ -88,8 +88,9 @@ SIMT_FN void fft_exec(FftOpPacked op, const FftTwiddle *tw, float *x)
 {
     const double SQ = 0.707106781186547524401;  // SQHALF, subs.c:26
     const unsigned lo = (unsigned)op, hi = (unsigned)(op >> 32);
-    const int ia = lo & 1023, ib = (lo >> 10) & 1023, ic = (lo >> 20) & 1023, id = ((lo >> 30) | (hi << 2)) & 1023;
-    const int type = (hi >> 18) & 7, neg = (hi >> 21) & 15;
+    const int type = (hi >> 22) & 7, neg = (hi >> 25) & 15;
+    if (type == FFT_NOP) return;
+    const int ia = lo & 2047, ib = (lo >> 11) & 2047, ic = ((lo >> 22) | (hi << 10)) & 2047, id = (hi >> 1) & 2047;
     float a = x[ia], c, b, d, t1, t2;
     if (neg & 1) a = -a;
     switch (type) {
@@ -109,7 +110,7 @@ SIMT_FN void fft_exec(FftOpPacked op, const FftTwiddle *tw, float *x)
         break;
     case FFT_ROT: {
         c = x[ic]; if (neg & 4) c = -c;
-        const FftTwiddle w = tw[(hi >> 8) & 1023];
+        const FftTwiddle w = tw[(hi >> 12) & 1023];
         t2 = simt::fmul(w.cn, simt::fadd(a, c));
         t1 = simt::fadd(simt::fmul(w.spcn, a), t2);
         x[ia] = simt::fadd(simt::fmul(w.smcn, c), t2);
@@ -135,17 +136,15 @@ SIMT_FN void fft_run(const WarpCtx &w, const FftDev &P, const FftTwiddle *tw, fl
     for (int l = 0; l < P.n_levels; l++) {
         const int lo = P.level_start[l], hi = P.level_start[l + 1];
         FOR_THREADS(w)
-        int i = lo + lane;
-        if (i < hi) {
-            FftOpPacked op = P.ops[i];
-            for (;;) {                       // the next op is in flight while this one executes
-                const int nx = i + 32;
-                const bool more = nx < hi;
-                const FftOpPacked nxt = P.ops[more ? nx : i];
-                fft_exec(op, tw, x);
-                if (!more) break;
-                op = nxt; i = nx;
-            }
+        int i = lo + lane;               // levels are whole rows of 32 ops (FFT_NOP padded)
+        FftOpPacked op = P.ops[i];
+        for (;;) {                       // the next op is in flight while this one executes
+            const int nx = i + 32;
+            const bool more = nx < hi;
+            const FftOpPacked nxt = P.ops[more ? nx : i];
+            fft_exec(op, tw, x);
+            if (!more) break;
+            op = nxt; i = nx;
         }
         END_THREADS
         w.sync();
@@ -194,7 +193,7 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
     PsyFrontView M(S);
     // long window + FFT, l3psy.c:483-494
     FOR_THREADS(w)
-    for (int j = lane; j < 1024; j += 32) M.x[j] = simt::fmul(T.hann_l[j], (float)(int)pcm[j - 768]);
+    for (int j = lane; j < 1024; j += 32) M.x[FFT_SKEW(j)] = simt::fmul(T.hann_l[j], (float)(int)pcm[j - 768]);
     END_THREADS
     w.sync();
     fft_run(w, D.f1024, D.tw, M.x);
@@ -210,7 +209,7 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
     // three short FFTs, l3psy.c:518-527
     for (int sb = 0; sb < 3; sb++) {
         FOR_THREADS(w)
-        for (int j = lane; j < 256; j += 32) M.x[j] = simt::fmul(T.hann_s[j], (float)(int)pcm[j - 768 + 128 * (2 + sb)]);
+        for (int j = lane; j < 256; j += 32) M.x[FFT_SKEW(j)] = simt::fmul(T.hann_s[j], (float)(int)pcm[j - 768 + 128 * (2 + sb)]);
         END_THREADS
         w.sync();
         fft_run(w, D.f256, D.tw, M.x);
@@ -267,11 +266,12 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
     for (int h = 0; h < 2; h++) {
         const int b = lane + 32 * h;
         float ecb = 0.0f;
-        if (b < 63) {
-            for (int k = T.spr_lo[b]; k <= T.spr_hi[b]; k++) {
-                double s = T.s3_l[b * 64 + k];
-                if (T.sparse || s != 1.0) ecb = (float)simt::dadd((double)ecb, simt::dmul(s, M.eb[k]));
-            }
+        // every lane walks the whole row range with a predicate: the transposed matrix makes each load one
+        // coalesced 256-byte request and eb[k] a broadcast; the terms are added in the reference's order
+        const int klo = (b < 63) ? T.spr_lo[b] : 1, khi = (b < 63) ? T.spr_hi[b] : 0;
+        for (int k = 0; k < 63; k++) {
+            const double s = T.s3_lT[k * 64 + b];
+            if (k >= klo && k <= khi && (T.sparse || s != 1.0)) ecb = (float)simt::dadd((double)ecb, simt::dmul(s, M.eb[k]));
         }
         out->ecb[b] = ecb;
     }
@@ -298,7 +298,7 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
             const int b = lane + 32 * h;
             if (b < 42) {
                 float ecb = 0.0f;
-                for (int k = 0; k < 42; k++) ecb = (float)simt::dadd((double)ecb, simt::dmul(T.s3_l[b * 64 + k], M.eb[k]));
+                for (int k = 0; k < 42; k++) ecb = (float)simt::dadd((double)ecb, simt::dmul(T.s3_lT[k * 64 + b], M.eb[k]));
                 float nb = (float)simt::dmul(simt::dmul((double)ecb, T.norm_l[b]), T.snr_s_exp[b]);
                 M.thr[b] = (T.qthr_s[b] > (double)nb) ? T.qthr_s[b] : (double)nb;
             }
@@ -400,9 +400,10 @@ SIMT_FN void psy_scan_step(const WarpCtx &w, const PsyTables &T, PsyScanSmem &M,
         const int b = lane + 32 * h;
         if (b < 63) {
             double ctb = 0.0;
-            for (int k = T.spr_lo[b]; k <= T.spr_hi[b]; k++) {
-                double s = T.s3_l[b * 64 + k];
-                if (T.sparse || s != 1.0) ctb = simt::dadd(ctb, simt::dmul(s, (double)M.cb[k]));
+            const int klo = T.spr_lo[b], khi = T.spr_hi[b];
+            for (int k = 0; k < 63; k++) {
+                const double s = T.s3_lT[k * 64 + b];
+                if (k >= klo && k <= khi && (T.sparse || s != 1.0)) ctb = simt::dadd(ctb, simt::dmul(s, (double)M.cb[k]));
             }
             const float ecb = mid.ecb[b];
             double cbb;

@@ -56,6 +56,7 @@ struct alignas(16) RateTables {
     double pow43[2048];         // p^(4/3) (loop.c:1017-1021)
     double step[512];           // 2^(q/4), q = -256..255 (loop.c:1020,1386); index q + 256
     double ostep[512];          // 1 / step
+    float ostep34[512];         // (1 / step)^(3/4): scales the cached |xr|^(3/4) estimates (quantize_all)
     unsigned char hlen[1412];   // Table B.7 code lengths, flat (table builders / diagnostics)
     unsigned short hoff[34];
     unsigned char hxlen[34], hlinbits[34];
@@ -98,9 +99,11 @@ struct FrameGeom {
 //                               2m+1 of window w (the [192][3] view of loop.c:1375-1376)
 struct alignas(16) D2 { double x, y; };
 struct U2 { unsigned short x, y; };
+struct F2 { float x, y; };
 struct alignas(16) RateWarpSmem {
     D2 xs[288];        // |xr| of the slot's two elements (amplified in place by the outer loop)
-    double scr[288];   // per-slot energies / noise for the band sums
+    double scr[288];   // per-slot energies / noise for the band sums; between refresh_pow34() and calc_noise it holds
+                       // F2 ys[288] = FP32 estimates of |xr|^(3/4), the probe-invariant part of the quantiser
     U2 ix[288];        // quantised values of the slot
 };
 
@@ -126,15 +129,17 @@ SIMT_NOINLINE int quant1_exact(const double *tab, double x, int p)
     return p;
 }
 
-SIMT_FN int quant1(const double *tab, double x)
+// x^(3/4) + 0.4054 estimated in FP32 as t = |xr|^(3/4) * (1/step)^(3/4) + 0.4054 from the cached per-slot power:
+// unless t lies within a conservative error margin of an integer (or is out of range / not a number) the
+// truncation is exact, otherwise the FP64 table comparison on |xr| / step decides.  The estimate's relative
+// error is < 2.2e-6 (two MUFU ops on |log2| <= 24, two FP32 roundings); the margin is 1e-5 * t + 1e-6.
+SIMT_FN int quant1(const double *tab, float t, const double *x, double ostep)
 {
-    const float e = pow075_estimate((float)x);
-    const float t = e + 0.4054f;
     const int p0 = (t < 2047.0f) ? (int)t : 2047;   // also catches inf / nan estimates
     const float d = t - (float)p0;
     const float margin = 1e-5f * t + 1e-6f;
     if (t < 2040.0f && d > margin && d < 1.0f - margin) return p0;
-    return quant1_exact(tab, x, p0);
+    return quant1_exact(tab, simt::dmul(*x, ostep), p0);
 }
 
 // libm calls that sit outside the hot loop are kept out of line: the kernel's working set of
@@ -144,23 +149,32 @@ SIMT_NOINLINE double ref_exp(double x) { return exp(x); }
 
 SIMT_FN int nint_ref(double in) { return (in < 0) ? (int)(in - 0.5) : (int)(in + 0.5); }
 
-// first table whose range covers max (loop.c:1813-1818 / 1921-1928): max in 1..14
+// The three small selectors below are nibble look-ups in 64-bit immediates instead of compare chains or table
+// walks: the probe is the hot loop of the kernel and its code must stay resident in the 32 KB instruction cache.
+
+// first table whose range covers max (loop.c:1813-1818 / 1921-1928): max in 1..14 -> 1,2,5,7,7,10,10,13..13
 SIMT_FN int table_for_small_max(int max)
 {
-    return (max == 1) ? 1 : (max == 2) ? 2 : (max == 3) ? 5 : (max <= 5) ? 7 : (max <= 7) ? 10 : 13;
+    return (int)((0xddddddddaa775210ull >> (4 * (max & 15))) & 15);
 }
 
+// first ESC table in [lo, hi) whose linmax covers m15 = max - 15 (loop.c:1873-1884, 1930-1941).
+// linmax is 2^linbits - 1, so the choice only depends on the bit length n of m15:
+//   tables 16..23 linbits 1,2,3,4,6,8,10,13   tables 24..31 linbits 4,5,6,7,8,9,11,13   (table 15: m15 == 0 only)
 SIMT_FN int esc_table(const RateHot &H, int lo, int hi, int m15)
 {
-    for (int i = lo; i < hi; i++)
-        if ((int)H.hlinmax[i] >= m15) return i;
-    return 0;
+    (void)H; (void)hi;
+    if (m15 <= 0 && lo == 15) return 15;
+    const int n = m15 > 0 ? 32 - simt::clz((unsigned)m15) : 0;       // 0..13
+    if (n > 13) return 0;
+    return (lo >= 24) ? 24 + (int)((0x77665432100000ull >> (4 * n)) & 15)
+                      : 16 + (int)((0x77766554432100ull >> (4 * n)) & 15);
 }
 
-// glut group of a region whose largest value is max (> 0)
+// glut group of a region whose largest value is max (> 0): 1->0, 2->1, 3->2, 4..5->3, 6..7->4, 8..14->5, 15->7, >15->6
 SIMT_FN int group_for_max(int max)
 {
-    return (max == 1) ? 0 : (max == 2) ? 1 : (max == 3) ? 2 : (max <= 5) ? 3 : (max <= 7) ? 4 : (max < 15) ? 5 : (max == 15) ? 7 : 6;
+    return max > 15 ? 6 : (int)((0x7555555544332100ull >> (4 * max)) & 15);
 }
 
 struct BandRegs {   // band per lane: band b lives in lane b & 31 of register b >> 5
@@ -186,21 +200,42 @@ SIMT_FN int slot_e0(bool is_short, int s)
 // > 1 (calc_runlen's scan, loop.c:1498-1517) since the values are at hand.
 SIMT_FN void quantize_all(const WarpCtx &w, const RateTables &T, RateWarpSmem &M, int q, PerThread<int> &nzmax, PerThread<int> &bigmax)
 {
-    const double ostep = T.ostep[(q > 255 ? 255 : q) + 256];
+    const int qi = (q > 255 ? 255 : q) + 256;
+    const double ostep = T.ostep[qi];
+    const float of = T.ostep34[qi];
+    const F2 *ys = reinterpret_cast<const F2 *>(M.scr);
     FOR_THREADS(w)
     int nz = -1, bg = -1;
 #pragma unroll 1
     for (int k = 0; k < 9; k++) {
         const int s = lane + 32 * k;
-        const D2 x = M.xs[s];
-        const int a = quant1(T.pow_nint_tab, simt::dmul(x.x, ostep));
-        const int b = quant1(T.pow_nint_tab, simt::dmul(x.y, ostep));
+        const F2 y = ys[s];
+        const int a = quant1(T.pow_nint_tab, simt::fadd(simt::fmul(y.x, of), 0.4054f), &M.xs[s].x, ostep);
+        const int b = quant1(T.pow_nint_tab, simt::fadd(simt::fmul(y.y, of), 0.4054f), &M.xs[s].y, ostep);
         U2 v; v.x = (unsigned short)a; v.y = (unsigned short)b;
         M.ix[s] = v;
         if ((a | b) != 0) nz = s;
         if (a > 1 || b > 1) bg = s;
     }
     nzmax() = nz; bigmax() = bg;
+    END_THREADS
+    w.sync();
+}
+
+// ys[s] = |xr|^(3/4) of the slot's two elements (FP32 estimate), into the scratch area: valid until calc_noise
+// overwrites it.  Called once per outer-loop iteration (xs only changes between iterations).
+SIMT_FN void refresh_pow34(const WarpCtx &w, RateWarpSmem &M)
+{
+    F2 *ys = reinterpret_cast<F2 *>(M.scr);
+    w.sync();
+    FOR_THREADS(w)
+#pragma unroll 1
+    for (int k = 0; k < 9; k++) {
+        const int s = lane + 32 * k;
+        const D2 x = M.xs[s];
+        F2 y; y.x = pow075_estimate((float)x.x); y.y = pow075_estimate((float)x.y);
+        ys[s] = y;
+    }
     END_THREADS
     w.sync();
 }
@@ -233,6 +268,7 @@ SIMT_FN int count_all(const WarpCtx &w, const RateHot &H, const RateWarpSmem &M,
             PerThread<int> acc;
             FOR_THREADS(w)
             int a = 0;
+#pragma unroll 1
             for (int t = lane; t < count1; t += 32) {
                 const U2 u = M.ix[bv + 2 * t], v = M.ix[bv + 2 * t + 1];
                 const int p = (u.x & 1) | ((u.y & 1) << 1) | ((v.x & 1) << 2) | ((v.y & 1) << 3);
@@ -577,6 +613,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
         PerThread<int> save_sf[2];
         do {
             iteration++;
+            refresh_pow34(w, M);
             part2 = part2_length_of(is_short, gr, compress, scfsi);
             const int huff_bits = max_bits - part2;
             // bin_search_StepSize(max_bits, ...) on the first iteration (loop.c:2119-2140), then inner_loop

@@ -89,6 +89,7 @@ SIMT_FN float fmul(float a, float b) { return __fmul_rn(a, b); }
 SIMT_FN float fadd(float a, float b) { return __fadd_rn(a, b); }
 SIMT_FN float fsub(float a, float b) { return __fsub_rn(a, b); }
 SIMT_FN int popc(unsigned v) { return __popc(v); }
+SIMT_FN int clz(unsigned v) { return __clz(v); }
 
 #else
 // ------------------------------------------------------------------------------------------------
@@ -139,6 +140,7 @@ inline float fmul(float a, float b) { return a * b; }
 inline float fadd(float a, float b) { return a + b; }
 inline float fsub(float a, float b) { return a - b; }
 inline int popc(unsigned v) { return __builtin_popcount(v); }
+inline int clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 #endif
 
 }  // namespace simt

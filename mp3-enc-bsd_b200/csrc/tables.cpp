@@ -116,6 +116,7 @@ void build_rate_tables(int sr, RateTables *R)
         double step = (q == 0) ? 1.0 : pow(2.0, (double)q * 0.25);
         R->step[q + 256] = step;
         R->ostep[q + 256] = 1.0 / step;
+        R->ostep34[q + 256] = (float)pow(1.0 / step, 0.75);
     }
     RateHot &H = R->hot;
     const double ifq = sqrt(2.);
@@ -222,6 +223,8 @@ void build_psy_tables(int sr, PsyTables *P)
     P->tail_l = k2;  // lines k2..512 keep the zero-initialised partition 0 (l3psy.c:93,805-806)
     for (int i = 0; i < L.n; i++)
         for (int j = 0; j < L.n; j++) P->s3_l[i * 64 + j] = spread_value(L.bval[i], L.bval[j], j >= i);
+    for (int i = 0; i < 63; i++)
+        for (int j = 0; j < 64; j++) P->s3_lT[j * 64 + i] = P->s3_l[i * 64 + j];
     k2 = 0;
     for (int i = 0; i < S.n; i++) {
         P->numlines_pe[i] = S.lines[i];  // l3psy.c:868 overwrites the long counts read at :796
@@ -392,11 +395,39 @@ void build_fft_program(int logm, const std::vector<int> &tw_base, FftProgram *P)
     });
     P->n = n; P->logm = logm;
     P->ops.clear(); P->level_start.assign(n_levels + 1, 0);
-    for (size_t i = 0; i < order.size(); i++) {
-        P->ops.push_back(B.ops[order[i]]);
-        P->level_start[level[order[i]]] = (int)i + 1;  // running "end of level l"
+    // Pack every level into rows of 32 ops (one op per lane).  A row holds ops of one operand shape only
+    // (butterfly / cross / the three rotations) and no two of its ops touch the same shared-memory bank with the
+    // same operand, so each of the row's loads and stores is a single wavefront; rows are padded with FFT_NOP.
+    {
+        auto cls = [](uint8_t t) { return t == FFT_BFLY ? 0 : t == FFT_CROSS ? 1 : 2; };
+        FftOp nop; memset(&nop, 0, sizeof(nop)); nop.a = nop.b = nop.c = nop.d = 0xffff; nop.type = FFT_NOP;
+        size_t i = 0;
+        for (int l = 1; l <= n_levels; l++) {
+            std::vector<int> grp[3];
+            for (; i < order.size() && level[order[i]] == l; i++) grp[cls(B.ops[order[i]].type)].push_back(order[i]);
+            for (int c = 0; c < 3; c++) {
+                std::vector<int> rem = grp[c];
+                while (!rem.empty()) {
+                    uint32_t used[4] = {0, 0, 0, 0};
+                    std::vector<int> rest;
+                    int in_row = 0;
+                    for (int id : rem) {
+                        const FftOp &o = B.ops[id];
+                        const uint16_t s4[4] = {o.a, o.b, o.c, o.d};
+                        bool ok = in_row < 32;
+                        uint32_t bit[4] = {0, 0, 0, 0};
+                        for (int j = 0; j < 4 && ok; j++)
+                            if (s4[j] != 0xffff) { bit[j] = 1u << (FFT_SKEW((unsigned)s4[j]) & 31); ok = !(used[j] & bit[j]); }
+                        if (ok) { for (int j = 0; j < 4; j++) used[j] |= bit[j]; P->ops.push_back(o); in_row++; }
+                        else rest.push_back(id);
+                    }
+                    for (; in_row < 32; in_row++) P->ops.push_back(nop);
+                    rem.swap(rest);
+                }
+            }
+            P->level_start[l] = (int)P->ops.size();
+        }
     }
-    for (int l = 1; l <= n_levels; l++) if (P->level_start[l] == 0) P->level_start[l] = P->level_start[l - 1];
     P->packed.clear();
     for (const FftOp &o : P->ops) P->packed.push_back(fft_pack(o));
     P->out_slot.resize(n); P->out_neg.resize(n);
@@ -409,6 +440,7 @@ void run_fft_program_host(const FftProgram &P, const std::vector<FftTwiddle> &tw
     for (size_t i = 0; i < P.ops.size(); i++) {
         const FftOp &o = P.ops[i];
         float a = 0, b = 0, c = 0, d = 0, t1, t2;
+        if (o.type == FFT_NOP) continue;
         if (o.a != 0xffff) a = (o.neg & 1) ? -x[o.a] : x[o.a];
         if (o.b != 0xffff) b = (o.neg & 2) ? -x[o.b] : x[o.b];
         if (o.c != 0xffff) c = (o.neg & 4) ? -x[o.c] : x[o.c];

@@ -32,7 +32,13 @@ enum FftOpType : uint8_t {
     FFT_ROT = 2,    // t2=cn*(a+c); t1=spcn*a+t2; a=smcn*c+t2; c=t1
     FFT_ROT8A = 3,  // t1=SQ*(a+c); c=SQ*(c-a); a=t1        (double multiply, rounded to float)
     FFT_ROT8B = 4,  // t2=SQ*(d-b); d=-SQ*(b+d); b=t2       (operands passed as a:=b, c:=d)
+    FFT_NOP = 7,    // padding: rows of 32 ops are packed so that no two ops of a row hit the same bank
 };
+
+// Shared-memory address of logical slot s: one pad word per 32 slots, so that the power-of-two strides of the
+// butterflies spread over the banks.  Device ops, the window store and the output map all use skewed addresses.
+#define FFT_SKEW(s) ((s) + ((s) >> 5))
+#define FFT_X_WORDS (1024 + 32)
 
 struct FftOp {
     uint16_t a, b, c, d;  // physical slots
@@ -42,20 +48,22 @@ struct FftOp {
     uint32_t pad;
 };
 
-// device encoding of an op, 8 bytes: a | b<<10 | c<<20 | d<<30 | tw<<40 | type<<50 | neg<<53
+// device encoding of an op, 8 bytes, operands as SKEWED addresses:
+//   a | b<<11 | c<<22 | d<<33 | tw<<44 | type<<54 | neg<<57
 typedef unsigned long long FftOpPacked;
 inline FftOpPacked fft_pack(const FftOp &o)
 {
-    return (FftOpPacked)(o.a & 1023) | ((FftOpPacked)(o.b & 1023) << 10) | ((FftOpPacked)(o.c & 1023) << 20) |
-           ((FftOpPacked)(o.d & 1023) << 30) | ((FftOpPacked)(o.tw & 1023) << 40) | ((FftOpPacked)(o.type & 7) << 50) |
-           ((FftOpPacked)(o.neg & 15) << 53);
+    if (o.type == FFT_NOP) return (FftOpPacked)FFT_NOP << 54;
+    auto sk = [](uint16_t s) { return (FftOpPacked)(s == 0xffff ? 0 : FFT_SKEW((unsigned)s)) & 2047; };
+    return sk(o.a) | (sk(o.b) << 11) | (sk(o.c) << 22) | (sk(o.d) << 33) | ((FftOpPacked)(o.tw & 1023) << 44) |
+           ((FftOpPacked)(o.type & 7) << 54) | ((FftOpPacked)(o.neg & 15) << 57);
 }
 
 struct FftProgram {
     int n, logm;
-    std::vector<FftOp> ops;            // sorted by level
+    std::vector<FftOp> ops;            // sorted by level, packed into bank-conflict-free rows of 32 (FFT_NOP padded)
     std::vector<FftOpPacked> packed;   // same ops in the device encoding
-    std::vector<int> level_start;      // size n_levels+1
+    std::vector<int> level_start;      // size n_levels+1, multiples of 32
     std::vector<uint16_t> out_slot;    // logical output index -> physical slot (after bit reversal)
     std::vector<uint8_t> out_neg;      // ... stored negated?
 };
@@ -81,6 +89,7 @@ struct PsyTables {
     double qthr_s[64], norm_s[64];
     double snr_s_exp[64];         // exp(SNR_s[b] * LN_TO_LOG10), host libm (l3psy.c:712)
     double s3_l[63 * 64];         // [b*64 + k]
+    double s3_lT[64 * 64];        // [k*64 + b]: the layout the kernels read (lane = b, coalesced)
     short spr_lo[64], spr_hi[64]; // spreading row range actually summed (44.1 kHz sparse, else dense+skip)
     int sparse;                   // 1 for 44.1 kHz (sprdngf1/2), 0 otherwise (dense with != 1.0 test)
     short bu_l[24], bo_l[24], bu_s[12], bo_s[12];

@@ -20,7 +20,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmp3gpu.so")
+# MP3GPU_LIB selects another build of the same library (A/B runs of kernel variants); default: the in-tree build
+LIB_PATH = os.environ.get("MP3GPU_LIB") or os.path.join(HERE, "libmp3gpu.so")
 
 PSY_DT = np.dtype([("pe", "f8"), ("ratio_l", "f8", 21), ("ratio_s", "f8", 36), ("block_type", "i4"), ("pad", "i4")])
 FO_DT = np.dtype([("resv_drain", "i4"), ("main_data_begin", "i4"), ("scfsi", "u1", (2, 4))])
@@ -35,7 +36,7 @@ EXPORTS = ["mp3gpu_last_error", "mp3gpu_version", "mp3gpu_create", "mp3gpu_destr
            "mp3gpu_L3psycho_anal_batch", "mp3gpu_iteration_loop_batch", "mp3gpu_quantize_count_batch",
            "mp3gpu_kernel_launches", "mp3gpu_profile_enable", "mp3gpu_profile_collect",
            "mp3gpu_encode_frames_mp3", "mp3gpu_encode_frames_mp3_dev", "mp3gpu_flush_mp3", "mp3gpu_flush_mp3_dev",
-           "mp3gpu_frame_bytes", "mp3gpu_format_bitstream_batch", "mp3gpu_begin_segment"]
+           "mp3gpu_frame_bytes", "mp3gpu_format_bitstream_batch", "mp3gpu_begin_segment", "mp3gpu_stream_wave"]
 LEGACY_EXPORTS = ["window_subband", "filter_subband", "mdct_sub", "L3psycho_anal", "iteration_loop",
                   "mp3gpu_legacy_reset", "mp3gpu_legacy_kernel_launches"]
 KERNEL_NAMES = ["psy_front", "psy_scan", "front_polyphase_mdct", "rate_loop", "bitstream"]
@@ -95,6 +96,14 @@ def load_library():
 def _torch():
     import torch
     return torch
+
+
+def stream_wave(device=0):
+    """streams that fill the device exactly once in the rate loop (mp3gpu.h)"""
+    n = load_library().mp3gpu_stream_wave(int(device))
+    if n < 0:
+        raise Mp3GpuError(f"mp3gpu_stream_wave failed ({n}): {load_library().mp3gpu_last_error().decode()}")
+    return n
 
 
 class Encoder:

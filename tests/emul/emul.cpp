@@ -35,6 +35,21 @@ int emul_fft(float *x, int n, int *n_ops, int *n_levels)
             for (int j = 0; j < 4; j++) if (s[j] != 0xffff) { if (used[s[j]]) return -1; used[s[j]] = 1; }
         }
     }
+    // row sanity: levels are whole rows of 32; within a row no two ops hit the same bank with the same operand
+    for (size_t r = 0; r + 32 <= P.ops.size(); r += 32) {
+        unsigned used[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 32; i++) {
+            const FftOp &o = P.ops[r + i];
+            const uint16_t s[4] = {o.a, o.b, o.c, o.d};
+            for (int j = 0; j < 4; j++)
+                if (o.type != FFT_NOP && s[j] != 0xffff) {
+                    const unsigned bit = 1u << (FFT_SKEW((unsigned)s[j]) & 31);
+                    if (used[j] & bit) return -2;
+                    used[j] |= bit;
+                }
+        }
+    }
+    for (size_t l = 0; l < P.level_start.size(); l++) if (P.level_start[l] % 32) return -3;
     return 0;
 }
 
@@ -75,7 +90,7 @@ int emul_encode_stream(int sfreq, int n_ch, int bitrate, int n_frames, const sho
     build_fft_program(10, base, &P10); build_fft_program(8, base, &P8);
     auto mkdev = [](const FftProgram &P, std::vector<uint16_t> &outmap) {
         outmap.resize(P.n);
-        for (int i = 0; i < P.n; i++) outmap[i] = (uint16_t)(P.out_slot[i] | (P.out_neg[i] ? 0x8000 : 0));
+        for (int i = 0; i < P.n; i++) outmap[i] = (uint16_t)(FFT_SKEW((unsigned)P.out_slot[i]) | (P.out_neg[i] ? 0x8000 : 0));
         FftDev d; d.ops = P.packed.data(); d.level_start = P.level_start.data(); d.n_levels = (int)P.level_start.size() - 1; d.out = outmap.data();
         return d;
     };

@@ -59,7 +59,7 @@ def test_stitched_equals_one_shot_single_process(pkg):
     pcm = rng.integers(-3000, 3000, (2, 23 * 1152 - 100), dtype=np.int16)
     calls = []
     whole = seg.encode_long_stream(pcm, 1, fake_batch_encoder(), FB)
-    cut = seg.encode_long_stream(pcm, 6, fake_batch_encoder(calls), FB)
+    cut = seg.encode_long_stream(pcm, 6, fake_batch_encoder(calls), FB, preroll_frames=2)
     assert whole == cut and len(whole) == 23 * FB - 5
     # 23 frames over 6 segments: sizes 4,4,4,4,4,3; first has no pre-roll -> three batches
     assert sorted(calls) == [(1, 3, 2), (1, 4, 0), (4, 4, 2)]
