@@ -13,7 +13,7 @@
 //   stage B  32x31 matrixing (encode.c:399-408).  thread = SLOT: the 31 folded inputs live in
 //            registers, the cosine matrix is read as immediate constant-bank operands of fully
 //            unrolled DMUL/DADD (no loads in the inner loop), results overwrite the thread's own row.
-//   stage C  MDCT (mdct.c:171-198), warp = granule, lane = band, cosine tables again as immediates.
+//   stage C  MDCT (mdct.c:171-198), three warps per granule (6 outputs each), lane = band, cosine tables as immediates.
 //   stage D  alias butterflies (mdct.c:83-91) in shared memory, then coalesced 128-bit stores of xr.
 //
 // Arithmetic: every sum is evaluated in the reference's order with unfused IEEE mul/add, so subband
@@ -70,46 +70,50 @@ __device__ __forceinline__ void ft_matrix_rows8(const double (&ys)[32], double *
     }
 }
 
-// ---- stage C: MDCT of one band held in registers ---------------------------------------------------
-__device__ __forceinline__ void ft_mdct_long(double (&fin)[36], int bt, double (&out)[18])
+// ---- stage C: MDCT of one band held in registers, one THIRD of the outputs per call ------------------
+// A granule's 18 outputs per band are computed by three warps (6 outputs each): 15 granules x 3 = 45 work items
+// = 5 full rounds of the 9 warps, and 6 independent accumulation chains per thread.  The window products
+// fin[k] = win[bt][k] * in[k] (mdct.c:190-192) are recomputed by each of the three warps (36 of 468 operations).
+template <int WIN>
+__device__ __forceinline__ void ft_window(double (&fin)[36])
 {
-    // fin[k] = win[bt][k] * in[k] (mdct.c:190-192): the window is selected with a switch so that every
-    // table read has a compile-time address (a register-indexed __constant__ read goes through the ADU)
-    if (bt == 0) {
+    // the window is a template parameter so that every table read has a compile-time address (a register-indexed
+    // __constant__ read goes through the ADU)
 #pragma unroll
-        for (int k = 0; k < 36; k++) fin[k] = __dmul_rn(c_front.win[0][k], fin[k]);
-    } else if (bt == 1) {
+    for (int k = 0; k < 36; k++) fin[k] = __dmul_rn(c_front.win[WIN][k], fin[k]);
+}
+
+template <int M0>
+__device__ __forceinline__ void ft_mdct_long6(const double (&fin)[36], double (&out)[6])
+{
 #pragma unroll
-        for (int k = 0; k < 36; k++) fin[k] = __dmul_rn(c_front.win[1][k], fin[k]);
-    } else {
+    for (int m = 0; m < 6; m++) out[m] = 0.0;
 #pragma unroll
-        for (int k = 0; k < 36; k++) fin[k] = __dmul_rn(c_front.win[3][k], fin[k]);
-    }
+    for (int k = 0; k < 36; k++)                                                    // mdct.c:193-198, k ascending per output
 #pragma unroll
-    for (int m = 0; m < 18; m++) {                                                  // mdct.c:193-198
-        double sum = 0.0;
+        for (int m = 0; m < 6; m++) out[m] = __dadd_rn(out[m], __dmul_rn(fin[k], c_front.cos_l[M0 + m][k]));
+}
+
+template <int L>
+__device__ __forceinline__ void ft_mdct_short6(const double (&in)[36], double (&out)[6])
+{
 #pragma unroll
-        for (int k = 0; k < 36; k++) sum = __dadd_rn(sum, __dmul_rn(fin[k], c_front.cos_l[m][k]));
-        out[m] = sum;
+    for (int m = 0; m < 6; m++) out[m] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {                                                  // mdct.c:171-185, window L
+        const double f = __dmul_rn(c_front.win[2][k], in[k + 6 * L + 6]);
+#pragma unroll
+        for (int m = 0; m < 6; m++) out[m] = __dadd_rn(out[m], __dmul_rn(f, c_front.cos_s[m][k]));
     }
 }
 
-__device__ __forceinline__ void ft_mdct_short(const double (&in)[36], double (&out)[18])
+__device__ __forceinline__ void ft_group_barrier(int group)   // the three warps of one granule
 {
-#pragma unroll
-    for (int l = 0; l < 3; l++)                                                     // mdct.c:171-185
-#pragma unroll
-        for (int m = 0; m < 6; m++) {
-            double sum = 0.0;
-#pragma unroll
-            for (int k = 0; k < 12; k++)
-                sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(c_front.win[2][k], in[k + 6 * l + 6]), c_front.cos_s[m][k]));
-            out[3 * m + l] = sum;
-        }
+    asm volatile("bar.sync %0, 96;" ::"r"(group + 1) : "memory");
 }
 
 // pcm_rows: [n_streams*n_ch] rows of `row` samples, HIST samples of history first (see mp3gpu.cu)
-__global__ void __launch_bounds__(FT_THREADS, 1)
+__global__ void __launch_bounds__(FT_THREADS, 2)
 k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_stride, int hist, int n_streams, int n_ch, int n_gran,
              const PsyOut *__restrict__ psy, double *__restrict__ xr)
 {
@@ -193,12 +197,16 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
     }
     __syncthreads();
 
-    // ---- stage C + D: warp = granule, lane = band ---------------------------------------------------
+    // ---- stage C + D: (granule, third) per warp, lane = band ------------------------------------------
+    // Warps 3j, 3j+1, 3j+2 share a granule.  Outputs are staged in the rows of the PREVIOUS granule, which are
+    // inputs of this round only: every warp loads its inputs, one CTA barrier, then compute / butterflies / store
+    // with barriers among the three warps of the granule.
     const long gc_stride = n_ch;
-    for (int r = 0; r * FT_WARPS < ng; r++) {
-        const int gl = 1 + r * FT_WARPS + warp;            // local granule index, 1..ng (0 is the warm-up granule)
+    const int third = warp % 3, group = warp / 3;
+    for (int r = 0; 3 * r < ng; r++) {
+        const int gl = 1 + 3 * r + group;                  // local granule index, 1..ng (0 is the warm-up granule)
         const bool active = gl <= ng;
-        double in[36], out[18];
+        double in[36], out[6];
         int bt = 0;
         if (active) {
             const double *p = M.rows + (size_t)(18 * (gl - 1)) * FT_ROW + lane;
@@ -208,15 +216,20 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
         }
         __syncthreads();                                    // every warp has its inputs: previous granules' rows are free
         if (active) {
-            if (bt == 2) ft_mdct_short(in, out);
-            else ft_mdct_long(in, bt, out);
-            double *st = M.rows + (size_t)(18 * (gl - 1)) * FT_ROW;   // 594 doubles of the previous granule's rows
+            double *st = M.rows + (size_t)(18 * (gl - 1)) * FT_ROW;   // 576 doubles in the previous granule's rows
+            if (bt == 2) {
+                if (third == 0) ft_mdct_short6<0>(in, out); else if (third == 1) ft_mdct_short6<1>(in, out); else ft_mdct_short6<2>(in, out);
 #pragma unroll
-            for (int m = 0; m < 18; m++) st[lane * 18 + m] = out[m];
-            __syncwarp();
-            if (bt != 2 && lane < 31) {                                                 // mdct.c:83-91
+                for (int m = 0; m < 6; m++) st[lane * 18 + 3 * m + third] = out[m];
+            } else {
+                if (bt == 0) ft_window<0>(in); else if (bt == 1) ft_window<1>(in); else ft_window<3>(in);
+                if (third == 0) ft_mdct_long6<0>(in, out); else if (third == 1) ft_mdct_long6<6>(in, out); else ft_mdct_long6<12>(in, out);
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
+                for (int m = 0; m < 6; m++) st[lane * 18 + 6 * third + m] = out[m];
+            }
+            ft_group_barrier(group);
+            if (bt != 2 && lane < 31) {                                                 // mdct.c:83-91, butterflies k = third, third+3, third+6
+                for (int k = third; k < 8; k += 3) {
                     const double a = st[lane * 18 + 17 - k], b = st[(lane + 1) * 18 + k];
                     const double bu = __dadd_rn(__dmul_rn(a, c_front.cs[k]), __dmul_rn(b, c_front.ca[k]));
                     const double bd = __dsub_rn(__dmul_rn(b, c_front.cs[k]), __dmul_rn(a, c_front.ca[k]));
@@ -224,13 +237,12 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
                     st[(lane + 1) * 18 + k] = bd;
                 }
             }
-            __syncwarp();
+            ft_group_barrier(group);
             double2 *dst = reinterpret_cast<double2 *>(xr + ((s * n_gran + g_first + gl - 1) * gc_stride + ch) * 576);
             const double2 *src = reinterpret_cast<const double2 *>(st);
 #pragma unroll
-            for (int i = 0; i < 9; i++) dst[lane + 32 * i] = src[lane + 32 * i];
+            for (int i = 0; i < 3; i++) dst[lane + 32 * (3 * third + i)] = src[lane + 32 * (3 * third + i)];
         }
-        __syncthreads();                                    // staging rows are reused as inputs of nobody, but keep rounds ordered
     }
 }
 

@@ -415,6 +415,10 @@ extern "C" int mp3gpu_create(const mp3gpu_config *cfg, mp3gpu_ctx **out)
     cudaFuncSetAttribute(k_front_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontTileSmem));
     cudaFuncSetAttribute(k_mdct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FRONT_WARPS * sizeof(FrontWarpSmem)));
     cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES);
+    // all three hot kernels want several CTAs per SM out of shared memory: ask for the largest carve-out
+    cudaFuncSetAttribute(k_front_tile, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_psy_front, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(k_quantize_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES);
     *out = c;
     rc = mp3gpu_reset(c);
