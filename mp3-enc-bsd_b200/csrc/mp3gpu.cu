@@ -333,7 +333,7 @@ static int upload_fft(const FftProgram &P, FftOpPacked **ops, int **lv, uint16_t
     CU(cudaMemcpy(*ops, P.packed.data(), P.packed.size() * sizeof(FftOpPacked), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(*lv, P.level_start.data(), P.level_start.size() * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(*out, o.data(), o.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    dev->ops = *ops; dev->level_start = *lv; dev->n_levels = (int)P.level_start.size() - 1; dev->out = *out;
+    dev->ops = *ops; dev->level_start = *lv; dev->n_levels = ((int)P.level_start.size() - 1) / 3; dev->out = *out;
     return 0;
 }
 

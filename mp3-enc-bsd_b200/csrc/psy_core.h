@@ -84,68 +84,89 @@ struct PsyChanState {  // persistent per (stream, channel)
 
 static const double kLn2Log10 = 0.2302585093;  // LN_TO_LOG10, common.h:204
 
-SIMT_FN void fft_exec(FftOpPacked op, const FftTwiddle *tw, float *x)
+// One op = decode, load, compute, store.  The three phases are separate functions so that fft_rows() can run the
+// loads of TWO independent ops (two rows of the same level) before either op's stores: the compiler cannot prove that
+// x[] stores of one op do not alias the loads of the next, the level structure guarantees it.
+struct FftDec { int ia, ib, ic, id, type, neg, tw; };
+
+SIMT_FN FftDec fft_decode(FftOpPacked op)
+{
+    const unsigned lo = (unsigned)op, hi = (unsigned)(op >> 32);
+    FftDec d;
+    d.type = (hi >> 22) & 7; d.neg = (hi >> 25) & 15; d.tw = (hi >> 12) & 1023;
+    d.ia = lo & 2047; d.ib = (lo >> 11) & 2047; d.ic = ((lo >> 22) | (hi << 10)) & 2047; d.id = (hi >> 1) & 2047;
+    return d;
+}
+
+struct FftVals { float a, b, c, d; FftTwiddle w; };
+
+// CLS 0: butterflies (a, b); 1: crosses (a, b, c, d); 2: rotations (a, c [+ twiddle]).  FFT_NOP decodes to slot 0.
+template <int CLS>
+SIMT_FN void fft_load(const FftDec &o, const FftTwiddle *tw, const float *x, FftVals &v)
+{
+    v.a = x[o.ia]; if (o.neg & 1) v.a = -v.a;
+    if (CLS != 2) { v.b = x[o.ib]; if (o.neg & 2) v.b = -v.b; }
+    if (CLS != 0) { v.c = x[o.ic]; if (o.neg & 4) v.c = -v.c; }
+    if (CLS == 1) { v.d = x[o.id]; if (o.neg & 8) v.d = -v.d; }
+    if (CLS == 2) v.w = tw[o.tw];
+}
+
+template <int CLS>
+SIMT_FN void fft_store(const FftDec &o, float *x, const FftVals &v)
 {
     const double SQ = 0.707106781186547524401;  // SQHALF, subs.c:26
-    const unsigned lo = (unsigned)op, hi = (unsigned)(op >> 32);
-    const int type = (hi >> 22) & 7, neg = (hi >> 25) & 15;
-    if (type == FFT_NOP) return;
-    const int ia = lo & 2047, ib = (lo >> 11) & 2047, ic = ((lo >> 22) | (hi << 10)) & 2047, id = (hi >> 1) & 2047;
-    float a = x[ia], c, b, d, t1, t2;
-    if (neg & 1) a = -a;
-    switch (type) {
-    case FFT_BFLY:
-        b = x[ib]; if (neg & 2) b = -b;
-        t1 = simt::fadd(a, b); b = simt::fsub(a, b);
-        x[ia] = t1; x[ib] = b;
-        break;
-    case FFT_CROSS:
-        b = x[ib]; c = x[ic]; d = x[id];
-        if (neg & 2) b = -b;
-        if (neg & 4) c = -c;
-        if (neg & 8) d = -d;
-        t1 = simt::fadd(a, d); t2 = simt::fadd(c, b);
-        x[ic] = simt::fsub(c, b); x[ib] = simt::fsub(a, d);
-        x[ia] = t1; x[id] = t2;
-        break;
-    case FFT_ROT: {
-        c = x[ic]; if (neg & 4) c = -c;
-        const FftTwiddle w = tw[(hi >> 12) & 1023];
-        t2 = simt::fmul(w.cn, simt::fadd(a, c));
-        t1 = simt::fadd(simt::fmul(w.spcn, a), t2);
-        x[ia] = simt::fadd(simt::fmul(w.smcn, c), t2);
-        x[ic] = t1;
-        break; }
-    case FFT_ROT8A:
-        c = x[ic]; if (neg & 4) c = -c;
-        t1 = (float)simt::dmul(SQ, (double)simt::fadd(a, c));
-        x[ic] = (float)simt::dmul(SQ, (double)simt::fsub(c, a));
-        x[ia] = t1;
-        break;
-    default:  // FFT_ROT8B
-        c = x[ic]; if (neg & 4) c = -c;
-        t2 = (float)simt::dmul(SQ, (double)simt::fsub(c, a));
-        x[ic] = (float)simt::dmul(-SQ, (double)simt::fadd(a, c));
-        x[ia] = t2;
-        break;
+    if (o.type == FFT_NOP) return;
+    if (CLS == 0) {                                           // t=a+b; b=a-b; a=t
+        x[o.ia] = simt::fadd(v.a, v.b); x[o.ib] = simt::fsub(v.a, v.b);
+    } else if (CLS == 1) {                                    // t1=a+d; t2=c+b; c=c-b; b=a-d; a=t1; d=t2
+        const float t1 = simt::fadd(v.a, v.d), t2 = simt::fadd(v.c, v.b);
+        x[o.ic] = simt::fsub(v.c, v.b); x[o.ib] = simt::fsub(v.a, v.d);
+        x[o.ia] = t1; x[o.id] = t2;
+    } else if (o.type == FFT_ROT) {                           // t2=cn*(a+c); t1=spcn*a+t2; a=smcn*c+t2; c=t1
+        const float t2 = simt::fmul(v.w.cn, simt::fadd(v.a, v.c));
+        const float t1 = simt::fadd(simt::fmul(v.w.spcn, v.a), t2);
+        x[o.ia] = simt::fadd(simt::fmul(v.w.smcn, v.c), t2);
+        x[o.ic] = t1;
+    } else if (o.type == FFT_ROT8A) {                         // t1=SQ*(a+c); c=SQ*(c-a); a=t1 (double multiply)
+        const float t1 = (float)simt::dmul(SQ, (double)simt::fadd(v.a, v.c));
+        x[o.ic] = (float)simt::dmul(SQ, (double)simt::fsub(v.c, v.a));
+        x[o.ia] = t1;
+    } else {                                                  // FFT_ROT8B: t2=SQ*(c-a); c=-SQ*(a+c); a=t2
+        const float t2 = (float)simt::dmul(SQ, (double)simt::fsub(v.c, v.a));
+        x[o.ic] = (float)simt::dmul(-SQ, (double)simt::fadd(v.a, v.c));
+        x[o.ia] = t2;
+    }
+}
+
+// rows [lo, hi) of one level and one operand class, U rows per trip
+#ifndef FFT_ROWS_PER_TRIP
+#define FFT_ROWS_PER_TRIP 2
+#endif
+template <int CLS>
+SIMT_FN void fft_rows(const FftOpPacked *ops, int lo, int hi, const FftTwiddle *tw, float *x, int lane)
+{
+    constexpr int U = FFT_ROWS_PER_TRIP;
+    for (int i = lo + lane; i < hi; i += 32 * U) {
+        FftDec o[U];
+        FftVals v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) o[u] = fft_decode(i + 32 * u < hi ? ops[i + 32 * u] : ((FftOpPacked)FFT_NOP << 54));
+#pragma unroll
+        for (int u = 0; u < U; u++) fft_load<CLS>(o[u], tw, x, v[u]);
+#pragma unroll
+        for (int u = 0; u < U; u++) fft_store<CLS>(o[u], x, v[u]);
     }
 }
 
 SIMT_FN void fft_run(const WarpCtx &w, const FftDev &P, const FftTwiddle *tw, float *x)
 {
+    // level_start holds 3 segments per level (one per operand class), each a whole number of rows of 32 ops
     for (int l = 0; l < P.n_levels; l++) {
-        const int lo = P.level_start[l], hi = P.level_start[l + 1];
+        const int s0 = P.level_start[3 * l], s1 = P.level_start[3 * l + 1], s2 = P.level_start[3 * l + 2], s3 = P.level_start[3 * l + 3];
         FOR_THREADS(w)
-        int i = lo + lane;               // levels are whole rows of 32 ops (FFT_NOP padded)
-        FftOpPacked op = P.ops[i];
-        for (;;) {                       // the next op is in flight while this one executes
-            const int nx = i + 32;
-            const bool more = nx < hi;
-            const FftOpPacked nxt = P.ops[more ? nx : i];
-            fft_exec(op, tw, x);
-            if (!more) break;
-            op = nxt; i = nx;
-        }
+        fft_rows<0>(P.ops, s0, s1, tw, x, lane);
+        fft_rows<1>(P.ops, s1, s2, tw, x, lane);
+        fft_rows<2>(P.ops, s2, s3, tw, x, lane);
         END_THREADS
         w.sync();
     }

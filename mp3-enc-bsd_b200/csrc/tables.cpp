@@ -394,7 +394,7 @@ void build_fft_program(int logm, const std::vector<int> &tw_base, FftProgram *P)
         return B.ops[x].type < B.ops[y].type;
     });
     P->n = n; P->logm = logm;
-    P->ops.clear(); P->level_start.assign(n_levels + 1, 0);
+    P->ops.clear(); P->level_start.assign(3 * n_levels + 1, 0);
     // Pack every level into rows of 32 ops (one op per lane).  A row holds ops of one operand shape only
     // (butterfly / cross / the three rotations) and no two of its ops touch the same shared-memory bank with the
     // same operand, so each of the row's loads and stores is a single wavefront; rows are padded with FFT_NOP.
@@ -424,8 +424,8 @@ void build_fft_program(int logm, const std::vector<int> &tw_base, FftProgram *P)
                     for (; in_row < 32; in_row++) P->ops.push_back(nop);
                     rem.swap(rest);
                 }
+                P->level_start[3 * (l - 1) + c + 1] = (int)P->ops.size();   // end of (level, class) segment
             }
-            P->level_start[l] = (int)P->ops.size();
         }
     }
     P->packed.clear();

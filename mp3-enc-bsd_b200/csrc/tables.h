@@ -63,7 +63,7 @@ struct FftProgram {
     int n, logm;
     std::vector<FftOp> ops;            // sorted by level, packed into bank-conflict-free rows of 32 (FFT_NOP padded)
     std::vector<FftOpPacked> packed;   // same ops in the device encoding
-    std::vector<int> level_start;      // size n_levels+1, multiples of 32
+    std::vector<int> level_start;      // size 3*n_levels+1: segment (level l, operand class c) = [3l+c, 3l+c+1), multiples of 32
     std::vector<uint16_t> out_slot;    // logical output index -> physical slot (after bit reversal)
     std::vector<uint8_t> out_neg;      // ... stored negated?
 };

@@ -25,11 +25,11 @@ int emul_fft(float *x, int n, int *n_ops, int *n_levels)
     std::vector<float> buf(x, x + n);
     run_fft_program_host(P, tw, buf.data());
     for (int i = 0; i < n; i++) x[i] = P.out_neg[i] ? -buf[P.out_slot[i]] : buf[P.out_slot[i]];
-    *n_ops = (int)P.ops.size(); *n_levels = (int)P.level_start.size() - 1;
+    *n_ops = (int)P.ops.size(); *n_levels = ((int)P.level_start.size() - 1) / 3;
     // level sanity: ops of one level must touch disjoint slots
-    for (size_t l = 0; l + 1 < P.level_start.size(); l++) {
+    for (size_t l = 0; l + 3 < P.level_start.size(); l += 3) {   // 3 operand-class segments per level
         std::vector<char> used(n, 0);
-        for (int i = P.level_start[l]; i < P.level_start[l + 1]; i++) {
+        for (int i = P.level_start[l]; i < P.level_start[l + 3]; i++) {
             const FftOp &o = P.ops[i];
             const uint16_t s[4] = {o.a, o.b, o.c, o.d};
             for (int j = 0; j < 4; j++) if (s[j] != 0xffff) { if (used[s[j]]) return -1; used[s[j]] = 1; }
@@ -91,7 +91,7 @@ int emul_encode_stream(int sfreq, int n_ch, int bitrate, int n_frames, const sho
     auto mkdev = [](const FftProgram &P, std::vector<uint16_t> &outmap) {
         outmap.resize(P.n);
         for (int i = 0; i < P.n; i++) outmap[i] = (uint16_t)(FFT_SKEW((unsigned)P.out_slot[i]) | (P.out_neg[i] ? 0x8000 : 0));
-        FftDev d; d.ops = P.packed.data(); d.level_start = P.level_start.data(); d.n_levels = (int)P.level_start.size() - 1; d.out = outmap.data();
+        FftDev d; d.ops = P.packed.data(); d.level_start = P.level_start.data(); d.n_levels = ((int)P.level_start.size() - 1) / 3; d.out = outmap.data();
         return d;
     };
     std::vector<uint16_t> o10, o8;
