@@ -98,6 +98,14 @@ int mp3gpu_stream_wave(int device);
 /* frame geometry the reference derives in musicin.c:562-572,729-746 */
 int mp3gpu_frame_geometry(const mp3gpu_ctx *ctx, int *bits_per_frame, int *mean_bits);
 
+/* Layout of the `pcm` argument of the mp3gpu_encode_frames* family.  PLANAR (default): [n_streams][n_ch][n_frames*1152],
+ * what get_audio() leaves in buffer[2][1152] (encode.c:181-269).  INTERLEAVED: [n_streams][n_frames*1152][n_ch], the
+ * sample order of a WAV / raw PCM file as read_samples() delivers it (encode.c:107-167); the channel split of
+ * get_audio() (encode.c:256-269) then runs as a CUDA kernel. */
+#define MP3GPU_PCM_PLANAR 0
+#define MP3GPU_PCM_INTERLEAVED 1
+int mp3gpu_set_pcm_layout(mp3gpu_ctx *ctx, int layout);
+
 /* ---- whole hot path: psy -> filterbank -> MDCT -> rate loop, continuing the ctx's streams ---------
  * Host variant: pcm and outputs are HOST pointers (pinned for async copies); H2D and D2H copies are
  * issued on `stream` and the call returns after they were enqueued; synchronise the stream (or call

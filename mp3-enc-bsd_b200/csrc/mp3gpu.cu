@@ -227,6 +227,22 @@ __global__ void k_roll_history(short *pcm, long row_stride, long n_rows, int n_n
     for (int i = threadIdx.x; i < HIST; i += blockDim.x) p[i] = p[n_new + i];
 }
 
+// get_audio()'s channel split (encode.c:256-269) for the batched path: interleaved frames [n_streams][n][n_ch]
+// -> planar rows behind each row's history.  One thread per sample frame.
+__global__ void k_deinterleave(const short *__restrict__ src, short *rows, long row_stride, int n_streams, int n_ch, long n)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)n_streams * n) return;
+    const long s = i / n, t = i - s * n;
+    if (n_ch == 2) {
+        const unsigned v = reinterpret_cast<const unsigned *>(src)[i];
+        rows[(2 * s) * row_stride + HIST + t] = (short)(v & 0xffffu);
+        rows[(2 * s + 1) * row_stride + HIST + t] = (short)(v >> 16);
+    } else {
+        rows[s * row_stride + HIST + t] = src[i];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------
@@ -286,6 +302,7 @@ struct mp3gpu_ctx {
     short *h2d_stage[2] = {nullptr, nullptr};
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     int h2d_turn = 0;
+    int pcm_layout = MP3GPU_PCM_PLANAR;
     long launches = 0;
     // per-kernel timing (mp3gpu_profile_*): events bracket every launch of the four hot kernels
     int prof_on = 0;
@@ -548,8 +565,33 @@ static int stage_pcm_host_overlapped(mp3gpu_ctx *c, const int16_t *pcm, int n_st
     CU(cudaMemcpyAsync(c->h2d_stage[t], pcm, rows * w, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaEventRecord(c->ev_ready[t], c->copy_stream));
     CU(cudaStreamWaitEvent(q, c->ev_ready[t], 0));
-    CU(cudaMemcpy2DAsync(c->pcm_main.buf + HIST, c->row * sizeof(short), c->h2d_stage[t], w, w, rows, cudaMemcpyDeviceToDevice, q));
+    if (c->pcm_layout == MP3GPU_PCM_INTERLEAVED) {
+        const long n = (long)n_frames * 1152, total = (long)n_streams * n;
+        k_deinterleave<<<(unsigned)((total + 255) / 256), 256, 0, q>>>(c->h2d_stage[t], c->pcm_main.buf, c->row, n_streams, c->cfg.n_ch, n);
+        c->launches++;
+        CU(cudaGetLastError());
+    } else {
+        CU(cudaMemcpy2DAsync(c->pcm_main.buf + HIST, c->row * sizeof(short), c->h2d_stage[t], w, w, rows, cudaMemcpyDeviceToDevice, q));
+    }
     CU(cudaEventRecord(c->ev_free[t], q));
+    return 0;
+}
+
+static int stage_pcm_dev(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, cudaStream_t q)
+{
+    if (c->pcm_layout != MP3GPU_PCM_INTERLEAVED) return stage_pcm(c, c->pcm_main, pcm, n_streams, n_frames, cudaMemcpyDeviceToDevice, q);
+    const long n = (long)n_frames * 1152, total = (long)n_streams * n;
+    k_deinterleave<<<(unsigned)((total + 255) / 256), 256, 0, q>>>(pcm, c->pcm_main.buf, c->row, n_streams, c->cfg.n_ch, n);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mp3gpu_set_pcm_layout(mp3gpu_ctx *c, int layout)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    if (layout != MP3GPU_PCM_PLANAR && layout != MP3GPU_PCM_INTERLEAVED) return fail(MP3GPU_EINVAL, "unknown PCM layout");
+    c->pcm_layout = layout;
     return 0;
 }
 
@@ -642,7 +684,7 @@ static int encode_common(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n
     cudaStream_t q = (cudaStream_t)stream;
     const size_t gcs = (size_t)n_streams * n_frames * 2 * c->cfg.n_ch;
     if (host) rc = stage_pcm_host_overlapped(c, pcm, n_streams, n_frames, q);
-    else rc = stage_pcm(c, c->pcm_main, pcm, n_streams, n_frames, cudaMemcpyDeviceToDevice, q);
+    else rc = stage_pcm_dev(c, pcm, n_streams, n_frames, q);
     if (rc) return rc;
     // musicin.c:751-779 order: psy first (it decides block_type), then filterbank + MDCT, then the rate loop
     if ((rc = launch_psy(c, c->pcm_main.buf, n_streams, n_frames, c->d_psyout, q))) return rc;

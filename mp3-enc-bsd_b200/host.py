@@ -36,7 +36,7 @@ EXPORTS = ["mp3gpu_last_error", "mp3gpu_version", "mp3gpu_create", "mp3gpu_destr
            "mp3gpu_L3psycho_anal_batch", "mp3gpu_iteration_loop_batch", "mp3gpu_quantize_count_batch",
            "mp3gpu_kernel_launches", "mp3gpu_profile_enable", "mp3gpu_profile_collect",
            "mp3gpu_encode_frames_mp3", "mp3gpu_encode_frames_mp3_dev", "mp3gpu_flush_mp3", "mp3gpu_flush_mp3_dev",
-           "mp3gpu_frame_bytes", "mp3gpu_format_bitstream_batch", "mp3gpu_begin_segment", "mp3gpu_stream_wave"]
+           "mp3gpu_frame_bytes", "mp3gpu_format_bitstream_batch", "mp3gpu_begin_segment", "mp3gpu_stream_wave", "mp3gpu_set_pcm_layout"]
 LEGACY_EXPORTS = ["window_subband", "filter_subband", "mdct_sub", "L3psycho_anal", "iteration_loop",
                   "mp3gpu_legacy_reset", "mp3gpu_legacy_kernel_launches"]
 KERNEL_NAMES = ["psy_front", "psy_scan", "front_polyphase_mdct", "rate_loop", "bitstream"]
@@ -87,6 +87,7 @@ def load_library():
         for name in ("mp3gpu_flush_mp3", "mp3gpu_flush_mp3_dev"):
             getattr(lib, name).argtypes = [vp, C.c_int, vp, C.c_long, C.POINTER(C.c_long), vp]
         lib.mp3gpu_begin_segment.argtypes = [vp, vp]
+        lib.mp3gpu_set_pcm_layout.argtypes = [vp, C.c_int]
         lib.mp3gpu_frame_bytes.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.mp3gpu_format_bitstream_batch.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, C.c_long, vp]
         _lib = lib
@@ -160,8 +161,16 @@ class Encoder:
         self._check(self.lib.mp3gpu_sync(self.ctx, C.c_void_p(stream or 0)), "mp3gpu_sync")
 
     # ---- helpers -------------------------------------------------------------------------------
+    def set_pcm_layout(self, interleaved):
+        """False: pcm is [S][n_ch][n] (default); True: pcm is [S][n][n_ch], the sample order of a WAV file"""
+        self._check(self.lib.mp3gpu_set_pcm_layout(self.ctx, 1 if interleaved else 0), "mp3gpu_set_pcm_layout")
+        self.interleaved = bool(interleaved)
+
     def _shape(self, pcm_shape):
-        S, n_ch, n = pcm_shape
+        if getattr(self, "interleaved", False):
+            S, n, n_ch = pcm_shape
+        else:
+            S, n_ch, n = pcm_shape
         assert n_ch == self.n_ch and n % 1152 == 0, (pcm_shape, self.n_ch)
         return S, n // 1152
 
@@ -325,6 +334,61 @@ class Encoder:
                                                   ix.data_ptr(), gi.data_ptr(), bits.data_ptr(), C.c_void_p(stream or 0))
         self._check(rc, "mp3gpu_quantize_count_batch")
         return ix, gi, bits
+
+
+def read_pcm_file(path, samples_per_read=2304):
+    """PCM of a WAV or raw file exactly as the reference reads it on a little-endian host (musicin.c:352-368,
+    encode.c:107-167): a file whose bytes 8..11 are "WAVE" has its samples at offset 0x2c (no chunk parsing), anything
+    else is raw from offset 0.  Both end up little-endian: raw data is meant to be byte-swapped (encode.c:157-159) but
+    SwapBytesInWords() never advances its pointer (common.c:619-628), so it only swaps the FIRST sample of each read,
+    once per sample read - a net change only when a read has an odd number of samples, i.e. in a short last frame.
+    That quirk is reproduced.  Returns a flat interleaved int16 array (channel count and rate come from the caller, as
+    with the reference's -m / -s flags); samples_per_read = 1152 * n_ch."""
+    data = open(path, "rb").read()
+    wav = data[8:12] == b"WAVE"
+    off = 0x2c if wav else 0
+    n = max(0, (len(data) - off) // 2)
+    x = np.frombuffer(data, dtype="<i2", count=n, offset=off).astype(np.int16)
+    rem = n % samples_per_read
+    if not wav and rem % 2 == 1:
+        x[n - rem] = x[n - rem:n - rem + 1].byteswap()[0]
+    return x
+
+
+def encode_files(paths, sfreq=44100, n_ch=2, bitrate=128, device=0, chunk_frames=32):
+    """Batch-encode PCM files of one format (WAV or raw, see read_pcm_file) to MPEG-1 Layer III byte streams on one
+    GPU: the batched equivalent of running the reference CLI once per file (minus the spurious last byte of
+    close_bit_stream_w, see mp3gpu.h).  Shorter files are zero-padded to the longest one for the lock-step batch and
+    cut back to their own frame count afterwards (trailing silence never influences earlier frames; the cut follows
+    BF_FlushBitstream like the reference: mp3gpu_flush semantics applied per file)."""
+    pcms = [read_pcm_file(p, 1152 * n_ch) for p in paths]
+    frames = [(len(x) + 1152 * n_ch - 1) // (1152 * n_ch) for x in pcms]   # the last frame is zero-filled (encode.c:162-166)
+    out = [None] * len(paths)
+    # files with equal frame counts share a batch (the reservoir cut at the end of a stream needs the true last frame)
+    groups = {}
+    for i, f in enumerate(frames):
+        groups.setdefault(f, []).append(i)
+    for F, idx in sorted(groups.items()):
+        if F == 0:
+            for i in idx:
+                out[i] = b""
+            continue
+        batch = np.zeros((len(idx), F * 1152 * n_ch), np.int16)
+        for k, i in enumerate(idx):
+            batch[k, :len(pcms[i])] = pcms[i]
+        batch = batch.reshape(len(idx), F * 1152, n_ch)
+        enc = Encoder(sfreq, n_ch, bitrate, max_streams=len(idx), max_frames=min(chunk_frames, F), device=device)
+        enc.set_pcm_layout(True)
+        mp3 = np.zeros((len(idx), F * enc.frame_bytes), np.uint8)
+        step = enc.cfg.max_frames
+        for f0 in range(0, F, step):
+            f1 = min(F, f0 + step)
+            enc.encode_frames_mp3(np.ascontiguousarray(batch[:, f0 * 1152:f1 * 1152]), mp3)
+        lengths = enc.flush_mp3(mp3, len(idx))
+        for k, i in enumerate(idx):
+            out[i] = mp3[k, :lengths[k]].tobytes()
+        enc.close()
+    return out
 
 
 def psy_to_numpy(psy_tensor):

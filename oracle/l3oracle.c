@@ -1394,3 +1394,21 @@ long l3o_format_stream(int sfreq, int n_ch, int bitrate_kbps, const l3o_frame *f
     len = (F.nbits >> 3) + 1;   /* empty_buffer(bs, buf_byte_idx) writes the partially filled byte too */
     return len <= cap ? len : -1;
 }
+
+/* ---- table access for the Python test decoder (oracle/mp3dec.py) ---- */
+int l3o_huff_table(int t, int *xlen, int *ylen, int *linbits, unsigned *codes, unsigned char *lens)
+{
+    int i, n;
+    if (t < 0 || t > 33) return -1;
+    *xlen = MP3T_HUFF[t].xlen; *ylen = MP3T_HUFF[t].ylen; *linbits = MP3T_HUFF[t].linbits;
+    n = (t >= 32) ? 16 : MP3T_HUFF[t].xlen * MP3T_HUFF[t].ylen;
+    for (i = 0; i < n; i++) { codes[i] = MP3T_HCODE[MP3T_HUFF[t].off + i]; lens[i] = MP3T_HLEN[MP3T_HUFF[t].off + i]; }
+    return n;
+}
+void l3o_sfb_tables(int sr_idx, short *l23, short *s14)
+{
+    int i;
+    for (i = 0; i < 23; i++) l23[i] = MP3T_SFB_LONG[sr_idx][i];
+    for (i = 0; i < 14; i++) s14[i] = MP3T_SFB_SHORT[sr_idx][i];
+}
+void l3o_analysis_window(double *c512) { int i; for (i = 0; i < 512; i++) c512[i] = MP3T_ANA_WINDOW[i]; }

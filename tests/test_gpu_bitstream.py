@@ -104,3 +104,29 @@ def test_mp3_bytes_vs_reference_cli_live(pkg):
     enc = pkg.Encoder(44100, 2, 128, max_streams=1, max_frames=16)
     got = enc.encode_streams(pcm[None])[0]
     assert got == ref[:-1], (len(got), len(ref), first_diff(got, ref))
+
+
+def test_interleaved_ingest_and_file_batch(pkg, tmp_path):
+    """WAV files in, MP3 byte streams out (interleaved PCM de-interleaved on the device, get_audio() encode.c:256-269):
+    three files of different length and a raw (header-less) file in one call; each equals the oracle's formatter output
+    and, where the reference CLI is present, the CLI's file."""
+    host = pkg.host
+    clips = [pkg.synth.config1(1.0 + 0.37 * i, 44100, seeds=(90 + i, 95 + i)) for i in range(3)]
+    clips[1] = clips[1][:, :clips[0].shape[1]]                    # two files with the same frame count share a batch
+    paths = []
+    for i, c in enumerate(clips):
+        p = str(tmp_path / f"clip{i}.wav")
+        write_wav(p, c, 44100)
+        paths.append(p)
+    raw = str(tmp_path / "clip_raw.pcm")
+    np.ascontiguousarray(clips[2].T).astype("<i2").tofile(raw)     # raw is little-endian in effect, see host.read_pcm_file
+    paths.append(raw)
+    got = host.encode_files(paths, 44100, 2, 128, chunk_frames=8)
+    for i, c in enumerate(clips + [clips[2]]):
+        ref, _ = oracle.format_stream(oracle.encode_stream(c, 44100, 128), 2, 44100, 128)
+        assert got[i] == ref[:-1], (i, len(got[i]), len(ref), first_diff(got[i], ref))
+    cli = os.path.join(ROOT, "oracle", "_ref", "encode")
+    if os.path.exists(cli):
+        out = str(tmp_path / "ref.mp3")
+        subprocess.run([cli] + cli_flags(2, 44100, 128) + [paths[3], out], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        assert open(out, "rb").read()[:-1] == got[3]
