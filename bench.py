@@ -33,9 +33,9 @@ sys.path.insert(0, ROOT)
 FS, NCH, KBPS = 44100, 2, 128
 BYTES_PER_GC = {"front_polyphase_mdct": 5764, "psy_front": 1152 + 1568, "psy_scan": 1568 + 472,
                 "rate_loop": 4608 + 472 + 1152 + 80 + 40, "bitstream": 1152 + 80 + 40 + 417 // 4}
-# DRAM bytes per granule-channel of k_front_tile from the ncu --set full capture profiles/r01_b_capture.md
-# (dram__bytes_read.sum + dram__bytes_write.sum = 173.4 + 547.3 MB for 131 072 gc)
-FRONT_TRAFFIC_PER_GC = (173.369856e6 + 547.285248e6) / 131072
+# DRAM bytes per granule-channel of k_front_tile from the ncu --set full capture profiles/r01_d_capture.md
+# (dram__bytes_read.sum + dram__bytes_write.sum = 0.597320 + 2.040849 GB for one launch of 454 656 gc)
+FRONT_TRAFFIC_PER_GC = (0.597320e9 + 2.040849e9) / 454656
 
 
 def shard_range(n, rank, world):
@@ -322,7 +322,7 @@ def main():
                      "achieved": fk["achieved_gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": fk["frac_hbm"],
                      "traffic": FRONT_TRAFFIC_PER_GC * S * chunks[0][1] * 2 * NCH,
                      "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per granule-channel "
-                                       "(profiles/r01_b_capture.md) x granule-channels per launch",
+                                       "(profiles/r01_d_capture.md) x granule-channels per launch",
                      "achieved_per_launch_bytes": 5764 * S * chunks[0][1] * 2 * NCH},
         "kernels": kernels,
         "clocks": clocks,

@@ -421,10 +421,9 @@ SIMT_FN void psy_scan_step(const WarpCtx &w, const PsyTables &T, PsyScanSmem &M,
         const int b = lane + 32 * h;
         if (b < 63) {
             double ctb = 0.0;
-            const int klo = T.spr_lo[b], khi = T.spr_hi[b];
-            for (int k = 0; k < 63; k++) {
+            for (int k = T.spr_lo[b]; k <= T.spr_hi[b]; k++) {   // latency-bound scan: the short per-lane range wins here
                 const double s = T.s3_lT[k * 64 + b];
-                if (k >= klo && k <= khi && (T.sparse || s != 1.0)) ctb = simt::dadd(ctb, simt::dmul(s, (double)M.cb[k]));
+                if (T.sparse || s != 1.0) ctb = simt::dadd(ctb, simt::dmul(s, (double)M.cb[k]));
             }
             const float ecb = mid.ecb[b];
             double cbb;
