@@ -307,18 +307,25 @@ SIMT_FN int count_all(const WarpCtx &w, const RateHot &H, const RateWarpSmem &M,
     if (has2) e_end = bvr;
     if (e_end > 576) e_end = 576;
     const int k_end = (e_end + 63) >> 6;     // slots s = lane + 32 k hold elements 2 s, 2 s + 1
+    // Both passes are written branch-free on purpose (selects and unconditional loads): the compiler turned the
+    // nested conditionals of the straightforward form into ~10 divergent branches per slot.  a1, a2 and bvr are even,
+    // so "element e = 2 s below a" is "slot s below a / 2".
+    const int S1 = a1 >> 1, S2 = a2 >> 1, S3 = bvr >> 1;
+    const unsigned *ixw = reinterpret_cast<const unsigned *>(M.ix);      // x | y << 16
     PerThread<int> mx0, mx1, mx2;
     FOR_THREADS(w)
-    int m0 = 0, m1 = 0, m2 = 0;
+    unsigned m0 = 0, m1 = 0, m2 = 0;
+#pragma unroll 1
     for (int k = 0; k < k_end; k++) {
-        const int e = 2 * (lane + 32 * k);
-        const U2 u = M.ix[lane + 32 * k];
-        const int v = u.x > u.y ? u.x : u.y;
-        if (e < a1) m0 = v > m0 ? v : m0;
-        else if (e < a2) m1 = v > m1 ? v : m1;
-        else if (e < bvr) m2 = v > m2 ? v : m2;
+        const int sl = lane + 32 * k;
+        const unsigned u = ixw[sl];
+        const unsigned v = simt::umax(u & 0xffffu, u >> 16);
+        const bool p0 = sl < S1, p1 = sl < S2, p2 = sl < S3;
+        m0 = simt::umax(m0, p0 ? v : 0u);
+        m1 = simt::umax(m1, (!p0 && p1) ? v : 0u);
+        m2 = simt::umax(m2, (!p0 && !p1 && p2) ? v : 0u);
     }
-    mx0() = m0; mx1() = m1; mx2() = m2;
+    mx0() = (int)m0; mx1() = (int)m1; mx2() = (int)m2;
     END_THREADS
     int grp[3] = {-1, -1, -1}, rmax[3] = {0, 0, 0};
     if (has0) rmax[0] = w.reduce_max(mx0);
@@ -331,17 +338,21 @@ SIMT_FN int count_all(const WarpCtx &w, const RateHot &H, const RateWarpSmem &M,
     int bits = c1bits;
     if (any) {
         PerThread<int> lo[3], hi[3];
-        const int g0 = grp[0], g1 = grp[1], g2 = grp[2];
+        // a region without a group (all zero, or absent) is priced with group 0 and its sum is never looked at
+        const int bs0 = (grp[0] < 0 ? 0 : grp[0]) << 8, bs1 = (grp[1] < 0 ? 0 : grp[1]) << 8, bs2 = (grp[2] < 0 ? 0 : grp[2]) << 8;
+        const unsigned *gl = &H.glut[0][0];
         FOR_THREADS(w)
         unsigned acc0 = 0, acc1 = 0, acc2 = 0;
+#pragma unroll 1
         for (int k = 0; k < k_end; k++) {
-            const int e = 2 * (lane + 32 * k);
-            const U2 u = M.ix[lane + 32 * k];
-            const int x = u.x > 15 ? 15 : u.x, y = u.y > 15 ? 15 : u.y;
-            const int r = (e < a1) ? 0 : (e < a2) ? 1 : (e < bvr) ? 2 : 3;
-            const int g = (r == 0) ? g0 : (r == 1) ? g1 : (r == 2) ? g2 : -1;
-            const unsigned wv = (g >= 0) ? H.glut[g][16 * x + y] : 0u;
-            if (r == 0) acc0 += wv; else if (r == 1) acc1 += wv; else acc2 += wv;
+            const int sl = lane + 32 * k;
+            const unsigned c = simt::vminu2(ixw[sl], 0x000f000fu);              // min(x, 15) | min(y, 15) << 16
+            const unsigned idx = ((c << 4) | (c >> 16)) & 0xffu;                    // 16 x + y
+            const bool p0 = sl < S1, p1 = sl < S2, p2 = sl < S3;
+            const unsigned wv = gl[(p0 ? bs0 : p1 ? bs1 : bs2) + idx];
+            acc0 += p0 ? wv : 0u;
+            acc1 += (!p0 && p1) ? wv : 0u;
+            acc2 += (!p0 && !p1 && p2) ? wv : 0u;
         }
         // per lane <= 9 pairs x <= 63 per field: no carry between the 10-bit fields
         lo[0]() = (int)((acc0 & 1023u) | (((acc0 >> 10) & 1023u) << 16)); hi[0]() = (int)(acc0 >> 20);

@@ -90,6 +90,8 @@ SIMT_FN float fadd(float a, float b) { return __fadd_rn(a, b); }
 SIMT_FN float fsub(float a, float b) { return __fsub_rn(a, b); }
 SIMT_FN int popc(unsigned v) { return __popc(v); }
 SIMT_FN int clz(unsigned v) { return __clz(v); }
+SIMT_FN unsigned umax(unsigned a, unsigned b) { return max(a, b); }
+SIMT_FN unsigned vminu2(unsigned a, unsigned b) { return __vminu2(a, b); }   // per-halfword unsigned minimum
 
 #else
 // ------------------------------------------------------------------------------------------------
@@ -141,6 +143,13 @@ inline float fadd(float a, float b) { return a + b; }
 inline float fsub(float a, float b) { return a - b; }
 inline int popc(unsigned v) { return __builtin_popcount(v); }
 inline int clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+inline unsigned umax(unsigned a, unsigned b) { return a > b ? a : b; }
+inline unsigned vminu2(unsigned a, unsigned b)
+{
+    const unsigned lo = (a & 0xffffu) < (b & 0xffffu) ? (a & 0xffffu) : (b & 0xffffu);
+    const unsigned hi = (a >> 16) < (b >> 16) ? (a >> 16) : (b >> 16);
+    return lo | (hi << 16);
+}
 #endif
 
 }  // namespace simt
