@@ -283,18 +283,21 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
     w.sync();
     // energy spreading, l3psy.c:586-605 (ecb is a float accumulator)
     FOR_THREADS(w)
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int b = lane + 32 * h;
-        float ecb = 0.0f;
-        // every lane walks the whole row range with a predicate: the transposed matrix makes each load one
-        // coalesced 256-byte request and eb[k] a broadcast; the terms are added in the reference's order
-        const int klo = (b < 63) ? T.spr_lo[b] : 1, khi = (b < 63) ? T.spr_hi[b] : 0;
+    {
+        // every lane walks the whole row range with a predicate: the transposed matrix makes each load one coalesced
+        // 256-byte request and eb[k] a broadcast; the terms are added in the reference's order.  The two partitions of
+        // a lane (b and b + 32) advance together: two independent float <- double accumulation chains in flight.
+        const int b0 = lane, b1 = lane + 32;
+        const int lo0 = T.spr_lo[b0], hi0 = T.spr_hi[b0];
+        const int lo1 = (b1 < 63) ? T.spr_lo[b1] : 1, hi1 = (b1 < 63) ? T.spr_hi[b1] : 0;
+        float e0 = 0.0f, e1 = 0.0f;
         for (int k = 0; k < 63; k++) {
-            const double s = T.s3_lT[k * 64 + b];
-            if (k >= klo && k <= khi && (T.sparse || s != 1.0)) ecb = (float)simt::dadd((double)ecb, simt::dmul(s, M.eb[k]));
+            const double s0 = T.s3_lT[k * 64 + b0], s1 = T.s3_lT[k * 64 + b1], ebk = M.eb[k];
+            if (k >= lo0 && k <= hi0 && (T.sparse || s0 != 1.0)) e0 = (float)simt::dadd((double)e0, simt::dmul(s0, ebk));
+            if (k >= lo1 && k <= hi1 && (T.sparse || s1 != 1.0)) e1 = (float)simt::dadd((double)e1, simt::dmul(s1, ebk));
         }
-        out->ecb[b] = ecb;
+        out->ecb[b0] = e0;
+        out->ecb[b1] = e1;
     }
     END_THREADS
     w.sync();
@@ -314,14 +317,19 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
         END_THREADS
         w.sync();
         FOR_THREADS(w)
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int b = lane + 32 * h;
-            if (b < 42) {
-                float ecb = 0.0f;
-                for (int k = 0; k < 42; k++) ecb = (float)simt::dadd((double)ecb, simt::dmul(T.s3_lT[k * 64 + b], M.eb[k]));
-                float nb = (float)simt::dmul(simt::dmul((double)ecb, T.norm_l[b]), T.snr_s_exp[b]);
-                M.thr[b] = (T.qthr_s[b] > (double)nb) ? T.qthr_s[b] : (double)nb;
+        {
+            const int b0 = lane, b1 = lane + 32;            // partitions 0..41: b1 is live in lanes 0..9 only
+            float e0 = 0.0f, e1 = 0.0f;
+            for (int k = 0; k < 42; k++) {
+                const double ebk = M.eb[k];
+                e0 = (float)simt::dadd((double)e0, simt::dmul(T.s3_lT[k * 64 + b0], ebk));
+                e1 = (float)simt::dadd((double)e1, simt::dmul(T.s3_lT[k * 64 + b1], ebk));
+            }
+            const float nb0 = (float)simt::dmul(simt::dmul((double)e0, T.norm_l[b0]), T.snr_s_exp[b0]);
+            M.thr[b0] = (T.qthr_s[b0] > (double)nb0) ? T.qthr_s[b0] : (double)nb0;
+            if (b1 < 42) {
+                const float nb1 = (float)simt::dmul(simt::dmul((double)e1, T.norm_l[b1]), T.snr_s_exp[b1]);
+                M.thr[b1] = (T.qthr_s[b1] > (double)nb1) ? T.qthr_s[b1] : (double)nb1;
             }
         }
         END_THREADS
