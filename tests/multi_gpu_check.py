@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Multi-GPU check of the single-long-stream path (BASELINE configs[4]) under torchrun, NCCL gather:
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29555 tools/multi_gpu_check.py [seconds]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29555 tests/multi_gpu_check.py [seconds]
 Every rank encodes its share of the segments on its own GPU; rank 0 stitches, compares with the one-GPU whole-stream
 encode (identical-frame fraction) and decodes both (test decoder) for the SNR report."""
 import json
