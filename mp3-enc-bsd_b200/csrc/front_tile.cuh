@@ -39,29 +39,48 @@ struct FrontTileSmem {
     double rows[FT_SLOTS * FT_ROW];     // stage A: ysum/ysub/y16; stage B: subband samples (in place);
                                         // stage D: xr staging in the rows of the previous granule
     double window[512];
-    short pcm[FT_PCM];
+    short pcm[FT_PCM];                  // dead after stage A: the matrixing / MDCT cosine tables are then staged here
 };
+// layout of the table overlay (doubles, from the start of FrontTileSmem::pcm)
+#define FT_TAB_AM 0                     // am[32][32]
+#define FT_TAB_COS (32 * 32)            // cos_l[18][36]
+#define FT_TAB_END (FT_TAB_COS + 18 * 36)
+static_assert(FT_TAB_END * 8 <= FT_PCM * 2, "cosine tables must fit the dead PCM staging area");
+#ifndef FT_TABLES_IN_SMEM
+#define FT_TABLES_IN_SMEM 1
+#endif
 
 __constant__ FrontTables c_front;  // defined here: this header is included by exactly one translation unit (mp3gpu.cu)
 
 // ---- stage B: s[sb] = y16 + sum_j am[sb][j] * ys[j], j ascending (encode.c:399-408) ----------------
 template <int SB>
-__device__ __forceinline__ double ft_matrix_row(const double (&ys)[32])
+__device__ __forceinline__ double ft_matrix_row(const double (&ys)[32], const double *tab)
 {
     double s = ys[31];
+#if FT_TABLES_IN_SMEM
+    const double2 *a = reinterpret_cast<const double2 *>(tab + FT_TAB_AM + SB * 32);   // uniform address: broadcast loads
+#pragma unroll
+    for (int j = 0; j < 30; j += 2) {
+        const double2 c = a[j >> 1];
+        s = __dadd_rn(s, __dmul_rn(c.x, ys[j]));
+        s = __dadd_rn(s, __dmul_rn(c.y, ys[j + 1]));
+    }
+    s = __dadd_rn(s, __dmul_rn(a[15].x, ys[30]));
+#else
 #pragma unroll
     for (int j = 0; j < 31; j++) s = __dadd_rn(s, __dmul_rn(c_front.am[SB][j], ys[j]));
+#endif
     return s;
 }
 
 template <int SB0>
-__device__ __forceinline__ void ft_matrix_rows8(const double (&ys)[32], double *row, bool odd_slot)
+__device__ __forceinline__ void ft_matrix_rows8(const double (&ys)[32], double *row, bool odd_slot, const double *tab)
 {
     double s[8];
-    s[0] = ft_matrix_row<SB0 + 0>(ys); s[1] = ft_matrix_row<SB0 + 1>(ys);
-    s[2] = ft_matrix_row<SB0 + 2>(ys); s[3] = ft_matrix_row<SB0 + 3>(ys);
-    s[4] = ft_matrix_row<SB0 + 4>(ys); s[5] = ft_matrix_row<SB0 + 5>(ys);
-    s[6] = ft_matrix_row<SB0 + 6>(ys); s[7] = ft_matrix_row<SB0 + 7>(ys);
+    s[0] = ft_matrix_row<SB0 + 0>(ys, tab); s[1] = ft_matrix_row<SB0 + 1>(ys, tab);
+    s[2] = ft_matrix_row<SB0 + 2>(ys, tab); s[3] = ft_matrix_row<SB0 + 3>(ys, tab);
+    s[4] = ft_matrix_row<SB0 + 4>(ys, tab); s[5] = ft_matrix_row<SB0 + 5>(ys, tab);
+    s[6] = ft_matrix_row<SB0 + 6>(ys, tab); s[7] = ft_matrix_row<SB0 + 7>(ys, tab);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         // mdct.c:57-60: odd band, odd time slot -> * -1 (applied here, the raw value is never needed)
@@ -84,14 +103,25 @@ __device__ __forceinline__ void ft_window(double (&fin)[36])
 }
 
 template <int M0>
-__device__ __forceinline__ void ft_mdct_long6(const double (&fin)[36], double (&out)[6])
+__device__ __forceinline__ void ft_mdct_long6(const double (&fin)[36], double (&out)[6], const double *tab)
 {
 #pragma unroll
     for (int m = 0; m < 6; m++) out[m] = 0.0;
+#if FT_TABLES_IN_SMEM
 #pragma unroll
-    for (int k = 0; k < 36; k++)                                                    // mdct.c:193-198, k ascending per output
+    for (int k = 0; k < 36; k += 2)                                                 // mdct.c:193-198, k ascending per output
+#pragma unroll
+        for (int m = 0; m < 6; m++) {
+            const double2 c = *reinterpret_cast<const double2 *>(tab + FT_TAB_COS + (M0 + m) * 36 + k);
+            out[m] = __dadd_rn(out[m], __dmul_rn(fin[k], c.x));
+            out[m] = __dadd_rn(out[m], __dmul_rn(fin[k + 1], c.y));
+        }
+#else
+#pragma unroll
+    for (int k = 0; k < 36; k++)
 #pragma unroll
         for (int m = 0; m < 6; m++) out[m] = __dadd_rn(out[m], __dmul_rn(fin[k], c_front.cos_l[M0 + m][k]));
+#endif
 }
 
 template <int L>
@@ -182,6 +212,12 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
         }
     }
     __syncthreads();
+    double *tab = reinterpret_cast<double *>(M.pcm);          // the PCM tile is dead: stage the cosine tables over it
+#if FT_TABLES_IN_SMEM
+    for (int i = tid; i < 32 * 32; i += FT_THREADS) tab[FT_TAB_AM + i] = (&c_front.am[0][0])[i];
+    for (int i = tid; i < 18 * 36; i += FT_THREADS) tab[FT_TAB_COS + i] = (&c_front.cos_l[0][0])[i];
+    __syncthreads();
+#endif
 
     // ---- stage B: thread = slot ---------------------------------------------------------------------
     if (tid < n_chunks * 32) {
@@ -190,10 +226,10 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
 #pragma unroll
         for (int j = 0; j < 32; j++) ys[j] = row[j];
         const bool odd_slot = ((tid % 18) & 1) != 0;
-        ft_matrix_rows8<0>(ys, row, odd_slot);
-        ft_matrix_rows8<8>(ys, row, odd_slot);
-        ft_matrix_rows8<16>(ys, row, odd_slot);
-        ft_matrix_rows8<24>(ys, row, odd_slot);
+        ft_matrix_rows8<0>(ys, row, odd_slot, tab);
+        ft_matrix_rows8<8>(ys, row, odd_slot, tab);
+        ft_matrix_rows8<16>(ys, row, odd_slot, tab);
+        ft_matrix_rows8<24>(ys, row, odd_slot, tab);
     }
     __syncthreads();
 
@@ -223,7 +259,7 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
                 for (int m = 0; m < 6; m++) st[lane * 18 + 3 * m + third] = out[m];
             } else {
                 if (bt == 0) ft_window<0>(in); else if (bt == 1) ft_window<1>(in); else ft_window<3>(in);
-                if (third == 0) ft_mdct_long6<0>(in, out); else if (third == 1) ft_mdct_long6<6>(in, out); else ft_mdct_long6<12>(in, out);
+                if (third == 0) ft_mdct_long6<0>(in, out, tab); else if (third == 1) ft_mdct_long6<6>(in, out, tab); else ft_mdct_long6<12>(in, out, tab);
 #pragma unroll
                 for (int m = 0; m < 6; m++) st[lane * 18 + 6 * third + m] = out[m];
             }
