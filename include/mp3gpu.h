@@ -159,6 +159,12 @@ int mp3gpu_iteration_loop_batch(mp3gpu_ctx *ctx, const double *xr, const mp3gpu_
  * (big_values,count1,count1table_select,region0/1_count,table_select,address1-3), bits [n]. */
 int mp3gpu_quantize_count_batch(mp3gpu_ctx *ctx, const double *xr_abs, const int *q, const int *block_type, int n,
                                 int16_t *ix, mp3gpu_gr_info *gi, int *bits, void *stream);
+/* count_bits() (loop.c:2099-2113: calc_runlen, count1_bitcount, subdivide, bigv_tab_select / new_choose_table,
+ * bigv_bitcount) on n given quantised granules: ix [n][576] magnitudes, block_type [n]; gi [n] is in/out: address1..3 are
+ * read (subdivide() leaves them untouched when big_values == 0) and every field the reference's count_bits() sets is
+ * written; bits [n] receives the return values. */
+int mp3gpu_count_bits_batch(mp3gpu_ctx *ctx, const int16_t *ix, const int *block_type, int n, mp3gpu_gr_info *gi, int *bits,
+                            void *stream);
 /* III_format_bitstream (l3bitstream.c:68) batched: ix (signed) / gi / sf / fo as produced by the rate loop -> byte
  * stream, continuing the ctx's streams (same window semantics as mp3gpu_encode_frames_mp3_dev; mp3 may be NULL). */
 int mp3gpu_format_bitstream_batch(mp3gpu_ctx *ctx, const int16_t *ix, const mp3gpu_gr_info *gi, const uint8_t *sf,

@@ -13,6 +13,8 @@
  *   mdct_sub            mdct.h:22   / mdct.c:25        k_legacy_mdct: MDCT + alias butterflies; sign fix and slot save as the reference
  *   L3psycho_anal       l3psy.h:32  / l3psy.c:53       k_psy_front + k_psy_scan for one granule of one channel
  *   iteration_loop      loop.h:48   / loop.c:232       k_rate_loop for one frame (reservoir state on the device)
+ *   quantize            loop-pvt.h  / loop.c:1360      k_quantize_count (one probe: pow_nint quantiser)
+ *   count_bits          loop-pvt.h  / loop.c:2099      k_quantize_count in count-only mode (run lengths, table selection, bit count)
  *
  * Every call copies its operands to the device, launches the kernels and copies the results back
  * (one stream, one frame at a time: this is the drop-in/parity path, the batched API in mp3gpu.h is the
@@ -88,6 +90,12 @@ void L3psycho_anal(short *buffer, short savebuf[1344], int chn, int lay, float s
 void iteration_loop(double pe[][2], double xr_org[2][2][576], III_psy_ratio *ratio, III_side_info_t *l3_side,
                     int l3_enc[2][2][576], int mean_bits, int stereo, double xr_dec[2][2][576],
                     III_scalefac_t *scalefac, frame_params *fr_ps, int ancillary_pad, int bitsPerFrame);
+/* the inner-loop pair the rate loop is built from (loop-pvt.h:27-117, loop.c:1360 and :2099), one granule per call:
+ * quantize() at cod_info->quantizerStepSize, count_bits() = calc_runlen + count1_bitcount + subdivide + bigv_tab_select
+ * (new_choose_table) + bigv_bitcount, updating cod_info like the reference.  Like the reference's they use the
+ * scalefactor-band tables of the last iteration_loop() call (44.1 kHz before any). */
+void quantize(double xr[576], int ix[576], gr_info *cod_info);
+int count_bits(int *ix, gr_info *cod_info);
 #endif
 
 /* forget the hidden per-stream state of all five entry points */

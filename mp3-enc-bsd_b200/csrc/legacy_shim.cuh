@@ -347,3 +347,91 @@ extern "C" void iteration_loop(double pe[][2], double xr_org[2][2][576], III_psy
                 for (int wdw = 0; wdw < 3; wdw++) scalefac->s[gr][ch][b][wdw] = sf[g][3 * b + wdw];
         }
 }
+
+
+// ---- the inner-loop functions the north star names, single-call legacy form (loop-pvt.h:27-117) ----------------
+// quantize() and count_bits() have no sampling-frequency argument: like the reference (loop.c:242-250 sets the file-level
+// scalefac_band_long/short in iteration_loop) they use the tables of the last iteration_loop() call, 44.1 kHz before any.
+static bool legacy_rate_tables(LegacyState &L)
+{
+    if (L.loop_sr >= 0 && L.d_rate_tab) return true;
+    RateTables *R = new RateTables;
+    build_rate_tables(1, R);
+    cudaError_t e = L.d_rate_tab ? cudaSuccess : cudaMalloc(&L.d_rate_tab, sizeof(RateTables));
+    if (e == cudaSuccess) e = cudaMemcpy(L.d_rate_tab, R, sizeof(RateTables), cudaMemcpyHostToDevice);
+    delete R;
+    if (e != cudaSuccess) { legacy_fail(MP3GPU_ECUDA, "rate tables", e); return false; }
+    L.loop_sr = 1;
+    return true;
+}
+
+struct LegacyProbe { double *d_x = nullptr; int *d_q = nullptr, *d_bt = nullptr, *d_bits = nullptr; };
+static LegacyProbe g_probe;
+
+static bool legacy_probe_buffers()
+{
+    if (g_probe.d_x) return true;
+    if (cudaMalloc(&g_probe.d_x, 576 * sizeof(double)) != cudaSuccess || cudaMalloc(&g_probe.d_q, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&g_probe.d_bt, sizeof(int)) != cudaSuccess || cudaMalloc(&g_probe.d_bits, sizeof(int)) != cudaSuccess)
+        legacy_fatal("out of device memory");
+    cudaFuncSetAttribute(k_quantize_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES);
+    return true;
+}
+
+static void legacy_count_result(const GrInfoOut &o, gr_info *c)
+{
+    c->big_values = o.big_values; c->count1 = o.count1; c->count1table_select = o.count1table_select;
+    c->region0_count = o.region0_count; c->region1_count = o.region1_count;
+    c->table_select[0] = o.table_select[0]; c->table_select[1] = o.table_select[1]; c->table_select[2] = o.table_select[2];
+    c->address1 = o.address1; c->address2 = o.address2; c->address3 = o.address3;
+}
+
+// loop.c:1360-1428: ix[i] = pow_nint(fabs(xr[i]) / 2^(quantizerStepSize/4)); subblock_gain 0, no mixed blocks
+extern "C" void quantize(double xr[576], int ix[576], gr_info *cod_info)
+{
+    if (!legacy_init()) return;
+    LegacyState &L = g_legacy;
+    if (!legacy_rate_tables(L) || !legacy_probe_buffers()) return;
+    double ax[576];
+    for (int i = 0; i < 576; i++) ax[i] = fabs(xr[i]);
+    const int q = (int)cod_info->quantizerStepSize;
+    const int bt = cod_info->window_switching_flag ? (int)cod_info->block_type : 0;
+    LCU(cudaMemcpy(g_probe.d_x, ax, sizeof(ax), cudaMemcpyHostToDevice));
+    LCU(cudaMemcpy(g_probe.d_q, &q, sizeof(int), cudaMemcpyHostToDevice));
+    LCU(cudaMemcpy(g_probe.d_bt, &bt, sizeof(int), cudaMemcpyHostToDevice));
+    k_quantize_count<<<1, RL_WARPS * 32, RL_SMEM_BYTES>>>(L.d_rate_tab, g_probe.d_x, g_probe.d_q, g_probe.d_bt, 1, L.d_ix, L.d_gi, g_probe.d_bits, 0);
+    L.launches++;
+    LCU(cudaGetLastError());
+    short out[576];
+    LCU(cudaMemcpy(out, L.d_ix, sizeof(out), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 576; i++) ix[i] = out[i];
+}
+
+// loop.c:2099-2113: bits of the quantised granule; sets big_values, count1, count1table_select, region0/1_count,
+// table_select[3] and address1..3 in cod_info exactly like calc_runlen / count1_bitcount / subdivide / bigv_tab_select do
+extern "C" int count_bits(int *ix, gr_info *cod_info)
+{
+    if (!legacy_init()) return 0;
+    LegacyState &L = g_legacy;
+    if (!legacy_rate_tables(L) || !legacy_probe_buffers()) return 0;
+    short in[576];
+    for (int i = 0; i < 576; i++) in[i] = (short)(ix[i] < 0 ? -ix[i] : ix[i]);
+    const int bt = cod_info->window_switching_flag ? (int)cod_info->block_type : 0;
+    GrInfoOut g;
+    memset(&g, 0, sizeof(g));
+    g.address1 = (int)cod_info->address1; g.address2 = (int)cod_info->address2; g.address3 = (int)cod_info->address3;
+    int bits = 0;
+    cudaError_t e = cudaMemcpy(L.d_ix, in, sizeof(in), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(L.d_gi, &g, sizeof(g), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g_probe.d_bt, &bt, sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_quantize_count<<<1, RL_WARPS * 32, RL_SMEM_BYTES>>>(L.d_rate_tab, nullptr, nullptr, g_probe.d_bt, 1, L.d_ix, L.d_gi, g_probe.d_bits, 1);
+        L.launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(&g, L.d_gi, sizeof(g), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(&bits, g_probe.d_bits, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { legacy_fail(MP3GPU_ECUDA, "count_bits", e); return 0; }
+    legacy_count_result(g, cod_info);
+    return bits;
+}

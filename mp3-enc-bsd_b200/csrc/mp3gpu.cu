@@ -171,10 +171,11 @@ k_rate_loop(const RateTables *__restrict__ gT, FrameGeom G, LoopStreamState *sta
     if (lane == 0) states[s] = S;
 }
 
-// quantize + count_bits on n independent granules
+// quantize + count_bits on n independent granules.  count_only: ix[] holds magnitudes already (count_bits(), loop.c:2099)
+// and gi[] carries address1..3 in (subdivide() leaves them untouched when big_values == 0, loop.c:1642-1647).
 __global__ void __launch_bounds__(RL_WARPS * 32)
 k_quantize_count(const RateTables *__restrict__ gT, const double *xr_abs, const int *q, const int *block_type, int n, short *ix,
-                 GrInfoOut *gi, int *bits)
+                 GrInfoOut *gi, int *bits, int count_only)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RateHot &H = load_rate_hot(gT, smem_raw);
@@ -185,26 +186,46 @@ k_quantize_count(const RateTables *__restrict__ gT, const double *xr_abs, const 
     WarpCtx w;
     const int bt = block_type[i];
     const bool is_short = (bt == 2), wsf = (bt != 0);
-    for (int k = 0; k < 9; k++) {
-        const int s = lane + 32 * k;
-        const int e0 = slot_e0(is_short, s), e1 = is_short ? e0 + 3 : e0 + 1;
-        D2 x; x.x = xr_abs[i * 576 + e0]; x.y = xr_abs[i * 576 + e1];
-        M.xs[s] = x;
-    }
-    refresh_pow34(w, M);
     CountResult C;
     memset(&C, 0, sizeof(C));
-    int qq = q[i];
-    qq = qq < -256 ? -256 : (qq > 255 ? 255 : qq);
-    const int b = probe(w, H, *gT, M, is_short, wsf, qq, C);
-    __syncwarp();
-    for (int k = 0; k < 9; k++) {
-        const int s = lane + 32 * k;
-        const int e0 = slot_e0(is_short, s), e1 = is_short ? e0 + 3 : e0 + 1;
-        const U2 v = M.ix[s];
-        ix[i * 576 + e0] = (short)v.x;
-        ix[i * 576 + e1] = (short)v.y;
+    int b;
+    if (!count_only) {
+        for (int k = 0; k < 9; k++) {
+            const int s = lane + 32 * k;
+            const int e0 = slot_e0(is_short, s), e1 = is_short ? e0 + 3 : e0 + 1;
+            D2 x; x.x = xr_abs[i * 576 + e0]; x.y = xr_abs[i * 576 + e1];
+            M.xs[s] = x;
+        }
+        refresh_pow34(w, M);
+        int qq = q[i];
+        qq = qq < -256 ? -256 : (qq > 255 ? 255 : qq);
+        b = probe(w, H, *gT, M, is_short, wsf, qq, C);
+    } else {
+        C.address1 = gi[i].address1; C.address2 = gi[i].address2; C.address3 = gi[i].address3;
+        PerThread<int> nzmax, bigmax;
+        int nz = -1, bg = -1;
+        for (int k = 0; k < 9; k++) {
+            const int s = lane + 32 * k;
+            const int e0 = slot_e0(is_short, s), e1 = is_short ? e0 + 3 : e0 + 1;
+            const int a = ix[i * 576 + e0], c = ix[i * 576 + e1];
+            U2 v; v.x = (unsigned short)a; v.y = (unsigned short)c;
+            M.ix[s] = v;
+            if ((a | c) != 0) nz = s;
+            if (a > 1 || c > 1) bg = s;
+        }
+        nzmax.v = nz; bigmax.v = bg;
+        __syncwarp();
+        b = count_all(w, H, M, is_short, wsf, nzmax, bigmax, C);
     }
+    __syncwarp();
+    if (!count_only)
+        for (int k = 0; k < 9; k++) {
+            const int s = lane + 32 * k;
+            const int e0 = slot_e0(is_short, s), e1 = is_short ? e0 + 3 : e0 + 1;
+            const U2 v = M.ix[s];
+            ix[i * 576 + e0] = (short)v.x;
+            ix[i * 576 + e1] = (short)v.y;
+        }
     if (lane == 0) {
         GrInfoOut g;
         memset(&g, 0, sizeof(g));
@@ -915,7 +936,19 @@ extern "C" int mp3gpu_quantize_count_batch(mp3gpu_ctx *c, const double *xr_abs, 
     if (!c) return fail(MP3GPU_EINVAL, "null ctx");
     if (n < 1 || !xr_abs || !q || !block_type || !ix || !gi || !bits) return fail(MP3GPU_EINVAL, "bad argument");
     k_quantize_count<<<(unsigned)((n + RL_WARPS - 1) / RL_WARPS), RL_WARPS * 32, RL_SMEM_BYTES, (cudaStream_t)stream>>>(
-        c->d_rate_tab, xr_abs, q, block_type, n, ix, (GrInfoOut *)gi, bits);
+        c->d_rate_tab, xr_abs, q, block_type, n, ix, (GrInfoOut *)gi, bits, 0);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mp3gpu_count_bits_batch(mp3gpu_ctx *c, const int16_t *ix, const int *block_type, int n, mp3gpu_gr_info *gi, int *bits,
+                                       void *stream)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    if (n < 1 || !ix || !block_type || !gi || !bits) return fail(MP3GPU_EINVAL, "bad argument");
+    k_quantize_count<<<(unsigned)((n + RL_WARPS - 1) / RL_WARPS), RL_WARPS * 32, RL_SMEM_BYTES, (cudaStream_t)stream>>>(
+        c->d_rate_tab, nullptr, nullptr, block_type, n, const_cast<int16_t *>(ix), (GrInfoOut *)gi, bits, 1);
     c->launches++;
     CU(cudaGetLastError());
     return 0;

@@ -36,8 +36,8 @@ EXPORTS = ["mp3gpu_last_error", "mp3gpu_version", "mp3gpu_create", "mp3gpu_destr
            "mp3gpu_L3psycho_anal_batch", "mp3gpu_iteration_loop_batch", "mp3gpu_quantize_count_batch",
            "mp3gpu_kernel_launches", "mp3gpu_profile_enable", "mp3gpu_profile_collect",
            "mp3gpu_encode_frames_mp3", "mp3gpu_encode_frames_mp3_dev", "mp3gpu_flush_mp3", "mp3gpu_flush_mp3_dev",
-           "mp3gpu_frame_bytes", "mp3gpu_format_bitstream_batch", "mp3gpu_begin_segment", "mp3gpu_stream_wave", "mp3gpu_set_pcm_layout"]
-LEGACY_EXPORTS = ["window_subband", "filter_subband", "mdct_sub", "L3psycho_anal", "iteration_loop",
+           "mp3gpu_frame_bytes", "mp3gpu_format_bitstream_batch", "mp3gpu_begin_segment", "mp3gpu_stream_wave", "mp3gpu_set_pcm_layout", "mp3gpu_count_bits_batch"]
+LEGACY_EXPORTS = ["window_subband", "filter_subband", "mdct_sub", "L3psycho_anal", "iteration_loop", "quantize", "count_bits",
                   "mp3gpu_legacy_reset", "mp3gpu_legacy_kernel_launches"]
 KERNEL_NAMES = ["psy_front", "psy_scan", "front_polyphase_mdct", "rate_loop", "bitstream"]
 
@@ -87,6 +87,7 @@ def load_library():
         for name in ("mp3gpu_flush_mp3", "mp3gpu_flush_mp3_dev"):
             getattr(lib, name).argtypes = [vp, C.c_int, vp, C.c_long, C.POINTER(C.c_long), vp]
         lib.mp3gpu_begin_segment.argtypes = [vp, vp]
+        lib.mp3gpu_count_bits_batch.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
         lib.mp3gpu_set_pcm_layout.argtypes = [vp, C.c_int]
         lib.mp3gpu_frame_bytes.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.mp3gpu_format_bitstream_batch.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, C.c_long, vp]
@@ -389,6 +390,23 @@ def encode_files(paths, sfreq=44100, n_ch=2, bitrate=128, device=0, chunk_frames
             out[i] = mp3[k, :lengths[k]].tobytes()
         enc.close()
     return out
+
+
+def _count_bits_batch(self, ix, block_type, gi=None, stream=None):
+    """count_bits() batched (mp3gpu_count_bits_batch): ix int16 [n][576] magnitudes, block_type int32 [n] (device
+    tensors); gi int32 [n][20] in/out (address1..3 read).  Returns (gi, bits)."""
+    torch = _torch()
+    n = ix.shape[0]
+    if gi is None:
+        gi = torch.zeros((n, 20), dtype=torch.int32, device=self._dev())
+    bits = self._empty((n,), torch.int32)
+    rc = self.lib.mp3gpu_count_bits_batch(self.ctx, ix.data_ptr(), block_type.data_ptr(), n, gi.data_ptr(), bits.data_ptr(),
+                                          C.c_void_p(stream or 0))
+    self._check(rc, "mp3gpu_count_bits_batch")
+    return gi, bits
+
+
+Encoder.count_bits_batch = _count_bits_batch
 
 
 def psy_to_numpy(psy_tensor):

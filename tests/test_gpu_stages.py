@@ -116,3 +116,78 @@ def test_quantize_count_batch_bit_exact(pkg, golden):
         assert np.array_equal(ix[i].astype(np.int32), ix_ref), i
         assert bits[i] == b_ref, (i, bits[i], b_ref)
         assert np.array_equal(gi[i][cols], gi_ref[cols]), (i, gi[i], gi_ref)
+
+
+def _legacy_gr_info():
+    import ref_harness
+    return ref_harness.GrInfo
+
+
+def test_legacy_quantize_and_count_bits(pkg, golden):
+    """the reference's own inner-loop pair (loop.c:1360, :2099) as exported by libmp3gpu.so with the reference's
+    signatures (include/mp3gpu_legacy.h): one granule per call, cod_info updated like the reference does.  Checked against
+    the oracle, and against the reference's own functions where oracle/_ref/libref.so is present."""
+    import ctypes as C
+    import ref_harness
+    lib = pkg.load_library()
+    GrInfo = _legacy_gr_info()
+    lib.quantize.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(GrInfo)]
+    lib.count_bits.argtypes = [C.c_void_p, C.POINTER(GrInfo)]
+    lib.count_bits.restype = C.c_int
+    ref = None
+    if ref_harness.have_ref():
+        ref = C.CDLL(ref_harness.LIBREF)
+        ref.quantize.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(GrInfo)]
+        ref.count_bits.argtypes = [C.c_void_p, C.POINTER(GrInfo)]
+        ref.count_bits.restype = C.c_int
+    g = golden["cfg1_44k_stereo_128"]
+    o = oracle.encode_stream(g["pcm"], 44100, 128)
+    rng = np.random.default_rng(3)
+    n_ref = 0
+    for t in range(40):
+        f, gr, ch = int(rng.integers(2, len(o))), int(rng.integers(0, 2)), int(rng.integers(0, 2))
+        xr = np.ascontiguousarray(o["xr"][f, gr, ch]) * float(rng.choice([1.0, 30.0, 1e-3, 400.0]))
+        bt = int(rng.choice([0, 0, 1, 2, 3]))
+        q = int(rng.integers(-60, 40))
+        ci = GrInfo()
+        ci.window_switching_flag = 1 if bt else 0
+        ci.block_type = bt
+        ci.quantizerStepSize = float(q)
+        ix = np.zeros(576, np.int32)
+        lib.quantize(xr.ctypes.data, ix.ctypes.data, C.byref(ci))
+        bits = lib.count_bits(ix.ctypes.data, C.byref(ci))
+        b_ref, ix_ref, gi_ref = oracle.quantize_count(np.abs(xr), q, bt, 1)
+        assert np.array_equal(ix, ix_ref), (t, q, bt)
+        row = np.array(ref_harness.gr_to_row(ci), np.int64)
+        for k in ("big_values", "count1", "count1table_select", "region0_count", "region1_count", "table_select0",
+                  "table_select1", "table_select2", "address1", "address2", "address3"):
+            j = ref_harness.GR_FIELDS.index(k)
+            assert row[j] == gi_ref[j], (t, k, row[j], gi_ref[j])
+        assert bits == b_ref, (t, bits, b_ref)
+        if ref is not None and ix.max() <= 8191 + 14:
+            cr = GrInfo()
+            cr.window_switching_flag = 1 if bt else 0
+            cr.block_type = bt
+            cr.quantizerStepSize = float(q)
+            ixr = np.zeros(576, np.int32)
+            ref.quantize(xr.ctypes.data, ixr.ctypes.data, C.byref(cr))
+            assert np.array_equal(ix, ixr)
+            n_ref += 1
+    print(f"40 probes identical to the oracle; quantize() identical to the reference's own in {n_ref} of them")
+
+
+def test_count_bits_batch(pkg, golden):
+    """count_bits() batched on given quantised spectra (mp3gpu_count_bits_batch) vs the oracle's count_bits"""
+    g = golden["cfg3_48k_stereo_320"]
+    ixs = np.ascontiguousarray(g["ix"][:, :, :2]).reshape(-1, 576).astype(np.int16)
+    bts = np.ascontiguousarray(g["gi"][:, :, :2, 6]).reshape(-1).astype(np.int32)
+    n = len(ixs)
+    enc = pkg.Encoder(48000, 2, 320, max_streams=1, max_frames=1)
+    dev = torch.device("cuda", 0)
+    gi, bits = enc.count_bits_batch(torch.from_numpy(ixs).to(dev), torch.from_numpy(bts).to(dev))
+    gi, bits = gi.cpu().numpy(), bits.cpu().numpy()
+    for i in range(n):
+        b_ref, gi_ref = oracle.count_bits(ixs[i].astype(np.int32), int(bts[i]), 2)
+        assert bits[i] == b_ref, (i, bits[i], b_ref)
+        for j in (1, 2, 8, 9, 10, 11, 12, 15, 17, 18, 19):
+            assert gi[i, j] == gi_ref[j], (i, j, gi[i, j], gi_ref[j])
