@@ -829,7 +829,12 @@ extern "C" int mp3gpu_format_bitstream_batch(mp3gpu_ctx *c, const int16_t *ix, c
 
 static int encode_mp3_common(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, uint8_t *mp3, long stride, void *stream, bool host)
 {
-    int rc = encode_common(c, pcm, n_streams, n_frames, nullptr, nullptr, nullptr, nullptr, stream, host);
+    int rc = check_shape(c, n_streams, n_frames);
+    if (rc) return rc;
+    // validate before any stream state advances
+    if (mp3 && stride < (c->frames_done + n_frames) * (long)c->frame_bytes)
+        return fail(MP3GPU_EINVAL, "mp3 stride too small for the frames encoded so far");
+    rc = encode_common(c, pcm, n_streams, n_frames, nullptr, nullptr, nullptr, nullptr, stream, host);
     if (rc) return rc;
     return format_common(c, c->d_ix, c->d_gi, c->d_sf, c->d_fo, n_streams, n_frames, mp3, stride, host, (cudaStream_t)stream);
 }

@@ -118,3 +118,30 @@ def test_full_size_properties(pkg):
     assert np.array_equal(lhs, resv_after[:, :-1])
     assert (fo["main_data_begin"] * 8 <= 4088).all() and (fo["main_data_begin"] >= 0).all()
     assert (gi[:, :, 0] <= 4095).all() and (gi[:, :, 1] <= 288).all() and (gi[:, :, 3] < 256).all()
+
+
+def test_error_codes_instead_of_exit(pkg):
+    """the batched API returns MP3GPU_E* codes where the reference exit()s / abort()s: capacity overflow,
+    null pointers, a too-small output row, unknown PCM layout; the ctx stays usable afterwards"""
+    import ctypes as C
+    host = pkg.host
+    enc = pkg.Encoder(44100, 2, 128, max_streams=2, max_frames=3)
+    lib = enc.lib
+    pcm = np.zeros((2, 2, 3 * 1152), np.int16)
+    mp3 = np.zeros((2, 3 * enc.frame_bytes), np.uint8)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    assert lib.mp3gpu_encode_frames(enc.ctx, vp(pcm), 3, 3, None, None, None, None, None) == -4          # MP3GPU_ESTATE: 3 streams > capacity
+    assert b"capacity" in lib.mp3gpu_last_error()
+    assert lib.mp3gpu_encode_frames(enc.ctx, vp(pcm), 2, 4, None, None, None, None, None) == -4          # 4 frames > capacity
+    assert lib.mp3gpu_encode_frames(enc.ctx, None, 2, 3, None, None, None, None, None) == -1             # MP3GPU_EINVAL
+    assert lib.mp3gpu_encode_frames(enc.ctx, vp(pcm), 0, 3, None, None, None, None, None) == -1
+    assert lib.mp3gpu_encode_frames_mp3(enc.ctx, vp(pcm), 2, 3, vp(mp3), 10, None) == -1                  # row shorter than 3 frames
+    assert lib.mp3gpu_set_pcm_layout(enc.ctx, 7) == -1
+    assert lib.mp3gpu_flush_mp3(enc.ctx, 5, None, 0, None, None) == -1
+    assert lib.mp3gpu_reset(None) == -1
+    # still works, and the failed calls left no trace in the stream state
+    enc.reset()
+    x = np.ascontiguousarray(pkg.synth.config1(3 * 1152 / 44100.0 + 0.01, seeds=(5, 6))[:, :3 * 1152])
+    got = enc.encode_streams(np.stack([x, x]))
+    ref, _ = oracle.format_stream(oracle.encode_stream(x, 44100, 128), 2, 44100, 128)
+    assert got[0] == ref[:-1] and got[1] == ref[:-1]
