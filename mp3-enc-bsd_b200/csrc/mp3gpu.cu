@@ -153,12 +153,13 @@ k_rate_loop(const RateTables *__restrict__ gT, FrameGeom G, LoopStreamState *sta
             const double *__restrict__ xr, const PsyOut *__restrict__ psy, short *ix, GrInfoOut *gi, unsigned char *sf, FrameOut *fo)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const RateHot &H = load_rate_hot(gT, smem_raw);
+    const RateHot &H0 = load_rate_hot(gT, smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    RateWarpSmem &M = reinterpret_cast<RateWarpSmem *>(smem_raw + RL_HOT_BYTES)[warp];
     const long s = (long)blockIdx.x * RL_WARPS + warp;
     if (s >= n_streams) return;
-    WarpCtx w;
+    const RateHot &H = simt::pin_smem(H0);
+    RateWarpSmem &M = simt::pin_smem(reinterpret_cast<RateWarpSmem *>(smem_raw + RL_HOT_BYTES)[warp]);
+    WarpCtx w{WarpCtx::Pinned()};
     LoopStreamState S = states[s];
     PerThread<int> st_en[4], st_xm[4];
 #pragma unroll

@@ -98,8 +98,8 @@ struct FrameGeom {
 //   short blocks (type 2):      slot s = 3 m + w holds elements (6m+w, 6m+3+w), i.e. lines 2m and
 //                               2m+1 of window w (the [192][3] view of loop.c:1375-1376)
 struct alignas(16) D2 { double x, y; };
-struct U2 { unsigned short x, y; };
-struct F2 { float x, y; };
+struct alignas(4) U2 { unsigned short x, y; };
+struct alignas(8) F2 { float x, y; };
 struct alignas(16) RateWarpSmem {
     D2 xs[288];        // |xr| of the slot's two elements (amplified in place by the outer loop)
     double scr[288];   // per-slot energies / noise for the band sums; between refresh_pow34() and calc_noise it holds
@@ -118,28 +118,14 @@ SIMT_FN float pow075_estimate(float x)
 }
 
 // pow_nint(): largest p in [0,2047] with x >= tab[p] (tab strictly increasing, tab[0] := -inf) — the
-// value the reference finds with gallop + binary search (pow_nint.h:16-50).  x^(3/4) + 0.4054 is
-// estimated in FP32; unless the estimate lies within a conservative error margin of an integer the
-// truncation is already exact, otherwise the exact FP64 comparison against the table decides.
+// value the reference finds with gallop + binary search (pow_nint.h:16-50).  p is only a starting guess.
 SIMT_NOINLINE int quant1_exact(const double *tab, double x, int p)
 {
     if (p < 0) p = 0;
+    if (p > 2047) p = 2047;
     while (p > 0 && x < tab[p]) p--;
     while (p < 2047 && x >= tab[p + 1]) p++;
     return p;
-}
-
-// x^(3/4) + 0.4054 estimated in FP32 as t = |xr|^(3/4) * (1/step)^(3/4) + 0.4054 from the cached per-slot power:
-// unless t lies within a conservative error margin of an integer (or is out of range / not a number) the
-// truncation is exact, otherwise the FP64 table comparison on |xr| / step decides.  The estimate's relative
-// error is < 2.2e-6 (two MUFU ops on |log2| <= 24, two FP32 roundings); the margin is 1e-5 * t + 1e-6.
-SIMT_FN int quant1(const double *tab, float t, const double *x, double ostep)
-{
-    const int p0 = (t < 2047.0f) ? (int)t : 2047;   // also catches inf / nan estimates
-    const float d = t - (float)p0;
-    const float margin = 1e-5f * t + 1e-6f;
-    if (t < 2040.0f && d > margin && d < 1.0f - margin) return p0;
-    return quant1_exact(tab, simt::dmul(*x, ostep), p0);
 }
 
 // libm calls that sit outside the hot loop are kept out of line: the kernel's working set of
@@ -196,26 +182,40 @@ SIMT_FN int slot_e0(bool is_short, int s)
 }
 
 // quantize(): loop.c:1360-1428 with subblock_gain == 0 and mixed_block_flag == 0 (always, l3psy.c:739).
+// x^(3/4) + 0.4054 is estimated in FP32 as t = |xr|^(3/4) * (1/step)^(3/4) + 0.4054 from the cached per-slot power.
+// The estimate's relative error is < 2.2e-6 (two MUFU ops on |log2| <= 24, FP32 roundings); with the 5x-conservative
+// margin m = 1e-5 t + 1e-6 the truncation is exact whenever trunc(t - m) == trunc(t + m) (and t is in range and a
+// number), otherwise the FP64 table comparison on |xr| / step decides (pow_nint.h:16-50) — exact by construction.
 // Also returns, per lane, the last slot holding a non-zero value and the last slot holding a value
 // > 1 (calc_runlen's scan, loop.c:1498-1517) since the values are at hand.
+// The loop is the hottest of the kernel (30 probes x 9 trips per granule-channel): one trip is ~35 instructions.
 SIMT_FN void quantize_all(const WarpCtx &w, const RateTables &T, RateWarpSmem &M, int q, PerThread<int> &nzmax, PerThread<int> &bigmax)
 {
     const int qi = (q > 255 ? 255 : q) + 256;
     const double ostep = T.ostep[qi];
     const float of = T.ostep34[qi];
-    const F2 *ys = reinterpret_cast<const F2 *>(M.scr);
     FOR_THREADS(w)
+    const F2 *ys = reinterpret_cast<const F2 *>(M.scr);
+    unsigned *ixw = reinterpret_cast<unsigned *>(M.ix);
     int nz = -1, bg = -1;
 #pragma unroll 1
-    for (int k = 0; k < 9; k++) {
-        const int s = lane + 32 * k;
+    for (int s = lane; s < 288; s += 32) {
         const F2 y = ys[s];
-        const int a = quant1(T.pow_nint_tab, simt::fadd(simt::fmul(y.x, of), 0.4054f), &M.xs[s].x, ostep);
-        const int b = quant1(T.pow_nint_tab, simt::fadd(simt::fmul(y.y, of), 0.4054f), &M.xs[s].y, ostep);
-        U2 v; v.x = (unsigned short)a; v.y = (unsigned short)b;
-        M.ix[s] = v;
-        if ((a | b) != 0) nz = s;
-        if (a > 1 || b > 1) bg = s;
+        // clamped at 2040: an out-of-range (or nan) estimate sits exactly on an integer and therefore fails the test below
+        const float ta = simt::fmin_(simt::ffma(y.x, of, 0.4054f), 2040.0f), tb = simt::fmin_(simt::ffma(y.y, of, 0.4054f), 2040.0f);
+        const float ma = simt::ffma(ta, 1e-5f, 1e-6f), mb = simt::ffma(tb, 1e-5f, 1e-6f);
+        int a = simt::f2i_trunc(simt::fsub(ta, ma)), b = simt::f2i_trunc(simt::fsub(tb, mb));
+        const bool oka = (a == simt::f2i_trunc(simt::fadd(ta, ma)));
+        const bool okb = (b == simt::f2i_trunc(simt::fadd(tb, mb)));
+        if (!(oka && okb)) {
+            const D2 x = M.xs[s];
+            if (!oka) a = quant1_exact(T.pow_nint_tab, simt::dmul(x.x, ostep), a);
+            if (!okb) b = quant1_exact(T.pow_nint_tab, simt::dmul(x.y, ostep), b);
+        }
+        ixw[s] = (unsigned)a | ((unsigned)b << 16);
+        const int ab = a | b;
+        if (ab != 0) nz = s;
+        if (ab > 1) bg = s;           // a > 1 || b > 1
     }
     nzmax() = nz; bigmax() = bg;
     END_THREADS
@@ -302,77 +302,59 @@ SIMT_FN int count_all(const WarpCtx &w, const RateHot &H, const RateWarpSmem &M,
     // start/stop/short blocks, where region 2 is never selected, so [a2,bvr) covers both.)
     const int a1 = C.address1, a2 = C.address2;
     const bool has0 = a1 > 0, has1 = a2 > a1, has2 = !is_short && bvr > a2;
-    int e_end = has0 ? a1 : 0;
-    if (has1) e_end = a2;
-    if (has2) e_end = bvr;
-    if (e_end > 576) e_end = 576;
-    const int k_end = (e_end + 63) >> 6;     // slots s = lane + 32 k hold elements 2 s, 2 s + 1
-    // Both passes are written branch-free on purpose (selects and unconditional loads): the compiler turned the
-    // nested conditionals of the straightforward form into ~10 divergent branches per slot.  a1, a2 and bvr are even,
-    // so "element e = 2 s below a" is "slot s below a / 2".
+    // Slots s hold elements 2 s, 2 s + 1 and a1, a2, bvr are even, so region r is the slot range [lo[r], hi[r]) (empty when
+    // the region is absent; everything is capped at the 288 slots of the granule).  One loop per region, lanes striding
+    // through it: a trip is a load and one packed max (or one table look-up and an add) instead of three-way selects.
     const int S1 = a1 >> 1, S2 = a2 >> 1, S3 = bvr >> 1;
+    int lo[3], hi[3];
+    lo[0] = 0;                  hi[0] = has0 ? (S1 < 288 ? S1 : 288) : 0;
+    lo[1] = S1;                 hi[1] = has1 ? (S2 < 288 ? S2 : 288) : 0;
+    lo[2] = S1 > S2 ? S1 : S2;  hi[2] = has2 ? (S3 < 288 ? S3 : 288) : 0;
     const unsigned *ixw = reinterpret_cast<const unsigned *>(M.ix);      // x | y << 16
-    PerThread<int> mx0, mx1, mx2;
-    FOR_THREADS(w)
-    unsigned m0 = 0, m1 = 0, m2 = 0;
-#pragma unroll 1
-    for (int k = 0; k < k_end; k++) {
-        const int sl = lane + 32 * k;
-        const unsigned u = ixw[sl];
-        const unsigned v = simt::umax(u & 0xffffu, u >> 16);
-        const bool p0 = sl < S1, p1 = sl < S2, p2 = sl < S3;
-        m0 = simt::umax(m0, p0 ? v : 0u);
-        m1 = simt::umax(m1, (!p0 && p1) ? v : 0u);
-        m2 = simt::umax(m2, (!p0 && !p1 && p2) ? v : 0u);
-    }
-    mx0() = (int)m0; mx1() = (int)m1; mx2() = (int)m2;
-    END_THREADS
     int grp[3] = {-1, -1, -1}, rmax[3] = {0, 0, 0};
-    if (has0) rmax[0] = w.reduce_max(mx0);
-    if (has1) rmax[1] = w.reduce_max(mx1);
-    if (has2) rmax[2] = w.reduce_max(mx2);
     bool any = false;
 #pragma unroll
-    for (int r = 0; r < 3; r++)
+    for (int r = 0; r < 3; r++) {
+        if (hi[r] <= lo[r]) continue;
+        PerThread<int> mx;
+        FOR_THREADS(w)
+        unsigned m = 0;
+#pragma unroll 1
+        for (int sl = lo[r] + lane; sl < hi[r]; sl += 32) m = simt::vmaxu2(m, ixw[sl]);   // per-halfword maximum
+        mx() = (int)simt::umax(m & 0xffffu, m >> 16);
+        END_THREADS
+        rmax[r] = w.reduce_max(mx);
         if (rmax[r] > 0) { grp[r] = group_for_max(rmax[r]); any = true; }
+    }
     int bits = c1bits;
     if (any) {
-        PerThread<int> lo[3], hi[3];
-        // a region without a group (all zero, or absent) is priced with group 0 and its sum is never looked at
-        const int bs0 = (grp[0] < 0 ? 0 : grp[0]) << 8, bs1 = (grp[1] < 0 ? 0 : grp[1]) << 8, bs2 = (grp[2] < 0 ? 0 : grp[2]) << 8;
         const unsigned *gl = &H.glut[0][0];
-        FOR_THREADS(w)
-        unsigned acc0 = 0, acc1 = 0, acc2 = 0;
-#pragma unroll 1
-        for (int k = 0; k < k_end; k++) {
-            const int sl = lane + 32 * k;
-            const unsigned c = simt::vminu2(ixw[sl], 0x000f000fu);              // min(x, 15) | min(y, 15) << 16
-            const unsigned idx = ((c << 4) | (c >> 16)) & 0xffu;                    // 16 x + y
-            const bool p0 = sl < S1, p1 = sl < S2, p2 = sl < S3;
-            const unsigned wv = gl[(p0 ? bs0 : p1 ? bs1 : bs2) + idx];
-            acc0 += p0 ? wv : 0u;
-            acc1 += (!p0 && p1) ? wv : 0u;
-            acc2 += (!p0 && !p1 && p2) ? wv : 0u;
-        }
-        // per lane <= 9 pairs x <= 63 per field: no carry between the 10-bit fields
-        lo[0]() = (int)((acc0 & 1023u) | (((acc0 >> 10) & 1023u) << 16)); hi[0]() = (int)(acc0 >> 20);
-        lo[1]() = (int)((acc1 & 1023u) | (((acc1 >> 10) & 1023u) << 16)); hi[1]() = (int)(acc1 >> 20);
-        lo[2]() = (int)((acc2 & 1023u) | (((acc2 >> 10) & 1023u) << 16)); hi[2]() = (int)(acc2 >> 20);
-        END_THREADS
 #pragma unroll
         for (int r = 0; r < 3; r++) {
             if (grp[r] < 0) continue;
             const int g = grp[r], max = rmax[r];
-            const int both = w.reduce_add(lo[r]);
+            PerThread<int> lo_, hi_;
+            FOR_THREADS(w)
+            const unsigned *gt = gl + (g << 8);
+            unsigned acc = 0;
+#pragma unroll 1
+            for (int sl = lo[r] + lane; sl < hi[r]; sl += 32) {
+                const unsigned c = simt::vminu2(ixw[sl], 0x000f000fu);              // min(x, 15) | min(y, 15) << 16
+                acc += gt[((c << 4) | (c >> 16)) & 0xffu];                            // 16 x + y
+            }
+            // per lane <= 9 pairs x <= 63 per field: no carry between the 10-bit fields
+            lo_() = (int)((acc & 1023u) | (((acc >> 10) & 1023u) << 16)); hi_() = (int)(acc >> 20);
+            END_THREADS
+            const int both = w.reduce_add(lo_);
             int s0 = both & 0xffff, s1 = both >> 16, choice;
             if (is_short) {
                 // choose_table (by max alone), loop.c:1908-1943: first table covering max; 15 -> table 15
                 if (g == 7) { choice = 15; }                               // glut g7 field 0 = table 15
-                else if (g == 6) { choice = esc_table(H, 16, 24, max - 15); s0 += (int)H.hlinbits[choice] * w.reduce_add(hi[r]); }
+                else if (g == 6) { choice = esc_table(H, 16, 24, max - 15); s0 += (int)H.hlinbits[choice] * w.reduce_add(hi_); }
                 else choice = table_for_small_max(max);
             } else if (g >= 6) {
                 // ESC pair, strict '<' (loop.c:1870-1898)
-                const int nesc = w.reduce_add(hi[r]);
+                const int nesc = w.reduce_add(hi_);
                 const int c0 = esc_table(H, 15, 24, max - 15), c1 = esc_table(H, 24, 32, max - 15);
                 s0 += (int)H.hlinbits[c0] * nesc;
                 s1 += (int)H.hlinbits[c1] * nesc;
@@ -385,7 +367,7 @@ SIMT_FN int count_all(const WarpCtx &w, const RateHot &H, const RateWarpSmem &M,
                     const int c1 = (g == 1) ? 3 : (g == 2) ? 6 : (g == 3) ? 8 : (g == 4) ? 11 : 15;
                     if (s1 <= s0) { choice = c1; s0 = s1; }
                     if (g == 3 || g == 4) {
-                        const int s2 = w.reduce_add(hi[r]);
+                        const int s2 = w.reduce_add(hi_);
                         if (s2 <= s0) { choice = (g == 3) ? 9 : 12; s0 = s2; }
                     }
                 }

@@ -44,6 +44,9 @@ struct WarpCtx {  // one warp == one group
     int lane;
     static constexpr int kThreads = 32;
     SIMT_FN WarpCtx() : lane(threadIdx.x & 31) {}
+    // lane index that the optimiser cannot rematerialise from %tid inside hot loops (it lives in a register instead)
+    struct Pinned {};
+    SIMT_FN explicit WarpCtx(Pinned) { const int l = threadIdx.x & 31; lane = __shfl_sync(0xffffffffu, l, l); }
     SIMT_FN void sync() const { __syncwarp(); }
     SIMT_FN int reduce_max(const PerThread<int> &x) const { return __reduce_max_sync(0xffffffffu, x.v); }
     SIMT_FN int reduce_add(const PerThread<int> &x) const { return __reduce_add_sync(0xffffffffu, x.v); }
@@ -71,6 +74,18 @@ struct WarpCtx {  // one warp == one group
     SIMT_FN T broadcast(const PerThread<T> &x, int src_lane) const { return __shfl_sync(0xffffffffu, x.v, src_lane); }
 };
 
+// Reference to a per-warp shared-memory object whose address is opaque to the optimiser.  Under register pressure
+// ptxas otherwise re-derives the shared-window address from %tid / %cgaid in every trip of every hot loop (S2R + 6
+// integer instructions per access site, profiles/r01_e_capture.md); a value that went through a shuffle has to stay in a
+// register.  All lanes of the warp must pass the same object.
+template <class T>
+SIMT_FN T &pin_smem(T &m)
+{
+    unsigned a = (unsigned)__cvta_generic_to_shared(&m);
+    a = __shfl_sync(0xffffffffu, a, 0);
+    return *reinterpret_cast<T *>(__cvta_shared_to_generic(a));
+}
+
 struct BlockCtx {  // a whole CTA
     int tid, nthreads;
     SIMT_FN BlockCtx() : tid(threadIdx.x), nthreads(blockDim.x) {}
@@ -88,10 +103,14 @@ SIMT_FN double dsub(double a, double b) { return __dsub_rn(a, b); }
 SIMT_FN float fmul(float a, float b) { return __fmul_rn(a, b); }
 SIMT_FN float fadd(float a, float b) { return __fadd_rn(a, b); }
 SIMT_FN float fsub(float a, float b) { return __fsub_rn(a, b); }
+SIMT_FN float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+SIMT_FN float fmin_(float a, float b) { return fminf(a, b); }                 // nan-suppressing: fmin_(nan, b) == b
+SIMT_FN int f2i_trunc(float a) { return __float2int_rz(a); }   // saturating; nan -> 0
 SIMT_FN int popc(unsigned v) { return __popc(v); }
 SIMT_FN int clz(unsigned v) { return __clz(v); }
 SIMT_FN unsigned umax(unsigned a, unsigned b) { return max(a, b); }
 SIMT_FN unsigned vminu2(unsigned a, unsigned b) { return __vminu2(a, b); }   // per-halfword unsigned minimum
+SIMT_FN unsigned vmaxu2(unsigned a, unsigned b) { return __vmaxu2(a, b); }   // per-halfword unsigned maximum
 
 #else
 // ------------------------------------------------------------------------------------------------
@@ -141,6 +160,9 @@ inline double dsub(double a, double b) { return a - b; }
 inline float fmul(float a, float b) { return a * b; }
 inline float fadd(float a, float b) { return a + b; }
 inline float fsub(float a, float b) { return a - b; }
+inline float ffma(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline float fmin_(float a, float b) { return std::fmin(a, b); }
+inline int f2i_trunc(float a) { return (a != a) ? 0 : (a >= 2147483648.0f) ? 2147483647 : (a <= -2147483648.0f) ? (-2147483647 - 1) : (int)a; }
 inline int popc(unsigned v) { return __builtin_popcount(v); }
 inline int clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 inline unsigned umax(unsigned a, unsigned b) { return a > b ? a : b; }
@@ -148,6 +170,12 @@ inline unsigned vminu2(unsigned a, unsigned b)
 {
     const unsigned lo = (a & 0xffffu) < (b & 0xffffu) ? (a & 0xffffu) : (b & 0xffffu);
     const unsigned hi = (a >> 16) < (b >> 16) ? (a >> 16) : (b >> 16);
+    return lo | (hi << 16);
+}
+inline unsigned vmaxu2(unsigned a, unsigned b)
+{
+    const unsigned lo = (a & 0xffffu) > (b & 0xffffu) ? (a & 0xffffu) : (b & 0xffffu);
+    const unsigned hi = (a >> 16) > (b >> 16) ? (a >> 16) : (b >> 16);
     return lo | (hi << 16);
 }
 #endif
