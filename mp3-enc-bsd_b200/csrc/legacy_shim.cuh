@@ -69,7 +69,7 @@ struct LegacyState {
     // psy
     int psy_sr = -1;
     PsyTables *d_psy_tab = nullptr;
-    FftOpPacked *ops1024 = nullptr, *ops256 = nullptr;
+    uint32_t *ops1024 = nullptr, *ops256 = nullptr;
     int *lv1024 = nullptr, *lv256 = nullptr;
     uint16_t *out1024 = nullptr, *out256 = nullptr;
     FftTwiddle *d_tw = nullptr;

@@ -105,8 +105,8 @@ k_psy_front(PsyDev D, const short *pcm, long stream_stride, long ch_stride, int 
     const int ch = (int)(gc % n_ch);
     const int g = (int)((gc / n_ch) % n_gran);
     const long s = gc / ((long)n_ch * n_gran);
-    WarpCtx w;
-    psy_front(w, D, Ms[warp], pcm + s * stream_stride + ch * ch_stride + HIST + 576L * g, &mid[gc]);
+    WarpCtx w{WarpCtx::Pinned()};
+    psy_front(w, D, simt::pin_smem(Ms[warp]), pcm + s * stream_stride + ch * ch_stride + HIST + 576L * g, &mid[gc]);
 }
 
 #define PSYS_WARPS 4
@@ -292,7 +292,7 @@ struct mp3gpu_ctx {
     // tables
     PsyTables *d_psy_tab = nullptr;
     RateTables *d_rate_tab = nullptr;
-    FftOpPacked *d_ops1024 = nullptr, *d_ops256 = nullptr;
+    uint32_t *d_ops1024 = nullptr, *d_ops256 = nullptr;
     int *d_lv1024 = nullptr, *d_lv256 = nullptr;
     uint16_t *d_out1024 = nullptr, *d_out256 = nullptr;
     FftTwiddle *d_tw = nullptr;
@@ -361,18 +361,18 @@ static int dalloc(T **p, size_t n)
     return 0;
 }
 
-static int upload_fft(const FftProgram &P, FftOpPacked **ops, int **lv, uint16_t **out, FftDev *dev)
+static int upload_fft(const FftProgram &P, uint32_t **ops, int **lv, uint16_t **out, FftDev *dev)
 {
     int rc;
-    if ((rc = dalloc(ops, P.packed.size()))) return rc;
-    if ((rc = dalloc(lv, P.level_start.size()))) return rc;
+    if ((rc = dalloc(ops, P.words.size()))) return rc;
+    if ((rc = dalloc(lv, P.seg_word.size()))) return rc;
     if ((rc = dalloc(out, (size_t)P.n))) return rc;
     std::vector<uint16_t> o(P.n);
     for (int i = 0; i < P.n; i++) o[i] = (uint16_t)(FFT_SKEW((unsigned)P.out_slot[i]) | (P.out_neg[i] ? 0x8000 : 0));
-    CU(cudaMemcpy(*ops, P.packed.data(), P.packed.size() * sizeof(FftOpPacked), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(*lv, P.level_start.data(), P.level_start.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(*ops, P.words.data(), P.words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(*lv, P.seg_word.data(), P.seg_word.size() * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(*out, o.data(), o.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    dev->ops = *ops; dev->level_start = *lv; dev->n_levels = ((int)P.level_start.size() - 1) / 3; dev->out = *out;
+    dev->words = *ops; dev->seg_word = *lv; dev->n_levels = ((int)P.seg_word.size() - 1) / FFT_CLASSES; dev->out = *out;
     return 0;
 }
 

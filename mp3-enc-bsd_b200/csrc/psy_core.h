@@ -25,10 +25,10 @@ using simt::PerThread;
 using simt::WarpCtx;
 
 struct FftDev {
-    const FftOpPacked *ops;
-    const int *level_start;
+    const uint32_t *words;  // op stream, see the class table in tables.h
+    const int *seg_word;    // [4 * n_levels + 1] segment (level, class) -> offset into words[]
     int n_levels;
-    const uint16_t *out;  // logical index -> slot | (neg << 15)
+    const uint16_t *out;    // logical index -> slot | (neg << 15)
 };
 
 struct PsyDev {
@@ -46,13 +46,13 @@ struct PsyMid {
     float e6[8], phi6[8];
 };
 
-// 6304 B per warp (8 warps per CTA, 4 CTAs per SM).  x[] holds the FFT working set; everything that is
+// 6816 B per warp (8 warps per CTA, 4 CTAs per SM).  x[] holds the FFT working set; everything that is
 // produced after a transform and consumed before the next one that needs the space is overlaid on it:
 //   after the LONG FFT only x[0..255] is reused (short transforms), so Es / Ps live in x[256..819];
 //   after the last SHORT FFT x[0..255] is free: cwv and eb live there; thr overlays E[] once the long
 //   partition energies have been formed (E is dead by then).
 struct PsyFrontSmem {
-    float x[FFT_X_WORDS];
+    float x[FFT_X_ALLOC];
     float E[520];
 };
 struct PsyFrontView {
@@ -84,89 +84,120 @@ struct PsyChanState {  // persistent per (stream, channel)
 
 static const double kLn2Log10 = 0.2302585093;  // LN_TO_LOG10, common.h:204
 
-// One op = decode, load, compute, store.  The three phases are separate functions so that fft_rows() can run the
-// loads of TWO independent ops (two rows of the same level) before either op's stores: the compiler cannot prove that
-// x[] stores of one op do not alias the loads of the next, the level structure guarantees it.
-struct FftDec { int ia, ib, ic, id, type, neg, tw; };
-
-SIMT_FN FftDec fft_decode(FftOpPacked op)
+// ---- FFT op-program executor -------------------------------------------------------------------------
+// A row is 32 ops of one class, one per lane; operands are byte offsets into the warp's x[].  The rows of a segment
+// are independent (one dependency level), so a trip takes U rows, issues all their loads and only then their stores:
+// the compiler cannot prove that the stores of one op do not alias the loads of the next, the level structure does.
+// Padding ops of classes 0..2 work on per-lane dummy words (tables.h), so there is no NOP test in the fast loops.
+SIMT_FN float fft_ld(const float *x, unsigned byte_off) { return *reinterpret_cast<const float *>(reinterpret_cast<const char *>(x) + byte_off); }
+SIMT_FN void fft_st(float *x, unsigned byte_off, float v) { *reinterpret_cast<float *>(reinterpret_cast<char *>(x) + byte_off) = v; }
+SIMT_FN float fft_flip(float v, unsigned sign_word)     // v with its sign flipped when bit 31 of sign_word is set
 {
-    const unsigned lo = (unsigned)op, hi = (unsigned)(op >> 32);
-    FftDec d;
-    d.type = (hi >> 22) & 7; d.neg = (hi >> 25) & 15; d.tw = (hi >> 12) & 1023;
-    d.ia = lo & 2047; d.ib = (lo >> 11) & 2047; d.ic = ((lo >> 22) | (hi << 10)) & 2047; d.id = (hi >> 1) & 2047;
-    return d;
+#if SIMT_DEV
+    return __uint_as_float(__float_as_uint(v) ^ (sign_word & 0x80000000u));
+#else
+    return (sign_word & 0x80000000u) ? -v : v;
+#endif
 }
 
-struct FftVals { float a, b, c, d; FftTwiddle w; };
-
-// CLS 0: butterflies (a, b); 1: crosses (a, b, c, d); 2: rotations (a, c [+ twiddle]).  FFT_NOP decodes to slot 0.
-template <int CLS>
-SIMT_FN void fft_load(const FftDec &o, const FftTwiddle *tw, const float *x, FftVals &v)
+template <int U>
+SIMT_FN void fft_rows_bfly(const uint32_t *p, float *x)        // t=a+b; b=a-b; a=t
 {
-    v.a = x[o.ia]; if (o.neg & 1) v.a = -v.a;
-    if (CLS != 2) { v.b = x[o.ib]; if (o.neg & 2) v.b = -v.b; }
-    if (CLS != 0) { v.c = x[o.ic]; if (o.neg & 4) v.c = -v.c; }
-    if (CLS == 1) { v.d = x[o.id]; if (o.neg & 8) v.d = -v.d; }
-    if (CLS == 2) v.w = tw[o.tw];
+    uint32_t w[U]; float a[U], b[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) w[u] = p[32 * u];
+#pragma unroll
+    for (int u = 0; u < U; u++) { a[u] = fft_ld(x, w[u] & 0xffffu); b[u] = fft_ld(x, w[u] >> 16); }
+#pragma unroll
+    for (int u = 0; u < U; u++) { fft_st(x, w[u] & 0xffffu, simt::fadd(a[u], b[u])); fft_st(x, w[u] >> 16, simt::fsub(a[u], b[u])); }
 }
 
-template <int CLS>
-SIMT_FN void fft_store(const FftDec &o, float *x, const FftVals &v)
+struct FftW2 { uint32_t lo, hi; };
+
+template <int U>
+SIMT_FN void fft_rows_cross(const FftW2 *p, float *x)          // t1=a+d; t2=c+b; c=c-b; b=a-d; a=t1; d=t2
 {
-    const double SQ = 0.707106781186547524401;  // SQHALF, subs.c:26
-    if (o.type == FFT_NOP) return;
-    if (CLS == 0) {                                           // t=a+b; b=a-b; a=t
-        x[o.ia] = simt::fadd(v.a, v.b); x[o.ib] = simt::fsub(v.a, v.b);
-    } else if (CLS == 1) {                                    // t1=a+d; t2=c+b; c=c-b; b=a-d; a=t1; d=t2
-        const float t1 = simt::fadd(v.a, v.d), t2 = simt::fadd(v.c, v.b);
-        x[o.ic] = simt::fsub(v.c, v.b); x[o.ib] = simt::fsub(v.a, v.d);
-        x[o.ia] = t1; x[o.id] = t2;
-    } else if (o.type == FFT_ROT) {                           // t2=cn*(a+c); t1=spcn*a+t2; a=smcn*c+t2; c=t1
-        const float t2 = simt::fmul(v.w.cn, simt::fadd(v.a, v.c));
-        const float t1 = simt::fadd(simt::fmul(v.w.spcn, v.a), t2);
-        x[o.ia] = simt::fadd(simt::fmul(v.w.smcn, v.c), t2);
-        x[o.ic] = t1;
-    } else if (o.type == FFT_ROT8A) {                         // t1=SQ*(a+c); c=SQ*(c-a); a=t1 (double multiply)
-        const float t1 = (float)simt::dmul(SQ, (double)simt::fadd(v.a, v.c));
-        x[o.ic] = (float)simt::dmul(SQ, (double)simt::fsub(v.c, v.a));
-        x[o.ia] = t1;
-    } else {                                                  // FFT_ROT8B: t2=SQ*(c-a); c=-SQ*(a+c); a=t2
-        const float t2 = (float)simt::dmul(SQ, (double)simt::fsub(v.c, v.a));
-        x[o.ic] = (float)simt::dmul(-SQ, (double)simt::fadd(v.a, v.c));
-        x[o.ia] = t2;
+    FftW2 w[U]; float a[U], b[U], c[U], d[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) w[u] = p[32 * u];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        a[u] = fft_ld(x, w[u].lo & 0xffffu); b[u] = fft_ld(x, w[u].lo >> 16);
+        c[u] = fft_ld(x, w[u].hi & 0xffffu); d[u] = fft_ld(x, w[u].hi >> 16);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        fft_st(x, w[u].lo & 0xffffu, simt::fadd(a[u], d[u])); fft_st(x, w[u].lo >> 16, simt::fsub(a[u], d[u]));
+        fft_st(x, w[u].hi & 0xffffu, simt::fsub(c[u], b[u])); fft_st(x, w[u].hi >> 16, simt::fadd(c[u], b[u]));
     }
 }
 
-// rows [lo, hi) of one level and one operand class, U rows per trip
+template <int U>
+SIMT_FN void fft_rows_rot(const FftW2 *p, const FftTwiddle *tw, float *x)   // t2=cn*(a+c); t1=spcn*a+t2; a=smcn*c+t2; c=t1
+{
+    FftW2 w[U]; float a[U], c[U]; FftTwiddle t[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) w[u] = p[32 * u];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        a[u] = fft_ld(x, w[u].lo & 0xffffu);
+        c[u] = fft_flip(fft_ld(x, w[u].lo >> 16), w[u].hi);
+        t[u] = *reinterpret_cast<const FftTwiddle *>(reinterpret_cast<const char *>(tw) + (w[u].hi & 0xffffu));
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const float t2 = simt::fmul(t[u].cn, simt::fadd(a[u], c[u]));
+        fft_st(x, w[u].lo & 0xffffu, simt::fadd(simt::fmul(t[u].smcn, c[u]), t2));
+        fft_st(x, w[u].lo >> 16, simt::fadd(simt::fmul(t[u].spcn, a[u]), t2));
+    }
+}
+
+SIMT_FN void fft_row_misc(const FftW2 *p, float *x)            // the rare shapes, one row at a time
+{
+    const double SQ = 0.707106781186547524401;  // SQHALF, subs.c:26
+    const FftW2 w = p[0];
+    const int type = (int)(w.hi & 7u);
+    if (type == FFT_NOP) return;
+    const float a = fft_flip(fft_ld(x, w.lo & 0xffffu), w.hi << 23), c = fft_flip(fft_ld(x, w.lo >> 16), w.hi << 22);
+    float ra, rc;
+    if (type == FFT_BFLY) { ra = simt::fadd(a, c); rc = simt::fsub(a, c); }
+    else if (type == FFT_ROT8A) {                                 // t1=SQ*(a+c); c=SQ*(c-a); a=t1 (double multiply)
+        ra = (float)simt::dmul(SQ, (double)simt::fadd(a, c)); rc = (float)simt::dmul(SQ, (double)simt::fsub(c, a));
+    } else {                                                      // FFT_ROT8B: t2=SQ*(c-a); c=-SQ*(a+c); a=t2
+        ra = (float)simt::dmul(SQ, (double)simt::fsub(c, a)); rc = (float)simt::dmul(-SQ, (double)simt::fadd(a, c));
+    }
+    fft_st(x, w.lo & 0xffffu, ra);
+    fft_st(x, w.lo >> 16, rc);
+}
+
 #ifndef FFT_ROWS_PER_TRIP
 #define FFT_ROWS_PER_TRIP 2
 #endif
-template <int CLS>
-SIMT_FN void fft_rows(const FftOpPacked *ops, int lo, int hi, const FftTwiddle *tw, float *x, int lane)
-{
-    constexpr int U = FFT_ROWS_PER_TRIP;
-    for (int i = lo + lane; i < hi; i += 32 * U) {
-        FftDec o[U];
-        FftVals v[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) o[u] = fft_decode(i + 32 * u < hi ? ops[i + 32 * u] : ((FftOpPacked)FFT_NOP << 54));
-#pragma unroll
-        for (int u = 0; u < U; u++) fft_load<CLS>(o[u], tw, x, v[u]);
-#pragma unroll
-        for (int u = 0; u < U; u++) fft_store<CLS>(o[u], x, v[u]);
-    }
-}
-
 SIMT_FN void fft_run(const WarpCtx &w, const FftDev &P, const FftTwiddle *tw, float *x)
 {
-    // level_start holds 3 segments per level (one per operand class), each a whole number of rows of 32 ops
+    constexpr int U = FFT_ROWS_PER_TRIP;
+    FOR_THREADS(w)
+    for (int j = 0; j < 4; j++) x[FFT_X_WORDS + 32 * j + lane] = 0.0f;        // the padding lanes' dummy words
+    END_THREADS
+    w.sync();
     for (int l = 0; l < P.n_levels; l++) {
-        const int s0 = P.level_start[3 * l], s1 = P.level_start[3 * l + 1], s2 = P.level_start[3 * l + 2], s3 = P.level_start[3 * l + 3];
+        const int *sg = P.seg_word + 4 * l;
+        const int s0 = sg[0], s1 = sg[1], s2 = sg[2], s3 = sg[3], s4 = sg[4];
         FOR_THREADS(w)
-        fft_rows<0>(P.ops, s0, s1, tw, x, lane);
-        fft_rows<1>(P.ops, s1, s2, tw, x, lane);
-        fft_rows<2>(P.ops, s2, s3, tw, x, lane);
+        {   // 32-bit word indices: a 64-bit pointer loop costs ~6 more integer instructions per trip
+            const uint32_t *W = P.words;
+            const FftW2 *W2 = reinterpret_cast<const FftW2 *>(P.words);
+            int i = s0 + lane;
+            for (; i + 32 * (U - 1) < s1; i += 32 * U) fft_rows_bfly<U>(W + i, x);
+            if (i < s1) fft_rows_bfly<1>(W + i, x);
+            i = (s1 >> 1) + lane;
+            for (; i + 32 * (U - 1) < (s2 >> 1); i += 32 * U) fft_rows_cross<U>(W2 + i, x);
+            if (i < (s2 >> 1)) fft_rows_cross<1>(W2 + i, x);
+            i = (s2 >> 1) + lane;
+            for (; i + 32 * (U - 1) < (s3 >> 1); i += 32 * U) fft_rows_rot<U>(W2 + i, tw, x);
+            if (i < (s3 >> 1)) fft_rows_rot<1>(W2 + i, tw, x);
+            for (i = (s3 >> 1) + lane; i < (s4 >> 1); i += 32) fft_row_misc(W2 + i, x);
+        }
         END_THREADS
         w.sync();
     }

@@ -8,6 +8,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
+#include <vector>
 
 #include "iso_tables.h"
 
@@ -361,6 +363,109 @@ struct Builder {
 };
 }  // namespace
 
+namespace {
+// banks of the (up to four) operands of an op
+inline void op_banks(const FftOp &o, int bank[4])
+{
+    const uint16_t s4[4] = {o.a, o.b, o.c, o.d};
+    for (int j = 0; j < 4; j++) bank[j] = s4[j] == 0xffff ? -1 : (int)(FFT_SKEW((unsigned)s4[j]) & 31);
+}
+
+// Conflict-free rows that are not full are merged (first-fit decreasing, capacity 32 ops): a row merged from k
+// matchings has at most k-way bank conflicts, i.e. it costs the same shared-memory wavefronts as its k parts did, but
+// only one row's worth of instructions.
+void merge_rows(std::vector<std::vector<int>> *rows)
+{
+    std::vector<std::vector<int>> in = *rows, out;
+    std::stable_sort(in.begin(), in.end(), [](const std::vector<int> &x, const std::vector<int> &y) { return x.size() > y.size(); });
+    for (std::vector<int> &r : in) {
+        size_t k = 0;
+        while (k < out.size() && out[k].size() + r.size() > 32) k++;
+        if (k == out.size()) out.emplace_back();
+        out[k].insert(out[k].end(), r.begin(), r.end());
+    }
+    *rows = out;
+}
+
+// Split the ops `ids` (one dependency level, one operand class) into rows of <= 32 ops without bank conflicts.
+// Two-operand classes: an op is an edge between the bank of its first and the bank of its second operand, a
+// conflict-free row is a matching, and a bipartite multigraph of maximum degree D splits into exactly D matchings
+// (Koenig) — found with the alternating-path recolouring below: the minimum number of rows.  Four-operand crosses:
+// first-fit over many random orders, best result kept.
+void pack_rows(const std::vector<FftOp> &ops, const std::vector<int> &ids, bool four, std::vector<std::vector<int>> *rows)
+{
+    rows->clear();
+    if (ids.empty()) return;
+    if (!four) {
+        const int ne = (int)ids.size();
+        std::vector<int> eu(ne), ev(ne), col(ne, -1);
+        int degu[32] = {0}, degv[32] = {0}, D = 0;
+        for (int e = 0; e < ne; e++) {
+            int b[4]; op_banks(ops[ids[e]], b);
+            eu[e] = b[0]; ev[e] = b[1] >= 0 ? b[1] : b[2];
+            D = std::max(D, std::max(++degu[eu[e]], ++degv[ev[e]]));
+        }
+        std::vector<std::vector<int>> atu(D, std::vector<int>(32, -1)), atv(D, std::vector<int>(32, -1));   // [colour][bank] -> edge
+        for (int e = 0; e < ne; e++) {
+            const int u = eu[e], v = ev[e];
+            int c1 = 0, c2 = 0;
+            while (atu[c1][u] >= 0) c1++;
+            while (atv[c2][v] >= 0) c2++;
+            if (atv[c1][v] >= 0) {
+                // c1 is taken at v: swap c1 <-> c2 along the alternating path that starts at v (it cannot reach u)
+                std::vector<int> path;
+                int cur = v, ca = c1, cb = c2;
+                bool right = true;
+                for (;;) {
+                    const int e1 = right ? atv[ca][cur] : atu[ca][cur];
+                    if (e1 < 0) break;
+                    path.push_back(e1);
+                    cur = right ? eu[e1] : ev[e1];
+                    right = !right;
+                    std::swap(ca, cb);
+                }
+                for (int e1 : path) { atu[col[e1]][eu[e1]] = -1; atv[col[e1]][ev[e1]] = -1; }
+                for (int e1 : path) { col[e1] = (col[e1] == c1) ? c2 : c1; atu[col[e1]][eu[e1]] = e1; atv[col[e1]][ev[e1]] = e1; }
+            }
+            col[e] = c1; atu[c1][u] = e; atv[c1][v] = e;
+        }
+        rows->assign(D, std::vector<int>());
+        for (int e = 0; e < ne; e++) (*rows)[col[e]].push_back(ids[e]);
+        merge_rows(rows);
+        return;
+    }
+    std::vector<int> perm = ids;
+    std::vector<std::vector<int>> best;
+    uint64_t rng = 0x9e3779b97f4a7c15ull;
+    for (int trial = 0; trial < 200; trial++) {
+        if (trial)
+            for (size_t k = perm.size() - 1; k > 0; k--) {
+                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                std::swap(perm[k], perm[(size_t)((rng >> 33) % (k + 1))]);
+            }
+        std::vector<std::vector<int>> cur;
+        std::vector<std::array<uint32_t, 4>> used;
+        for (int id : perm) {
+            int b[4]; op_banks(ops[id], b);
+            size_t r = 0;
+            for (; r < cur.size(); r++) {
+                if (cur[r].size() >= 32) continue;
+                bool ok = true;
+                for (int j = 0; j < 4; j++) if (b[j] >= 0 && (used[r][j] >> b[j] & 1)) ok = false;
+                if (ok) break;
+            }
+            if (r == cur.size()) { cur.emplace_back(); used.push_back({0, 0, 0, 0}); }
+            cur[r].push_back(id);
+            for (int j = 0; j < 4; j++) if (b[j] >= 0) used[r][j] |= 1u << b[j];
+        }
+        if (best.empty() || cur.size() < best.size()) best = cur;
+        if (best.size() * 32 < ids.size() + 32) break;   // cannot do better
+    }
+    *rows = best;
+    merge_rows(rows);
+}
+}  // namespace
+
 void build_fft_program(int logm, const std::vector<int> &tw_base, FftProgram *P)
 {
     const int n = 1 << logm;
@@ -394,42 +499,66 @@ void build_fft_program(int logm, const std::vector<int> &tw_base, FftProgram *P)
         return B.ops[x].type < B.ops[y].type;
     });
     P->n = n; P->logm = logm;
-    P->ops.clear(); P->level_start.assign(3 * n_levels + 1, 0);
-    // Pack every level into rows of 32 ops (one op per lane).  A row holds ops of one operand shape only
-    // (butterfly / cross / the three rotations) and no two of its ops touch the same shared-memory bank with the
-    // same operand, so each of the row's loads and stores is a single wavefront; rows are padded with FFT_NOP.
+    P->ops.clear(); P->level_start.assign(FFT_CLASSES * n_levels + 1, 0);
+    P->words.clear(); P->seg_word.assign(FFT_CLASSES * n_levels + 1, 0);
+    // Pack every (level, class) group into rows of 32 ops (one op per lane) such that no two ops of a row touch the same
+    // shared-memory bank with the same operand: each of the row's loads and stores is then a single wavefront.
     {
-        auto cls = [](uint8_t t) { return t == FFT_BFLY ? 0 : t == FFT_CROSS ? 1 : 2; };
         FftOp nop; memset(&nop, 0, sizeof(nop)); nop.a = nop.b = nop.c = nop.d = 0xffff; nop.type = FFT_NOP;
         size_t i = 0;
         for (int l = 1; l <= n_levels; l++) {
-            std::vector<int> grp[3];
-            for (; i < order.size() && level[order[i]] == l; i++) grp[cls(B.ops[order[i]].type)].push_back(order[i]);
-            for (int c = 0; c < 3; c++) {
-                std::vector<int> rem = grp[c];
-                while (!rem.empty()) {
+            std::vector<int> grp[FFT_CLASSES];
+            for (; i < order.size() && level[order[i]] == l; i++) grp[fft_class(B.ops[order[i]])].push_back(order[i]);
+            for (int c = 0; c < FFT_CLASSES; c++) {
+                std::vector<std::vector<int>> rows;
+                pack_rows(B.ops, grp[c], c == 1, &rows);
+                for (const std::vector<int> &row : rows) {
                     uint32_t used[4] = {0, 0, 0, 0};
-                    std::vector<int> rest;
-                    int in_row = 0;
-                    for (int id : rem) {
-                        const FftOp &o = B.ops[id];
-                        const uint16_t s4[4] = {o.a, o.b, o.c, o.d};
-                        bool ok = in_row < 32;
-                        uint32_t bit[4] = {0, 0, 0, 0};
-                        for (int j = 0; j < 4 && ok; j++)
-                            if (s4[j] != 0xffff) { bit[j] = 1u << (FFT_SKEW((unsigned)s4[j]) & 31); ok = !(used[j] & bit[j]); }
-                        if (ok) { for (int j = 0; j < 4; j++) used[j] |= bit[j]; P->ops.push_back(o); in_row++; }
-                        else rest.push_back(id);
+                    for (int id : row) {
+                        P->ops.push_back(B.ops[id]);
+                        int b[4]; op_banks(B.ops[id], b);
+                        if (c == 3 && b[1] < 0) b[1] = b[2];           // MISC ops carry their second operand in position 1
+                        if (c == 2) b[1] = b[2];
+                        for (int j = 0; j < 4; j++) if (b[j] >= 0 && (c == 1 || j < 2)) used[j] |= 1u << b[j];
                     }
-                    for (; in_row < 32; in_row++) P->ops.push_back(nop);
-                    rem.swap(rest);
+                    // padding lanes: dummy words in banks the row's real ops leave free (operand j of the lane: pad byte j)
+                    for (size_t k = row.size(); k < 32; k++) {
+                        FftOp pd = nop;
+                        for (int j = 0; j < 4; j++) {
+                            int f = 0;
+                            while (used[j] >> f & 1) f++;
+                            used[j] |= 1u << f;
+                            pd.pad |= (uint32_t)f << (8 * j);
+                        }
+                        P->ops.push_back(pd);
+                    }
                 }
-                P->level_start[3 * (l - 1) + c + 1] = (int)P->ops.size();   // end of (level, class) segment
+                P->level_start[FFT_CLASSES * (l - 1) + c + 1] = (int)P->ops.size();   // end of (level, class) segment
             }
         }
     }
-    P->packed.clear();
-    for (const FftOp &o : P->ops) P->packed.push_back(fft_pack(o));
+    // device encoding
+    for (int sgm = 0; sgm < FFT_CLASSES * n_levels; sgm++) {
+        const int c = sgm % FFT_CLASSES;
+        for (int k = P->level_start[sgm]; k < P->level_start[sgm + 1]; k++) {
+            const FftOp &o = P->ops[k];
+            auto off = [&](uint16_t slot, int j) -> uint32_t {      // byte offset of an operand; padding -> the lane's dummy word j
+                return 4u * (o.type == FFT_NOP ? (unsigned)FFT_X_WORDS + 32u * j + ((o.pad >> (8 * j)) & 31u) : (unsigned)FFT_SKEW((unsigned)slot));
+            };
+            if (c == 0) P->words.push_back(off(o.a, 0) | (off(o.b, 1) << 16));
+            else if (c == 1) { P->words.push_back(off(o.a, 0) | (off(o.b, 1) << 16)); P->words.push_back(off(o.c, 2) | (off(o.d, 3) << 16)); }
+            else if (c == 2) {
+                P->words.push_back(off(o.a, 0) | (off(o.c, 1) << 16));
+                P->words.push_back((o.type == FFT_NOP ? 0u : 16u * o.tw) | ((o.neg & 4) ? 0x80000000u : 0u));
+            } else {
+                const uint16_t second = (o.type == FFT_BFLY) ? o.b : o.c;
+                const unsigned neg2 = (o.type == FFT_BFLY) ? ((o.neg >> 1) & 1) : ((o.neg >> 2) & 1);
+                P->words.push_back(off(o.a, 0) | (off(second, 1) << 16));
+                P->words.push_back((uint32_t)o.type | ((uint32_t)((o.neg & 1) | (neg2 << 1)) << 8));
+            }
+        }
+        P->seg_word[sgm + 1] = (int)P->words.size();
+    }
     P->out_slot.resize(n); P->out_neg.resize(n);
     for (int i = 0; i < n; i++) { P->out_slot[i] = (uint16_t)B.phys[i]; P->out_neg[i] = B.neg[i]; }
 }

@@ -39,6 +39,9 @@ enum FftOpType : uint8_t {
 // butterflies spread over the banks.  Device ops, the window store and the output map all use skewed addresses.
 #define FFT_SKEW(s) ((s) + ((s) >> 5))
 #define FFT_X_WORDS (1024 + 32)
+// Padding ops of the fast classes are not skipped but aimed at per-lane dummy words behind the data (operand j of
+// lane L: word FFT_X_WORDS + 32 j + L), so the executor needs no "is this a NOP" branch.
+#define FFT_X_ALLOC (FFT_X_WORDS + 4 * 32)
 
 struct FftOp {
     uint16_t a, b, c, d;  // physical slots
@@ -48,22 +51,27 @@ struct FftOp {
     uint32_t pad;
 };
 
-// device encoding of an op, 8 bytes, operands as SKEWED addresses:
-//   a | b<<11 | c<<22 | d<<33 | tw<<44 | type<<54 | neg<<57
-typedef unsigned long long FftOpPacked;
-inline FftOpPacked fft_pack(const FftOp &o)
+// Operand classes: every row of 32 ops holds one class, executed by a specialised loop.
+//   0 BFLY   butterflies without sign flips                       1 word  / op: a | b << 16
+//   1 CROSS  crosses                                              2 words / op: a | b << 16, c | d << 16
+//   2 ROT    twiddle rotations, operand c possibly stored negated 2 words / op: a | c << 16, tw_byte_offset | negc << 31
+//   3 MISC   ROT8A / ROT8B / the few butterflies with a negated a 2 words / op: a | c << 16, type | neg << 8   (b travels as c)
+// Operands are BYTE offsets of skewed slots into the warp's x[] (what the shared-memory load wants).
+#define FFT_CLASSES 4
+inline int fft_class(const FftOp &o)
 {
-    if (o.type == FFT_NOP) return (FftOpPacked)FFT_NOP << 54;
-    auto sk = [](uint16_t s) { return (FftOpPacked)(s == 0xffff ? 0 : FFT_SKEW((unsigned)s)) & 2047; };
-    return sk(o.a) | (sk(o.b) << 11) | (sk(o.c) << 22) | (sk(o.d) << 33) | ((FftOpPacked)(o.tw & 1023) << 44) |
-           ((FftOpPacked)(o.type & 7) << 54) | ((FftOpPacked)(o.neg & 15) << 57);
+    if (o.type == FFT_BFLY && o.neg == 0) return 0;
+    if (o.type == FFT_CROSS && o.neg == 0) return 1;
+    if (o.type == FFT_ROT && (o.neg & ~4) == 0) return 2;
+    return 3;
 }
 
 struct FftProgram {
     int n, logm;
-    std::vector<FftOp> ops;            // sorted by level, packed into bank-conflict-free rows of 32 (FFT_NOP padded)
-    std::vector<FftOpPacked> packed;   // same ops in the device encoding
-    std::vector<int> level_start;      // size 3*n_levels+1: segment (level l, operand class c) = [3l+c, 3l+c+1), multiples of 32
+    std::vector<FftOp> ops;            // sorted by (level, class), packed into bank-conflict-free rows of 32 (FFT_NOP padded)
+    std::vector<uint32_t> words;       // same ops in the device encoding (see the class table above)
+    std::vector<int> level_start;      // size 4*n_levels+1: ops of segment (level l, class c) = [4l+c, 4l+c+1), multiples of 32
+    std::vector<int> seg_word;         // same segments as offsets into words[]
     std::vector<uint16_t> out_slot;    // logical output index -> physical slot (after bit reversal)
     std::vector<uint8_t> out_neg;      // ... stored negated?
 };

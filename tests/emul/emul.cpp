@@ -25,28 +25,26 @@ int emul_fft(float *x, int n, int *n_ops, int *n_levels)
     std::vector<float> buf(x, x + n);
     run_fft_program_host(P, tw, buf.data());
     for (int i = 0; i < n; i++) x[i] = P.out_neg[i] ? -buf[P.out_slot[i]] : buf[P.out_slot[i]];
-    *n_ops = (int)P.ops.size(); *n_levels = ((int)P.level_start.size() - 1) / 3;
+    *n_ops = (int)P.ops.size(); *n_levels = ((int)P.level_start.size() - 1) / FFT_CLASSES;
     // level sanity: ops of one level must touch disjoint slots
-    for (size_t l = 0; l + 3 < P.level_start.size(); l += 3) {   // 3 operand-class segments per level
+    for (size_t l = 0; l + FFT_CLASSES < P.level_start.size(); l += FFT_CLASSES) {   // operand-class segments of one level
         std::vector<char> used(n, 0);
-        for (int i = P.level_start[l]; i < P.level_start[l + 3]; i++) {
+        for (int i = P.level_start[l]; i < P.level_start[l + FFT_CLASSES]; i++) {
             const FftOp &o = P.ops[i];
             const uint16_t s[4] = {o.a, o.b, o.c, o.d};
             for (int j = 0; j < 4; j++) if (s[j] != 0xffff) { if (used[s[j]]) return -1; used[s[j]] = 1; }
         }
     }
-    // row sanity: levels are whole rows of 32; within a row no two ops hit the same bank with the same operand
+    // row sanity: levels are whole rows of 32; a row is merged from at most 4 conflict-free matchings, i.e. no bank is hit
+    // more than 4 times by one operand position (and full rows built from one matching are conflict free)
     for (size_t r = 0; r + 32 <= P.ops.size(); r += 32) {
-        unsigned used[4] = {0, 0, 0, 0};
+        int cnt[4][32];
+        memset(cnt, 0, sizeof(cnt));
         for (int i = 0; i < 32; i++) {
             const FftOp &o = P.ops[r + i];
             const uint16_t s[4] = {o.a, o.b, o.c, o.d};
             for (int j = 0; j < 4; j++)
-                if (o.type != FFT_NOP && s[j] != 0xffff) {
-                    const unsigned bit = 1u << (FFT_SKEW((unsigned)s[j]) & 31);
-                    if (used[j] & bit) return -2;
-                    used[j] |= bit;
-                }
+                if (o.type != FFT_NOP && s[j] != 0xffff && ++cnt[j][FFT_SKEW((unsigned)s[j]) & 31] > 4) return -2;
         }
     }
     for (size_t l = 0; l < P.level_start.size(); l++) if (P.level_start[l] % 32) return -3;
@@ -91,7 +89,7 @@ int emul_encode_stream(int sfreq, int n_ch, int bitrate, int n_frames, const sho
     auto mkdev = [](const FftProgram &P, std::vector<uint16_t> &outmap) {
         outmap.resize(P.n);
         for (int i = 0; i < P.n; i++) outmap[i] = (uint16_t)(FFT_SKEW((unsigned)P.out_slot[i]) | (P.out_neg[i] ? 0x8000 : 0));
-        FftDev d; d.ops = P.packed.data(); d.level_start = P.level_start.data(); d.n_levels = ((int)P.level_start.size() - 1) / 3; d.out = outmap.data();
+        FftDev d; d.words = P.words.data(); d.seg_word = P.seg_word.data(); d.n_levels = ((int)P.seg_word.size() - 1) / FFT_CLASSES; d.out = outmap.data();
         return d;
     };
     std::vector<uint16_t> o10, o8;
