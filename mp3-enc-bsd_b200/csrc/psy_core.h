@@ -101,11 +101,9 @@ SIMT_FN float fft_flip(float v, unsigned sign_word)     // v with its sign flipp
 }
 
 template <int U>
-SIMT_FN void fft_rows_bfly(const uint32_t *p, float *x)        // t=a+b; b=a-b; a=t
+SIMT_FN void fft_rows_bfly(const uint32_t *w, float *x)        // t=a+b; b=a-b; a=t
 {
-    uint32_t w[U]; float a[U], b[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) w[u] = p[32 * u];
+    float a[U], b[U];
 #pragma unroll
     for (int u = 0; u < U; u++) { a[u] = fft_ld(x, w[u] & 0xffffu); b[u] = fft_ld(x, w[u] >> 16); }
 #pragma unroll
@@ -115,11 +113,9 @@ SIMT_FN void fft_rows_bfly(const uint32_t *p, float *x)        // t=a+b; b=a-b; 
 struct FftW2 { uint32_t lo, hi; };
 
 template <int U>
-SIMT_FN void fft_rows_cross(const FftW2 *p, float *x)          // t1=a+d; t2=c+b; c=c-b; b=a-d; a=t1; d=t2
+SIMT_FN void fft_rows_cross(const FftW2 *w, float *x)          // t1=a+d; t2=c+b; c=c-b; b=a-d; a=t1; d=t2
 {
-    FftW2 w[U]; float a[U], b[U], c[U], d[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) w[u] = p[32 * u];
+    float a[U], b[U], c[U], d[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
         a[u] = fft_ld(x, w[u].lo & 0xffffu); b[u] = fft_ld(x, w[u].lo >> 16);
@@ -133,11 +129,9 @@ SIMT_FN void fft_rows_cross(const FftW2 *p, float *x)          // t1=a+d; t2=c+b
 }
 
 template <int U>
-SIMT_FN void fft_rows_rot(const FftW2 *p, const FftTwiddle *tw, float *x)   // t2=cn*(a+c); t1=spcn*a+t2; a=smcn*c+t2; c=t1
+SIMT_FN void fft_rows_rot(const FftW2 *w, const FftTwiddle *tw, float *x)   // t2=cn*(a+c); t1=spcn*a+t2; a=smcn*c+t2; c=t1
 {
-    FftW2 w[U]; float a[U], c[U]; FftTwiddle t[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) w[u] = p[32 * u];
+    float a[U], c[U]; FftTwiddle t[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
         a[u] = fft_ld(x, w[u].lo & 0xffffu);
@@ -152,10 +146,9 @@ SIMT_FN void fft_rows_rot(const FftW2 *p, const FftTwiddle *tw, float *x)   // t
     }
 }
 
-SIMT_FN void fft_row_misc(const FftW2 *p, float *x)            // the rare shapes, one row at a time
+SIMT_FN void fft_row_misc(const FftW2 w, float *x)             // the rare shapes, one row at a time
 {
     const double SQ = 0.707106781186547524401;  // SQHALF, subs.c:26
-    const FftW2 w = p[0];
     const int type = (int)(w.hi & 7u);
     if (type == FFT_NOP) return;
     const float a = fft_flip(fft_ld(x, w.lo & 0xffffu), w.hi << 23), c = fft_flip(fft_ld(x, w.lo >> 16), w.hi << 22);
@@ -184,19 +177,50 @@ SIMT_FN void fft_run(const WarpCtx &w, const FftDev &P, const FftTwiddle *tw, fl
         const int *sg = P.seg_word + 4 * l;
         const int s0 = sg[0], s1 = sg[1], s2 = sg[2], s3 = sg[3], s4 = sg[4];
         FOR_THREADS(w)
-        {   // 32-bit word indices: a 64-bit pointer loop costs ~6 more integer instructions per trip
+        {
+            // Op words are fetched one trip ahead (the first trip of all four class loops up front): a trip otherwise
+            // starts with a global-load round trip that nothing in the warp can overlap (ncu: 25 % of the stall samples).
+            // Fetches run past the end of a segment on purpose (into the next segment / the pad words behind the program).
+            // 32-bit word indices: a 64-bit pointer loop costs ~6 more integer instructions per trip.
             const uint32_t *W = P.words;
             const FftW2 *W2 = reinterpret_cast<const FftW2 *>(P.words);
-            int i = s0 + lane;
-            for (; i + 32 * (U - 1) < s1; i += 32 * U) fft_rows_bfly<U>(W + i, x);
-            if (i < s1) fft_rows_bfly<1>(W + i, x);
-            i = (s1 >> 1) + lane;
-            for (; i + 32 * (U - 1) < (s2 >> 1); i += 32 * U) fft_rows_cross<U>(W2 + i, x);
-            if (i < (s2 >> 1)) fft_rows_cross<1>(W2 + i, x);
-            i = (s2 >> 1) + lane;
-            for (; i + 32 * (U - 1) < (s3 >> 1); i += 32 * U) fft_rows_rot<U>(W2 + i, tw, x);
-            if (i < (s3 >> 1)) fft_rows_rot<1>(W2 + i, tw, x);
-            for (i = (s3 >> 1) + lane; i < (s4 >> 1); i += 32) fft_row_misc(W2 + i, x);
+            int ib = s0 + lane, ic = (s1 >> 1) + lane, ir = (s2 >> 1) + lane, im = (s3 >> 1) + lane;
+            uint32_t wb[U]; FftW2 wc[U], wr[U], wm;
+#pragma unroll
+            for (int u = 0; u < U; u++) { wb[u] = W[ib + 32 * u]; wc[u] = W2[ic + 32 * u]; wr[u] = W2[ir + 32 * u]; }
+            wm = W2[im];
+            for (; ib + 32 * (U - 1) < s1; ib += 32 * U) {
+                uint32_t nx[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) nx[u] = W[ib + 32 * (U + u)];
+                fft_rows_bfly<U>(wb, x);
+#pragma unroll
+                for (int u = 0; u < U; u++) wb[u] = nx[u];
+            }
+            if (ib < s1) fft_rows_bfly<1>(wb, x);
+            for (; ic + 32 * (U - 1) < (s2 >> 1); ic += 32 * U) {
+                FftW2 nx[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) nx[u] = W2[ic + 32 * (U + u)];
+                fft_rows_cross<U>(wc, x);
+#pragma unroll
+                for (int u = 0; u < U; u++) wc[u] = nx[u];
+            }
+            if (ic < (s2 >> 1)) fft_rows_cross<1>(wc, x);
+            for (; ir + 32 * (U - 1) < (s3 >> 1); ir += 32 * U) {
+                FftW2 nx[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) nx[u] = W2[ir + 32 * (U + u)];
+                fft_rows_rot<U>(wr, tw, x);
+#pragma unroll
+                for (int u = 0; u < U; u++) wr[u] = nx[u];
+            }
+            if (ir < (s3 >> 1)) fft_rows_rot<1>(wr, tw, x);
+            for (; im < (s4 >> 1); im += 32) {
+                const FftW2 nx = W2[im + 32];
+                fft_row_misc(wm, x);
+                wm = nx;
+            }
         }
         END_THREADS
         w.sync();

@@ -559,6 +559,7 @@ void build_fft_program(int logm, const std::vector<int> &tw_base, FftProgram *P)
         }
         P->seg_word[sgm + 1] = (int)P->words.size();
     }
+    P->words.resize(P->words.size() + FFT_WORDS_PAD, 0u);   // the executor fetches op words one trip ahead, past the last segment
     P->out_slot.resize(n); P->out_neg.resize(n);
     for (int i = 0; i < n; i++) { P->out_slot[i] = (uint16_t)B.phys[i]; P->out_neg[i] = B.neg[i]; }
 }

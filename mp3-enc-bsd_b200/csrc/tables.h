@@ -58,6 +58,7 @@ struct FftOp {
 //   3 MISC   ROT8A / ROT8B / the few butterflies with a negated a 2 words / op: a | c << 16, type | neg << 8   (b travels as c)
 // Operands are BYTE offsets of skewed slots into the warp's x[] (what the shared-memory load wants).
 #define FFT_CLASSES 4
+#define FFT_WORDS_PAD 512   // readable words behind the last segment (look-ahead of the executor: <= 4 rows of 2 words)
 inline int fft_class(const FftOp &o)
 {
     if (o.type == FFT_BFLY && o.neg == 0) return 0;
