@@ -46,26 +46,24 @@ struct PsyMid {
     float e6[8], phi6[8];
 };
 
-// 6816 B per warp (8 warps per CTA, 4 CTAs per SM).  x[] holds the FFT working set; everything that is
-// produced after a transform and consumed before the next one that needs the space is overlaid on it:
-//   after the LONG FFT only x[0..255] is reused (short transforms), so Es / Ps live in x[256..819];
-//   after the last SHORT FFT x[0..255] is free: cwv and eb live there; thr overlays E[] once the long
-//   partition energies have been formed (E is dead by then).
+// 6816 B per warp (8 warps per CTA, 4 CTAs per SM).  x[] holds the FFT working set: the 1024-point transform, then the three
+// 256-point transforms side by side (data set sb at x + sb * FFT_BATCH_BYTES / 4: 264 skewed words + 128 dummy words).
+// The short energies / phases stay IN PLACE (energy of bin i over re(i), phase over im(i) = re(256 - i); each pair is
+// touched by one lane only) and are read through the output map; cwv and eb live in the (by then dead) dummy words of
+// data sets 0 and 1; thr overlays E[] once the long partition energies have been formed (E is dead by then).
 struct PsyFrontSmem {
     float x[FFT_X_ALLOC];
     float E[520];
 };
 struct PsyFrontView {
     float *x, *E;
-    float (*Es)[132];   // [3][132] at x + 272 (the short transforms use skewed x[0..263])
-    float (*Ps)[56];    // [3][56]  at x + 668
-    double *cwv;        // [52]  at x + 0   (after the short FFTs)
-    double *eb;         // [64]  at x + 104
+    double *cwv;        // [52]  at x + 264
+    double *eb;         // [64]  at x + 656
     double *thr;        // [64]  at E + 0   (after the long partition energies)
     SIMT_FN explicit PsyFrontView(PsyFrontSmem &S)
-        : x(S.x), E(S.E), Es(reinterpret_cast<float (*)[132]>(S.x + 272)), Ps(reinterpret_cast<float (*)[56]>(S.x + 668)),
-          cwv(reinterpret_cast<double *>(S.x)), eb(reinterpret_cast<double *>(S.x + 104)), thr(reinterpret_cast<double *>(S.E)) {}
+        : x(S.x), E(S.E), cwv(reinterpret_cast<double *>(S.x + 264)), eb(reinterpret_cast<double *>(S.x + 656)), thr(reinterpret_cast<double *>(S.E)) {}
 };
+static_assert(264 + 2 * 52 <= FFT_BATCH_BYTES / 4 && 656 >= FFT_BATCH_BYTES / 4 + 264 && 656 + 2 * 64 <= 2 * (FFT_BATCH_BYTES / 4), "overlays must sit in dummy words");
 
 struct PsyScanSmem {
     double eb[64], thr[64], prod[64];
@@ -100,77 +98,101 @@ SIMT_FN float fft_flip(float v, unsigned sign_word)     // v with its sign flipp
 #endif
 }
 
-template <int U>
+// NB transforms of the same length run through one pass over the op program: data set b lives FFT_BATCH_BYTES * b
+// behind the first one, so a fetched and decoded op is applied NB times (the three short transforms of a granule).
+template <int U, int NB>
 SIMT_FN void fft_rows_bfly(const uint32_t *w, float *x)        // t=a+b; b=a-b; a=t
 {
-    float a[U], b[U];
+    float a[U][NB], b[U][NB];
 #pragma unroll
-    for (int u = 0; u < U; u++) { a[u] = fft_ld(x, w[u] & 0xffffu); b[u] = fft_ld(x, w[u] >> 16); }
+    for (int u = 0; u < U; u++)
 #pragma unroll
-    for (int u = 0; u < U; u++) { fft_st(x, w[u] & 0xffffu, simt::fadd(a[u], b[u])); fft_st(x, w[u] >> 16, simt::fsub(a[u], b[u])); }
+        for (int n = 0; n < NB; n++) { a[u][n] = fft_ld(x, (w[u] & 0xffffu) + n * FFT_BATCH_BYTES); b[u][n] = fft_ld(x, (w[u] >> 16) + n * FFT_BATCH_BYTES); }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int n = 0; n < NB; n++) {
+            fft_st(x, (w[u] & 0xffffu) + n * FFT_BATCH_BYTES, simt::fadd(a[u][n], b[u][n]));
+            fft_st(x, (w[u] >> 16) + n * FFT_BATCH_BYTES, simt::fsub(a[u][n], b[u][n]));
+        }
 }
 
 struct FftW2 { uint32_t lo, hi; };
 
-template <int U>
+template <int U, int NB>
 SIMT_FN void fft_rows_cross(const FftW2 *w, float *x)          // t1=a+d; t2=c+b; c=c-b; b=a-d; a=t1; d=t2
 {
-    float a[U], b[U], c[U], d[U];
+    float a[U][NB], b[U][NB], c[U][NB], d[U][NB];
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-        a[u] = fft_ld(x, w[u].lo & 0xffffu); b[u] = fft_ld(x, w[u].lo >> 16);
-        c[u] = fft_ld(x, w[u].hi & 0xffffu); d[u] = fft_ld(x, w[u].hi >> 16);
-    }
+    for (int u = 0; u < U; u++)
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-        fft_st(x, w[u].lo & 0xffffu, simt::fadd(a[u], d[u])); fft_st(x, w[u].lo >> 16, simt::fsub(a[u], d[u]));
-        fft_st(x, w[u].hi & 0xffffu, simt::fsub(c[u], b[u])); fft_st(x, w[u].hi >> 16, simt::fadd(c[u], b[u]));
-    }
+        for (int n = 0; n < NB; n++) {
+            a[u][n] = fft_ld(x, (w[u].lo & 0xffffu) + n * FFT_BATCH_BYTES); b[u][n] = fft_ld(x, (w[u].lo >> 16) + n * FFT_BATCH_BYTES);
+            c[u][n] = fft_ld(x, (w[u].hi & 0xffffu) + n * FFT_BATCH_BYTES); d[u][n] = fft_ld(x, (w[u].hi >> 16) + n * FFT_BATCH_BYTES);
+        }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int n = 0; n < NB; n++) {
+            fft_st(x, (w[u].lo & 0xffffu) + n * FFT_BATCH_BYTES, simt::fadd(a[u][n], d[u][n]));
+            fft_st(x, (w[u].lo >> 16) + n * FFT_BATCH_BYTES, simt::fsub(a[u][n], d[u][n]));
+            fft_st(x, (w[u].hi & 0xffffu) + n * FFT_BATCH_BYTES, simt::fsub(c[u][n], b[u][n]));
+            fft_st(x, (w[u].hi >> 16) + n * FFT_BATCH_BYTES, simt::fadd(c[u][n], b[u][n]));
+        }
 }
 
-template <int U>
+template <int U, int NB>
 SIMT_FN void fft_rows_rot(const FftW2 *w, const FftTwiddle *tw, float *x)   // t2=cn*(a+c); t1=spcn*a+t2; a=smcn*c+t2; c=t1
 {
-    float a[U], c[U]; FftTwiddle t[U];
+    float a[U][NB], c[U][NB]; FftTwiddle t[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-        a[u] = fft_ld(x, w[u].lo & 0xffffu);
-        c[u] = fft_flip(fft_ld(x, w[u].lo >> 16), w[u].hi);
+#pragma unroll
+        for (int n = 0; n < NB; n++) {
+            a[u][n] = fft_ld(x, (w[u].lo & 0xffffu) + n * FFT_BATCH_BYTES);
+            c[u][n] = fft_flip(fft_ld(x, (w[u].lo >> 16) + n * FFT_BATCH_BYTES), w[u].hi);
+        }
         t[u] = *reinterpret_cast<const FftTwiddle *>(reinterpret_cast<const char *>(tw) + (w[u].hi & 0xffffu));
     }
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-        const float t2 = simt::fmul(t[u].cn, simt::fadd(a[u], c[u]));
-        fft_st(x, w[u].lo & 0xffffu, simt::fadd(simt::fmul(t[u].smcn, c[u]), t2));
-        fft_st(x, w[u].lo >> 16, simt::fadd(simt::fmul(t[u].spcn, a[u]), t2));
-    }
+    for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int n = 0; n < NB; n++) {
+            const float t2 = simt::fmul(t[u].cn, simt::fadd(a[u][n], c[u][n]));
+            fft_st(x, (w[u].lo & 0xffffu) + n * FFT_BATCH_BYTES, simt::fadd(simt::fmul(t[u].smcn, c[u][n]), t2));
+            fft_st(x, (w[u].lo >> 16) + n * FFT_BATCH_BYTES, simt::fadd(simt::fmul(t[u].spcn, a[u][n]), t2));
+        }
 }
 
+template <int NB>
 SIMT_FN void fft_row_misc(const FftW2 w, float *x)             // the rare shapes, one row at a time
 {
     const double SQ = 0.707106781186547524401;  // SQHALF, subs.c:26
     const int type = (int)(w.hi & 7u);
     if (type == FFT_NOP) return;
-    const float a = fft_flip(fft_ld(x, w.lo & 0xffffu), w.hi << 23), c = fft_flip(fft_ld(x, w.lo >> 16), w.hi << 22);
-    float ra, rc;
-    if (type == FFT_BFLY) { ra = simt::fadd(a, c); rc = simt::fsub(a, c); }
-    else if (type == FFT_ROT8A) {                                 // t1=SQ*(a+c); c=SQ*(c-a); a=t1 (double multiply)
-        ra = (float)simt::dmul(SQ, (double)simt::fadd(a, c)); rc = (float)simt::dmul(SQ, (double)simt::fsub(c, a));
-    } else {                                                      // FFT_ROT8B: t2=SQ*(c-a); c=-SQ*(a+c); a=t2
-        ra = (float)simt::dmul(SQ, (double)simt::fsub(c, a)); rc = (float)simt::dmul(-SQ, (double)simt::fadd(a, c));
+#pragma unroll
+    for (int n = 0; n < NB; n++) {
+        const unsigned oa = (w.lo & 0xffffu) + n * FFT_BATCH_BYTES, oc = (w.lo >> 16) + n * FFT_BATCH_BYTES;
+        const float a = fft_flip(fft_ld(x, oa), w.hi << 23), c = fft_flip(fft_ld(x, oc), w.hi << 22);
+        float ra, rc;
+        if (type == FFT_BFLY) { ra = simt::fadd(a, c); rc = simt::fsub(a, c); }
+        else if (type == FFT_ROT8A) {                                 // t1=SQ*(a+c); c=SQ*(c-a); a=t1 (double multiply)
+            ra = (float)simt::dmul(SQ, (double)simt::fadd(a, c)); rc = (float)simt::dmul(SQ, (double)simt::fsub(c, a));
+        } else {                                                      // FFT_ROT8B: t2=SQ*(c-a); c=-SQ*(a+c); a=t2
+            ra = (float)simt::dmul(SQ, (double)simt::fsub(c, a)); rc = (float)simt::dmul(-SQ, (double)simt::fadd(a, c));
+        }
+        fft_st(x, oa, ra);
+        fft_st(x, oc, rc);
     }
-    fft_st(x, w.lo & 0xffffu, ra);
-    fft_st(x, w.lo >> 16, rc);
 }
 
-#ifndef FFT_ROWS_PER_TRIP
-#define FFT_ROWS_PER_TRIP 2
-#endif
-SIMT_FN void fft_run(const WarpCtx &w, const FftDev &P, const FftTwiddle *tw, float *x)
+// U rows per trip, NB data sets; dummy_word: first of the 128 padding-lane words of data set 0 (n + n / 32)
+template <int U, int NB>
+SIMT_FN void fft_run(const WarpCtx &w, const FftDev &P, const FftTwiddle *tw, float *x, int dummy_word)
 {
-    constexpr int U = FFT_ROWS_PER_TRIP;
     FOR_THREADS(w)
-    for (int j = 0; j < 4; j++) x[FFT_X_WORDS + 32 * j + lane] = 0.0f;        // the padding lanes' dummy words
+    for (int n = 0; n < NB; n++)
+        for (int j = 0; j < 4; j++) x[n * (FFT_BATCH_BYTES / 4) + dummy_word + 32 * j + lane] = 0.0f;   // the padding lanes' dummy words
     END_THREADS
     w.sync();
     for (int l = 0; l < P.n_levels; l++) {
@@ -193,32 +215,32 @@ SIMT_FN void fft_run(const WarpCtx &w, const FftDev &P, const FftTwiddle *tw, fl
                 uint32_t nx[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) nx[u] = W[ib + 32 * (U + u)];
-                fft_rows_bfly<U>(wb, x);
+                fft_rows_bfly<U, NB>(wb, x);
 #pragma unroll
                 for (int u = 0; u < U; u++) wb[u] = nx[u];
             }
-            if (ib < s1) fft_rows_bfly<1>(wb, x);
+            if (ib < s1) fft_rows_bfly<1, NB>(wb, x);
             for (; ic + 32 * (U - 1) < (s2 >> 1); ic += 32 * U) {
                 FftW2 nx[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) nx[u] = W2[ic + 32 * (U + u)];
-                fft_rows_cross<U>(wc, x);
+                fft_rows_cross<U, NB>(wc, x);
 #pragma unroll
                 for (int u = 0; u < U; u++) wc[u] = nx[u];
             }
-            if (ic < (s2 >> 1)) fft_rows_cross<1>(wc, x);
+            if (ic < (s2 >> 1)) fft_rows_cross<1, NB>(wc, x);
             for (; ir + 32 * (U - 1) < (s3 >> 1); ir += 32 * U) {
                 FftW2 nx[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) nx[u] = W2[ir + 32 * (U + u)];
-                fft_rows_rot<U>(wr, tw, x);
+                fft_rows_rot<U, NB>(wr, tw, x);
 #pragma unroll
                 for (int u = 0; u < U; u++) wr[u] = nx[u];
             }
-            if (ir < (s3 >> 1)) fft_rows_rot<1>(wr, tw, x);
+            if (ir < (s3 >> 1)) fft_rows_rot<1, NB>(wr, tw, x);
             for (; im < (s4 >> 1); im += 32) {
                 const FftW2 nx = W2[im + 32];
-                fft_row_misc(wm, x);
+                fft_row_misc<NB>(wm, x);
                 wm = nx;
             }
         }
@@ -233,6 +255,10 @@ SIMT_FN float fft_logical(const FftDev &P, const float *x, int i)
     float v = x[s & 0x7fff];
     return (s & 0x8000) ? -v : v;
 }
+
+// energy / phase of bin i of short transform sb, left in place by psy_front
+SIMT_FN float short_energy(const FftDev &P, const float *x, int sb, int i) { return x[sb * (FFT_BATCH_BYTES / 4) + (P.out[i] & 0x7fff)]; }
+SIMT_FN float short_phase(const FftDev &P, const float *x, int sb, int i) { return x[sb * (FFT_BATCH_BYTES / 4) + (P.out[256 - i] & 0x7fff)]; }
 
 // energy + phase of bin i (enphinew, subs.c:53-123); n = transform length
 SIMT_FN void bin_energy_phase(const FftDev &P, const float *x, int n, int i, bool want_phi, float *e_out, float *phi_out)
@@ -272,7 +298,7 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
     for (int j = lane; j < 1024; j += 32) M.x[FFT_SKEW(j)] = simt::fmul(T.hann_l[j], (float)(int)pcm[j - 768]);
     END_THREADS
     w.sync();
-    fft_run(w, D.f1024, D.tw, M.x);
+    fft_run<2, 1>(w, D.f1024, D.tw, M.x, FFT_X_WORDS);
     FOR_THREADS(w)
     for (int i = lane; i <= 512; i += 32) {
         float e, ph = 0.f;
@@ -282,20 +308,25 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
     }
     END_THREADS
     w.sync();
-    // three short FFTs, l3psy.c:518-527
-    for (int sb = 0; sb < 3; sb++) {
+    // three short FFTs, l3psy.c:518-527: one pass over the 256-point program transforms all three windows
+    {
         FOR_THREADS(w)
-        for (int j = lane; j < 256; j += 32) M.x[FFT_SKEW(j)] = simt::fmul(T.hann_s[j], (float)(int)pcm[j - 768 + 128 * (2 + sb)]);
+        for (int sb = 0; sb < 3; sb++)
+            for (int j = lane; j < 256; j += 32)
+                M.x[sb * (FFT_BATCH_BYTES / 4) + FFT_SKEW(j)] = simt::fmul(T.hann_s[j], (float)(int)pcm[j - 768 + 128 * (2 + sb)]);
         END_THREADS
         w.sync();
-        fft_run(w, D.f256, D.tw, M.x);
+        fft_run<1, 3>(w, D.f256, D.tw, M.x, 256 + 8);
         FOR_THREADS(w)
-        for (int i = lane; i <= 128; i += 32) {
-            float e, ph = 0.f;
-            bool wp = (i >= 2 && i < 52);
-            bin_energy_phase(D.f256, M.x, 256, i, wp, &e, &ph);
-            M.Es[sb][i] = e;
-            if (wp) M.Ps[sb][i] = ph;
+        for (int sb = 0; sb < 3; sb++) {
+            float *xs = M.x + sb * (FFT_BATCH_BYTES / 4);
+            for (int i = lane; i <= 128; i += 32) {
+                float e, ph = 0.f;
+                const bool wp = (i >= 2 && i < 52);
+                bin_energy_phase(D.f256, xs, 256, i, wp, &e, &ph);
+                xs[D.f256.out[i] & 0x7fff] = e;
+                if (wp) xs[D.f256.out[256 - i] & 0x7fff] = ph;
+            }
         }
         END_THREADS
         w.sync();
@@ -304,10 +335,10 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
     FOR_THREADS(w)
     for (int i = lane; i < 50; i += 32) {
         const int k = i + 2;
-        double r_prime = simt::dsub(simt::dmul(2.0, sqrt((double)M.Es[0][k])), sqrt((double)M.Es[2][k]));
-        double phi_prime = simt::dsub(simt::dmul(2.0, (double)M.Ps[0][k]), (double)M.Ps[2][k]);
-        double r2 = sqrt((double)M.Es[1][k]);
-        M.cwv[i] = unpredictability(r2, (double)M.Ps[1][k], r_prime, phi_prime);
+        double r_prime = simt::dsub(simt::dmul(2.0, sqrt((double)short_energy(D.f256, M.x, 0, k))), sqrt((double)short_energy(D.f256, M.x, 2, k)));
+        double phi_prime = simt::dsub(simt::dmul(2.0, (double)short_phase(D.f256, M.x, 0, k)), (double)short_phase(D.f256, M.x, 2, k));
+        double r2 = sqrt((double)short_energy(D.f256, M.x, 1, k));
+        M.cwv[i] = unpredictability(r2, (double)short_phase(D.f256, M.x, 1, k), r_prime, phi_prime);
     }
     for (int j = T.tail_l + lane; j <= 512; j += 32) out->tail[j - T.tail_l] = M.E[j];
     END_THREADS
@@ -364,8 +395,8 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
             const int p = lane + 32 * h;
             if (p < 42) {
                 double eb = 0.0;
-                if (p < T.n_s) for (int j = T.lo_s[p]; j < T.hi_s[p]; j++) eb = simt::dadd(eb, (double)M.Es[sb][j]);
-                if (p == 0) for (int j = T.tail_s; j <= 128; j++) eb = simt::dadd(eb, (double)M.Es[sb][j]);
+                if (p < T.n_s) for (int j = T.lo_s[p]; j < T.hi_s[p]; j++) eb = simt::dadd(eb, (double)short_energy(D.f256, M.x, sb, j));
+                if (p == 0) for (int j = T.tail_s; j <= 128; j++) eb = simt::dadd(eb, (double)short_energy(D.f256, M.x, sb, j));
                 M.eb[p] = eb;
             }
         }

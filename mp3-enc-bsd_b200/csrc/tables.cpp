@@ -543,7 +543,9 @@ void build_fft_program(int logm, const std::vector<int> &tw_base, FftProgram *P)
         for (int k = P->level_start[sgm]; k < P->level_start[sgm + 1]; k++) {
             const FftOp &o = P->ops[k];
             auto off = [&](uint16_t slot, int j) -> uint32_t {      // byte offset of an operand; padding -> the lane's dummy word j
-                return 4u * (o.type == FFT_NOP ? (unsigned)FFT_X_WORDS + 32u * j + ((o.pad >> (8 * j)) & 31u) : (unsigned)FFT_SKEW((unsigned)slot));
+                // dummy word in the free bank f picked above: the dummy area starts at word n + n / 32 right behind the data
+                const unsigned dummy0 = (unsigned)FFT_SKEW((unsigned)n);
+                return 4u * (o.type == FFT_NOP ? dummy0 + 32u * j + ((((o.pad >> (8 * j)) & 31u) - dummy0) & 31u) : (unsigned)FFT_SKEW((unsigned)slot));
             };
             if (c == 0) P->words.push_back(off(o.a, 0) | (off(o.b, 1) << 16));
             else if (c == 1) { P->words.push_back(off(o.a, 0) | (off(o.b, 1) << 16)); P->words.push_back(off(o.c, 2) | (off(o.d, 3) << 16)); }

@@ -42,6 +42,9 @@ enum FftOpType : uint8_t {
 // Padding ops of the fast classes are not skipped but aimed at per-lane dummy words behind the data (operand j of
 // lane L: word FFT_X_WORDS + 32 j + L), so the executor needs no "is this a NOP" branch.
 #define FFT_X_ALLOC (FFT_X_WORDS + 4 * 32)
+// Batched short transforms: data set b of a 256-point batch starts FFT_BATCH_BYTES * b into x[] (264 skewed data words
+// + its own 128 dummy words; 3 * 392 = 1176 <= FFT_X_ALLOC)
+#define FFT_BATCH_BYTES (4 * (256 + 8 + 4 * 32))
 
 struct FftOp {
     uint16_t a, b, c, d;  // physical slots
