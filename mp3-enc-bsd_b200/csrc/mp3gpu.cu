@@ -197,10 +197,12 @@ k_quantize_count(const RateTables *__restrict__ gT, const double *xr_abs, const 
             D2 x; x.x = xr_abs[i * 576 + e0]; x.y = xr_abs[i * 576 + e1];
             M.xs[s] = x;
         }
-        refresh_pow34(w, M);
+        PerThread<float> rowmax;
+        refresh_pow34(w, M, rowmax);
         int qq = q[i];
         qq = qq < -256 ? -256 : (qq > 255 ? 255 : qq);
-        b = probe(w, H, *gT, M, is_short, wsf, qq, C);
+        C.kz = 9;   // nothing known about ix[] yet
+        b = probe(w, H, *gT, M, is_short, wsf, qq, rowmax, C);
     } else {
         C.address1 = gi[i].address1; C.address2 = gi[i].address2; C.address3 = gi[i].address3;
         PerThread<int> nzmax, bigmax;

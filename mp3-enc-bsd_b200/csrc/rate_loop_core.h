@@ -169,6 +169,7 @@ struct BandRegs {   // band per lane: band b lives in lane b & 31 of register b 
 };
 
 struct CountResult {
+    int kz;     // rows (32 slots) >= kz of the ix[] working set hold zeros (carried from probe to probe, see quantize_all)
     int bits, big_values, count1, count1table_select;
     int region0_count, region1_count, address1, address2, address3;
     int table_select[3];
@@ -189,17 +190,26 @@ SIMT_FN int slot_e0(bool is_short, int s)
 // Also returns, per lane, the last slot holding a non-zero value and the last slot holding a value
 // > 1 (calc_runlen's scan, loop.c:1498-1517) since the values are at hand.
 // The loop is the hottest of the kernel (30 probes x 9 trips per granule-channel): one trip is ~35 instructions.
-SIMT_FN void quantize_all(const WarpCtx &w, const RateTables &T, RateWarpSmem &M, int q, PerThread<int> &nzmax, PerThread<int> &bigmax)
+SIMT_FN void quantize_all(const WarpCtx &w, const RateTables &T, RateWarpSmem &M, int q, const PerThread<float> &rowmax, int &kz,
+                          PerThread<int> &nzmax, PerThread<int> &bigmax)
 {
     const int qi = (q > 255 ? 255 : q) + 256;
     const double ostep = T.ostep[qi];
     const float of = T.ostep34[qi];
+    // rows whose largest estimate stays below 0.999 quantise to zero for certain (the estimate is good to 2.2e-6): only the
+    // rows up to the last one that can hold a non-zero value are computed, the others are zero-filled if they are not yet
+    PerThread<int> live;
+    FOR_THREADS(w)
+    live() = lane < 9 && !(simt::ffma(rowmax(), of, 0.4054f) < 0.999f);      // nan estimates count as live
+    END_THREADS
+    const unsigned lm = w.ballot(live);
+    const int k_lim = 32 - simt::clz(lm);
     FOR_THREADS(w)
     const F2 *ys = reinterpret_cast<const F2 *>(M.scr);
     unsigned *ixw = reinterpret_cast<unsigned *>(M.ix);
     int nz = -1, bg = -1;
 #pragma unroll 1
-    for (int s = lane; s < 288; s += 32) {
+    for (int s = lane; s < 32 * k_lim; s += 32) {
         const F2 y = ys[s];
         // clamped at 2040: an out-of-range (or nan) estimate sits exactly on an integer and therefore fails the test below
         const float ta = simt::fmin_(simt::ffma(y.x, of, 0.4054f), 2040.0f), tb = simt::fmin_(simt::ffma(y.y, of, 0.4054f), 2040.0f);
@@ -217,26 +227,35 @@ SIMT_FN void quantize_all(const WarpCtx &w, const RateTables &T, RateWarpSmem &M
         if (ab != 0) nz = s;
         if (ab > 1) bg = s;           // a > 1 || b > 1
     }
+#pragma unroll 1
+    for (int s = lane + 32 * k_lim; s < 32 * kz; s += 32) ixw[s] = 0u;
     nzmax() = nz; bigmax() = bg;
     END_THREADS
+    kz = k_lim;
     w.sync();
 }
 
 // ys[s] = |xr|^(3/4) of the slot's two elements (FP32 estimate), into the scratch area: valid until calc_noise
 // overwrites it.  Called once per outer-loop iteration (xs only changes between iterations).
-SIMT_FN void refresh_pow34(const WarpCtx &w, RateWarpSmem &M)
+SIMT_FN void refresh_pow34(const WarpCtx &w, RateWarpSmem &M, PerThread<float> &rowmax)
 {
     F2 *ys = reinterpret_cast<F2 *>(M.scr);
     w.sync();
-    FOR_THREADS(w)
 #pragma unroll 1
     for (int k = 0; k < 9; k++) {
+        PerThread<float> m;
+        FOR_THREADS(w)
         const int s = lane + 32 * k;
         const D2 x = M.xs[s];
         F2 y; y.x = pow075_estimate((float)x.x); y.y = pow075_estimate((float)x.y);
         ys[s] = y;
+        m() = y.x > y.y ? y.x : y.y;
+        END_THREADS
+        const float r = w.reduce_max_nonneg(m);       // lane k keeps the largest estimate of row k (quantize_all)
+        FOR_THREADS(w)
+        if (lane == k) rowmax() = r;
+        END_THREADS
     }
-    END_THREADS
     w.sync();
 }
 
@@ -381,10 +400,11 @@ SIMT_FN int count_all(const WarpCtx &w, const RateHot &H, const RateWarpSmem &M,
 }
 
 // one quantize + count_bits probe at step q
-SIMT_FN int probe(const WarpCtx &w, const RateHot &H, const RateTables &T, RateWarpSmem &M, bool is_short, bool wsf, int q, CountResult &C)
+SIMT_FN int probe(const WarpCtx &w, const RateHot &H, const RateTables &T, RateWarpSmem &M, bool is_short, bool wsf, int q,
+                  const PerThread<float> &rowmax, CountResult &C)
 {
     PerThread<int> nzmax, bigmax;
-    quantize_all(w, T, M, q, nzmax, bigmax);
+    quantize_all(w, T, M, q, rowmax, C.kz, nzmax, bigmax);
     return count_all(w, H, M, is_short, wsf, nzmax, bigmax, C);
 }
 
@@ -584,6 +604,8 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
 
     // ---- iteration variables, loop.c:319-346 ------------------------------------------------------
     CountResult C;
+    C.kz = 0;   // ix[] was cleared above
+    PerThread<float> rowmax;
     C.bits = 0; C.big_values = 0; C.count1 = 0; C.count1table_select = 0;
     C.region0_count = C.region1_count = 0;
     C.address1 = S.addr[gr * 2 + ch][0]; C.address2 = S.addr[gr * 2 + ch][1]; C.address3 = S.addr[gr * 2 + ch][2];
@@ -606,7 +628,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
         PerThread<int> save_sf[2];
         do {
             iteration++;
-            refresh_pow34(w, M);
+            refresh_pow34(w, M, rowmax);
             part2 = part2_length_of(is_short, gr, compress, scfsi);
             const int huff_bits = max_bits - part2;
             // bin_search_StepSize(max_bits, ...) on the first iteration (loop.c:2119-2140), then inner_loop
@@ -619,7 +641,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
                 int top = q, bot = 200, next = q, last = q;
                 for (;;) {
                     if (searching) { last = next; next = (top + bot) / 2; q = next; }  // aint((top+bot)/2.0)
-                    bits = probe(w, H, T, M, is_short, wsf, q, C);
+                    bits = probe(w, H, T, M, is_short, wsf, q, rowmax, C);
                     if (searching) {
                         if (bits > max_bits) top = next; else bot = next;
                         if (bits != max_bits && (last - next > 1 || next - last > 1)) continue;

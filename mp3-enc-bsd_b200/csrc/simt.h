@@ -51,6 +51,8 @@ struct WarpCtx {  // one warp == one group
     SIMT_FN int reduce_max(const PerThread<int> &x) const { return __reduce_max_sync(0xffffffffu, x.v); }
     SIMT_FN int reduce_add(const PerThread<int> &x) const { return __reduce_add_sync(0xffffffffu, x.v); }
     SIMT_FN unsigned ballot(const PerThread<int> &x) const { return __ballot_sync(0xffffffffu, x.v != 0); }
+    // maximum of non-negative floats (their bit patterns order like unsigned integers): one redux instead of a shuffle tree
+    SIMT_FN float reduce_max_nonneg(const PerThread<float> &x) const { return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(x.v))); }
     SIMT_FN double reduce_max(const PerThread<double> &x) const {
         double v = x.v;
 #pragma unroll
@@ -133,6 +135,7 @@ struct WarpCtx {
     int reduce_max(const PerThread<int> &x) const { int m = x.v[0]; for (int i = 1; i < 32; i++) if (x.v[i] > m) m = x.v[i]; return m; }
     int reduce_add(const PerThread<int> &x) const { int s = 0; for (int i = 0; i < 32; i++) s += x.v[i]; return s; }
     unsigned ballot(const PerThread<int> &x) const { unsigned b = 0; for (int i = 0; i < 32; i++) if (x.v[i]) b |= 1u << i; return b; }
+    float reduce_max_nonneg(const PerThread<float> &x) const { float m = x.v[0]; for (int i = 1; i < 32; i++) if (x.v[i] > m) m = x.v[i]; return m; }
     double reduce_max(const PerThread<double> &x) const {
         double t[32]; for (int i = 0; i < 32; i++) t[i] = x.v[i];
         for (int o = 16; o > 0; o >>= 1) { double u[32]; for (int i = 0; i < 32; i++) u[i] = std::fmax(t[i], t[i ^ o]); std::memcpy(t, u, sizeof(t)); }
