@@ -40,6 +40,7 @@ struct FrontTileSmem {
                                         // stage D: xr staging in the rows of the previous granule
     double window[512];
     short pcm[FT_PCM];                  // dead after stage A: the matrixing / MDCT cosine tables are then staged here
+    int bt[FT_G + 1];                   // block types of the tile's granules (L3psycho_anal's decision)
 };
 // layout of the table overlay (doubles, from the start of FrontTileSmem::pcm)
 #define FT_TAB_AM 0                     // am[32][32]
@@ -51,6 +52,9 @@ static_assert(FT_TAB_END * 8 <= FT_PCM * 2, "cosine tables must fit the dead PCM
 #endif
 
 __constant__ FrontTables c_front;  // defined here: this header is included by exactly one translation unit (mp3gpu.cu)
+// the same tables in global memory: per-thread-indexed reads of __constant__ data serialise in the constant cache, so the
+// cooperative copies into shared memory read this copy with coalesced 16-byte loads instead
+__device__ __align__(16) FrontTables g_front;
 
 // ---- stage B: s[sb] = y16 + sum_j am[sb][j] * ys[j], j ascending (encode.c:399-408) ----------------
 template <int SB>
@@ -168,7 +172,8 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
         uint4 *dst4 = reinterpret_cast<uint4 *>(M.pcm);
         for (int i = tid; i < FT_PCM / 8; i += FT_THREADS)
             dst4[i] = (i < n_valid / 8) ? src4[i] : make_uint4(0, 0, 0, 0);
-        for (int i = tid; i < 512; i += FT_THREADS) M.window[i] = c_front.window[i];
+        if (tid < 256) reinterpret_cast<double2 *>(M.window)[tid] = reinterpret_cast<const double2 *>(g_front.window)[tid];
+        if (tid < ng) M.bt[tid] = psy[((s * n_gran + g_first + tid) * (long)n_ch + ch)].block_type;
     }
     __syncthreads();
 
@@ -214,8 +219,12 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
     __syncthreads();
     double *tab = reinterpret_cast<double *>(M.pcm);          // the PCM tile is dead: stage the cosine tables over it
 #if FT_TABLES_IN_SMEM
-    for (int i = tid; i < 32 * 32; i += FT_THREADS) tab[FT_TAB_AM + i] = (&c_front.am[0][0])[i];
-    for (int i = tid; i < 18 * 36; i += FT_THREADS) tab[FT_TAB_COS + i] = (&c_front.cos_l[0][0])[i];
+    {
+        double2 *t2 = reinterpret_cast<double2 *>(tab);
+        const double2 *am2 = reinterpret_cast<const double2 *>(&g_front.am[0][0]), *cos2 = reinterpret_cast<const double2 *>(&g_front.cos_l[0][0]);
+        for (int i = tid; i < 32 * 32 / 2; i += FT_THREADS) t2[FT_TAB_AM / 2 + i] = am2[i];
+        for (int i = tid; i < 18 * 36 / 2; i += FT_THREADS) t2[FT_TAB_COS / 2 + i] = cos2[i];
+    }
     __syncthreads();
 #endif
 
@@ -248,7 +257,7 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
             const double *p = M.rows + (size_t)(18 * (gl - 1)) * FT_ROW + lane;
 #pragma unroll
             for (int k = 0; k < 36; k++) in[k] = p[k * FT_ROW];
-            bt = psy[((s * n_gran + g_first + gl - 1) * gc_stride + ch)].block_type;
+            bt = M.bt[gl - 1];
         }
         __syncthreads();                                    // every warp has its inputs: previous granules' rows are free
         if (active) {

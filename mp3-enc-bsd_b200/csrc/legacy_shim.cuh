@@ -121,6 +121,7 @@ static bool legacy_init()
     FrontTables *F = new FrontTables;
     build_front_tables(F);
     cudaError_t e = cudaMemcpyToSymbol(c_front, F, sizeof(FrontTables));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_front, F, sizeof(FrontTables));
     delete F;
     if (e == cudaSuccess) e = cudaMalloc(&L.d_ring, 2 * 512 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&L.d_pcm32, 32 * sizeof(short));

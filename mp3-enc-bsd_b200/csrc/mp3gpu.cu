@@ -405,6 +405,7 @@ extern "C" int mp3gpu_create(const mp3gpu_config *cfg, mp3gpu_ctx **out)
         FrontTables *F = new FrontTables;
         build_front_tables(F);
         cudaError_t e = cudaMemcpyToSymbol(c_front, F, sizeof(FrontTables));
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_front, F, sizeof(FrontTables));
         delete F;
         if (e != cudaSuccess) { delete c; return fail(MP3GPU_ECUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString(e)); }
         PsyTables *P = new PsyTables;
