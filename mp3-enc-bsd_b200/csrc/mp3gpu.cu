@@ -130,7 +130,9 @@ k_psy_scan(const PsyTables *T, const PsyMid *mid, PsyChanState *states, int n_st
     psy_scan_store(w, states[wid], R);
 }
 
+#ifndef RL_WARPS
 #define RL_WARPS 8
+#endif
 #define RL_HOT_BYTES ((sizeof(RateHot) + 15) & ~(size_t)15)
 #define RL_SMEM_BYTES (RL_HOT_BYTES + RL_WARPS * sizeof(RateWarpSmem))
 static_assert(sizeof(RateHot) % 16 == 0, "RateHot must be int4-copyable");

@@ -487,7 +487,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
     // ---- load xr into registers -----------------------------------------------------------------
     FOR_THREADS(w)
     int sg = 0;
-    double mx = 0.0, e2 = 0.0, lg = 0.0;
+    double mx = 0.0, e2 = 0.0, lg = 0.0, pr = 1.0;
 #pragma unroll 3
     for (int k = 0; k < 9; k++) {
         int s = lane + 32 * k;
@@ -505,8 +505,12 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
         double a2 = simt::dmul(a, a), b2 = simt::dmul(b, b);
         scr[s] = simt::dadd(a2, b2);
         e2 = simt::dadd(e2, simt::dadd(a2, b2));
-        if (a != 0) lg = simt::dadd(lg, ref_log(a2));
-        if (b != 0) lg = simt::dadd(lg, ref_log(b2));
+        // quantanf_init's sum of log(xr^2) over the non-zero lines (loop.c:380-386): one log per six lines on the product of
+        // their squares (|xr| of non-zero MDCT lines lies within 1e+-40, far from over / underflow); like the lane-wise order
+        // of the sum this moves sum1 by a few ulp, which nint(8 ln(sfm)) only sees on an exact rounding boundary
+        pr = simt::dmul(pr, a != 0 ? a2 : 1.0);
+        pr = simt::dmul(pr, b != 0 ? b2 : 1.0);
+        if (k % 3 == 2) { lg = simt::dadd(lg, ref_log(pr)); pr = 1.0; }
     }
     sign() = sg; t0() = mx; t1() = e2;
     Bd.xfsf[0]() = lg;  // borrowed as scratch for the log sum
