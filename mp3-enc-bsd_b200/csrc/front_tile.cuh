@@ -57,39 +57,39 @@ __constant__ FrontTables c_front;  // defined here: this header is included by e
 __device__ __align__(16) FrontTables g_front;
 
 // ---- stage B: s[sb] = y16 + sum_j am[sb][j] * ys[j], j ascending (encode.c:399-408) ----------------
-template <int SB>
-__device__ __forceinline__ double ft_matrix_row(const double (&ys)[32], const double *tab)
-{
-    double s = ys[31];
-#if FT_TABLES_IN_SMEM
-    const double2 *a = reinterpret_cast<const double2 *>(tab + FT_TAB_AM + SB * 32);   // uniform address: broadcast loads
-#pragma unroll
-    for (int j = 0; j < 30; j += 2) {
-        const double2 c = a[j >> 1];
-        s = __dadd_rn(s, __dmul_rn(c.x, ys[j]));
-        s = __dadd_rn(s, __dmul_rn(c.y, ys[j + 1]));
-    }
-    s = __dadd_rn(s, __dmul_rn(a[15].x, ys[30]));
-#else
-#pragma unroll
-    for (int j = 0; j < 31; j++) s = __dadd_rn(s, __dmul_rn(c_front.am[SB][j], ys[j]));
-#endif
-    return s;
-}
-
-template <int SB0>
-__device__ __forceinline__ void ft_matrix_rows8(const double (&ys)[32], double *row, bool odd_slot, const double *tab)
+// Eight rows (independent accumulation chains) per call; the row group is a RUN-TIME offset so that the 496 FP64
+// instructions exist once and loop four times: fully unrolled over all 32 rows the stage streamed 38 KB of code per pass
+// and stalled on instruction fetch (ncu: stall_no_instruction 1.4 warps per issue).
+__device__ __forceinline__ void ft_matrix_rows8(const double (&ys)[32], double *row, int sb0, bool odd_slot, const double *tab)
 {
     double s[8];
-    s[0] = ft_matrix_row<SB0 + 0>(ys, tab); s[1] = ft_matrix_row<SB0 + 1>(ys, tab);
-    s[2] = ft_matrix_row<SB0 + 2>(ys, tab); s[3] = ft_matrix_row<SB0 + 3>(ys, tab);
-    s[4] = ft_matrix_row<SB0 + 4>(ys, tab); s[5] = ft_matrix_row<SB0 + 5>(ys, tab);
-    s[6] = ft_matrix_row<SB0 + 6>(ys, tab); s[7] = ft_matrix_row<SB0 + 7>(ys, tab);
+#if FT_TABLES_IN_SMEM
+    const double2 *a = reinterpret_cast<const double2 *>(tab + FT_TAB_AM + sb0 * 32);   // uniform address: broadcast loads
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = ys[31];
+#pragma unroll
+    for (int j = 0; j < 30; j += 2)
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const double2 c = a[16 * k + (j >> 1)];
+            s[k] = __dadd_rn(s[k], __dmul_rn(c.x, ys[j]));
+            s[k] = __dadd_rn(s[k], __dmul_rn(c.y, ys[j + 1]));
+        }
+#pragma unroll
+    for (int k = 0; k < 8; k++) s[k] = __dadd_rn(s[k], __dmul_rn(a[16 * k + 15].x, ys[30]));
+#else
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        // mdct.c:57-60: odd band, odd time slot -> * -1 (applied here, the raw value is never needed)
-        const double v = (((SB0 + k) & 1) && odd_slot) ? __dmul_rn(s[k], -1.0) : s[k];
-        row[SB0 + k] = v;
+        s[k] = ys[31];
+#pragma unroll
+        for (int j = 0; j < 31; j++) s[k] = __dadd_rn(s[k], __dmul_rn(c_front.am[sb0 + k][j], ys[j]));
+    }
+#endif
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        // mdct.c:57-60: odd band, odd time slot -> * -1 (applied here, the raw value is never needed); sb0 is a multiple of 8
+        const double v = ((k & 1) && odd_slot) ? __dmul_rn(s[k], -1.0) : s[k];
+        row[sb0 + k] = v;
     }
 }
 
@@ -106,17 +106,17 @@ __device__ __forceinline__ void ft_window(double (&fin)[36])
     for (int k = 0; k < 36; k++) fin[k] = __dmul_rn(c_front.win[WIN][k], fin[k]);
 }
 
-template <int M0>
-__device__ __forceinline__ void ft_mdct_long6(const double (&fin)[36], double (&out)[6], const double *tab)
+__device__ __forceinline__ void ft_mdct_long6(const double (&fin)[36], double (&out)[6], int m0, const double *tab)
 {
 #pragma unroll
     for (int m = 0; m < 6; m++) out[m] = 0.0;
 #if FT_TABLES_IN_SMEM
+    const double *ct = tab + FT_TAB_COS + m0 * 36;           // one copy of the code for the three thirds (run-time m0)
 #pragma unroll
     for (int k = 0; k < 36; k += 2)                                                 // mdct.c:193-198, k ascending per output
 #pragma unroll
         for (int m = 0; m < 6; m++) {
-            const double2 c = *reinterpret_cast<const double2 *>(tab + FT_TAB_COS + (M0 + m) * 36 + k);
+            const double2 c = *reinterpret_cast<const double2 *>(ct + m * 36 + k);
             out[m] = __dadd_rn(out[m], __dmul_rn(fin[k], c.x));
             out[m] = __dadd_rn(out[m], __dmul_rn(fin[k + 1], c.y));
         }
@@ -124,7 +124,7 @@ __device__ __forceinline__ void ft_mdct_long6(const double (&fin)[36], double (&
 #pragma unroll
     for (int k = 0; k < 36; k++)
 #pragma unroll
-        for (int m = 0; m < 6; m++) out[m] = __dadd_rn(out[m], __dmul_rn(fin[k], c_front.cos_l[M0 + m][k]));
+        for (int m = 0; m < 6; m++) out[m] = __dadd_rn(out[m], __dmul_rn(fin[k], c_front.cos_l[m0 + m][k]));
 #endif
 }
 
@@ -235,10 +235,8 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
 #pragma unroll
         for (int j = 0; j < 32; j++) ys[j] = row[j];
         const bool odd_slot = ((tid % 18) & 1) != 0;
-        ft_matrix_rows8<0>(ys, row, odd_slot, tab);
-        ft_matrix_rows8<8>(ys, row, odd_slot, tab);
-        ft_matrix_rows8<16>(ys, row, odd_slot, tab);
-        ft_matrix_rows8<24>(ys, row, odd_slot, tab);
+#pragma unroll 1
+        for (int sb0 = 0; sb0 < 32; sb0 += 8) ft_matrix_rows8(ys, row, sb0, odd_slot, tab);
     }
     __syncthreads();
 
@@ -268,7 +266,7 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
                 for (int m = 0; m < 6; m++) st[lane * 18 + 3 * m + third] = out[m];
             } else {
                 if (bt == 0) ft_window<0>(in); else if (bt == 1) ft_window<1>(in); else ft_window<3>(in);
-                if (third == 0) ft_mdct_long6<0>(in, out, tab); else if (third == 1) ft_mdct_long6<6>(in, out, tab); else ft_mdct_long6<12>(in, out, tab);
+                ft_mdct_long6(in, out, 6 * third, tab);
 #pragma unroll
                 for (int m = 0; m < 6; m++) st[lane * 18 + 6 * third + m] = out[m];
             }

@@ -130,8 +130,10 @@ k_psy_scan(const PsyTables *T, const PsyMid *mid, PsyChanState *states, int n_st
     psy_scan_store(w, states[wid], R);
 }
 
+// One CTA of 27 warps per SM: the hot tables are held once per SM and 27 x 8064 B of per-warp working set + 9.5 KB of tables
+// fill the 227 KB of shared memory (3 CTAs x 8 warps left room for 24 warps only); 72 registers per thread.
 #ifndef RL_WARPS
-#define RL_WARPS 8
+#define RL_WARPS 27
 #endif
 #define RL_HOT_BYTES ((sizeof(RateHot) + 15) & ~(size_t)15)
 #define RL_SMEM_BYTES (RL_HOT_BYTES + RL_WARPS * sizeof(RateWarpSmem))
@@ -148,7 +150,7 @@ __device__ __forceinline__ const RateHot &load_rate_hot(const RateTables *gT, un
 }
 
 #ifndef RL_MIN_CTAS
-#define RL_MIN_CTAS 3     // 80 registers, 24 warps per SM
+#define RL_MIN_CTAS 1
 #endif
 __global__ void __launch_bounds__(RL_WARPS * 32, RL_MIN_CTAS)
 k_rate_loop(const RateTables *__restrict__ gT, FrameGeom G, LoopStreamState *states, LoopLaneState *lane_states, int n_streams, int n_frames,
