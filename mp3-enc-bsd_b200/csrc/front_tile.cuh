@@ -38,15 +38,15 @@ namespace mp3gpu {
 struct FrontTileSmem {
     double rows[FT_SLOTS * FT_ROW];     // stage A: ysum/ysub/y16; stage B: subband samples (in place);
                                         // stage D: xr staging in the rows of the previous granule
-    double window[512];
-    short pcm[FT_PCM];                  // dead after stage A: the matrixing / MDCT cosine tables are then staged here
+    double window[512];                 // Table C.1                        } loaded once per CTA: the CTA is persistent and
+    double tab[32 * 32 + 18 * 36];      // am[32][32], cos_l[18][36]        } walks over tiles
+    short pcm[FT_PCM];
     int bt[FT_G + 1];                   // block types of the tile's granules (L3psycho_anal's decision)
 };
-// layout of the table overlay (doubles, from the start of FrontTileSmem::pcm)
+// layout of tab[] (doubles)
 #define FT_TAB_AM 0                     // am[32][32]
 #define FT_TAB_COS (32 * 32)            // cos_l[18][36]
 #define FT_TAB_END (FT_TAB_COS + 18 * 36)
-static_assert(FT_TAB_END * 8 <= FT_PCM * 2, "cosine tables must fit the dead PCM staging area");
 #ifndef FT_TABLES_IN_SMEM
 #define FT_TABLES_IN_SMEM 1
 #endif
@@ -147,15 +147,34 @@ __device__ __forceinline__ void ft_group_barrier(int group)   // the three warps
 }
 
 // pcm_rows: [n_streams*n_ch] rows of `row` samples, HIST samples of history first (see mp3gpu.cu)
+// One CTA per tile (with FT_PERSISTENT: 2 CTAs per SM, CTA b takes tiles b, b + gridDim.x, ... of the n_tiles_total =
+// streams x channels x tiles-per-row tiles).  The window and cosine tables have their own shared-memory area and are
+// fetched together with the PCM tile.
 __global__ void __launch_bounds__(FT_THREADS, 2)
 k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_stride, int hist, int n_streams, int n_ch, int n_gran,
-             const PsyOut *__restrict__ psy, double *__restrict__ xr)
+             long n_tiles_total, const PsyOut *__restrict__ psy, double *__restrict__ xr)
 {
     extern __shared__ __align__(16) unsigned char ft_smem_raw[];
     FrontTileSmem &M = *reinterpret_cast<FrontTileSmem *>(ft_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_tiles = (n_gran + FT_G - 1) / FT_G;
+    const double *tab = M.tab;
+    {
+        if (tid < 256) reinterpret_cast<double2 *>(M.window)[tid] = reinterpret_cast<const double2 *>(g_front.window)[tid];
+        double2 *t2 = reinterpret_cast<double2 *>(M.tab);
+        const double2 *am2 = reinterpret_cast<const double2 *>(&g_front.am[0][0]), *cos2 = reinterpret_cast<const double2 *>(&g_front.cos_l[0][0]);
+        for (int i = tid; i < 32 * 32 / 2; i += FT_THREADS) t2[FT_TAB_AM / 2 + i] = am2[i];
+        for (int i = tid; i < 18 * 36 / 2; i += FT_THREADS) t2[FT_TAB_COS / 2 + i] = cos2[i];
+    }
+#ifndef FT_PERSISTENT
+#define FT_PERSISTENT 0     // A/B: the tile loop costs registers (spills under the 96-register cap): 44 ms vs 28 ms per step
+#endif
+#if FT_PERSISTENT
+  for (long bid = blockIdx.x; bid < n_tiles_total; bid += gridDim.x) {
+#else
+  {
     const long bid = blockIdx.x;
+#endif
     const int t = (int)(bid % n_tiles);
     const int ch = (int)((bid / n_tiles) % n_ch);
     const long s = bid / ((long)n_tiles * n_ch);
@@ -172,7 +191,6 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
         uint4 *dst4 = reinterpret_cast<uint4 *>(M.pcm);
         for (int i = tid; i < FT_PCM / 8; i += FT_THREADS)
             dst4[i] = (i < n_valid / 8) ? src4[i] : make_uint4(0, 0, 0, 0);
-        if (tid < 256) reinterpret_cast<double2 *>(M.window)[tid] = reinterpret_cast<const double2 *>(g_front.window)[tid];
         if (tid < ng) M.bt[tid] = psy[((s * n_gran + g_first + tid) * (long)n_ch + ch)].block_type;
     }
     __syncthreads();
@@ -217,17 +235,6 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
         }
     }
     __syncthreads();
-    double *tab = reinterpret_cast<double *>(M.pcm);          // the PCM tile is dead: stage the cosine tables over it
-#if FT_TABLES_IN_SMEM
-    {
-        double2 *t2 = reinterpret_cast<double2 *>(tab);
-        const double2 *am2 = reinterpret_cast<const double2 *>(&g_front.am[0][0]), *cos2 = reinterpret_cast<const double2 *>(&g_front.cos_l[0][0]);
-        for (int i = tid; i < 32 * 32 / 2; i += FT_THREADS) t2[FT_TAB_AM / 2 + i] = am2[i];
-        for (int i = tid; i < 18 * 36 / 2; i += FT_THREADS) t2[FT_TAB_COS / 2 + i] = cos2[i];
-    }
-    __syncthreads();
-#endif
-
     // ---- stage B: thread = slot ---------------------------------------------------------------------
     if (tid < n_chunks * 32) {
         double *row = M.rows + (size_t)tid * FT_ROW;
@@ -287,6 +294,8 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
             for (int i = 0; i < 3; i++) dst[lane + 32 * (3 * third + i)] = src[lane + 32 * (3 * third + i)];
         }
     }
+    __syncthreads();        // the next tile's stages overwrite pcm[] and rows[]
+  }
 }
 
 }  // namespace mp3gpu

@@ -298,6 +298,7 @@ struct mp3gpu_ctx {
     // tables
     PsyTables *d_psy_tab = nullptr;
     RateTables *d_rate_tab = nullptr;
+    int sm_count = 148;
     uint32_t *d_ops1024 = nullptr, *d_ops256 = nullptr;
     int *d_lv1024 = nullptr, *d_lv256 = nullptr;
     uint16_t *d_out1024 = nullptr, *d_out256 = nullptr;
@@ -401,6 +402,7 @@ extern "C" int mp3gpu_create(const mp3gpu_config *cfg, mp3gpu_ctx **out)
     mp3gpu_ctx *c = new (std::nothrow) mp3gpu_ctx();
     if (!c) return fail(MP3GPU_ENOMEM, "out of host memory");
     c->cfg = *cfg; c->sr = sr;
+    if (cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess || c->sm_count < 1) c->sm_count = 148;
     frame_geometry(cfg->sfreq_hz, cfg->n_ch, cfg->bitrate_kbps, &c->geom);
     c->row = HIST + (long)cfg->max_frames * 1152;
     int rc = 0;
@@ -652,7 +654,8 @@ static int launch_front(mp3gpu_ctx *c, const short *pcm_rows, const PsyOut *psy,
         const long n_tiles = (n_gran + FT_G - 1) / FT_G;
         const long ctas = (long)n_streams * n_ch * n_tiles;
         prof_begin(c, MP3GPU_K_FRONT, q);
-        k_front_tile<<<(unsigned)ctas, FT_THREADS, sizeof(FrontTileSmem), q>>>(pcm_rows, c->row * n_ch, c->row, HIST, n_streams, n_ch, n_gran, psy, xr);
+        const long grid = (FT_PERSISTENT && ctas > 2L * c->sm_count) ? 2L * c->sm_count : ctas;
+        k_front_tile<<<(unsigned)grid, FT_THREADS, sizeof(FrontTileSmem), q>>>(pcm_rows, c->row * n_ch, c->row, HIST, n_streams, n_ch, n_gran, ctas, psy, xr);
         prof_end(c, q);
         c->launches++;
         CU(cudaGetLastError());
