@@ -111,7 +111,14 @@ struct alignas(16) RateWarpSmem {
 SIMT_FN float pow075_estimate(float x)
 {
 #if SIMT_DEV
-    return __powf(x, 0.75f);   // 2 MUFU; relative error ~1.3e-6, only ever used inside a verified margin
+    // ex2(0.75 lg2 x) on the MUFU unit — what __powf() computes, without its denormal scaling (6 more instructions per
+    // value): |xr| below 1.2e-38 gives the estimate 0, and such a line quantises to 0 at every step size.
+    // relative error ~1.3e-6 typical, only ever used inside a verified margin
+    float l, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+    l = __fmul_rn(l, 0.75f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l));
+    return r;
 #else
     return powf(x, 0.75f);
 #endif
@@ -185,7 +192,7 @@ SIMT_FN int slot_e0(bool is_short, int s)
 // quantize(): loop.c:1360-1428 with subblock_gain == 0 and mixed_block_flag == 0 (always, l3psy.c:739).
 // x^(3/4) + 0.4054 is estimated in FP32 as t = |xr|^(3/4) * (1/step)^(3/4) + 0.4054 from the cached per-slot power.
 // The estimate's relative error is < 2.2e-6 (two MUFU ops on |log2| <= 24, FP32 roundings); with the 5x-conservative
-// margin m = 1e-5 t + 1e-6 the truncation is exact whenever trunc(t - m) == trunc(t + m) (and t is in range and a
+// margin m = 1e-5 t + 1e-6 the truncation is exact whenever floor(t - m) == floor(t + m) (and t is in range and a
 // number), otherwise the FP64 table comparison on |xr| / step decides (pow_nint.h:16-50) — exact by construction.
 // Also returns, per lane, the last slot holding a non-zero value and the last slot holding a value
 // > 1 (calc_runlen's scan, loop.c:1498-1517) since the values are at hand.
@@ -214,16 +221,18 @@ SIMT_FN void quantize_all(const WarpCtx &w, const RateTables &T, RateWarpSmem &M
         // clamped at 2040: an out-of-range (or nan) estimate sits exactly on an integer and therefore fails the test below
         const float ta = simt::fmin_(simt::ffma(y.x, of, 0.4054f), 2040.0f), tb = simt::fmin_(simt::ffma(y.y, of, 0.4054f), 2040.0f);
         const float ma = simt::ffma(ta, 1e-5f, 1e-6f), mb = simt::ffma(tb, 1e-5f, 1e-6f);
-        int a = simt::f2i_trunc(simt::fsub(ta, ma)), b = simt::f2i_trunc(simt::fsub(tb, mb));
-        const bool oka = (a == simt::f2i_trunc(simt::fadd(ta, ma)));
-        const bool okb = (b == simt::f2i_trunc(simt::fadd(tb, mb)));
+        // floor(t - m) and floor(t + m) as "magic" floats 2^23 + floor(.) (t - m >= 0.4, t + m < 2041): equal <=> accepted
+        const float fa = simt::floor_magic(simt::fsub(ta, ma)), fb = simt::floor_magic(simt::fsub(tb, mb));
+        const bool oka = (fa == simt::floor_magic(simt::fadd(ta, ma)));
+        const bool okb = (fb == simt::floor_magic(simt::fadd(tb, mb)));
+        unsigned a = simt::fbits(fa) & 0xffffu, b = simt::fbits(fb) & 0xffffu;     // the value: the low mantissa bits
         if (!(oka && okb)) {
             const D2 x = M.xs[s];
-            if (!oka) a = quant1_exact(T.pow_nint_tab, simt::dmul(x.x, ostep), a);
-            if (!okb) b = quant1_exact(T.pow_nint_tab, simt::dmul(x.y, ostep), b);
+            if (!oka) a = (unsigned)quant1_exact(T.pow_nint_tab, simt::dmul(x.x, ostep), (int)a);
+            if (!okb) b = (unsigned)quant1_exact(T.pow_nint_tab, simt::dmul(x.y, ostep), (int)b);
         }
-        ixw[s] = (unsigned)a | ((unsigned)b << 16);
-        const int ab = a | b;
+        ixw[s] = a | (b << 16);
+        const unsigned ab = a | b;
         if (ab != 0) nz = s;
         if (ab > 1) bg = s;           // a > 1 || b > 1
     }
@@ -776,12 +785,14 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
                 status = (w.ballot(z0) | w.ballot(z1)) ? 0 : 1;
                 if (status == 0) {
                     const int ms1 = w.reduce_max(s1m), ms2 = w.reduce_max(s2m);
-                    int ep = 2, k;
-                    for (k = 0; k < 16; k++) {
-                        const int l1 = (0x4433322211130000ull >> (4 * k)) & 15, l2 = (0x3232132132103210ull >> (4 * k)) & 15;
-                        if (ms1 < (1 << l1) && ms2 < (1 << l2)) { ep = 0; break; }
+                    // first scalefac_compress k whose (slen1, slen2) hold n1 = bitlength(ms1), n2 = bitlength(ms2) bits: the
+                    // reference's walk over the 16 candidates as a look-up on (n1, n2), nibble 4 n1 + n2
+                    const int n1 = 32 - simt::clz((unsigned)ms1), n2 = 32 - simt::clz((unsigned)ms2);
+                    int ep = 2;
+                    if (n1 <= 4 && n2 <= 3) {
+                        ep = 0;
+                        compress = n1 < 4 ? (int)((0xdcb4a98476543210ull >> (4 * (4 * n1 + n2))) & 15) : (int)((0xfeeeu >> (4 * n2)) & 15);
                     }
-                    if (ep == 0) compress = k;
                     status = ep;
                 }
             }
