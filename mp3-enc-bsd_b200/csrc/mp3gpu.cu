@@ -110,7 +110,7 @@ k_psy_front(PsyDev D, const short *pcm, long stream_stride, long ch_stride, int 
 }
 
 #define PSYS_WARPS 4
-__global__ void __launch_bounds__(PSYS_WARPS * 32)
+__global__ void __launch_bounds__(PSYS_WARPS * 32, 7)
 k_psy_scan(const PsyTables *T, const PsyMid *mid, PsyChanState *states, int n_streams, int n_ch, int n_gran, PsyOut *psy)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

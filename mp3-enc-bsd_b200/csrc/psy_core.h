@@ -39,11 +39,12 @@ struct PsyDev {
 
 struct PsyMid {
     double eb[64];       // long partition energies (history free)
-    double ratio_s[36];  // short-block ratios this granule WOULD produce, [sfb][window]
     float ecb[64];       // spread energy
     float cb[64];        // weighted unpredictability, valid for partitions >= n_hist_part
     float tail[48];      // energies of lines >= tail_l (they fold into partition 0), line order
     float e6[8], phi6[8];
+    float es[3][132];    // energies of the three short transforms, lines 0..128 (the short-block ratios are formed from them
+                         // by psy_scan, and only for granules that do switch to short blocks: the cold tail of the record)
 };
 
 // 6816 B per warp (8 warps per CTA, 4 CTAs per SM).  x[] holds the FFT working set: the 1024-point transform, then the three
@@ -325,6 +326,7 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
                 const bool wp = (i >= 2 && i < 52);
                 bin_energy_phase(D.f256, xs, 256, i, wp, &e, &ph);
                 xs[D.f256.out[i] & 0x7fff] = e;
+                out->es[sb][i] = e;
                 if (wp) xs[D.f256.out[256 - i] & 0x7fff] = ph;
             }
         }
@@ -387,50 +389,6 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
     }
     END_THREADS
     w.sync();
-    // short-block thresholds, l3psy.c:698-729 (uses the LONG spreading matrix and norm_l, sic)
-    for (int sb = 0; sb < 3; sb++) {
-        FOR_THREADS(w)
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int p = lane + 32 * h;
-            if (p < 42) {
-                double eb = 0.0;
-                if (p < T.n_s) for (int j = T.lo_s[p]; j < T.hi_s[p]; j++) eb = simt::dadd(eb, (double)short_energy(D.f256, M.x, sb, j));
-                if (p == 0) for (int j = T.tail_s; j <= 128; j++) eb = simt::dadd(eb, (double)short_energy(D.f256, M.x, sb, j));
-                M.eb[p] = eb;
-            }
-        }
-        END_THREADS
-        w.sync();
-        FOR_THREADS(w)
-        {
-            const int b0 = lane, b1 = lane + 32;            // partitions 0..41: b1 is live in lanes 0..9 only
-            float e0 = 0.0f, e1 = 0.0f;
-            for (int k = 0; k < 42; k++) {
-                const double ebk = M.eb[k];
-                e0 = (float)simt::dadd((double)e0, simt::dmul(T.s3_lT[k * 64 + b0], ebk));
-                e1 = (float)simt::dadd((double)e1, simt::dmul(T.s3_lT[k * 64 + b1], ebk));
-            }
-            const float nb0 = (float)simt::dmul(simt::dmul((double)e0, T.norm_l[b0]), T.snr_s_exp[b0]);
-            M.thr[b0] = (T.qthr_s[b0] > (double)nb0) ? T.qthr_s[b0] : (double)nb0;
-            if (b1 < 42) {
-                const float nb1 = (float)simt::dmul(simt::dmul((double)e1, T.norm_l[b1]), T.snr_s_exp[b1]);
-                M.thr[b1] = (T.qthr_s[b1] > (double)nb1) ? T.qthr_s[b1] : (double)nb1;
-            }
-        }
-        END_THREADS
-        w.sync();
-        FOR_THREADS(w)
-        if (lane < 12) {
-            const int bu = T.bu_s[lane], bo = T.bo_s[lane];
-            double en = simt::dadd(simt::dmul(T.w1_s[lane], M.eb[bu]), simt::dmul(T.w2_s[lane], M.eb[bo]));
-            double thm = simt::dadd(simt::dmul(T.w1_s[lane], M.thr[bu]), simt::dmul(T.w2_s[lane], M.thr[bo]));
-            for (int b = bu + 1; b < bo; b++) { en = simt::dadd(en, M.eb[b]); thm = simt::dadd(thm, M.thr[b]); }
-            out->ratio_s[lane * 3 + sb] = (en != 0.0) ? thm / en : 0.0;
-        }
-        END_THREADS
-        w.sync();
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -469,6 +427,58 @@ SIMT_FN void psy_scan_store(const WarpCtx &w, PsyChanState &S, const PsyScanRegs
     if (lane < 4) S.ratio_s[32 + lane] = R.rs[1]();
     if (lane == 0) S.blocktype_old = R.blocktype_old;
     END_THREADS
+}
+
+// Short-block ratios of one granule, l3psy.c:698-729 (uses the LONG spreading matrix and norm_l, sic), from the short
+// energies psy_front left in PsyMid.  Only granules that switch to short blocks need them (the reference computes them in
+// the pe >= 1800 branch only), so psy_scan calls this on demand (out of line: the scan's common path stays small).
+// eb / thr: 64 doubles of scratch each; ratio: [36] out.
+SIMT_NOINLINE void psy_short_ratios(const WarpCtx &w, const PsyTables &T, const PsyMid &mid, double *eb_s, double *thr_s, double *ratio)
+{
+    for (int sb = 0; sb < 3; sb++) {
+        const float *es = mid.es[sb];
+        FOR_THREADS(w)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int p = lane + 32 * h;
+            if (p < 42) {
+                double eb = 0.0;
+                if (p < T.n_s) for (int j = T.lo_s[p]; j < T.hi_s[p]; j++) eb = simt::dadd(eb, (double)es[j]);
+                if (p == 0) for (int j = T.tail_s; j <= 128; j++) eb = simt::dadd(eb, (double)es[j]);
+                eb_s[p] = eb;
+            }
+        }
+        END_THREADS
+        w.sync();
+        FOR_THREADS(w)
+        {
+            const int b0 = lane, b1 = lane + 32;            // partitions 0..41: b1 is live in lanes 0..9 only
+            float e0 = 0.0f, e1 = 0.0f;
+            for (int k = 0; k < 42; k++) {
+                const double ebk = eb_s[k];
+                e0 = (float)simt::dadd((double)e0, simt::dmul(T.s3_lT[k * 64 + b0], ebk));
+                e1 = (float)simt::dadd((double)e1, simt::dmul(T.s3_lT[k * 64 + b1], ebk));
+            }
+            const float nb0 = (float)simt::dmul(simt::dmul((double)e0, T.norm_l[b0]), T.snr_s_exp[b0]);
+            thr_s[b0] = (T.qthr_s[b0] > (double)nb0) ? T.qthr_s[b0] : (double)nb0;
+            if (b1 < 42) {
+                const float nb1 = (float)simt::dmul(simt::dmul((double)e1, T.norm_l[b1]), T.snr_s_exp[b1]);
+                thr_s[b1] = (T.qthr_s[b1] > (double)nb1) ? T.qthr_s[b1] : (double)nb1;
+            }
+        }
+        END_THREADS
+        w.sync();
+        FOR_THREADS(w)
+        if (lane < 12) {
+            const int bu = T.bu_s[lane], bo = T.bo_s[lane];
+            double en = simt::dadd(simt::dmul(T.w1_s[lane], eb_s[bu]), simt::dmul(T.w2_s[lane], eb_s[bo]));
+            double thm = simt::dadd(simt::dmul(T.w1_s[lane], thr_s[bu]), simt::dmul(T.w2_s[lane], thr_s[bo]));
+            for (int b = bu + 1; b < bo; b++) { en = simt::dadd(en, eb_s[b]); thm = simt::dadd(thm, thr_s[b]); }
+            ratio[lane * 3 + sb] = (en != 0.0) ? thm / en : 0.0;
+        }
+        END_THREADS
+        w.sync();
+    }
 }
 
 SIMT_FN void psy_scan_step(const WarpCtx &w, const PsyTables &T, PsyScanSmem &M, const PsyMid &mid, PsyScanRegs &R, PsyOut *out)
@@ -573,9 +583,10 @@ SIMT_FN void psy_scan_step(const WarpCtx &w, const PsyTables &T, PsyScanSmem &M,
         blocktype = 2;
         if (R.blocktype_old == 0) R.blocktype_old = 1;
         if (R.blocktype_old == 3) R.blocktype_old = 2;
+        psy_short_ratios(w, T, mid, M.eb, M.thr, M.prod);
         FOR_THREADS(w)
-        R.rs[0]() = mid.ratio_s[lane];
-        if (lane < 4) R.rs[1]() = mid.ratio_s[32 + lane];
+        R.rs[0]() = M.prod[lane];
+        if (lane < 4) R.rs[1]() = M.prod[32 + lane];
         END_THREADS
     }
     FOR_THREADS(w)
