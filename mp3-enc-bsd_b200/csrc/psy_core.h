@@ -142,26 +142,26 @@ SIMT_FN void fft_rows_cross(const FftW2 *w, float *x)          // t1=a+d; t2=c+b
         }
 }
 
+struct alignas(16) FftW4 { uint32_t lo; float cn, spcn, smcn; };
+
 template <int U, int NB>
-SIMT_FN void fft_rows_rot(const FftW2 *w, const FftTwiddle *tw, float *x)   // t2=cn*(a+c); t1=spcn*a+t2; a=smcn*c+t2; c=t1
+SIMT_FN void fft_rows_rot(const FftW4 *w, float *x)            // t2=cn*(a+c); t1=spcn*a+t2; a=smcn*c+t2; c=t1
 {
-    float a[U][NB], c[U][NB]; FftTwiddle t[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-#pragma unroll
-        for (int n = 0; n < NB; n++) {
-            a[u][n] = fft_ld(x, (w[u].lo & 0xffffu) + n * FFT_BATCH_BYTES);
-            c[u][n] = fft_flip(fft_ld(x, (w[u].lo >> 16) + n * FFT_BATCH_BYTES), w[u].hi);
-        }
-        t[u] = *reinterpret_cast<const FftTwiddle *>(reinterpret_cast<const char *>(tw) + (w[u].hi & 0xffffu));
-    }
+    float a[U][NB], c[U][NB];
 #pragma unroll
     for (int u = 0; u < U; u++)
 #pragma unroll
         for (int n = 0; n < NB; n++) {
-            const float t2 = simt::fmul(t[u].cn, simt::fadd(a[u][n], c[u][n]));
-            fft_st(x, (w[u].lo & 0xffffu) + n * FFT_BATCH_BYTES, simt::fadd(simt::fmul(t[u].smcn, c[u][n]), t2));
-            fft_st(x, (w[u].lo >> 16) + n * FFT_BATCH_BYTES, simt::fadd(simt::fmul(t[u].spcn, a[u][n]), t2));
+            a[u][n] = fft_ld(x, (w[u].lo & 0xffffu) + n * FFT_BATCH_BYTES);
+            c[u][n] = fft_flip(fft_ld(x, ((w[u].lo >> 16) & 0x7fffu) + n * FFT_BATCH_BYTES), w[u].lo);
+        }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int n = 0; n < NB; n++) {
+            const float t2 = simt::fmul(w[u].cn, simt::fadd(a[u][n], c[u][n]));
+            fft_st(x, (w[u].lo & 0xffffu) + n * FFT_BATCH_BYTES, simt::fadd(simt::fmul(w[u].smcn, c[u][n]), t2));
+            fft_st(x, ((w[u].lo >> 16) & 0x7fffu) + n * FFT_BATCH_BYTES, simt::fadd(simt::fmul(w[u].spcn, a[u][n]), t2));
         }
 }
 
@@ -207,11 +207,17 @@ SIMT_FN void fft_run(const WarpCtx &w, const FftDev &P, const FftTwiddle *tw, fl
             // 32-bit word indices: a 64-bit pointer loop costs ~6 more integer instructions per trip.
             const uint32_t *W = P.words;
             const FftW2 *W2 = reinterpret_cast<const FftW2 *>(P.words);
-            int ib = s0 + lane, ic = (s1 >> 1) + lane, ir = (s2 >> 1) + lane, im = (s3 >> 1) + lane;
-            uint32_t wb[U]; FftW2 wc[U], wr[U], wm;
+            const FftW4 *W4 = reinterpret_cast<const FftW4 *>(P.words);
+            int ib = s0 + lane, ic = (s1 >> 1) + lane, ir = (s2 >> 2) + lane, im = (s3 >> 1) + lane;
+            uint32_t wb[U] = {}; FftW2 wc[U] = {}, wm = {}; FftW4 wr[U] = {};
+            // (empty segments are not fetched: the look-ahead words cost L2 bandwidth, which this kernel is short of)
 #pragma unroll
-            for (int u = 0; u < U; u++) { wb[u] = W[ib + 32 * u]; wc[u] = W2[ic + 32 * u]; wr[u] = W2[ir + 32 * u]; }
-            wm = W2[im];
+            for (int u = 0; u < U; u++) {
+                if (s1 > s0) wb[u] = W[ib + 32 * u];
+                if (s2 > s1) wc[u] = W2[ic + 32 * u];
+                if (s3 > s2) wr[u] = W4[ir + 32 * u];
+            }
+            if (s4 > s3) wm = W2[im];
             for (; ib + 32 * (U - 1) < s1; ib += 32 * U) {
                 uint32_t nx[U];
 #pragma unroll
@@ -230,15 +236,15 @@ SIMT_FN void fft_run(const WarpCtx &w, const FftDev &P, const FftTwiddle *tw, fl
                 for (int u = 0; u < U; u++) wc[u] = nx[u];
             }
             if (ic < (s2 >> 1)) fft_rows_cross<1, NB>(wc, x);
-            for (; ir + 32 * (U - 1) < (s3 >> 1); ir += 32 * U) {
-                FftW2 nx[U];
+            for (; ir + 32 * (U - 1) < (s3 >> 2); ir += 32 * U) {
+                FftW4 nx[U];
 #pragma unroll
-                for (int u = 0; u < U; u++) nx[u] = W2[ir + 32 * (U + u)];
-                fft_rows_rot<U, NB>(wr, tw, x);
+                for (int u = 0; u < U; u++) nx[u] = W4[ir + 32 * (U + u)];
+                fft_rows_rot<U, NB>(wr, x);
 #pragma unroll
                 for (int u = 0; u < U; u++) wr[u] = nx[u];
             }
-            if (ir < (s3 >> 1)) fft_rows_rot<1, NB>(wr, tw, x);
+            if (ir < (s3 >> 2)) fft_rows_rot<1, NB>(wr, x);
             for (; im < (s4 >> 1); im += 32) {
                 const FftW2 nx = W2[im + 32];
                 fft_row_misc<NB>(wm, x);
@@ -380,9 +386,13 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
         const int lo1 = (b1 < 63) ? T.spr_lo[b1] : 1, hi1 = (b1 < 63) ? T.spr_hi[b1] : 0;
         float e0 = 0.0f, e1 = 0.0f;
         for (int k = 0; k < 63; k++) {
-            const double s0 = T.s3_lT[k * 64 + b0], s1 = T.s3_lT[k * 64 + b1], ebk = M.eb[k];
-            if (k >= lo0 && k <= hi0 && (T.sparse || s0 != 1.0)) e0 = (float)simt::dadd((double)e0, simt::dmul(s0, ebk));
-            if (k >= lo1 && k <= hi1 && (T.sparse || s1 != 1.0)) e1 = (float)simt::dadd((double)e1, simt::dmul(s1, ebk));
+            // matrix elements outside a lane's row range are not fetched (predicated loads: the warp's request then covers
+            // the ~20 partitions around the diagonal instead of all 64)
+            const bool in0 = k >= lo0 && k <= hi0, in1 = k >= lo1 && k <= hi1;
+            const double ebk = M.eb[k];
+            const double s0 = in0 ? T.s3_lT[k * 64 + b0] : 1.0, s1 = in1 ? T.s3_lT[k * 64 + b1] : 1.0;
+            if (in0 && (T.sparse || s0 != 1.0)) e0 = (float)simt::dadd((double)e0, simt::dmul(s0, ebk));
+            if (in1 && (T.sparse || s1 != 1.0)) e1 = (float)simt::dadd((double)e1, simt::dmul(s1, ebk));
         }
         out->ecb[b0] = e0;
         out->ecb[b1] = e1;

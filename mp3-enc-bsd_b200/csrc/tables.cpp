@@ -538,6 +538,8 @@ void build_fft_program(int logm, const std::vector<int> &tw_base, FftProgram *P)
         }
     }
     // device encoding
+    std::vector<FftTwiddle> tw_all; std::vector<int> tw_base_chk;
+    build_fft_twiddles(&tw_all, &tw_base_chk);
     for (int sgm = 0; sgm < FFT_CLASSES * n_levels; sgm++) {
         const int c = sgm % FFT_CLASSES;
         for (int k = P->level_start[sgm]; k < P->level_start[sgm + 1]; k++) {
@@ -550,8 +552,13 @@ void build_fft_program(int logm, const std::vector<int> &tw_base, FftProgram *P)
             if (c == 0) P->words.push_back(off(o.a, 0) | (off(o.b, 1) << 16));
             else if (c == 1) { P->words.push_back(off(o.a, 0) | (off(o.b, 1) << 16)); P->words.push_back(off(o.c, 2) | (off(o.d, 3) << 16)); }
             else if (c == 2) {
-                P->words.push_back(off(o.a, 0) | (off(o.c, 1) << 16));
-                P->words.push_back((o.type == FFT_NOP ? 0u : 16u * o.tw) | ((o.neg & 4) ? 0x80000000u : 0u));
+                // the twiddle triple travels in the op itself (coalesced with it) instead of being gathered from a table
+                FftTwiddle t = {0.f, 0.f, 0.f, 0.f};
+                if (o.type != FFT_NOP) t = tw_all[o.tw];
+                uint32_t tb[3];
+                memcpy(&tb[0], &t.cn, 4); memcpy(&tb[1], &t.spcn, 4); memcpy(&tb[2], &t.smcn, 4);
+                P->words.push_back(off(o.a, 0) | (off(o.c, 1) << 16) | ((o.neg & 4) ? 0x80000000u : 0u));
+                P->words.push_back(tb[0]); P->words.push_back(tb[1]); P->words.push_back(tb[2]);
             } else {
                 const uint16_t second = (o.type == FFT_BFLY) ? o.b : o.c;
                 const unsigned neg2 = (o.type == FFT_BFLY) ? ((o.neg >> 1) & 1) : ((o.neg >> 2) & 1);

@@ -57,7 +57,7 @@ struct FftOp {
 // Operand classes: every row of 32 ops holds one class, executed by a specialised loop.
 //   0 BFLY   butterflies without sign flips                       1 word  / op: a | b << 16
 //   1 CROSS  crosses                                              2 words / op: a | b << 16, c | d << 16
-//   2 ROT    twiddle rotations, operand c possibly stored negated 2 words / op: a | c << 16, tw_byte_offset | negc << 31
+//   2 ROT    twiddle rotations, operand c possibly stored negated 4 words / op: a | c << 16 | negc << 31, cn, spcn, smcn
 //   3 MISC   ROT8A / ROT8B / the few butterflies with a negated a 2 words / op: a | c << 16, type | neg << 8   (b travels as c)
 // Operands are BYTE offsets of skewed slots into the warp's x[] (what the shared-memory load wants).
 #define FFT_CLASSES 4
