@@ -378,21 +378,20 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
     // energy spreading, l3psy.c:586-605 (ecb is a float accumulator)
     FOR_THREADS(w)
     {
-        // every lane walks the whole row range with a predicate: the transposed matrix makes each load one coalesced
-        // 256-byte request and eb[k] a broadcast; the terms are added in the reference's order.  The two partitions of
-        // a lane (b and b + 32) advance together: two independent float <- double accumulation chains in flight.
+        // The two partitions of a lane (b and b + 32) advance together: two independent float <- double accumulation
+        // chains in flight.
         const int b0 = lane, b1 = lane + 32;
-        const int lo0 = T.spr_lo[b0], hi0 = T.spr_hi[b0];
-        const int lo1 = (b1 < 63) ? T.spr_lo[b1] : 1, hi1 = (b1 < 63) ? T.spr_hi[b1] : 0;
+        const int lo0 = T.spr_lo[b0], n0 = T.spr_hi[b0] - lo0 + 1;
+        const int lo1 = (b1 < 63) ? T.spr_lo[b1] : 0, n1 = (b1 < 63) ? T.spr_hi[b1] - lo1 + 1 : 0;
         float e0 = 0.0f, e1 = 0.0f;
-        for (int k = 0; k < 63; k++) {
-            // matrix elements outside a lane's row range are not fetched (predicated loads: the warp's request then covers
-            // the ~20 partitions around the diagonal instead of all 64)
-            const bool in0 = k >= lo0 && k <= hi0, in1 = k >= lo1 && k <= hi1;
-            const double ebk = M.eb[k];
-            const double s0 = in0 ? T.s3_lT[k * 64 + b0] : 1.0, s1 = in1 ? T.s3_lT[k * 64 + b1] : 1.0;
-            if (in0 && (T.sparse || s0 != 1.0)) e0 = (float)simt::dadd((double)e0, simt::dmul(s0, ebk));
-            if (in1 && (T.sparse || s1 != 1.0)) e1 = (float)simt::dadd((double)e1, simt::dmul(s1, ebk));
+        for (int i = 0; i < T.spr_wmax; i++) {
+            // step i of each lane's own row range [lo, hi] (banded matrix layout: one coalesced request per step); the terms
+            // are added in the reference's order, k ascending
+            const bool in0 = i < n0, in1 = i < n1;
+            const double s0 = in0 ? T.s3_band[i * 64 + b0] : 1.0, s1 = in1 ? T.s3_band[i * 64 + b1] : 1.0;
+            const double eb0 = in0 ? M.eb[lo0 + i] : 0.0, eb1 = in1 ? M.eb[lo1 + i] : 0.0;
+            if (in0 && (T.sparse || s0 != 1.0)) e0 = (float)simt::dadd((double)e0, simt::dmul(s0, eb0));
+            if (in1 && (T.sparse || s1 != 1.0)) e1 = (float)simt::dadd((double)e1, simt::dmul(s1, eb1));
         }
         out->ecb[b0] = e0;
         out->ecb[b1] = e1;
@@ -535,8 +534,9 @@ SIMT_FN void psy_scan_step(const WarpCtx &w, const PsyTables &T, PsyScanSmem &M,
         const int b = lane + 32 * h;
         if (b < 63) {
             double ctb = 0.0;
-            for (int k = T.spr_lo[b]; k <= T.spr_hi[b]; k++) {   // latency-bound scan: the short per-lane range wins here
-                const double s = T.s3_lT[k * 64 + b];
+            const int klo = T.spr_lo[b];
+            for (int k = klo; k <= T.spr_hi[b]; k++) {   // latency-bound scan over the lane's own row range (banded layout)
+                const double s = T.s3_band[(k - klo) * 64 + b];
                 if (T.sparse || s != 1.0) ctb = simt::dadd(ctb, simt::dmul(s, (double)M.cb[k]));
             }
             const float ecb = mid.ecb[b];

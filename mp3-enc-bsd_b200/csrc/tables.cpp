@@ -248,6 +248,12 @@ void build_psy_tables(int sr, PsyTables *P)
         P->spr_lo[b] = P->sparse ? lo441[b] : 0;
         P->spr_hi[b] = P->sparse ? hi441[b] : 62;
     }
+    P->spr_wmax = 0; P->pad_spr = 0;
+    for (int i = 0; i < 64 * 64; i++) P->s3_band[i] = 1.0;
+    for (int b = 0; b < 63; b++) {
+        P->spr_wmax = std::max(P->spr_wmax, P->spr_hi[b] - P->spr_lo[b] + 1);
+        for (int k = P->spr_lo[b]; k <= P->spr_hi[b]; k++) P->s3_band[(k - P->spr_lo[b]) * 64 + b] = P->s3_lT[k * 64 + b];
+    }
     for (int i = 0; i < 21; i++) { P->bu_l[i] = ML.bu[i]; P->bo_l[i] = ML.bo[i]; P->w1_l[i] = ML.w1[i]; P->w2_l[i] = ML.w2[i]; }
     for (int i = 0; i < 12; i++) { P->bu_s[i] = MS.bu[i]; P->bo_s[i] = MS.bo[i]; P->w1_s[i] = MS.w1[i]; P->w2_s[i] = MS.w2[i]; }
     P->n_hist_part = P->part_l[5] + 1;

@@ -103,6 +103,9 @@ struct PsyTables {
     double s3_l[63 * 64];         // [b*64 + k]
     double s3_lT[64 * 64];        // [k*64 + b]: the layout the kernels read (lane = b, coalesced)
     short spr_lo[64], spr_hi[64]; // spreading row range actually summed (44.1 kHz sparse, else dense+skip)
+    double s3_band[64 * 64];      // [i*64 + b] = s3_lT[(spr_lo[b] + i)*64 + b]: step i of every lane's own row range is one
+                                  // coalesced request, and the loop is as long as the widest range (spr_wmax), not 63
+    int spr_wmax, pad_spr;
     int sparse;                   // 1 for 44.1 kHz (sprdngf1/2), 0 otherwise (dense with != 1.0 test)
     short bu_l[24], bo_l[24], bu_s[12], bo_s[12];
     double w1_l[24], w2_l[24], w1_s[12], w2_s[12];
