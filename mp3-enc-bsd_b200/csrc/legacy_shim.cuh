@@ -71,7 +71,7 @@ struct LegacyState {
     PsyTables *d_psy_tab = nullptr;
     uint32_t *ops1024 = nullptr, *ops256 = nullptr;
     int *lv1024 = nullptr, *lv256 = nullptr;
-    uint16_t *out1024 = nullptr, *out256 = nullptr;
+    uint32_t *out1024 = nullptr, *out256 = nullptr;
     FftTwiddle *d_tw = nullptr;
     PsyDev psy_dev;
     short *d_save = nullptr;            // [2][1344]

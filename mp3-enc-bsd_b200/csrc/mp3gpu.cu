@@ -301,7 +301,7 @@ struct mp3gpu_ctx {
     int sm_count = 148;
     uint32_t *d_ops1024 = nullptr, *d_ops256 = nullptr;
     int *d_lv1024 = nullptr, *d_lv256 = nullptr;
-    uint16_t *d_out1024 = nullptr, *d_out256 = nullptr;
+    uint32_t *d_out1024 = nullptr, *d_out256 = nullptr;
     FftTwiddle *d_tw = nullptr;
     PsyDev psy_dev;
     // state
@@ -368,17 +368,25 @@ static int dalloc(T **p, size_t n)
     return 0;
 }
 
-static int upload_fft(const FftProgram &P, uint32_t **ops, int **lv, uint16_t **out, FftDev *dev)
+// output map of an FFT program as the kernels read it: bin i (0..n/2) -> re | im << 16 (see FftDev::out)
+static void fft_out_pairs(const FftProgram &P, std::vector<uint32_t> *o)
+{
+    o->assign((size_t)P.n / 2 + 1, 0u);
+    auto one = [&](int i) { return (uint32_t)(FFT_SKEW((unsigned)P.out_slot[i]) | (P.out_neg[i] ? 0x8000 : 0)); };
+    for (int i = 0; i <= P.n / 2; i++) (*o)[i] = one(i) | ((i > 0 ? one(P.n - i) : 0u) << 16);
+}
+
+static int upload_fft(const FftProgram &P, uint32_t **ops, int **lv, uint32_t **out, FftDev *dev)
 {
     int rc;
+    std::vector<uint32_t> o;
+    fft_out_pairs(P, &o);
     if ((rc = dalloc(ops, P.words.size()))) return rc;
     if ((rc = dalloc(lv, P.seg_word.size()))) return rc;
-    if ((rc = dalloc(out, (size_t)P.n))) return rc;
-    std::vector<uint16_t> o(P.n);
-    for (int i = 0; i < P.n; i++) o[i] = (uint16_t)(FFT_SKEW((unsigned)P.out_slot[i]) | (P.out_neg[i] ? 0x8000 : 0));
+    if ((rc = dalloc(out, o.size()))) return rc;
     CU(cudaMemcpy(*ops, P.words.data(), P.words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(*lv, P.seg_word.data(), P.seg_word.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(*out, o.data(), o.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(*out, o.data(), o.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     dev->words = *ops; dev->seg_word = *lv; dev->n_levels = ((int)P.seg_word.size() - 1) / FFT_CLASSES; dev->out = *out;
     return 0;
 }

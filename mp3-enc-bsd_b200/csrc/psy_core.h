@@ -28,7 +28,7 @@ struct FftDev {
     const uint32_t *words;  // op stream, see the class table in tables.h
     const int *seg_word;    // [4 * n_levels + 1] segment (level, class) -> offset into words[]
     int n_levels;
-    const uint16_t *out;    // logical index -> slot | (neg << 15)
+    const uint32_t *out;    // bin i (0..n/2) -> re | im << 16, each = slot of logical index i resp. n - i | (stored negated) << 15
 };
 
 struct PsyDev {
@@ -256,27 +256,22 @@ SIMT_FN void fft_run(const WarpCtx &w, const FftDev &P, const FftTwiddle *tw, fl
     }
 }
 
-SIMT_FN float fft_logical(const FftDev &P, const float *x, int i)
-{
-    unsigned s = P.out[i];
-    float v = x[s & 0x7fff];
-    return (s & 0x8000) ? -v : v;
-}
+// energy / phase of bin i of short transform sb, left in place by psy_front (energy over re, phase over im)
+SIMT_FN float short_energy(const FftDev &P, const float *x, int sb, int i) { return x[sb * (FFT_BATCH_BYTES / 4) + (P.out[i] & 0x7fffu)]; }
+SIMT_FN float short_phase(const FftDev &P, const float *x, int sb, int i) { return x[sb * (FFT_BATCH_BYTES / 4) + ((P.out[i] >> 16) & 0x7fffu)]; }
 
-// energy / phase of bin i of short transform sb, left in place by psy_front
-SIMT_FN float short_energy(const FftDev &P, const float *x, int sb, int i) { return x[sb * (FFT_BATCH_BYTES / 4) + (P.out[i] & 0x7fff)]; }
-SIMT_FN float short_phase(const FftDev &P, const float *x, int sb, int i) { return x[sb * (FFT_BATCH_BYTES / 4) + (P.out[256 - i] & 0x7fff)]; }
-
-// energy + phase of bin i (enphinew, subs.c:53-123); n = transform length
-SIMT_FN void bin_energy_phase(const FftDev &P, const float *x, int n, int i, bool want_phi, float *e_out, float *phi_out)
+// energy + phase of bin i (enphinew, subs.c:53-123); n = transform length; om = P.out[i]
+SIMT_FN void bin_energy_phase(unsigned om, const float *x, int n, int i, bool want_phi, float *e_out, float *phi_out)
 {
-    float re = fft_logical(P, x, i);
+    float re = x[om & 0x7fffu];
+    if (om & 0x8000u) re = -re;
     if (i == 0 || i == n / 2) {
         *e_out = simt::fmul(re, re);
         if (want_phi) *phi_out = (float)atan2(0.0, (double)re);
         return;
     }
-    float im = fft_logical(P, x, n - i);
+    float im = x[(om >> 16) & 0x7fffu];
+    if (om & 0x80000000u) im = -im;
     float e = simt::fadd(simt::fmul(re, re), simt::fmul(im, im));
     if ((double)e < 0.0005) { *e_out = (float)0.0005; if (want_phi) *phi_out = 0.0f; }
     else { *e_out = e; if (want_phi) *phi_out = (float)atan2(-(double)im, (double)re); }
@@ -307,11 +302,16 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
     w.sync();
     fft_run<2, 1>(w, D.f1024, D.tw, M.x, FFT_X_WORDS);
     FOR_THREADS(w)
-    for (int i = lane; i <= 512; i += 32) {
-        float e, ph = 0.f;
-        bin_energy_phase(D.f1024, M.x, 1024, i, i < 6, &e, &ph);
+#pragma unroll 4
+    for (int i = lane; i <= 512; i += 32) {           // energies of all bins: four independent map-load -> x-load chains in flight
+        float e, ph;
+        bin_energy_phase(D.f1024.out[i], M.x, 1024, i, false, &e, &ph);
         M.E[i] = e;
-        if (i < 6) { out->e6[i] = e; out->phi6[i] = ph; }
+    }
+    if (lane < 6) {                                   // lines 0..5 also need the phase (psy_scan predicts them from history)
+        float e, ph = 0.f;
+        bin_energy_phase(D.f1024.out[lane], M.x, 1024, lane, true, &e, &ph);
+        out->e6[lane] = e; out->phi6[lane] = ph;
     }
     END_THREADS
     w.sync();
@@ -330,10 +330,11 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
             for (int i = lane; i <= 128; i += 32) {
                 float e, ph = 0.f;
                 const bool wp = (i >= 2 && i < 52);
-                bin_energy_phase(D.f256, xs, 256, i, wp, &e, &ph);
-                xs[D.f256.out[i] & 0x7fff] = e;
+                const unsigned om = D.f256.out[i];
+                bin_energy_phase(om, xs, 256, i, wp, &e, &ph);
+                xs[om & 0x7fffu] = e;
                 out->es[sb][i] = e;
-                if (wp) xs[D.f256.out[256 - i] & 0x7fff] = ph;
+                if (wp) xs[(om >> 16) & 0x7fffu] = ph;
             }
         }
         END_THREADS

@@ -86,13 +86,14 @@ int emul_encode_stream(int sfreq, int n_ch, int bitrate, int n_frames, const sho
     build_fft_twiddles(&tw, &base);
     FftProgram P10, P8;
     build_fft_program(10, base, &P10); build_fft_program(8, base, &P8);
-    auto mkdev = [](const FftProgram &P, std::vector<uint16_t> &outmap) {
-        outmap.resize(P.n);
-        for (int i = 0; i < P.n; i++) outmap[i] = (uint16_t)(FFT_SKEW((unsigned)P.out_slot[i]) | (P.out_neg[i] ? 0x8000 : 0));
+    auto mkdev = [](const FftProgram &P, std::vector<uint32_t> &outmap) {
+        outmap.assign((size_t)P.n / 2 + 1, 0u);
+        auto one = [&](int i) { return (uint32_t)(FFT_SKEW((unsigned)P.out_slot[i]) | (P.out_neg[i] ? 0x8000 : 0)); };
+        for (int i = 0; i <= P.n / 2; i++) outmap[i] = one(i) | ((i > 0 ? one(P.n - i) : 0u) << 16);
         FftDev d; d.words = P.words.data(); d.seg_word = P.seg_word.data(); d.n_levels = ((int)P.seg_word.size() - 1) / FFT_CLASSES; d.out = outmap.data();
         return d;
     };
-    std::vector<uint16_t> o10, o8;
+    std::vector<uint32_t> o10, o8;
     PsyDev D; D.T = &PT; D.tw = tw.data(); D.f1024 = mkdev(P10, o10); D.f256 = mkdev(P8, o8);
     const int n_gran = 2 * n_frames;
     WarpCtx w;
