@@ -297,6 +297,7 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
     PsyFrontView M(S);
     // long window + FFT, l3psy.c:483-494
     FOR_THREADS(w)
+#pragma unroll 8
     for (int j = lane; j < 1024; j += 32) M.x[FFT_SKEW(j)] = simt::fmul(T.hann_l[j], (float)(int)pcm[j - 768]);
     END_THREADS
     w.sync();
@@ -319,6 +320,7 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
     {
         FOR_THREADS(w)
         for (int sb = 0; sb < 3; sb++)
+#pragma unroll
             for (int j = lane; j < 256; j += 32)
                 M.x[sb * (FFT_BATCH_BYTES / 4) + FFT_SKEW(j)] = simt::fmul(T.hann_s[j], (float)(int)pcm[j - 768 + 128 * (2 + sb)]);
         END_THREADS
