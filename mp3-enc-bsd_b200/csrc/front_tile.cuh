@@ -234,7 +234,9 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
             }
         }
     }
-    __syncthreads();
+    // chunk c = warp of stage A is exactly the 32 slots the same warp transforms in stage B (n_chunks <= FT_WARPS): a warp
+    // barrier is enough, and warps drift from the FIR stage into the matrixing stage instead of meeting at a CTA barrier
+    __syncwarp();
     // ---- stage B: thread = slot ---------------------------------------------------------------------
     if (tid < n_chunks * 32) {
         double *row = M.rows + (size_t)tid * FT_ROW;
