@@ -109,8 +109,13 @@ k_psy_front(PsyDev D, const short *pcm, long stream_stride, long ch_stride, int 
     psy_front(w, D, simt::pin_smem(Ms[warp]), pcm + s * stream_stride + ch * ch_stride + HIST + 576L * g, &mid[gc]);
 }
 
+#ifndef PSYS_WARPS
 #define PSYS_WARPS 4
-__global__ void __launch_bounds__(PSYS_WARPS * 32, 7)
+#endif
+#ifndef PSYS_MIN_CTAS
+#define PSYS_MIN_CTAS 7
+#endif
+__global__ void __launch_bounds__(PSYS_WARPS * 32, PSYS_MIN_CTAS)
 k_psy_scan(const PsyTables *T, const PsyMid *mid, PsyChanState *states, int n_streams, int n_ch, int n_gran, PsyOut *psy)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
