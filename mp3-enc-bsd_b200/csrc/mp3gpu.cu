@@ -135,11 +135,12 @@ k_psy_scan(const PsyTables *T, const PsyMid *mid, PsyChanState *states, int n_st
     psy_scan_store(w, states[wid], R);
 }
 
-// One CTA of 27 warps per SM: the hot tables are held once per SM and 27 x 8064 B of per-warp working set + 9.5 KB of tables
+// One CTA of 28 warps per SM: the hot tables are held once per SM and 28 x 8064 B of per-warp working set + 5.9 KB of tables
 // fill the 227 KB of shared memory (3 CTAs x 8 warps left room for 24 warps only); 72 registers per thread.
 #ifndef RL_WARPS
-#define RL_WARPS 27
+#define RL_WARPS 28
 #endif
+static_assert(RL_WARPS * 32 * 72 <= 65536, "the rate loop needs 72 registers per thread");
 #define RL_HOT_BYTES ((sizeof(RateHot) + 15) & ~(size_t)15)
 #define RL_SMEM_BYTES (RL_HOT_BYTES + RL_WARPS * sizeof(RateWarpSmem))
 static_assert(sizeof(RateHot) % 16 == 0, "RateHot must be int4-copyable");

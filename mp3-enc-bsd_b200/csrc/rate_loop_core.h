@@ -33,8 +33,12 @@ using simt::WarpCtx;
 // compares (loop.c:1793-1900):
 //   g0 {1}   g1 {2,3}   g2 {5,6}   g3 {7,8,9}   g4 {10,11,12}   g5 {13,15}
 //   g6 {16..23, 24..31, #escapes}   g7 {15, 24, #escapes}   (x, y clamped to 15; linbits added per escape)
+// A region priced with group g holds no value above gmax = 1, 2, 3, 5, 7, 14, 15, 15, so only the rows x <= gmax are stored
+// (1120 instead of 2048 entries: the 3.6 KB buy the 28th warp of the CTA); group g starts at entry 16 * GLUT_OFF16(g).
+#define GLUT_ENTRIES 1120
+#define GLUT_OFF16(g) ((unsigned)((0x3626170f09050200ull >> (8 * (g))) & 0xff))
 struct alignas(16) RateHot {
-    unsigned int glut[8][256];
+    unsigned int glut[GLUT_ENTRIES];
     unsigned int c1lut[16];         // count1 quad p: (hlen32 + signs) | (hlen33 + signs) << 16
     double pre1[4], pre2[4];        // pow(sqrt 2, n), pow(sqrt 2, 2n)  (loop.c:1205-1210)
     double ifqstep, ifqstep2;       // sqrt(2), sqrt(2)*sqrt(2)          (loop.c:1252,1293)
@@ -356,14 +360,14 @@ SIMT_FN int count_all(const WarpCtx &w, const RateHot &H, const RateWarpSmem &M,
     }
     int bits = c1bits;
     if (any) {
-        const unsigned *gl = &H.glut[0][0];
+        const unsigned *gl = &H.glut[0];
 #pragma unroll
         for (int r = 0; r < 3; r++) {
             if (grp[r] < 0) continue;
             const int g = grp[r], max = rmax[r];
             PerThread<int> lo_, hi_;
             FOR_THREADS(w)
-            const unsigned *gt = gl + (g << 8);
+            const unsigned *gt = gl + 16 * GLUT_OFF16(g);
             unsigned acc = 0;
 #pragma unroll 1
             for (int sl = lo[r] + lane; sl < hi[r]; sl += 32) {

@@ -142,8 +142,9 @@ void build_rate_tables(int sr, RateTables *R)
     // (count_bit, loop.c:172-225: sum += hlen[x][y] + (x != 0) + (y != 0), escapes add linbits)
     {
         static const int members[8][3] = {{1, 0, 0}, {2, 3, 0}, {5, 6, 0}, {7, 8, 9}, {10, 11, 12}, {13, 15, 0}, {16, 24, -1}, {15, 24, -1}};
+        static const int gmax[8] = {1, 2, 3, 5, 7, 14, 15, 15};
         for (int g = 0; g < 8; g++)
-            for (int x = 0; x < 16; x++)
+            for (int x = 0; x <= gmax[g]; x++)
                 for (int y = 0; y < 16; y++) {
                     unsigned v = 0;
                     for (int c = 0; c < 3; c++) {
@@ -155,7 +156,7 @@ void build_rate_tables(int sr, RateTables *R)
                         } else if (t < 0) f = (x > 14) + (y > 14);   // number of escaped values of the pair
                         v |= f << (10 * c);
                     }
-                    H.glut[g][16 * x + y] = v;
+                    H.glut[16 * GLUT_OFF16(g) + 16 * x + y] = v;
                 }
         for (int p = 0; p < 16; p++) {
             const int sg = (p & 1) + ((p >> 1) & 1) + ((p >> 2) & 1) + ((p >> 3) & 1);
