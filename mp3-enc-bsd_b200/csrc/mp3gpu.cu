@@ -94,7 +94,7 @@ k_mdct(const double *sb, const PsyOut *psy, double *sb_prev, int n_streams, int 
 }
 
 #define PSYF_WARPS 8
-__global__ void __launch_bounds__(PSYF_WARPS * 32)
+__global__ void __launch_bounds__(PSYF_WARPS * 32, 4)   // 4 CTAs per SM (shared-memory limit): at most 64 registers
 k_psy_front(PsyDev D, const short *pcm, long stream_stride, long ch_stride, int n_streams, int n_ch, int n_gran, PsyMid *mid)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
