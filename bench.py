@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=int(os.environ.get("MP3GPU_BENCH_STREAMS", 0)),
-                    help="clips per GPU (default: one full wave of the rate loop, mp3gpu_stream_wave(): 3552 on a B200)")
+                    help="clips per GPU (default: one full wave of the rate loop, mp3gpu_stream_wave(): 4144 on a B200)")
     ap.add_argument("--seconds", type=float, default=10.0, help="clip length")
     ap.add_argument("--chunk-frames", type=int, default=32, help="frames per stream per library call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -184,11 +184,20 @@ def main():
     n_frames = int(args.seconds * FS) // 1152          # whole frames per clip (383 for 10 s)
     audio_per_stream = n_frames * 1152 / FS
     wl = lambda n: "batch of %d x %.0f s synthetic 44.1 kHz stereo clips at 128 kbps per GPU (BASELINE configs[3])" % (n, args.seconds)
-    workload = wl(args.streams or 3552)
+    workload = wl(args.streams or 4144)
 
     if args.impl == "reference":
         if rank != 0:
             return
+        if not args.streams:
+            # same workload name as the GPU arm: its default batch is one full wave of the rate loop on this device
+            # (28 warps = streams per SM; computed here so that this arm never loads libmp3gpu.so)
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    workload = wl(28 * torch.cuda.get_device_properties(local_rank).multi_processor_count)
+            except Exception:
+                pass
         steps, vals, walls = max(1, args.steps), [], []
         for i in range(args.warmup + steps):
             xrt, cores, kind, sample, wall = run_reference_cpu(args.seconds)
