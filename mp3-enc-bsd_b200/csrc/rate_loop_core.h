@@ -224,11 +224,11 @@ SIMT_FN void quantize_all(const WarpCtx &w, const RateTables &T, RateWarpSmem &M
         const F2 y = ys[s];
         // clamped at 2040: an out-of-range (or nan) estimate sits exactly on an integer and therefore fails the test below
         const float ta = simt::fmin_(simt::ffma(y.x, of, 0.4054f), 2040.0f), tb = simt::fmin_(simt::ffma(y.y, of, 0.4054f), 2040.0f);
-        const float ma = simt::ffma(ta, 1e-5f, 1e-6f), mb = simt::ffma(tb, 1e-5f, 1e-6f);
-        // floor(t - m) and floor(t + m) as "magic" floats 2^23 + floor(.) (t - m >= 0.4, t + m < 2041): equal <=> accepted
-        const float fa = simt::floor_magic(simt::fsub(ta, ma)), fb = simt::floor_magic(simt::fsub(tb, mb));
-        const bool oka = (fa == simt::floor_magic(simt::fadd(ta, ma)));
-        const bool okb = (fb == simt::floor_magic(simt::fadd(tb, mb)));
+        // floor(t - m) and floor(t + m), m = 1e-5 t + 1e-6 (one fused multiply-add each), as "magic" floats 2^23 + floor(.)
+        // (t - m >= 0.4, t + m < 2041): equal <=> accepted
+        const float fa = simt::floor_magic(simt::ffma(ta, 1.0f - 1e-5f, -1e-6f)), fb = simt::floor_magic(simt::ffma(tb, 1.0f - 1e-5f, -1e-6f));
+        const bool oka = (fa == simt::floor_magic(simt::ffma(ta, 1.0f + 1e-5f, 1e-6f)));
+        const bool okb = (fb == simt::floor_magic(simt::ffma(tb, 1.0f + 1e-5f, 1e-6f)));
         unsigned a = simt::fbits(fa) & 0xffffu, b = simt::fbits(fb) & 0xffffu;     // the value: the low mantissa bits
         if (!(oka && okb)) {
             const D2 x = M.xs[s];
