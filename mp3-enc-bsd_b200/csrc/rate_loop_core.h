@@ -229,16 +229,17 @@ SIMT_FN void quantize_all(const WarpCtx &w, const RateTables &T, RateWarpSmem &M
         const float fa = simt::floor_magic(simt::ffma(ta, 1.0f - 1e-5f, -1e-6f)), fb = simt::floor_magic(simt::ffma(tb, 1.0f - 1e-5f, -1e-6f));
         const bool oka = (fa == simt::floor_magic(simt::ffma(ta, 1.0f + 1e-5f, 1e-6f)));
         const bool okb = (fb == simt::floor_magic(simt::ffma(tb, 1.0f + 1e-5f, 1e-6f)));
-        unsigned a = simt::fbits(fa) & 0xffffu, b = simt::fbits(fb) & 0xffffu;     // the value: the low mantissa bits
+        unsigned pk = simt::pack_lo16(simt::fbits(fa), simt::fbits(fb));          // the values are the low mantissa bits: a | b << 16
         if (!(oka && okb)) {
             const D2 x = M.xs[s];
+            unsigned a = pk & 0xffffu, b = pk >> 16;
             if (!oka) a = (unsigned)quant1_exact(T.pow_nint_tab, simt::dmul(x.x, ostep), (int)a);
             if (!okb) b = (unsigned)quant1_exact(T.pow_nint_tab, simt::dmul(x.y, ostep), (int)b);
+            pk = a | (b << 16);
         }
-        ixw[s] = a | (b << 16);
-        const unsigned ab = a | b;
-        if (ab != 0) nz = s;
-        if (ab > 1) bg = s;           // a > 1 || b > 1
+        ixw[s] = pk;
+        if (pk != 0) nz = s;
+        if ((pk & 0xfffefffeu) != 0) bg = s;      // a > 1 || b > 1
     }
 #pragma unroll 1
     for (int s = lane + 32 * k_lim; s < 32 * kz; s += 32) ixw[s] = 0u;

@@ -111,6 +111,7 @@ SIMT_FN float fmin_(float a, float b) { return fminf(a, b); }                 //
 // where a float -> int conversion would go through the quarter-rate XU pipe
 SIMT_FN float floor_magic(float a) { return __fadd_rd(a, 8388608.0f); }
 SIMT_FN unsigned fbits(float a) { return __float_as_uint(a); }
+SIMT_FN unsigned pack_lo16(unsigned lo, unsigned hi) { return __byte_perm(lo, hi, 0x5410); }   // (lo & 0xffff) | (hi << 16)
 SIMT_FN int f2i_trunc(float a) { return __float2int_rz(a); }   // saturating; nan -> 0
 SIMT_FN int popc(unsigned v) { return __popc(v); }
 SIMT_FN int clz(unsigned v) { return __clz(v); }
@@ -171,6 +172,7 @@ inline float ffma(float a, float b, float c) { return std::fmaf(a, b, c); }
 inline float fmin_(float a, float b) { return std::fmin(a, b); }
 inline float floor_magic(float a) { return (float)(std::floor((double)a) + 8388608.0); }
 inline unsigned fbits(float a) { unsigned u; std::memcpy(&u, &a, 4); return u; }
+inline unsigned pack_lo16(unsigned lo, unsigned hi) { return (lo & 0xffffu) | (hi << 16); }
 inline int f2i_trunc(float a) { return (a != a) ? 0 : (a >= 2147483648.0f) ? 2147483647 : (a <= -2147483648.0f) ? (-2147483647 - 1) : (int)a; }
 inline int popc(unsigned v) { return __builtin_popcount(v); }
 inline int clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
