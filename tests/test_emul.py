@@ -29,6 +29,9 @@ def test_fft_program_bit_exact(emul, n):
         e[1:h] = np.where(e[1:h].astype(np.float64) < 0.0005, np.float32(0.0005), e[1:h])
         assert np.array_equal(e, e_ref)
         assert nlev <= 16
+        # packing density of the op program (rows of 32 op slots incl. padding): edge-coloured + merged rows need 188 resp.
+        # 49 rows; the greedy first-fit packing this replaced needed 236 resp. 65
+        assert nops <= {1024: 188, 256: 49}[n] * 32
 
 
 @pytest.mark.parametrize("name", ["cfg1_44k_stereo_128", "cfg2_32k_mono_64", "cfg3_48k_stereo_320", "loud_44k_stereo_128",
