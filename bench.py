@@ -289,6 +289,7 @@ def main():
     launches = enc.kernel_launches - l0
     prof = enc.profile_collect(reset=True)
     enc.profile_enable(False)
+    enc.set_host_delivery(True)     # the D2H of a chunk's bytes overlaps the next chunk's kernels; flush_mp3 joins (mp3gpu.h)
     for _ in range(2):
         step_host()
     torch.cuda.synchronize(device)

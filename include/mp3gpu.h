@@ -106,6 +106,16 @@ int mp3gpu_frame_geometry(const mp3gpu_ctx *ctx, int *bits_per_frame, int *mean_
 #define MP3GPU_PCM_INTERLEAVED 1
 int mp3gpu_set_pcm_layout(mp3gpu_ctx *ctx, int layout);
 
+/* Delivery of the MP3 bytes of the HOST-buffer calls (mp3gpu_encode_frames_mp3).  INORDER (default): the device-to-host
+ * copy of a call is issued on `stream`; its bytes have landed when the call's work on the stream has completed.
+ * PIPELINED: the copy runs on a private stream while the kernels of the next call execute; the bytes of a call are
+ * guaranteed once the work of the NEXT mp3gpu_encode_frames_mp3 call — or of mp3gpu_flush_mp3, which joins every copy
+ * still in flight — has completed on its stream.  (The reference has no counterpart: it fwrite()s frame by frame,
+ * formatBitstream.c:218-247.) */
+#define MP3GPU_DELIVER_INORDER 0
+#define MP3GPU_DELIVER_PIPELINED 1
+int mp3gpu_set_host_delivery(mp3gpu_ctx *ctx, int mode);
+
 /* ---- whole hot path: psy -> filterbank -> MDCT -> rate loop, continuing the ctx's streams ---------
  * Host variant: pcm and outputs are HOST pointers (pinned for async copies); H2D and D2H copies are
  * issued on `stream` and the call returns after they were enqueued; synchronise the stream (or call

@@ -338,6 +338,13 @@ struct mp3gpu_ctx {
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     int h2d_turn = 0;
     int pcm_layout = MP3GPU_PCM_PLANAR;
+    // host-MP3 delivery (MP3GPU_DELIVER_PIPELINED): the finished bytes of a call are staged densely on the device and
+    // copied to the host on a private stream while the next call's kernels run
+    int deliver = MP3GPU_DELIVER_INORDER;
+    cudaStream_t d2h_stream = nullptr;
+    uint8_t *d2h_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_staged[2] = {nullptr, nullptr}, ev_landed[2] = {nullptr, nullptr};
+    int d2h_turn = 0;
     long launches = 0;
     // per-kernel timing (mp3gpu_profile_*): events bracket every launch of the four hot kernels
     int prof_on = 0;
@@ -504,6 +511,12 @@ extern "C" void mp3gpu_destroy(mp3gpu_ctx *c)
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < 2; i++) {
+        if (c->d2h_stage[i]) cudaFree(c->d2h_stage[i]);
+        if (c->ev_staged[i]) cudaEventDestroy(c->ev_staged[i]);
+        if (c->ev_landed[i]) cudaEventDestroy(c->ev_landed[i]);
+    }
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     delete c;
 }
 
@@ -637,6 +650,22 @@ extern "C" int mp3gpu_set_pcm_layout(mp3gpu_ctx *c, int layout)
     if (!c) return fail(MP3GPU_EINVAL, "null ctx");
     if (layout != MP3GPU_PCM_PLANAR && layout != MP3GPU_PCM_INTERLEAVED) return fail(MP3GPU_EINVAL, "unknown PCM layout");
     c->pcm_layout = layout;
+    return 0;
+}
+
+extern "C" int mp3gpu_set_host_delivery(mp3gpu_ctx *c, int mode)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    if (mode != MP3GPU_DELIVER_INORDER && mode != MP3GPU_DELIVER_PIPELINED) return fail(MP3GPU_EINVAL, "unknown delivery mode");
+    c->deliver = mode;
+    return 0;
+}
+
+// every copy a pipelined delivery still has in flight must land before work enqueued on q after this point
+static int join_deliveries(mp3gpu_ctx *c, cudaStream_t q)
+{
+    for (int i = 0; i < 2; i++)
+        if (c->ev_landed[i]) CU(cudaStreamWaitEvent(q, c->ev_landed[i], 0));
     return 0;
 }
 
@@ -775,7 +804,29 @@ static int format_common(mp3gpu_ctx *c, const short *ix, const GrInfoOut *gi, co
     const cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     if (mp3) {  // window bytes [0, n_frames*FB) are final; clip what lies before the start of the stream
         const long skip = G.origin < 0 ? -G.origin : 0, width = (long)n_frames * FB - skip;
-        if (width > 0)
+        if (width > 0 && host && c->deliver == MP3GPU_DELIVER_PIPELINED) {
+            if (!c->d2h_stream) {
+                CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+                for (int i = 0; i < 2; i++) {
+                    int rc = dalloc(&c->d2h_stage[i], (size_t)c->cfg.max_streams * c->cfg.max_frames * FB);
+                    if (rc) return rc;
+                    CU(cudaEventCreateWithFlags(&c->ev_staged[i], cudaEventDisableTiming));
+                    CU(cudaEventCreateWithFlags(&c->ev_landed[i], cudaEventDisableTiming));
+                }
+            }
+            const int t = c->d2h_turn;
+            c->d2h_turn ^= 1;
+            // q waits for the copy that last used this staging buffer (two calls ago: long done) — which is also what makes
+            // the bytes of call i-2 ordered before anything enqueued on q from here on; call i-1 is joined by the next call
+            CU(cudaStreamWaitEvent(q, c->ev_landed[t], 0));
+            CU(cudaMemcpy2DAsync(c->d2h_stage[t], (size_t)width, c->d_win + skip, (size_t)c->wstride, (size_t)width, n_streams,
+                                 cudaMemcpyDeviceToDevice, q));
+            CU(cudaEventRecord(c->ev_staged[t], q));
+            CU(cudaStreamWaitEvent(c->d2h_stream, c->ev_staged[t], 0));
+            CU(cudaMemcpy2DAsync(mp3 + G.origin + skip, (size_t)stride, c->d2h_stage[t], (size_t)width, (size_t)width, n_streams,
+                                 cudaMemcpyDeviceToHost, c->d2h_stream));
+            CU(cudaEventRecord(c->ev_landed[t], c->d2h_stream));
+        } else if (width > 0)
             CU(cudaMemcpy2DAsync(mp3 + G.origin + skip, (size_t)stride, c->d_win + skip, (size_t)c->wstride, (size_t)width, n_streams, kind, q));
     }
     // slide: the last `tail` frames become the first ones (through a temporary: the ranges may overlap)
@@ -793,6 +844,7 @@ static int flush_common(mp3gpu_ctx *c, int n_streams, uint8_t *mp3, long stride,
     const long FB = c->frame_bytes, T = c->tail_frames;
     const long origin = (c->frames_done - T) * FB, skip = origin < 0 ? -origin : 0, width = T * FB - skip;
     if (mp3 && stride < c->frames_done * FB) return fail(MP3GPU_EINVAL, "mp3 stride too small");
+    if (host) { int rc = join_deliveries(c, q); if (rc) return rc; }
     if (mp3 && width > 0)
         CU(cudaMemcpy2DAsync(mp3 + origin + skip, (size_t)stride, c->d_win + skip, (size_t)c->wstride, (size_t)width, n_streams,
                              host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, q));

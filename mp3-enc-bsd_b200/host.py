@@ -36,7 +36,7 @@ EXPORTS = ["mp3gpu_last_error", "mp3gpu_version", "mp3gpu_create", "mp3gpu_destr
            "mp3gpu_L3psycho_anal_batch", "mp3gpu_iteration_loop_batch", "mp3gpu_quantize_count_batch",
            "mp3gpu_kernel_launches", "mp3gpu_profile_enable", "mp3gpu_profile_collect",
            "mp3gpu_encode_frames_mp3", "mp3gpu_encode_frames_mp3_dev", "mp3gpu_flush_mp3", "mp3gpu_flush_mp3_dev",
-           "mp3gpu_frame_bytes", "mp3gpu_format_bitstream_batch", "mp3gpu_begin_segment", "mp3gpu_stream_wave", "mp3gpu_set_pcm_layout", "mp3gpu_count_bits_batch"]
+           "mp3gpu_frame_bytes", "mp3gpu_format_bitstream_batch", "mp3gpu_begin_segment", "mp3gpu_stream_wave", "mp3gpu_set_pcm_layout", "mp3gpu_count_bits_batch", "mp3gpu_set_host_delivery"]
 LEGACY_EXPORTS = ["window_subband", "filter_subband", "mdct_sub", "L3psycho_anal", "iteration_loop", "quantize", "count_bits",
                   "mp3gpu_legacy_reset", "mp3gpu_legacy_kernel_launches"]
 KERNEL_NAMES = ["psy_front", "psy_scan", "front_polyphase_mdct", "rate_loop", "bitstream"]
@@ -89,6 +89,7 @@ def load_library():
         lib.mp3gpu_begin_segment.argtypes = [vp, vp]
         lib.mp3gpu_count_bits_batch.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
         lib.mp3gpu_set_pcm_layout.argtypes = [vp, C.c_int]
+        lib.mp3gpu_set_host_delivery.argtypes = [vp, C.c_int]
         lib.mp3gpu_frame_bytes.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.mp3gpu_format_bitstream_batch.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, C.c_long, vp]
         _lib = lib
@@ -162,6 +163,10 @@ class Encoder:
         self._check(self.lib.mp3gpu_sync(self.ctx, C.c_void_p(stream or 0)), "mp3gpu_sync")
 
     # ---- helpers -------------------------------------------------------------------------------
+    def set_host_delivery(self, pipelined):
+        """host-buffer MP3 delivery: in stream order (default) or pipelined behind the next call (see mp3gpu.h)"""
+        self._check(self.lib.mp3gpu_set_host_delivery(self.ctx, 1 if pipelined else 0), "mp3gpu_set_host_delivery")
+
     def set_pcm_layout(self, interleaved):
         """False: pcm is [S][n_ch][n] (default); True: pcm is [S][n][n_ch], the sample order of a WAV file"""
         self._check(self.lib.mp3gpu_set_pcm_layout(self.ctx, 1 if interleaved else 0), "mp3gpu_set_pcm_layout")

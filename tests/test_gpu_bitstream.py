@@ -39,8 +39,10 @@ def test_mp3_bytes_vs_reference_cli_golden(pkg, golden, name, chunk):
     print(f"{name}: {frames}/{frames} frames byte-identical to the reference CLI ({len(got)} bytes, chunk={chunk})")
 
 
-def test_batch_of_streams_vs_oracle_formatter(pkg):
-    """8 different streams (one silent, one going silent, one loud) in one batch, ragged chunks"""
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_batch_of_streams_vs_oracle_formatter(pkg, pipelined):
+    """8 different streams (one silent, one going silent, one loud) in one batch, ragged chunks; in-order and pipelined
+    delivery of the host bytes (mp3gpu_set_host_delivery) must give the same file"""
     S, F = 8, 20
     sy = pkg.synth
     pcm = np.stack([sy.config1(F * 1152 / 44100.0 + 0.01, seeds=(300 + 2 * i, 301 + 2 * i))[:, :F * 1152] for i in range(S)])
@@ -48,6 +50,7 @@ def test_batch_of_streams_vs_oracle_formatter(pkg):
     pcm[4, :, 9000:] = 0
     pcm[6] = np.clip(pcm[6].astype(np.int32) * 4, -32768, 32767).astype(np.int16)
     enc = pkg.Encoder(44100, 2, 128, max_streams=S, max_frames=6)
+    enc.set_host_delivery(pipelined)
     mp3 = np.zeros((S, F * enc.frame_bytes + 64), np.uint8)
     f0 = 0
     for c in [6, 1, 4, 2, 6, 1]:
