@@ -226,7 +226,8 @@ SIMT_FN void fft_run(const WarpCtx &w, const FftDev &P, const FftTwiddle *tw, fl
 #pragma unroll
                 for (int u = 0; u < U; u++) wb[u] = nx[u];
             }
-            if (ib < s1) fft_rows_bfly<1, NB>(wb, x);
+#pragma unroll
+            for (int u = 0; u < U - 1; u++) if (ib + 32 * u < s1) fft_rows_bfly<1, NB>(wb + u, x);     // the up to U - 1 rows left
             for (; ic + 32 * (U - 1) < (s2 >> 1); ic += 32 * U) {
                 FftW2 nx[U];
 #pragma unroll
@@ -235,7 +236,8 @@ SIMT_FN void fft_run(const WarpCtx &w, const FftDev &P, const FftTwiddle *tw, fl
 #pragma unroll
                 for (int u = 0; u < U; u++) wc[u] = nx[u];
             }
-            if (ic < (s2 >> 1)) fft_rows_cross<1, NB>(wc, x);
+#pragma unroll
+            for (int u = 0; u < U - 1; u++) if (ic + 32 * u < (s2 >> 1)) fft_rows_cross<1, NB>(wc + u, x);
             for (; ir + 32 * (U - 1) < (s3 >> 2); ir += 32 * U) {
                 FftW4 nx[U];
 #pragma unroll
@@ -244,7 +246,8 @@ SIMT_FN void fft_run(const WarpCtx &w, const FftDev &P, const FftTwiddle *tw, fl
 #pragma unroll
                 for (int u = 0; u < U; u++) wr[u] = nx[u];
             }
-            if (ir < (s3 >> 2)) fft_rows_rot<1, NB>(wr, x);
+#pragma unroll
+            for (int u = 0; u < U - 1; u++) if (ir + 32 * u < (s3 >> 2)) fft_rows_rot<1, NB>(wr + u, x);
             for (; im < (s4 >> 1); im += 32) {
                 const FftW2 nx = W2[im + 32];
                 fft_row_misc<NB>(wm, x);
@@ -301,7 +304,10 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
     for (int j = lane; j < 1024; j += 32) M.x[FFT_SKEW(j)] = simt::fmul(T.hann_l[j], (float)(int)pcm[j - 768]);
     END_THREADS
     w.sync();
-    fft_run<2, 1>(w, D.f1024, D.tw, M.x, FFT_X_WORDS);
+#ifndef FFT_LONG_U
+#define FFT_LONG_U 2     // rows per trip of the 1024-point transform
+#endif
+    fft_run<FFT_LONG_U, 1>(w, D.f1024, D.tw, M.x, FFT_X_WORDS);
     FOR_THREADS(w)
 #pragma unroll 4
     for (int i = lane; i <= 512; i += 32) {           // energies of all bins: four independent map-load -> x-load chains in flight
