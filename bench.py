@@ -295,6 +295,10 @@ def main():
     torch.cuda.synchronize(device)
     t_host = timed(step_host, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    # fingerprint of what the timed steps produced (first 8 clips of the last e2e step): lets A/B runs of library variants
+    # (tools/ab_bench.sh) see at once that a "faster" variant encodes something else
+    import zlib
+    out_crc = zlib.crc32(mp3_host[:min(S, 8)].numpy().tobytes()) & 0xffffffff
 
     audio_rank = S * audio_per_stream * args.steps
     t_dev_max, audio_total = reduce_timing(t_dev, audio_rank, device)
@@ -328,7 +332,8 @@ def main():
                        S * n_frames * 1152 * NCH * 2 / 1e9, gc_per_step * 4608 / 1e9)},
         "e2e": {"value": audio_total / t_host_max, "unit": "audio-s/s",
                 "h2d_bytes_per_step": int(S * n_frames * 1152 * NCH * 2), "d2h_bytes_per_step": int(S * mp3_bytes + 4 * S),
-                "output": "finished MPEG-1 Layer III byte streams (device bitstream formatter), %d bytes per clip" % mp3_bytes},
+                "output": "finished MPEG-1 Layer III byte streams (device bitstream formatter), %d bytes per clip" % mp3_bytes,
+                "output_crc32_first8": "%08x" % out_crc},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_front (fused polyphase filterbank + MDCT + alias reduction, FP64 exact path)",
                      "achieved": fk["achieved_gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": fk["frac_hbm"],
