@@ -35,7 +35,7 @@ FS, NCH, KBPS = 44100, 2, 128
 # psy_scan: the 1280-byte hot part of PsyMid in, PsyOut (472 B) out
 BYTES_PER_GC = {"front_polyphase_mdct": 5764, "psy_front": 1152 + 2864, "psy_scan": 1280 + 472,
                 "rate_loop": 4608 + 472 + 1152 + 80 + 40, "bitstream": 1152 + 80 + 40 + 417 // 4}
-# DRAM bytes per granule-channel of k_front_tile from the ncu --set full capture profiles/r01_g_capture.md
+# DRAM bytes per granule-channel of k_front_tile from the ncu --set full capture profiles/r01_h_capture.md
 # (dram__bytes_read.sum + dram__bytes_write.sum = 0.697168 + 2.390813 GB for one launch of 530 432 gc)
 FRONT_TRAFFIC_PER_GC = (0.697168e9 + 2.390813e9) / 530432
 
@@ -339,7 +339,7 @@ def main():
                      "achieved": fk["achieved_gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": fk["frac_hbm"],
                      "traffic": FRONT_TRAFFIC_PER_GC * S * chunks[0][1] * 2 * NCH,
                      "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per granule-channel "
-                                       "(profiles/r01_g_capture.md) x granule-channels per launch",
+                                       "(profiles/r01_h_capture.md) x granule-channels per launch",
                      "achieved_per_launch_bytes": 5764 * S * chunks[0][1] * 2 * NCH},
         "kernels": kernels,
         "clocks": clocks,
