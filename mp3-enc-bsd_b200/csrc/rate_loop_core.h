@@ -382,16 +382,18 @@ SIMT_FN int count_all(const WarpCtx &w, const RateHot &H, const RateWarpSmem &M,
             // per lane <= 9 pairs x <= 63 per field: no carry between the 10-bit fields
             lo_() = (int)((acc & 1023u) | (((acc >> 10) & 1023u) << 16)); hi_() = (int)(acc >> 20);
             END_THREADS
-            const int both = w.reduce_add(lo_);
+            // both reductions back to back, needed or not (the third field is read for groups 3, 4, 6, 7 only): a reduction
+            // issued behind a branch on the first one's result would wait for it
+            const int both = w.reduce_add(lo_), third = w.reduce_add(hi_);
             int s0 = both & 0xffff, s1 = both >> 16, choice;
             if (is_short) {
                 // choose_table (by max alone), loop.c:1908-1943: first table covering max; 15 -> table 15
                 if (g == 7) { choice = 15; }                               // glut g7 field 0 = table 15
-                else if (g == 6) { choice = esc_table(H, 16, 24, max - 15); s0 += (int)H.hlinbits[choice] * w.reduce_add(hi_); }
+                else if (g == 6) { choice = esc_table(H, 16, 24, max - 15); s0 += (int)H.hlinbits[choice] * third; }
                 else choice = table_for_small_max(max);
             } else if (g >= 6) {
                 // ESC pair, strict '<' (loop.c:1870-1898)
-                const int nesc = w.reduce_add(hi_);
+                const int nesc = third;
                 const int c0 = esc_table(H, 15, 24, max - 15), c1 = esc_table(H, 24, 32, max - 15);
                 s0 += (int)H.hlinbits[c0] * nesc;
                 s1 += (int)H.hlinbits[c1] * nesc;
@@ -404,7 +406,7 @@ SIMT_FN int count_all(const WarpCtx &w, const RateHot &H, const RateWarpSmem &M,
                     const int c1 = (g == 1) ? 3 : (g == 2) ? 6 : (g == 3) ? 8 : (g == 4) ? 11 : 15;
                     if (s1 <= s0) { choice = c1; s0 = s1; }
                     if (g == 3 || g == 4) {
-                        const int s2 = w.reduce_add(hi_);
+                        const int s2 = third;
                         if (s2 <= s0) { choice = (g == 3) ? 9 : 12; s0 = s2; }
                     }
                 }
