@@ -722,7 +722,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
                 preflag = 1;
                 FOR_THREADS(w)
                 if (lane < nb_l) Bd.xmin[0]() = simt::dmul(Bd.xmin[0](), H.pre2[H.pretab[lane]]);
-#pragma unroll 3
+#pragma unroll 1
                 for (int k = 0; k < 9; k++) {
                     const int s = lane + 32 * k;
                     const int b = H.band_long[s];        // preemphasis never runs for short blocks
@@ -763,7 +763,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
                 if ((amp0 >> lane) & 1) { Bd.xmin[0]() = simt::dmul(Bd.xmin[0](), H.ifqstep2); Bd.sf[0]()++; }
                 if ((amp1 >> lane) & 1) { Bd.xmin[1]() = simt::dmul(Bd.xmin[1](), H.ifqstep2); Bd.sf[1]()++; }
                 if (amp != 0) {
-#pragma unroll 3
+#pragma unroll 1
                     for (int k = 0; k < 9; k++) {
                         const int s = lane + 32 * k;
                         const int b = is_short ? H.band_short[s] : H.band_long[s];
@@ -839,7 +839,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
 
     // ---- outputs ------------------------------------------------------------------------------------
     FOR_THREADS(w)
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 9; k++) {
         int s = lane + 32 * k;
         int e0 = slot_e0(is_short, s);
