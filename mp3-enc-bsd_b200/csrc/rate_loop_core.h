@@ -592,6 +592,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
             END_THREADS
             if (w.reduce_add(d_en) < 100) condition++;
             if (condition == 6) {
+#pragma unroll 1
                 for (int band = 0; band < 4; band++) {
                     const int lo = (band == 0) ? 0 : (band == 1) ? 6 : (band == 2) ? 11 : 16;
                     const int hi = (band == 0) ? 6 : (band == 1) ? 11 : (band == 2) ? 16 : 21;
