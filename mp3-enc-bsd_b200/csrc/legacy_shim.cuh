@@ -306,6 +306,7 @@ extern "C" void iteration_loop(double pe[][2], double xr_org[2][2][576], III_psy
     LCU(cudaMemcpy(L.d_xr4, xr, sizeof(xr), cudaMemcpyHostToDevice));
     FrameGeom G;
     G.n_ch = stereo; G.mean_bits = mean_bits; G.bits_per_frame = bitsPerFrame;
+    frame_geom_derive(&G);
     k_rate_loop<<<1, RL_WARPS * 32, RL_SMEM_BYTES>>>(L.d_rate_tab, G, L.d_loop_state, L.d_lane_state, 1, 1, L.d_xr4, L.d_psyout, L.d_ix,
                                                       L.d_gi, L.d_sf, L.d_fo);
     L.launches++;

@@ -94,7 +94,14 @@ struct LoopLaneState {
 
 struct FrameGeom {
     int n_ch, mean_bits, bits_per_frame;
+    int mean_per_ch;   // mean_bits / n_ch           } derived once on the host (frame_geom_derive): a run-time integer division
+    int resv_max;      // ResvFrameBegin's ResvMax   } is ~25 instructions, and this kernel pays for code size
 };
+inline void frame_geom_derive(FrameGeom *G)
+{
+    G->mean_per_ch = G->mean_bits / G->n_ch;
+    G->resv_max = (G->bits_per_frame > 7680) ? 0 : ((7680 - G->bits_per_frame > 4088) ? 4088 : 7680 - G->bits_per_frame);   // reservoir.c:62-84
+}
 
 // ---- per-warp working set in shared memory ---------------------------------------------------------
 // Slot order (k = 0..8, lane = 0..31, slot s = lane + 32 k in [0,288)):
@@ -143,6 +150,7 @@ SIMT_NOINLINE int quant1_exact(const double *tab, double x, int p)
 // instructions must fit the instruction cache (see profiles/r01_a_baseline.md)
 SIMT_NOINLINE double ref_log(double x) { return log(x); }
 SIMT_NOINLINE double ref_exp(double x) { return exp(x); }
+SIMT_NOINLINE double ref_div(double a, double b) { return a / b; }   // IEEE division: ~30 instructions per inlined copy
 
 SIMT_FN int nint_ref(double in) { return (in < 0) ? (int)(in - 0.5) : (int)(in + 0.5); }
 
@@ -548,8 +556,8 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
     for (int h = 0; h < 2; h++) {
         int b = lane + 32 * h;
         double v = 0.0;
-        if (!is_short) { if (b < 21) v = simt::dmul(ratio_l[b], en[h]()) / band_width(H, false, b); }
-        else if (b < 36) v = simt::dmul(ratio_s[b], en[h]()) / band_width(H, true, b);
+        if (!is_short) { if (b < 21) v = ref_div(simt::dmul(ratio_l[b], en[h]()), band_width(H, false, b)); }
+        else if (b < 36) v = ref_div(simt::dmul(ratio_s[b], en[h]()), band_width(H, true, b));
         Bd.xmin[h]() = v;
         Bd.xfsf[h]() = 0.0;
         Bd.sf[h]() = 0;
@@ -560,13 +568,13 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
     {
         const int cur = gr * 2 + ch;
         S.xrmax[cur] = (int)xrmax;
-        S.en_tot[cur] = (sum2 == 0.0) ? 0 : (int)(ref_log(sum2) / H.log2c);
+        S.en_tot[cur] = (sum2 == 0.0) ? 0 : (int)ref_div(ref_log(sum2), H.log2c);
         if (!is_short) {
             FOR_THREADS(w)
             if (lane < 21) {
                 double e = en[0](), xm = Bd.xmin[0]();
-                int ev = (e == 0.0) ? 0 : (int)(ref_log(e) / H.log2c);
-                int xv = (xm == 0.0) ? 0 : (int)(ref_log(xm) / H.log2c);
+                int ev = (e == 0.0) ? 0 : (int)ref_div(ref_log(e), H.log2c);
+                int xv = (xm == 0.0) ? 0 : (int)ref_div(ref_log(xm), H.log2c);
 #pragma unroll
                 for (int i = 0; i < 4; i++) if (i == cur) { st_en[i]() = ev; st_xm[i]() = xv; }
             }
@@ -610,8 +618,8 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
     // ---- ResvMaxBits, reservoir.c:101-134 -------------------------------------------------------
     int max_bits;
     {
-        const int mean = G.mean_bits / G.n_ch;
-        const int resv_max = (G.bits_per_frame > 7680) ? 0 : ((7680 - G.bits_per_frame > 4088) ? 4088 : 7680 - G.bits_per_frame);
+        const int mean = G.mean_per_ch;
+        const int resv_max = G.resv_max;
         max_bits = mean > 4095 ? 4095 : mean;
         if (resv_max != 0) {
             int more_bits = (int)(pe * 3.1 - mean), add_bits = 0;
@@ -642,7 +650,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
         {
             int tp = 0;
             if (sum2 != 0.0) {
-                double sfm = ref_exp(sum1 / 576.0) / (sum2 / 576.0);
+                double sfm = ref_div(ref_exp(ref_div(sum1, 576.0)), ref_div(sum2, 576.0));
                 tp = nint_ref(8.0 * ref_log(sfm));
                 if (tp < -100) tp = -100;
             }
@@ -698,7 +706,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
                 for (int h = 0; h < 2; h++) {
                     int b = lane + 32 * h;
                     bool valid = is_short ? (b < 36) : (b < 21);
-                    Bd.xfsf[h]() = valid ? ns[h]() / band_width(H, is_short, b) : 0.0;
+                    Bd.xfsf[h]() = valid ? ref_div(ns[h](), band_width(H, is_short, b)) : 0.0;
                     save_sf[h]() = Bd.sf[h]();
                 }
                 END_THREADS
@@ -820,7 +828,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
     }
 
     // ---- ResvAdjust + global_gain, loop.c:355-358 -------------------------------------------------
-    S.resv_size += G.mean_bits / G.n_ch - part23;
+    S.resv_size += G.mean_per_ch - part23;
     FOR_THREADS(w)
     if (lane == 0) {   // part2_3_length is rewritten after ResvFrameEnd (stuffing bits)
         GrInfoOut gi;
@@ -868,7 +876,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
 // ResvFrameEnd, reservoir.c:155-226: trims the reservoir and pushes stuffing bits into part2_3_length.
 SIMT_FN void resv_frame_end(const FrameGeom &G, LoopStreamState &S, int p23[4], int *resv_drain)
 {
-    const int resv_max = (G.bits_per_frame > 7680) ? 0 : ((7680 - G.bits_per_frame > 4088) ? 4088 : 7680 - G.bits_per_frame);
+    const int resv_max = G.resv_max;
     if (G.n_ch == 2 && (G.mean_bits & 1)) S.resv_size += 1;
     int over_bits = S.resv_size - resv_max;
     if (over_bits < 0) over_bits = 0;

@@ -32,6 +32,7 @@ void frame_geometry(int sfreq_hz, int n_ch, int bitrate_kbps, FrameGeom *G)
     G->bits_per_frame = 8 * whole;
     int sideinfo_len = 32 + (n_ch == 1 ? 136 : 256);
     G->mean_bits = (G->bits_per_frame - sideinfo_len) / 2;
+    frame_geom_derive(G);
 }
 
 // Emit-side Huffman tables + emission order of short blocks + the constant 32 header bits
