@@ -1,24 +1,31 @@
 #!/usr/bin/env python3
-"""bench.py — x realtime (audio-s/s) of the Layer III hot path (psy + filterbank + MDCT + rate loop) on B200.
+"""bench.py — x realtime (audio-s/s) of the Layer III hot path (psy + filterbank + MDCT + rate loop + bitstream) on B200.
 
-Workload (BASELINE.json configs[3], the configuration the metric is quoted on): a batch of independent
-10 s 44.1 kHz stereo clips at 128 kbps, synthetic (config-1 recipe: 440 Hz tone + FM tone + noise, distinct
-seed per clip).  One "step" = one pass of the whole hot path over the rank's batch.  Streams are independent,
-so ranks just take their own batch — no data-path collective, "scaling": "weak" (per-GPU batch fixed).
+Default workload = BASELINE.json configs[3] AS WRITTEN: a batch of 10 000 x 10 s 44.1 kHz stereo clips at 128 kbps,
+sharded over the N ranks (10 000 / N clips per GPU: "scaling": "strong").  The clips are heterogeneous synthetic
+programme (synth.hetero_batch: the config-1 recipe at levels spread over 30 dB, sums of partials, transients on near
+silence, loud noise, digital silence followed by music, a -40 dB clip, an amplitude-modulated tone); clip i is a pure
+function of i, so a rank's shard is the same whatever N is.  Each clip is 441 000 samples = 383 frames, the last one
+zero-filled as the reference does (encode.c:162-166).  One "step" = one pass of the whole hot path over the rank's shard.
 
   value : whole-job throughput with the PCM already resident in HBM (mp3gpu_encode_frames_mp3_dev: psy, filterbank,
-          MDCT, rate loop + reservoir, and the device bitstream formatter; MP3 bytes land in a device buffer)
-  e2e   : the same through the reference-facing C ABI with HOST buffers (mp3gpu_encode_frames_mp3): pinned
-          host PCM -> H2D -> kernels -> D2H of the finished MP3 byte streams, all inside the timed region
-  roofline : fused polyphase+MDCT front-end kernel, algorithmic bytes (5764 B per granule-channel,
-          FP64 path) / CUDA-event time of that kernel, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline : the unmodified reference CLI encoder (oracle/_ref/encode), one process per host core
+          MDCT, rate loop + reservoir, device bitstream formatter; MP3 bytes land in a device buffer); profiling off
+  e2e   : the same through the reference-facing C ABI with HOST buffers (mp3gpu_encode_frames_mp3): pinned host PCM
+          -> H2D -> kernels -> D2H of the finished MP3 byte streams, all inside the timed region
+  roofline : the fused polyphase+MDCT front-end kernel: algorithmic bytes / its CUDA-event time, measured in a
+          SEPARATE profiled pass (events around every launch), against MEASURED_PEAKS.json hbm_gbs
+  parity : after the timed region, k clips of the batch go through the unmodified reference CLI (oracle/_ref/encode) on
+          the host: fraction of byte-identical frames, identical streams, decoded SNR (oracle/mp3dec.py) — checker leg
+  cpu_baseline : the unmodified reference CLI, one process per host core, one clip of the same batch each
 
+--config 1|2|3 : BASELINE configs[0..2] as batches of 30 s clips; --config 5 : configs[4], ONE 1-hour stream cut into
+segments over the ranks with the NCCL gather of the byte streams inside the timed region.
 `--impl reference` times the reference's own CPU implementation (all host cores) on the same config.
 """
 import argparse
 import json
 import os
+import struct
 import subprocess
 import sys
 import tempfile
@@ -30,14 +37,28 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FS, NCH, KBPS = 44100, 2, 128
-# psy_front: PCM in, PsyMid out (2864 B: partition energies, spread energy, unpredictability, short-transform energies);
-# psy_scan: the 1280-byte hot part of PsyMid in, PsyOut (472 B) out
+# algorithmic bytes per granule-channel.  front: FP64 xr (5764) or FP32 xr (3460)
 BYTES_PER_GC = {"front_polyphase_mdct": 5764, "psy_front": 1152 + 2864, "psy_scan": 1280 + 472,
                 "rate_loop": 4608 + 472 + 1152 + 80 + 40, "bitstream": 1152 + 80 + 40 + 417 // 4}
-# DRAM bytes per granule-channel of k_front_tile from the ncu --set full capture profiles/r01_h_capture.md
-# (dram__bytes_read.sum + dram__bytes_write.sum = 0.697168 + 2.390813 GB for one launch of 530 432 gc)
+# DRAM bytes per granule-channel of the front-end kernel from the ncu --set full capture (dram__bytes_read + write)
 FRONT_TRAFFIC_PER_GC = (0.697168e9 + 2.390813e9) / 530432
+FRONT_TRAFFIC_SOURCE = "profiles/r01_h_capture.md"
+
+CONFIGS = {
+    1: dict(fs=44100, n_ch=2, kbps=128, seconds=30.0, clips=2048, cls=0,
+            name="batch of %d x 30 s synthetic 44.1 kHz stereo clips at 128 kbps, config-1 recipe (BASELINE configs[0] as a batch)"),
+    2: dict(fs=32000, n_ch=1, kbps=64, seconds=30.0, clips=4096, cls=3,
+            name="batch of %d x 30 s 32 kHz mono 64 kbps transient-heavy clips (BASELINE configs[1] as a batch)"),
+    3: dict(fs=48000, n_ch=2, kbps=320, seconds=30.0, clips=2048, cls=2,
+            name="batch of %d x 30 s 48 kHz stereo 320 kbps music-like clips (BASELINE configs[2] as a batch; plain stereo: the "
+                 "reference refuses joint stereo for Layer III)"),
+    4: dict(fs=44100, n_ch=2, kbps=128, seconds=10.0, clips=10000, cls=None,
+            name="batch of %d x 10 s synthetic 44.1 kHz stereo clips at 128 kbps, heterogeneous content, sharded over the GPUs "
+                 "(BASELINE configs[3])"),
+    5: dict(fs=44100, n_ch=2, kbps=128, seconds=3600.0, clips=1, cls=7,
+            name="single %d-s 44.1 kHz stereo stream at 128 kbps segmented at frame boundaries across the GPUs, byte streams "
+                 "gathered on rank 0 (BASELINE configs[4])"),
+}
 
 
 def shard_range(n, rank, world):
@@ -57,7 +78,7 @@ def reduce_timing(seconds, units, device):
     u = torch.tensor([units], dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(u, op=dist.ReduceOp.SUM)
-    return float(t.item()), int(round(u.item()))
+    return float(t.item()), float(u.item())
 
 
 class ClockSampler(threading.Thread):
@@ -93,122 +114,182 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def synth_batch_device(torch, n_streams, n_samples, first_seed, device):
-    """config-1 recipe generated on the device (torch RNG; the numpy version is used for parity tests)"""
-    out = torch.empty((n_streams, NCH, n_samples), dtype=torch.int16, device=device)
-    t = torch.arange(n_samples, dtype=torch.float64, device=device) / FS
-    tone = 0.25 * torch.sin(2 * np.pi * 440.0 * t)
-    fm = 0.15 * torch.sin(2 * np.pi * 1000.0 * t - (500.0 / 0.3) * torch.cos(2 * np.pi * 0.3 * t))
-    base = (tone + fm).to(torch.float32)
-    g = torch.Generator(device=device)
-    step = 256
-    for s0 in range(0, n_streams, step):
-        s1 = min(n_streams, s0 + step)
-        g.manual_seed(first_seed + s0)
-        noise = torch.randn((s1 - s0, NCH, n_samples), generator=g, device=device, dtype=torch.float32)
-        # per-clip level and tone detune so that clips differ in more than the noise
-        lvl = 0.5 + 0.5 * torch.rand((s1 - s0, 1, 1), generator=g, device=device)
-        x = (base[None, None, :] + 0.05 * noise) * lvl
-        out[s0:s1] = torch.clamp(torch.round(x * 32767.0), -32768, 32767).to(torch.int16)
+# ---------------------------------------------------------------------------------------------------------------------
+# host-side helpers of the checker legs (reference CLI, decoder): never inside a timed GPU region
+# ---------------------------------------------------------------------------------------------------------------------
+def wav_bytes(pcm, fs):
+    """44-byte-header WAV as the reference sniffs it (musicin.c:352-368); pcm int16 [n_ch][n]"""
+    n_ch = pcm.shape[0]
+    inter = np.ascontiguousarray(pcm.T).reshape(-1).astype("<i2")
+    return b"RIFF" + struct.pack("<I", 36 + inter.nbytes) + b"WAVEfmt " + \
+        struct.pack("<IHHIIHH", 16, 1, n_ch, fs, fs * 2 * n_ch, 2 * n_ch, 16) + b"data" + struct.pack("<I", inter.nbytes) + inter.tobytes()
+
+
+def cli_flags(cfg):
+    return (["-m", "m"] if cfg["n_ch"] == 1 else ["-m", "s"]) + ["-s", {32000: "32", 44100: "44.1", 48000: "48"}[cfg["fs"]],
+                                                                  "-b", str(cfg["kbps"])]
+
+
+def reference_encode_many(cfg, pcms, cores=None):
+    """run the reference encoder on each PCM array (int16 [n_ch][n]) -> (list of byte streams as the CLI writes them minus
+    its spurious last byte, wall seconds, kind).  oracle/_ref/encode when it was built here, else the oracle port."""
+    cores = cores or os.cpu_count() or 1
+    enc = os.path.join(ROOT, "oracle", "_ref", "encode")
+    if os.path.exists(enc):
+        tmp = tempfile.mkdtemp(prefix="mp3ref_")
+        for i, p in enumerate(pcms):
+            with open(os.path.join(tmp, "c%d.wav" % i), "wb") as f:
+                f.write(wav_bytes(p, cfg["fs"]))
+        t0 = time.perf_counter()
+        running, nxt, outs = [], 0, [None] * len(pcms)
+        while nxt < len(pcms) or running:
+            while nxt < len(pcms) and len(running) < cores:
+                cmd = [enc] + cli_flags(cfg) + [os.path.join(tmp, "c%d.wav" % nxt), os.path.join(tmp, "o%d.mp3" % nxt)]
+                running.append((nxt, subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)))
+                nxt += 1
+            i, p = running.pop(0)
+            p.wait()
+        wall = time.perf_counter() - t0
+        for i in range(len(pcms)):
+            outs[i] = open(os.path.join(tmp, "o%d.mp3" % i), "rb").read()[:-1]      # close_bit_stream_w's extra byte, common.c:968-974
+        subprocess.run(["rm", "-rf", tmp])
+        return outs, wall, "reference"
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(min(cores, len(pcms))) as pool:
+        outs = pool.starmap(_oracle_job, [(p, cfg["fs"], cfg["kbps"]) for p in pcms])
+    return outs, time.perf_counter() - t0, "port"
+
+
+def _oracle_job(pcm, fs, kbps):
+    import oracle
+    data, _ = oracle.format_stream(oracle.encode_stream(pcm, fs, kbps), pcm.shape[0], fs, kbps)
+    return data[:-1]
+
+
+def _decode_job(args):
+    data, pcm = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mp3dec
+    _, dec, ok = mp3dec.decode(data)
+    return dec, bool(ok.all()), mp3dec.snr_vs_original(pcm, dec)
+
+
+def parity_report(cfg, pcms, ours, frame_bytes, n_snr=4):
+    """ours[i] (bytes) against the reference bitstream of pcms[i]: identical-frame fraction, identical streams, decoded SNR"""
+    refs, wall, kind = reference_encode_many(cfg, pcms)
+    frames = same = streams_same = 0
+    first_bad = None
+    for i, (a, b) in enumerate(zip(ours, refs)):
+        n = (max(len(a), len(b)) + frame_bytes - 1) // frame_bytes
+        ok = sum(1 for k in range(n) if a[k * frame_bytes:(k + 1) * frame_bytes] == b[k * frame_bytes:(k + 1) * frame_bytes])
+        frames += n
+        same += ok
+        streams_same += int(a == b)
+        if ok != n and first_bad is None:
+            first_bad = i
+    rep = {"reference": kind, "clips": len(pcms), "frames": frames, "identical_frame_fraction": same / max(frames, 1),
+           "identical_streams": streams_same}
+    sel = list(range(min(n_snr, len(pcms))))
+    if first_bad is not None and first_bad not in sel:
+        sel.append(first_bad)
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import multiprocessing as mp
+        import mp3dec
+        jobs = [(ours[i], pcms[i]) for i in sel] + [(refs[i], pcms[i]) for i in sel if refs[i] != ours[i]]
+        with mp.get_context("fork").Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
+            res = pool.map(_decode_job, jobs)
+        mine = res[:len(sel)]
+        theirs, k = [], len(sel)
+        for j, i in enumerate(sel):
+            if refs[i] != ours[i]:
+                theirs.append(res[k]); k += 1
+            else:
+                theirs.append(mine[j])
+        vs = [mp3dec.snr_db(t[0], m[0]) for m, t in zip(mine, theirs)]
+        finite = [v for v in vs if np.isfinite(v)]
+        rep.update(decoded_clips=len(sel), decodable=bool(all(m[1] for m in mine)),
+                   decoded_snr_db=float(np.mean([m[2] for m in mine])), decoded_snr_reference_db=float(np.mean([t[2] for t in theirs])),
+                   decoded_snr_vs_reference_decode_db=(float(min(finite)) if finite else None),
+                   identical_decodes=len(vs) - len(finite))
+    except Exception as e:     # the SNR part needs liboracle.so; the byte comparison above does not
+        rep["decode_error"] = str(e)[:200]
+    return rep
+
+
+def make_clips_cpu(mod, cfg, indices, n_samples):
+    import torch
+    out = []
+    for i in indices:
+        out.append(mod.synth.hetero_batch(torch, int(i), 1, n_samples, cfg["fs"], cfg["n_ch"], "cpu", force_class=cfg["cls"])[0].numpy())
     return out
 
 
-def run_reference_cpu(seconds_per_clip, clips_per_core=1, cores=None):
-    """the unmodified reference CLI (oracle/_ref/encode), one process per host core, each encoding
-    `clips_per_core` distinct config-1 clips.  Returns (x_realtime, cores, kind, sample description)."""
-    import mp3gpu_pkg
-    synth = mp3gpu_pkg.load().synth
+def run_reference_cpu(mod, cfg, n_samples, cores=None):
+    """the unmodified reference CLI, one process per host core, one clip of the bench batch each"""
     cores = cores or os.cpu_count() or 1
-    enc = os.path.join(ROOT, "oracle", "_ref", "encode")
-    kind = "reference" if os.path.exists(enc) else "port"
-    tmp = tempfile.mkdtemp(prefix="mp3ref_")
-    import struct
-    n_distinct = min(8, cores * clips_per_core)
-    wavs = []
-    for c in range(n_distinct):
-        pcm = synth.config1(seconds_per_clip, FS, (2 * c + 1, 2 * c + 2))
-        inter = np.ascontiguousarray(pcm.T).reshape(-1)
-        hdr = b"RIFF" + struct.pack("<I", 36 + inter.nbytes) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 2, FS, FS * 4, 4, 16) + \
-            b"data" + struct.pack("<I", inter.nbytes)
-        path = os.path.join(tmp, "c%d.wav" % c)
-        with open(path, "wb") as f:
-            f.write(hdr + inter.tobytes())
-        wavs.append(path)
-    t0 = time.perf_counter()
-    if kind == "reference":
-        procs = []
-        for p in range(cores):
-            cmd = " && ".join("%s %s %s/o%d_%d.mp3 >/dev/null 2>&1" % (enc, wavs[(p * clips_per_core + j) % n_distinct], tmp, p, j)
-                              for j in range(clips_per_core))
-            procs.append(subprocess.Popen(cmd, shell=True))
-        for p in procs:
-            p.wait()
-    else:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import multiprocessing as mp
-        import oracle
-        oracle.lib()
-        pcms = [synth.config1(seconds_per_clip, FS, (2 * c + 1, 2 * c + 2)) for c in range(n_distinct)]
-        with mp.get_context("fork").Pool(cores) as pool:
-            pool.starmap(_oracle_job, [(pcms[(p * clips_per_core + j) % n_distinct],) for p in range(cores) for j in range(clips_per_core)])
-    wall = time.perf_counter() - t0
-    audio = cores * clips_per_core * seconds_per_clip
-    subprocess.run(["rm", "-rf", tmp])
-    sample = "%d processes x %d clip(s) of %.1f s 44.1 kHz stereo 128 kbps (whole encoder incl. bitstream formatting)" % (
-        cores, clips_per_core, seconds_per_clip)
+    pcms = make_clips_cpu(mod, cfg, range(cores), n_samples)
+    _, wall, kind = reference_encode_many(cfg, pcms, cores)
+    audio = cores * n_samples / cfg["fs"]
+    sample = "%d processes x 1 clip of %.1f s (%d Hz, %d ch, %d kbps; clips 0..%d of the bench batch; whole encoder incl. bitstream " \
+             "formatting, process start and table initialisation per clip as the reference runs)" % (
+                 cores, n_samples / cfg["fs"], cfg["fs"], cfg["n_ch"], cfg["kbps"], cores - 1)
     return audio / wall, cores, kind, sample, wall
 
 
-def _oracle_job(pcm):
-    import oracle
-    oracle.encode_stream(pcm, FS, KBPS)
-    return 0
-
-
+# ---------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("MP3GPU_BENCH_STREAMS", 0)),
-                    help="clips per GPU (default: one full wave of the rate loop, mp3gpu_stream_wave(): 4144 on a B200)")
-    ap.add_argument("--seconds", type=float, default=10.0, help="clip length")
+    ap.add_argument("--config", type=int, default=4, choices=[1, 2, 3, 4, 5], help="BASELINE.json configs[config - 1]; default 4 = configs[3]")
+    ap.add_argument("--clips", type=int, default=int(os.environ.get("MP3GPU_BENCH_CLIPS", 0)), help="total clips of the batch (all ranks)")
+    ap.add_argument("--seconds", type=float, default=0.0, help="clip (or stream) length; default: the config's")
     ap.add_argument("--chunk-frames", type=int, default=32, help="frames per stream per library call")
+    ap.add_argument("--parity-clips", type=int, default=32, help="clips checked against the reference CLI after the timed region")
+    ap.add_argument("--segment-frames", type=int, default=116, help="config 5: frames per segment")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--front", default=os.environ.get("MP3GPU_FRONT", ""), help="front-end variant (see mp3gpu.h); default: the library's")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    n_frames = int(args.seconds * FS) // 1152          # whole frames per clip (383 for 10 s)
-    audio_per_stream = n_frames * 1152 / FS
-    wl = lambda n: "batch of %d x %.0f s synthetic 44.1 kHz stereo clips at 128 kbps per GPU (BASELINE configs[3])" % (n, args.seconds)
-    workload = wl(args.streams or 4144)
+    cfg = dict(CONFIGS[args.config])
+    if args.seconds:
+        cfg["seconds"] = args.seconds
+    if args.clips and args.config != 5:
+        cfg["clips"] = args.clips
+    FS, NCH, KBPS = cfg["fs"], cfg["n_ch"], cfg["kbps"]
+    n_samples = int(round(cfg["seconds"] * FS))
+    n_frames = (n_samples + 1151) // 1152              # the last frame is zero-filled (encode.c:162-166): 383 for 10 s at 44.1 kHz
+    workload = cfg["name"] % (cfg["clips"] if args.config != 5 else int(cfg["seconds"]))
+    config_common = {"workload": workload, "baseline_config": "configs[%d]" % (args.config - 1), "sfreq_hz": FS, "channels": NCH,
+                     "bitrate_kbps": KBPS, "clip_seconds": cfg["seconds"], "frames_per_clip": n_frames}
+
+    import mp3gpu_pkg
+    mod = mp3gpu_pkg.load()
 
     if args.impl == "reference":
         if rank != 0:
             return
-        if not args.streams:
-            # same workload name as the GPU arm: its default batch is one full wave of the rate loop on this device
-            # (28 warps = streams per SM; computed here so that this arm never loads libmp3gpu.so)
-            try:
-                import torch
-                if torch.cuda.is_available():
-                    workload = wl(28 * torch.cuda.get_device_properties(local_rank).multi_processor_count)
-            except Exception:
-                pass
         steps, vals, walls = max(1, args.steps), [], []
+        # bounded sample of the workload: one clip per host core and step (config 5: a 20 s piece of the stream per core)
+        ns = n_samples if args.config != 5 else 20 * FS
         for i in range(args.warmup + steps):
-            xrt, cores, kind, sample, wall = run_reference_cpu(args.seconds)
+            xrt, cores, kind, sample, wall = run_reference_cpu(mod, cfg, ns)
             if i >= args.warmup:
                 vals.append(xrt)
                 walls.append(wall)
         v = float(np.mean(vals))
         print(json.dumps({"impl": "reference", "metric": "x_realtime", "value": v, "unit": "audio-s/s", "n_gpus": args.gpus,
                           "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(walls)), "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": workload, "sfreq_hz": FS, "channels": NCH, "bitrate_kbps": KBPS},
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_common,
                           "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample},
                           "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "gpu_launches": 0}))
@@ -216,28 +297,30 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import mp3gpu_pkg
-    mod = mp3gpu_pkg.load()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    if args.config == 5:
+        import bench_stream
+        return bench_stream.run(args, cfg, config_common, mod, rank, world, local_rank, device)
 
-    if not args.streams:
-        args.streams = mod.host.stream_wave(local_rank)
-        workload = wl(args.streams)
-    S, F = args.streams, min(args.chunk_frames, n_frames)
+    lo, hi = shard_range(cfg["clips"], rank, world)
+    S, F = hi - lo, min(args.chunk_frames, n_frames)
     chunks = []
     f0 = 0
     while f0 < n_frames:
         chunks.append((f0, min(F, n_frames - f0)))
         f0 += F
     enc = mod.Encoder(FS, NCH, KBPS, max_streams=S, max_frames=F, device=local_rank)
+    if args.front:
+        enc.set_front_variant(args.front)
     # ---- synthetic PCM: generated on the device, kept (a) on the device chunk-major for `value`,
     #      (b) in pinned host memory chunk-major for `e2e`
-    pcm_all = synth_batch_device(torch, S, n_frames * 1152, 1000 * rank + 1, device)
+    pcm_all = torch.zeros((S, NCH, n_frames * 1152), dtype=torch.int16, device=device)
+    mod.synth.hetero_batch(torch, lo, S, n_samples, FS, NCH, device, out=pcm_all[:, :, :n_samples], force_class=cfg["cls"])
     dev_chunks = [pcm_all[:, :, a * 1152:(a + n) * 1152].contiguous() for a, n in chunks]
     del pcm_all
     host_chunks = [torch.empty(c.shape, dtype=torch.int16, pin_memory=True) for c in dev_chunks]
@@ -248,18 +331,19 @@ def main():
     mp3_host = torch.zeros((S, mp3_bytes), dtype=torch.uint8, pin_memory=True)
     stream = torch.cuda.current_stream(device)
     sptr = stream.cuda_stream
+    lengths_last = [None]
 
     def step_dev():
-        enc.reset()
-        for i, (a, n) in enumerate(chunks):
+        enc.reset(stream=sptr)
+        for i in range(len(chunks)):
             enc.encode_frames_mp3_dev(dev_chunks[i], mp3_dev, stream=sptr)
         return enc.flush_mp3(mp3_dev, S, stream=sptr)
 
     def step_host():
-        enc.reset()
-        for i, (a, n) in enumerate(chunks):
+        enc.reset(stream=sptr)
+        for i in range(len(chunks)):
             enc.encode_frames_mp3(host_chunks[i].numpy(), mp3_host.numpy(), stream=sptr)
-        return enc.flush_mp3(mp3_host.numpy(), S, stream=sptr)
+        lengths_last[0] = enc.flush_mp3(mp3_host.numpy(), S, stream=sptr)
 
     def timed(fn, k):
         if world > 1:
@@ -275,32 +359,34 @@ def main():
             dist.barrier()
         return e0.elapsed_time(e1) * 1e-3
 
-    for _ in range(max(3, args.warmup)):
+    warmup = max(3, args.warmup)
+    for _ in range(warmup):
         step_dev()
     torch.cuda.synchronize(device)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    enc.profile_enable(True)
-    enc.profile_collect(reset=True)
     l0 = enc.kernel_launches
-    t_dev = timed(step_dev, args.steps)
+    t_dev = timed(step_dev, args.steps)                  # `value`: profiling off
     launches = enc.kernel_launches - l0
-    prof = enc.profile_collect(reset=True)
-    enc.profile_enable(False)
     enc.set_host_delivery(True)     # the D2H of a chunk's bytes overlaps the next chunk's kernels; flush_mp3 joins (mp3gpu.h)
     for _ in range(2):
         step_host()
     torch.cuda.synchronize(device)
     t_host = timed(step_host, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    # fingerprint of what the timed steps produced (first 8 clips of the last e2e step): lets A/B runs of library variants
-    # (tools/ab_bench.sh) see at once that a "faster" variant encodes something else
-    import zlib
-    out_crc = zlib.crc32(mp3_host[:min(S, 8)].numpy().tobytes()) & 0xffffffff
+    # separate profiled pass: CUDA events around every launch of the hot kernels (per-kernel split + the roofline figure)
+    enc.set_host_delivery(False)
+    enc.profile_enable(True)
+    enc.profile_collect(reset=True)
+    prof_steps = max(1, min(args.steps, 2))
+    for _ in range(prof_steps):
+        step_dev()
+    prof = enc.profile_collect(reset=True)
+    enc.profile_enable(False)
 
-    audio_rank = S * audio_per_stream * args.steps
+    audio_rank = S * n_samples / FS * args.steps
     t_dev_max, audio_total = reduce_timing(t_dev, audio_rank, device)
     t_host_max, _ = reduce_timing(t_host, audio_rank, device)
     if rank != 0:
@@ -315,37 +401,53 @@ def main():
         pass
     peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
     gc_per_step = S * n_frames * 2 * NCH
+    front_info = enc.front_variant_info() if hasattr(enc, "front_variant_info") else {"name": "exact", "bytes_per_gc": 5764}
+    bpg = dict(BYTES_PER_GC)
+    bpg["front_polyphase_mdct"] = front_info["bytes_per_gc"]
     kernels = {}
     tot_ms = sum(v[0] for v in prof.values()) or 1.0
     for name, (ms, n) in prof.items():
-        gbs = BYTES_PER_GC[name] * gc_per_step * args.steps / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        kernels[name] = {"ms_per_step": ms / args.steps, "launches_per_step": n / args.steps, "share": ms / tot_ms,
-                         "algorithmic_bytes_per_gc": BYTES_PER_GC[name], "achieved_gbs": gbs, "frac_hbm": gbs / peak}
+        gbs = bpg[name] * gc_per_step * prof_steps / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        kernels[name] = {"ms_per_step": ms / prof_steps, "launches_per_step": n / prof_steps, "share": ms / tot_ms,
+                         "algorithmic_bytes_per_gc": bpg[name], "achieved_gbs": gbs, "frac_hbm": gbs / peak}
     fk = kernels["front_polyphase_mdct"]
+    gc_per_launch = S * chunks[0][1] * 2 * NCH
     out = {
         "metric": "x_realtime", "value": audio_total / t_dev_max, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": 1e3 * t_dev_max / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": 1e3 * t_dev_max / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "sfreq_hz": FS, "channels": NCH, "bitrate_kbps": KBPS, "streams_per_gpu": S,
-                   "frames_per_stream": n_frames, "chunk_frames": F, "precision": "fp64 filterbank/MDCT/rate loop, fp32 FFT (as the reference)",
-                   "l2": "inputs larger than L2: %.1f GB PCM and %.1f GB of spectra per step" % (
-                       S * n_frames * 1152 * NCH * 2 / 1e9, gc_per_step * 4608 / 1e9)},
+        "config": dict(config_common, clips_total=cfg["clips"], clips_this_rank=S, chunk_frames=F, content=mod.synth.HETERO_CLASSES
+                       if cfg["cls"] is None else mod.synth.HETERO_CLASSES[cfg["cls"]],
+                       precision="fp64 filterbank/MDCT/rate loop, fp32 FFT (as the reference); front-end variant: " + front_info["name"],
+                       l2="inputs larger than L2: %.1f GB PCM and %.1f GB of spectra per step and GPU" % (
+                           S * n_frames * 1152 * NCH * 2 / 1e9, gc_per_step * 4608 / 1e9)),
         "e2e": {"value": audio_total / t_host_max, "unit": "audio-s/s",
                 "h2d_bytes_per_step": int(S * n_frames * 1152 * NCH * 2), "d2h_bytes_per_step": int(S * mp3_bytes + 4 * S),
-                "output": "finished MPEG-1 Layer III byte streams (device bitstream formatter), %d bytes per clip" % mp3_bytes,
-                "output_crc32_first8": "%08x" % out_crc},
+                "output": "finished MPEG-1 Layer III byte streams (device bitstream formatter), %d bytes per clip" % mp3_bytes},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_front (fused polyphase filterbank + MDCT + alias reduction, FP64 exact path)",
+        "roofline": {"bound": "hbm", "kernel": "k_front_tile (fused polyphase filterbank + MDCT + alias reduction), variant " + front_info["name"],
                      "achieved": fk["achieved_gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": fk["frac_hbm"],
-                     "traffic": FRONT_TRAFFIC_PER_GC * S * chunks[0][1] * 2 * NCH,
-                     "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per granule-channel "
-                                       "(profiles/r01_h_capture.md) x granule-channels per launch",
-                     "achieved_per_launch_bytes": 5764 * S * chunks[0][1] * 2 * NCH},
+                     "traffic": FRONT_TRAFFIC_PER_GC * gc_per_launch,
+                     "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per granule-channel (%s) x "
+                                       "granule-channels per launch" % FRONT_TRAFFIC_SOURCE,
+                     "achieved_per_launch_bytes": front_info["bytes_per_gc"] * gc_per_launch,
+                     "measured_in": "separate profiled pass of %d step(s) (CUDA events around every launch)" % prof_steps},
         "kernels": kernels,
         "clocks": clocks,
     }
+    if not args.no_parity and args.parity_clips > 0:
+        # checker leg, outside every timed region: clips of this batch through the unmodified reference CLI
+        k = min(args.parity_clips, S)
+        pick = sorted(np.random.default_rng(20261017).choice(S, size=k, replace=False).tolist())
+        for c in range(min(8, S)):                       # every content class at least once
+            if c not in pick and len(pick) < k + 8:
+                pick.append(c)
+        pcms = [np.concatenate([h[i].numpy() for h in host_chunks], axis=1)[:, :n_samples] for i in pick]
+        ours = [mp3_host[i, :int(lengths_last[0][i])].numpy().tobytes() for i in pick]
+        out["parity"] = parity_report(cfg, pcms, ours, enc.frame_bytes)
+        out["parity"]["clip_indices"] = [lo + i for i in pick]
     if not args.no_cpu_baseline:
-        xrt, cores, kind, sample, wall = run_reference_cpu(args.seconds)
+        xrt, cores, kind, sample, wall = run_reference_cpu(mod, cfg, n_samples)
         out["cpu_baseline"] = {"value": xrt, "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample}
     print(json.dumps(out))
     if world > 1:

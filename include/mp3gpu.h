@@ -90,10 +90,26 @@ const char *mp3gpu_version(void);
 
 int mp3gpu_create(const mp3gpu_config *cfg, mp3gpu_ctx **out);
 void mp3gpu_destroy(mp3gpu_ctx *ctx);
-/* forget all per-stream state (filterbank/MDCT history, psy history, reservoir): start of new streams */
+/* forget all per-stream state (filterbank/MDCT history, psy history, reservoir, stream lengths): start of new streams.
+ * mp3gpu_reset waits for everything in flight on the ctx's device, clears and returns when the clears are done;
+ * mp3gpu_reset_async enqueues the clears on `stream` (behind the ctx's private copy streams) and does not block the host. */
 int mp3gpu_reset(mp3gpu_ctx *ctx);
-/* number of streams that fills the device exactly once in the rate loop (one warp per stream); batches that are a
- * multiple of it leave no partially filled last wave.  Negative MP3GPU_E* on error. */
+int mp3gpu_reset_async(mp3gpu_ctx *ctx, void *stream);
+/* Streams of different lengths in one batch: stream s ends after frames[s] frames, counted from the last reset (or
+ * mp3gpu_begin_segment).  Calls keep the lockstep shape [n_streams][n_frames]; the frames of a stream beyond its end are
+ * ignored (their PCM is not read, no output is produced) and mp3gpu_flush_mp3 reports every stream's own length, exactly as
+ * if the stream had been encoded alone.  frames == NULL removes the limits.  `frames` is a host array of n_streams longs.
+ * (The reference encodes one stream of any length per process: its frame loop runs until get_audio() returns 0,
+ * musicin.c:585, the last frame zero-filled, encode.c:162-166.) */
+int mp3gpu_set_stream_frames(mp3gpu_ctx *ctx, int n_streams, const long *frames, void *stream);
+/* restart streams [first, first + count) as new streams (zero history / psychoacoustic state / reservoir / byte window)
+ * while the others keep their state; ordered on `stream`.  All streams of a ctx share the absolute frame position, so
+ * this belongs at the start of a batch or right after mp3gpu_begin_segment (e.g. the first segment of a long stream, which
+ * has no pre-roll and must start exactly like the reference's process does). */
+int mp3gpu_reset_streams(mp3gpu_ctx *ctx, int first, int count, void *stream);
+/* number of streams the rate loop keeps in flight at once (one warp per stream and frame: SMs x warps per SM).  The rate
+ * loop is a persistent kernel drawing (stream, frame) work items from a queue, so any batch size keeps the device busy;
+ * batches below this number run with fewer warps per SM.  Negative MP3GPU_E* on error. */
 int mp3gpu_stream_wave(int device);
 /* frame geometry the reference derives in musicin.c:562-572,729-746 */
 int mp3gpu_frame_geometry(const mp3gpu_ctx *ctx, int *bits_per_frame, int *mean_bits);

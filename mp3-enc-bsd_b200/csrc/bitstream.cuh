@@ -28,7 +28,7 @@ namespace mp3gpu {
 struct BitsGeom {
     int n_streams, n_frames, n_ch;
     int frame_bytes, si_bytes;      // FB, SIB
-    long frame0;                    // absolute index of the call's first frame (per stream, all in lockstep)
+    long frame0;                    // absolute index of the call's first frame (streams advance in lockstep until their own end)
     long origin;                    // absolute file byte that window byte 0 corresponds to (may be negative)
     long wstride;                   // window bytes per stream
 };
@@ -89,7 +89,7 @@ __device__ __forceinline__ int huff_pair(const BitTables &T, int t, int x, int y
 
 // One warp per granule-channel: scalefactors + Huffman code bits + stuffing, placed at their final position.
 __global__ void __launch_bounds__(BITS_WARPS * 32)
-k_bits_emit(const BitTables *__restrict__ Tg, BitsGeom G, const short *__restrict__ ix, const GrInfoOut *__restrict__ gi,
+k_bits_emit(const BitTables *__restrict__ Tg, BitsGeom G, const int *__restrict__ nfr, const short *__restrict__ ix, const GrInfoOut *__restrict__ gi,
             const unsigned char *__restrict__ sf, const FrameOut *__restrict__ fo, unsigned char *win)
 {
     __shared__ BitsWarpSmem Ms[BITS_WARPS];
@@ -103,6 +103,7 @@ k_bits_emit(const BitTables *__restrict__ Tg, BitsGeom G, const short *__restric
     const long sfr = gc / gpf;                                    // stream * n_frames + frame
     const int f = (int)(sfr % G.n_frames);
     const long s = sfr / G.n_frames;
+    if (nfr && f >= nfr[s]) return;                               // the stream ended before this frame
     BitsWarpSmem &M = Ms[warp];
     const GrInfoOut g = gi[gc];
     const int p23 = g.part2_3_length;
@@ -230,13 +231,15 @@ struct SiPacker {
 // One thread per frame: 32 header bits + side info (encodeSideInfo, l3bitstream.c:314-458, MPEG-1), written at the
 // frame's fixed position; the thread of a stream's last frame also records the next frame's back pointer
 // (formatBitstream.c:76-79) for the end-of-stream length.
-__global__ void k_bits_headers(const BitTables *__restrict__ Tg, BitsGeom G, const GrInfoOut *__restrict__ gi,
+__global__ void k_bits_headers(const BitTables *__restrict__ Tg, BitsGeom G, const int *__restrict__ nfr, const GrInfoOut *__restrict__ gi,
                                const FrameOut *__restrict__ fo, unsigned char *win, int *next_begin)
 {
     const long sfr = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (sfr >= (long)G.n_streams * G.n_frames) return;
     const int f = (int)(sfr % G.n_frames);
     const long s = sfr / G.n_frames;
+    const int n_live = nfr ? nfr[s] : G.n_frames;                 // frames of this stream in this call
+    if (f >= n_live) return;
     const FrameOut F = fo[sfr];
     unsigned char buf[36];
     for (int i = 0; i < 36; i++) buf[i] = 0;
@@ -263,7 +266,7 @@ __global__ void k_bits_headers(const BitTables *__restrict__ Tg, BitsGeom G, con
     }
     unsigned char *dst = win + s * G.wstride + ((G.frame0 + f) * (long)G.frame_bytes - G.origin);
     for (int i = 0; i < G.si_bytes; i++) dst[i] = buf[i];
-    if (f == G.n_frames - 1) next_begin[s] = F.main_data_begin + (G.frame_bytes - G.si_bytes) - mainbits / 8;
+    if (f == n_live - 1) next_begin[s] = F.main_data_begin + (G.frame_bytes - G.si_bytes) - mainbits / 8;
 }
 
 }  // namespace mp3gpu

@@ -152,7 +152,7 @@ __device__ __forceinline__ void ft_group_barrier(int group)   // the three warps
 // fetched together with the PCM tile.
 __global__ void __launch_bounds__(FT_THREADS, 2)
 k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_stride, int hist, int n_streams, int n_ch, int n_gran,
-             long n_tiles_total, const PsyOut *__restrict__ psy, double *__restrict__ xr)
+             long n_tiles_total, const int *__restrict__ nfr, const PsyOut *__restrict__ psy, double *__restrict__ xr)
 {
     extern __shared__ __align__(16) unsigned char ft_smem_raw[];
     FrontTileSmem &M = *reinterpret_cast<FrontTileSmem *>(ft_smem_raw);
@@ -179,7 +179,13 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
     const int ch = (int)((bid / n_tiles) % n_ch);
     const long s = bid / ((long)n_tiles * n_ch);
     const int g_first = t * FT_G;
-    const int ng = min(FT_G, n_gran - g_first);
+    const int n_live = nfr ? min(n_gran, 2 * nfr[s]) : n_gran;      // granules of this stream in this call (mp3gpu_set_stream_frames)
+    const int ng = min(FT_G, n_live - g_first);
+#if FT_PERSISTENT
+    if (ng <= 0) continue;
+#else
+    if (ng <= 0) return;                                            // CTA-uniform: the stream ended before this tile
+#endif
     const int n_slots = 18 * (ng + 1);
     const int n_chunks = (n_slots + 31) >> 5;
 

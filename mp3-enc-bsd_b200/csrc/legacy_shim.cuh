@@ -87,6 +87,7 @@ struct LegacyState {
     GrInfoOut *d_gi = nullptr;
     unsigned char *d_sf = nullptr;
     FrameOut *d_fo = nullptr;
+    int *d_sched = nullptr;     // work queue of the persistent rate loop (one stream: ticket counter + one progress word)
     double *d_xr4 = nullptr;
 };
 static LegacyState g_legacy;
@@ -140,6 +141,7 @@ static bool legacy_init()
     if (e == cudaSuccess) e = cudaMalloc(&L.d_gi, 4 * sizeof(GrInfoOut));
     if (e == cudaSuccess) e = cudaMalloc(&L.d_sf, 4 * 40);
     if (e == cudaSuccess) e = cudaMalloc(&L.d_fo, sizeof(FrameOut));
+    if (e == cudaSuccess) e = cudaMalloc(&L.d_sched, 2 * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&L.d_xr4, 4 * 576 * sizeof(double));
     if (e != cudaSuccess) { legacy_fail(MP3GPU_ECUDA, "init", e); return false; }
     cudaFuncSetAttribute(k_psy_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PSYF_WARPS * sizeof(PsyFrontSmem)));
@@ -254,8 +256,8 @@ extern "C" void L3psycho_anal(short *buffer, short savebuf[1344], int chn, int l
     short *row = L.d_save + 1344 * chn;
     LCU(cudaMemcpy(row, savebuf, 1344 * sizeof(short), cudaMemcpyHostToDevice));
     // the granule's first new sample is savebuf[768]; psy_front reads [-768, 576) around it
-    k_psy_front<<<1, PSYF_WARPS * 32, PSYF_WARPS * sizeof(PsyFrontSmem)>>>(L.psy_dev, row + 768 - HIST, 0, 0, 1, 1, 1, L.d_mid);
-    k_psy_scan<<<1, PSYS_WARPS * 32, PSYS_WARPS * sizeof(PsyScanSmem)>>>(L.d_psy_tab, L.d_mid, L.d_psy_state + chn, 1, 1, 1, L.d_psyout);
+    k_psy_front<<<1, PSYF_WARPS * 32, PSYF_WARPS * sizeof(PsyFrontSmem)>>>(L.psy_dev, row + 768 - HIST, 0, 0, 1, 1, 1, nullptr, L.d_mid);
+    k_psy_scan<<<1, PSYS_WARPS * 32, PSYS_WARPS * sizeof(PsyScanSmem)>>>(L.d_psy_tab, L.d_mid, L.d_psy_state + chn, 1, 1, 1, nullptr, L.d_psyout);
     L.launches += 2;
     LCU(cudaGetLastError());
     PsyOut po;
@@ -307,8 +309,9 @@ extern "C" void iteration_loop(double pe[][2], double xr_org[2][2][576], III_psy
     FrameGeom G;
     G.n_ch = stereo; G.mean_bits = mean_bits; G.bits_per_frame = bitsPerFrame;
     frame_geom_derive(&G);
-    k_rate_loop<<<1, RL_WARPS * 32, RL_SMEM_BYTES>>>(L.d_rate_tab, G, L.d_loop_state, L.d_lane_state, 1, 1, L.d_xr4, L.d_psyout, L.d_ix,
-                                                      L.d_gi, L.d_sf, L.d_fo);
+    LCU(cudaMemset(L.d_sched, 0, 2 * sizeof(int)));
+    k_rate_loop<<<1, 32, RL_HOT_BYTES + sizeof(RateWarpSmem)>>>(L.d_rate_tab, G, L.d_loop_state, L.d_lane_state, 1, 1, nullptr, L.d_sched, L.d_xr4,
+                                                                 L.d_psyout, L.d_ix, L.d_gi, L.d_sf, L.d_fo);
     L.launches++;
     LCU(cudaGetLastError());
     short ix[4][576];

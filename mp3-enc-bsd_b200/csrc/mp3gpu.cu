@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stddef.h>
+#include <limits.h>
 #include <string.h>
 
 #include <new>
@@ -95,7 +96,7 @@ k_mdct(const double *sb, const PsyOut *psy, double *sb_prev, int n_streams, int 
 
 #define PSYF_WARPS 8
 __global__ void __launch_bounds__(PSYF_WARPS * 32, 4)   // 4 CTAs per SM (shared-memory limit): at most 64 registers
-k_psy_front(PsyDev D, const short *pcm, long stream_stride, long ch_stride, int n_streams, int n_ch, int n_gran, PsyMid *mid)
+k_psy_front(PsyDev D, const short *pcm, long stream_stride, long ch_stride, int n_streams, int n_ch, int n_gran, const int *nfr, PsyMid *mid)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PsyFrontSmem *Ms = reinterpret_cast<PsyFrontSmem *>(smem_raw);
@@ -105,6 +106,7 @@ k_psy_front(PsyDev D, const short *pcm, long stream_stride, long ch_stride, int 
     const int ch = (int)(gc % n_ch);
     const int g = (int)((gc / n_ch) % n_gran);
     const long s = gc / ((long)n_ch * n_gran);
+    if (nfr && g >= 2 * nfr[s]) return;          // the stream ended before this granule (mp3gpu_set_stream_frames)
     WarpCtx w{WarpCtx::Pinned()};
     psy_front(w, D, simt::pin_smem(Ms[warp]), pcm + s * stream_stride + ch * ch_stride + HIST + 576L * g, &mid[gc]);
 }
@@ -116,7 +118,7 @@ k_psy_front(PsyDev D, const short *pcm, long stream_stride, long ch_stride, int 
 #define PSYS_MIN_CTAS 7
 #endif
 __global__ void __launch_bounds__(PSYS_WARPS * 32, PSYS_MIN_CTAS)
-k_psy_scan(const PsyTables *T, const PsyMid *mid, PsyChanState *states, int n_streams, int n_ch, int n_gran, PsyOut *psy)
+k_psy_scan(const PsyTables *T, const PsyMid *mid, PsyChanState *states, int n_streams, int n_ch, int n_gran, const int *nfr, PsyOut *psy)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PsyScanSmem *Ms = reinterpret_cast<PsyScanSmem *>(smem_raw);
@@ -127,8 +129,10 @@ k_psy_scan(const PsyTables *T, const PsyMid *mid, PsyChanState *states, int n_st
     const long s = wid / n_ch;
     WarpCtx w;
     PsyScanRegs R;
+    const int n_live = nfr ? min(n_gran, 2 * nfr[s]) : n_gran;
+    if (n_live <= 0) return;
     psy_scan_load(w, states[wid], R);
-    for (int g = 0; g < n_gran; g++) {
+    for (int g = 0; g < n_live; g++) {
         const long gc = (s * n_gran + g) * n_ch + ch;
         psy_scan_step(w, *T, Ms[warp], mid[gc], R, &psy[gc]);
     }
@@ -158,28 +162,69 @@ __device__ __forceinline__ const RateHot &load_rate_hot(const RateTables *gT, un
 #ifndef RL_MIN_CTAS
 #define RL_MIN_CTAS 1
 #endif
+// Rate loop, PERSISTENT: the grid is one CTA per SM (fewer when there are fewer streams than SMs) and every warp pulls work
+// items from a ticket counter until none are left.  A work item is ONE FRAME of one stream; tickets are handed out frame-major
+// (ticket t -> frame t / n_streams of stream t % n_streams), so the frames of a stream are taken in order and, with S streams
+// in flight, S tickets apart.  The reservoir recurrence (reservoir.c:101-145) makes frame f of a stream depend on frame f - 1:
+// the warp that draws (f, s) waits until sched[1 + s] — the number of frames of stream s finished in this launch — has
+// reached f, then loads the stream's state (LoopStreamState + LoopLaneState, 1.1 KB), encodes the frame and publishes
+// f + 1.  An awaited frame is always in the hands of a running warp (tickets are only drawn by running warps), so waiting
+// cannot deadlock whatever part of the grid is resident.
+// Why: with one warp owning a stream for a whole call, 10 000 streams on 4144 warp slots ran as 3 rounds for 2.41 rounds of
+// work and every CTA waited for its slowest warp; below one wave the CTAs of 28 warps left most SMs empty (1250 streams =
+// 45 SMs).  Frame-granular items balance to within one frame (~0.7 ms of ~60 ms), and the launch spreads min(28, S / SMs)
+// warps over ALL SMs.
+__device__ __forceinline__ int ld_acquire_gpu(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(RL_WARPS * 32, RL_MIN_CTAS)
 k_rate_loop(const RateTables *__restrict__ gT, FrameGeom G, LoopStreamState *states, LoopLaneState *lane_states, int n_streams, int n_frames,
-            const double *__restrict__ xr, const PsyOut *__restrict__ psy, short *ix, GrInfoOut *gi, unsigned char *sf, FrameOut *fo)
+            const int *__restrict__ nfr, int *sched, const double *__restrict__ xr, const PsyOut *__restrict__ psy, short *ix, GrInfoOut *gi,
+            unsigned char *sf, FrameOut *fo)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RateHot &H0 = load_rate_hot(gT, smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long s = (long)blockIdx.x * RL_WARPS + warp;
-    if (s >= n_streams) return;
+    const int warp = threadIdx.x >> 5;
     const RateHot &H = simt::pin_smem(H0);
     RateWarpSmem &M = simt::pin_smem(reinterpret_cast<RateWarpSmem *>(smem_raw + RL_HOT_BYTES)[warp]);
     WarpCtx w{WarpCtx::Pinned()};
-    LoopStreamState S = states[s];
-    PerThread<int> st_en[4], st_xm[4];
+    const int lane = w.lane;
+    const int gpf = 2 * G.n_ch;                                  // granule-channels per frame
+    const long total = (long)n_streams * n_frames;
+    for (;;) {
+        long t = 0;
+        if (lane == 0) t = (long)atomicAdd(reinterpret_cast<unsigned int *>(sched), 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= total) break;
+        const int f = (int)(t / n_streams);
+        const long s = t - (long)f * n_streams;
+        if (nfr && f >= nfr[s]) continue;                        // the stream ended before this frame
+        if (f > 0) {
+            if (lane == 0) while (ld_acquire_gpu(sched + 1 + s) < f) __nanosleep(200);
+            __syncwarp();
+        }
+        LoopStreamState S = states[s];
+        PerThread<int> st_en[4], st_xm[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) { st_en[i].v = lane_states[s].en[i][lane]; st_xm[i].v = lane_states[s].xm[i][lane]; }
-    const long gcs = (long)n_frames * 2 * G.n_ch;
-    rate_loop_stream(w, H, *gT, M, G, S, st_en, st_xm, n_frames, xr + s * gcs * 576, psy + s * gcs, ix + s * gcs * 576,
-                     gi + s * gcs, sf + s * gcs * 40, fo + s * (long)n_frames, nullptr);
+        for (int i = 0; i < 4; i++) { st_en[i].v = lane_states[s].en[i][lane]; st_xm[i].v = lane_states[s].xm[i][lane]; }
+        const long g0 = (s * n_frames + f) * gpf;                // first granule-channel of the frame
+        rate_loop_stream(w, H, *gT, M, G, S, st_en, st_xm, 1, xr + g0 * 576, psy + g0, ix + g0 * 576, gi + g0, sf + g0 * 40,
+                         fo + s * (long)n_frames + f, nullptr);
 #pragma unroll
-    for (int i = 0; i < 4; i++) { lane_states[s].en[i][lane] = st_en[i].v; lane_states[s].xm[i][lane] = st_xm[i].v; }
-    if (lane == 0) states[s] = S;
+        for (int i = 0; i < 4; i++) { lane_states[s].en[i][lane] = st_en[i].v; lane_states[s].xm[i][lane] = st_xm[i].v; }
+        if (lane == 0) states[s] = S;
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_gpu(sched + 1 + s, f + 1);
+    }
 }
 
 // quantize + count_bits on n independent granules.  count_only: ix[] holds magnitudes already (count_bits(), loop.c:2099)
@@ -277,6 +322,16 @@ __global__ void k_deinterleave(const short *__restrict__ src, short *rows, long 
     }
 }
 
+// frames of each stream in the current call: streams advance in lockstep (frames_done) until their own end
+// (mp3gpu_set_stream_frames); nfr[s] = clamp(total[s] - frames_done, 0, n_frames)
+__global__ void k_call_frames(const int *__restrict__ total, long frames_done, int n_frames, int n_streams, int *nfr)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    const long left = (long)total[s] - frames_done;
+    nfr[s] = left <= 0 ? 0 : (left < n_frames ? (int)left : n_frames);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------
@@ -330,7 +385,13 @@ struct mp3gpu_ctx {
     int *d_next_begin = nullptr;
     int frame_bytes = 0, si_bytes = 0, tail_frames = 0;
     long wstride = 0;
-    long frames_done = 0;      // frames already formatted per stream (all streams of a ctx advance in lockstep)
+    long frames_done = 0;      // frames every stream has been offered so far (streams advance in lockstep until their own end)
+    long frames_done_loop = 0; // same, for the stage pipeline up to the rate loop (equal to frames_done on the mp3 entry points)
+    // per-stream lengths (mp3gpu_set_stream_frames): total frames of each stream, the frames of the current call, host copy
+    int *d_total = nullptr, *d_nfr = nullptr;
+    std::vector<int> h_total;
+    bool have_total = false;
+    int *d_sched = nullptr;    // rate-loop work queue: [0] ticket counter, [1 + s] frames of stream s finished in this launch
     // host-PCM ingest: double-buffered dense staging filled on a private copy stream, so that the H2D copy of
     // call i+1 overlaps the kernels of call i (the caller only ever sees its own stream)
     cudaStream_t copy_stream = nullptr;
@@ -348,8 +409,9 @@ struct mp3gpu_ctx {
     long launches = 0;
     // per-kernel timing (mp3gpu_profile_*): events bracket every launch of the four hot kernels
     int prof_on = 0;
-    std::vector<cudaEvent_t> prof_ev;     // pairs (start, stop)
+    std::vector<cudaEvent_t> prof_ev;     // pairs (start, stop) in use since the last collect
     std::vector<int> prof_kind;           // kernel id of each pair
+    std::vector<cudaEvent_t> prof_pool;   // events recycled by collect (no cudaEventCreate inside a timed region)
     double prof_ms[MP3GPU_N_KERNELS] = {0, 0, 0, 0, 0};
     long prof_n[MP3GPU_N_KERNELS] = {0, 0, 0, 0, 0};
 };
@@ -357,8 +419,13 @@ struct mp3gpu_ctx {
 static void prof_begin(mp3gpu_ctx *c, int kind, cudaStream_t q)
 {
     if (!c->prof_on) return;
-    cudaEvent_t a, b;
-    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (c->prof_pool.size() >= 2) {
+        a = c->prof_pool.back(); c->prof_pool.pop_back();
+        b = c->prof_pool.back(); c->prof_pool.pop_back();
+    } else {
+        cudaEventCreate(&a); cudaEventCreate(&b);
+    }
     cudaEventRecord(a, q);
     c->prof_ev.push_back(a); c->prof_ev.push_back(b);
     c->prof_kind.push_back(kind);
@@ -368,6 +435,22 @@ static void prof_end(mp3gpu_ctx *c, cudaStream_t q)
     if (!c->prof_on) return;
     cudaEventRecord(c->prof_ev.back(), q);
 }
+
+// A ctx is bound to cfg.device: every entry point makes that device current for its duration and restores the
+// caller's device afterwards (kernels, events and the __constant__ / __device__ table symbols are per device).
+struct DeviceGuard {
+    int prev = -1, want;
+    bool ok = true;
+    explicit DeviceGuard(int dev) : want(dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != want) cudaSetDevice(prev); }
+};
+#define DEV_GUARD(c)                                                                                  \
+    DeviceGuard dev_guard_((c)->cfg.device);                                                           \
+    if (!dev_guard_.ok) return fail(MP3GPU_ECUDA, "cudaSetDevice(ctx device) failed")
 
 extern "C" const char *mp3gpu_last_error(void) { return g_err; }
 extern "C" const char *mp3gpu_version(void) { return "mp3gpu 0.1 (sm_100a)"; }
@@ -404,6 +487,8 @@ static int upload_fft(const FftProgram &P, uint32_t **ops, int **lv, uint32_t **
     return 0;
 }
 
+static int create_body(mp3gpu_ctx *c);
+
 extern "C" int mp3gpu_create(const mp3gpu_config *cfg, mp3gpu_ctx **out)
 {
     if (!cfg || !out) return fail(MP3GPU_EINVAL, "null argument");
@@ -419,13 +504,34 @@ extern "C" int mp3gpu_create(const mp3gpu_config *cfg, mp3gpu_ctx **out)
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(MP3GPU_ECUDA, "no CUDA device: libmp3gpu has no CPU fallback");
-    CU(cudaSetDevice(cfg->device));
+    DeviceGuard guard(cfg->device);
+    if (!guard.ok) return fail(MP3GPU_ECUDA, "cudaSetDevice(%s) failed", std::to_string(cfg->device).c_str());
     mp3gpu_ctx *c = new (std::nothrow) mp3gpu_ctx();
     if (!c) return fail(MP3GPU_ENOMEM, "out of host memory");
     c->cfg = *cfg; c->sr = sr;
     if (cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, cfg->device) != cudaSuccess || c->sm_count < 1) c->sm_count = 148;
     frame_geometry(cfg->sfreq_hz, cfg->n_ch, cfg->bitrate_kbps, &c->geom);
     c->row = HIST + (long)cfg->max_frames * 1152;
+    int rc = create_body(c);
+    if (rc) { mp3gpu_destroy(c); return rc; }
+    *out = c;
+    return 0;
+}
+
+// allocate a device object and upload its host image; every CUDA call is checked
+template <class T>
+static int upload(T **dst, const T *src, size_t n = 1)
+{
+    int rc = dalloc(dst, n);
+    if (rc) return rc;
+    CU(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int create_body(mp3gpu_ctx *c)
+{
+    const mp3gpu_config *cfg = &c->cfg;
+    const int sr = c->sr;
     int rc = 0;
     // ---- tables ----
     {
@@ -434,73 +540,78 @@ extern "C" int mp3gpu_create(const mp3gpu_config *cfg, mp3gpu_ctx **out)
         cudaError_t e = cudaMemcpyToSymbol(c_front, F, sizeof(FrontTables));
         if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_front, F, sizeof(FrontTables));
         delete F;
-        if (e != cudaSuccess) { delete c; return fail(MP3GPU_ECUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString(e)); }
+        if (e != cudaSuccess) return fail(MP3GPU_ECUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString(e));
         PsyTables *P = new PsyTables;
         build_psy_tables(sr, P);
-        if (!(rc = dalloc(&c->d_psy_tab, 1))) cudaMemcpy(c->d_psy_tab, P, sizeof(PsyTables), cudaMemcpyHostToDevice);
+        rc = upload(&c->d_psy_tab, P);
         delete P;
+        if (rc) return rc;
         RateTables *R = new RateTables;
         build_rate_tables(sr, R);
-        if (!rc && !(rc = dalloc(&c->d_rate_tab, 1))) cudaMemcpy(c->d_rate_tab, R, sizeof(RateTables), cudaMemcpyHostToDevice);
+        rc = upload(&c->d_rate_tab, R);
         delete R;
+        if (rc) return rc;
         std::vector<FftTwiddle> tw; std::vector<int> base;
         build_fft_twiddles(&tw, &base);
         FftProgram P10, P8;
         build_fft_program(10, base, &P10);
         build_fft_program(8, base, &P8);
-        if (!rc && !(rc = dalloc(&c->d_tw, tw.size()))) cudaMemcpy(c->d_tw, tw.data(), tw.size() * sizeof(FftTwiddle), cudaMemcpyHostToDevice);
-        if (!rc) rc = upload_fft(P10, &c->d_ops1024, &c->d_lv1024, &c->d_out1024, &c->psy_dev.f1024);
-        if (!rc) rc = upload_fft(P8, &c->d_ops256, &c->d_lv256, &c->d_out256, &c->psy_dev.f256);
+        if ((rc = upload(&c->d_tw, tw.data(), tw.size()))) return rc;
+        if ((rc = upload_fft(P10, &c->d_ops1024, &c->d_lv1024, &c->d_out1024, &c->psy_dev.f1024))) return rc;
+        if ((rc = upload_fft(P8, &c->d_ops256, &c->d_lv256, &c->d_out256, &c->psy_dev.f256))) return rc;
         c->psy_dev.T = c->d_psy_tab; c->psy_dev.tw = c->d_tw;
         BitTables *B = new BitTables;
         build_bit_tables(sr, cfg->sfreq_hz, cfg->n_ch, cfg->bitrate_kbps, B);
         c->frame_bytes = B->frame_bytes; c->si_bytes = B->si_bytes;
-        if (!rc && !(rc = dalloc(&c->d_bit_tab, 1))) cudaMemcpy(c->d_bit_tab, B, sizeof(BitTables), cudaMemcpyHostToDevice);
+        rc = upload(&c->d_bit_tab, B);
         delete B;
+        if (rc) return rc;
         // main data reaches back at most 511 main-data bytes (9-bit main_data_begin)
         c->tail_frames = 511 / (c->frame_bytes - c->si_bytes) + 1;
         c->wstride = (((long)(c->tail_frames + cfg->max_frames) * c->frame_bytes + 15) / 16) * 16;
     }
     // ---- state + workspace ----
     const size_t S = cfg->max_streams, NCH = cfg->n_ch, GC = (size_t)cfg->max_frames * 2 * NCH;
-    if (!rc) rc = dalloc(&c->pcm_main.buf, S * NCH * c->row);
-    if (!rc) rc = dalloc(&c->d_psy_state, S * NCH);
-    if (!rc) rc = dalloc(&c->d_loop_state, S);
-    if (!rc) rc = dalloc(&c->d_lane_state, S);
-    if (!rc) rc = dalloc(&c->d_mid, S * GC);
-    if (!rc) rc = dalloc(&c->d_psyout, S * GC);
-    if (!rc) rc = dalloc(&c->d_xr, S * GC * 576);
-    if (!rc) rc = dalloc(&c->d_ix, S * GC * 576);
-    if (!rc) rc = dalloc(&c->d_gi, S * GC);
-    if (!rc) rc = dalloc(&c->d_sf, S * GC * 40);
-    if (!rc) rc = dalloc(&c->d_fo, S * (size_t)cfg->max_frames);
-    if (!rc) rc = dalloc(&c->d_win, S * (size_t)c->wstride);
-    if (!rc) rc = dalloc(&c->d_win_tmp, S * (size_t)c->tail_frames * c->frame_bytes);
-    if (!rc) rc = dalloc(&c->d_next_begin, S);
-    if (rc) { mp3gpu_destroy(c); return rc; }
-    // opt in to large dynamic shared memory
-    cudaFuncSetAttribute(k_psy_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PSYF_WARPS * sizeof(PsyFrontSmem)));
-    cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(512 * 8 + FRONT_WARPS * sizeof(FrontWarpSmem)));
-    cudaFuncSetAttribute(k_front_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontTileSmem));
-    cudaFuncSetAttribute(k_mdct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FRONT_WARPS * sizeof(FrontWarpSmem)));
-    cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES);
-    // all three hot kernels want several CTAs per SM out of shared memory: ask for the largest carve-out
-    cudaFuncSetAttribute(k_front_tile, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(k_psy_front, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(k_quantize_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES);
-    *out = c;
-    rc = mp3gpu_reset(c);
-    if (rc) { mp3gpu_destroy(c); *out = nullptr; return rc; }
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { mp3gpu_destroy(c); *out = nullptr; return fail(MP3GPU_ECUDA, "context init: %s", cudaGetErrorString(e)); }
-    return 0;
+    if ((rc = dalloc(&c->pcm_main.buf, S * NCH * c->row))) return rc;
+    if ((rc = dalloc(&c->d_psy_state, S * NCH))) return rc;
+    if ((rc = dalloc(&c->d_loop_state, S))) return rc;
+    if ((rc = dalloc(&c->d_lane_state, S))) return rc;
+    if ((rc = dalloc(&c->d_mid, S * GC))) return rc;
+    if ((rc = dalloc(&c->d_psyout, S * GC))) return rc;
+    if ((rc = dalloc(&c->d_xr, S * GC * 576))) return rc;
+    if ((rc = dalloc(&c->d_ix, S * GC * 576))) return rc;
+    if ((rc = dalloc(&c->d_gi, S * GC))) return rc;
+    if ((rc = dalloc(&c->d_sf, S * GC * 40))) return rc;
+    if ((rc = dalloc(&c->d_fo, S * (size_t)cfg->max_frames))) return rc;
+    if ((rc = dalloc(&c->d_win, S * (size_t)c->wstride))) return rc;
+    if ((rc = dalloc(&c->d_win_tmp, S * (size_t)c->tail_frames * c->frame_bytes))) return rc;
+    if ((rc = dalloc(&c->d_next_begin, S))) return rc;
+    if ((rc = dalloc(&c->d_total, S))) return rc;
+    if ((rc = dalloc(&c->d_nfr, S))) return rc;
+    if ((rc = dalloc(&c->d_sched, S + 1))) return rc;
+    c->h_total.assign(S, INT_MAX);
+    // opt in to large dynamic shared memory; all three hot kernels want the largest shared-memory carve-out
+    CU(cudaFuncSetAttribute(k_psy_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PSYF_WARPS * sizeof(PsyFrontSmem))));
+    CU(cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(512 * 8 + FRONT_WARPS * sizeof(FrontWarpSmem))));
+    CU(cudaFuncSetAttribute(k_front_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontTileSmem)));
+    CU(cudaFuncSetAttribute(k_mdct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FRONT_WARPS * sizeof(FrontWarpSmem))));
+    CU(cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_quantize_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_front_tile, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_psy_front, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    return mp3gpu_reset(c);
 }
 
 extern "C" void mp3gpu_destroy(mp3gpu_ctx *c)
 {
     if (!c) return;
-    void *ptrs[] = {c->d_psy_tab, c->d_rate_tab, c->d_ops1024, c->d_ops256, c->d_lv1024, c->d_lv256, c->d_out1024, c->d_out256,
+    DeviceGuard guard(c->cfg.device);
+    cudaDeviceSynchronize();          // nothing of this ctx may still be in flight when its buffers go
+    for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
+    void *ptrs[] = {c->d_total, c->d_nfr, c->d_sched,
+                    c->d_psy_tab, c->d_rate_tab, c->d_ops1024, c->d_ops256, c->d_lv1024, c->d_lv256, c->d_out1024, c->d_out256,
                     c->d_tw, c->pcm_main.buf, c->pcm_fb.buf, c->pcm_psy.buf, c->d_psy_state, c->d_loop_state, c->d_lane_state,
                     c->d_sb_prev, c->d_mid, c->d_psyout, c->d_xr, c->d_ix, c->d_gi, c->d_sf, c->d_fo,
                     c->d_bit_tab, c->d_win, c->d_win_tmp, c->d_next_begin};
@@ -520,20 +631,111 @@ extern "C" void mp3gpu_destroy(mp3gpu_ctx *c)
     delete c;
 }
 
+// every copy a pipelined delivery still has in flight must land before work enqueued on q after this point
+static int join_deliveries(mp3gpu_ctx *c, cudaStream_t q)
+{
+    for (int i = 0; i < 2; i++)
+        if (c->ev_landed[i]) CU(cudaStreamWaitEvent(q, c->ev_landed[i], 0));
+    return 0;
+}
+
+// forget all per-stream state, ordered on stream q behind everything the ctx has in flight on its private streams
+static int reset_on(mp3gpu_ctx *c, cudaStream_t q)
+{
+    const size_t S = c->cfg.max_streams, NCH = c->cfg.n_ch;
+    int rc = join_deliveries(c, q);
+    if (rc) return rc;
+    for (int i = 0; i < 2; i++)
+        if (c->ev_ready[i]) CU(cudaStreamWaitEvent(q, c->ev_ready[i], 0));      // host-PCM staging copies
+    CU(cudaMemsetAsync(c->pcm_main.buf, 0, S * NCH * c->row * sizeof(short), q));
+    if (c->pcm_fb.buf) CU(cudaMemsetAsync(c->pcm_fb.buf, 0, S * NCH * c->row * sizeof(short), q));
+    if (c->pcm_psy.buf) CU(cudaMemsetAsync(c->pcm_psy.buf, 0, S * NCH * c->row * sizeof(short), q));
+    if (c->d_sb_prev) CU(cudaMemsetAsync(c->d_sb_prev, 0, S * NCH * 576 * sizeof(double), q));
+    CU(cudaMemsetAsync(c->d_psy_state, 0, S * NCH * sizeof(PsyChanState), q));
+    CU(cudaMemsetAsync(c->d_loop_state, 0, S * sizeof(LoopStreamState), q));
+    CU(cudaMemsetAsync(c->d_lane_state, 0, S * sizeof(LoopLaneState), q));
+    CU(cudaMemsetAsync(c->d_win, 0, S * (size_t)c->wstride, q));
+    CU(cudaMemsetAsync(c->d_next_begin, 0, S * sizeof(int), q));
+    c->frames_done = 0;
+    c->frames_done_loop = 0;
+    c->have_total = false;
+    c->h_total.assign(S, INT_MAX);
+    return 0;
+}
+
+// Synchronous reset: waits for everything in flight on the ctx's device (any stream), clears, returns when cleared.
 extern "C" int mp3gpu_reset(mp3gpu_ctx *c)
 {
     if (!c) return fail(MP3GPU_EINVAL, "null ctx");
-    const size_t S = c->cfg.max_streams, NCH = c->cfg.n_ch;
-    CU(cudaMemset(c->pcm_main.buf, 0, S * NCH * c->row * sizeof(short)));
-    if (c->pcm_fb.buf) CU(cudaMemset(c->pcm_fb.buf, 0, S * NCH * c->row * sizeof(short)));
-    if (c->pcm_psy.buf) CU(cudaMemset(c->pcm_psy.buf, 0, S * NCH * c->row * sizeof(short)));
-    if (c->d_sb_prev) CU(cudaMemset(c->d_sb_prev, 0, S * NCH * 576 * sizeof(double)));
-    CU(cudaMemset(c->d_psy_state, 0, S * NCH * sizeof(PsyChanState)));
-    CU(cudaMemset(c->d_loop_state, 0, S * sizeof(LoopStreamState)));
-    CU(cudaMemset(c->d_lane_state, 0, S * sizeof(LoopLaneState)));
-    CU(cudaMemset(c->d_win, 0, S * (size_t)c->wstride));
-    CU(cudaMemset(c->d_next_begin, 0, S * sizeof(int)));
-    c->frames_done = 0;
+    DEV_GUARD(c);
+    CU(cudaDeviceSynchronize());
+    int rc = reset_on(c, nullptr);
+    if (rc) return rc;
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+
+// Stream-ordered reset: the clears are enqueued on `stream` behind the ctx's private copy streams; no host synchronisation.
+extern "C" int mp3gpu_reset_async(mp3gpu_ctx *c, void *stream)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    DEV_GUARD(c);
+    return reset_on(c, (cudaStream_t)stream);
+}
+
+// Restart `count` streams from stream `first` as NEW streams (zero signal history, psychoacoustic state, reservoir, byte
+// window) while the others keep theirs; ordered on `stream`.  The absolute frame position of the ctx (byte offsets of the
+// mp3 rows) is shared by all streams, so this is meant for the start of a batch or right after mp3gpu_begin_segment.
+extern "C" int mp3gpu_reset_streams(mp3gpu_ctx *c, int first, int count, void *stream)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    if (first < 0 || count < 1 || (long)first + count > c->cfg.max_streams) return fail(MP3GPU_EINVAL, "stream range out of bounds");
+    DEV_GUARD(c);
+    cudaStream_t q = (cudaStream_t)stream;
+    const size_t NCH = c->cfg.n_ch, rows = (size_t)count * NCH, r0 = (size_t)first * NCH, pitch = (size_t)c->row * sizeof(short);
+    short *bufs[3] = {c->pcm_main.buf, c->pcm_fb.buf, c->pcm_psy.buf};
+    for (short *b : bufs)
+        if (b) CU(cudaMemset2DAsync(b + r0 * c->row, pitch, 0, HIST * sizeof(short), rows, q));
+    if (c->d_sb_prev) CU(cudaMemsetAsync(c->d_sb_prev + r0 * 576, 0, rows * 576 * sizeof(double), q));
+    CU(cudaMemsetAsync(c->d_psy_state + r0, 0, rows * sizeof(PsyChanState), q));
+    CU(cudaMemsetAsync(c->d_loop_state + first, 0, (size_t)count * sizeof(LoopStreamState), q));
+    CU(cudaMemsetAsync(c->d_lane_state + first, 0, (size_t)count * sizeof(LoopLaneState), q));
+    CU(cudaMemsetAsync(c->d_win + (size_t)first * c->wstride, 0, (size_t)count * c->wstride, q));
+    CU(cudaMemsetAsync(c->d_next_begin + first, 0, (size_t)count * sizeof(int), q));
+    return 0;
+}
+
+// Per-stream lengths: stream s ends after frames[s] frames (counted from the last reset).  Calls keep the lockstep shape
+// [n_streams][n_frames]; frames of a stream beyond its end are ignored (their PCM is not read, nothing is written for them)
+// and mp3gpu_flush_mp3 reports each stream's own length.  frames == NULL removes the limits.  The reference encodes one
+// stream of any length per process (musicin.c:585: the frame loop runs until get_audio() returns 0).
+extern "C" int mp3gpu_set_stream_frames(mp3gpu_ctx *c, int n_streams, const long *frames, void *stream)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    if (n_streams < 1 || n_streams > c->cfg.max_streams) return fail(MP3GPU_EINVAL, "bad n_streams");
+    DEV_GUARD(c);
+    c->h_total.assign((size_t)c->cfg.max_streams, INT_MAX);
+    c->have_total = frames != nullptr;
+    if (!frames) return 0;
+    for (int s = 0; s < n_streams; s++) {
+        if (frames[s] < 0) return fail(MP3GPU_EINVAL, "negative stream length");
+        c->h_total[s] = frames[s] > INT_MAX ? INT_MAX : (int)frames[s];
+    }
+    cudaStream_t q = (cudaStream_t)stream;
+    CU(cudaMemcpyAsync(c->d_total, c->h_total.data(), c->h_total.size() * sizeof(int), cudaMemcpyHostToDevice, q));
+    CU(cudaStreamSynchronize(q));     // h_total is pageable and may change before an asynchronous copy would read it
+    return 0;
+}
+
+// the frames each stream contributes to a call starting at absolute frame `done` (nullptr: all of them, no limits set)
+static int call_frames(mp3gpu_ctx *c, long done, int n_streams, int n_frames, cudaStream_t q, const int **nfr)
+{
+    *nfr = nullptr;
+    if (!c->have_total) return 0;
+    k_call_frames<<<(unsigned)((n_streams + 255) / 256), 256, 0, q>>>(c->d_total, done, n_frames, n_streams, c->d_nfr);
+    c->launches++;
+    CU(cudaGetLastError());
+    *nfr = c->d_nfr;
     return 0;
 }
 
@@ -548,6 +750,7 @@ extern "C" int mp3gpu_profile_enable(mp3gpu_ctx *c, int on)
 extern "C" int mp3gpu_profile_collect(mp3gpu_ctx *c, double ms[MP3GPU_N_KERNELS], long launches[MP3GPU_N_KERNELS], int reset)
 {
     if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    DEV_GUARD(c);
     CU(cudaDeviceSynchronize());
     for (size_t i = 0; i < c->prof_kind.size(); i++) {
         float t = 0.f;
@@ -555,7 +758,7 @@ extern "C" int mp3gpu_profile_collect(mp3gpu_ctx *c, double ms[MP3GPU_N_KERNELS]
             c->prof_ms[c->prof_kind[i]] += t;
             c->prof_n[c->prof_kind[i]]++;
         }
-        cudaEventDestroy(c->prof_ev[2 * i]); cudaEventDestroy(c->prof_ev[2 * i + 1]);
+        c->prof_pool.push_back(c->prof_ev[2 * i]); c->prof_pool.push_back(c->prof_ev[2 * i + 1]);
     }
     c->prof_ev.clear(); c->prof_kind.clear();
     for (int k = 0; k < MP3GPU_N_KERNELS; k++) {
@@ -577,6 +780,7 @@ extern "C" int mp3gpu_frame_geometry(const mp3gpu_ctx *c, int *bits_per_frame, i
 extern "C" int mp3gpu_sync(mp3gpu_ctx *c, void *stream)
 {
     if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    DEV_GUARD(c);
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
 }
@@ -661,14 +865,6 @@ extern "C" int mp3gpu_set_host_delivery(mp3gpu_ctx *c, int mode)
     return 0;
 }
 
-// every copy a pipelined delivery still has in flight must land before work enqueued on q after this point
-static int join_deliveries(mp3gpu_ctx *c, cudaStream_t q)
-{
-    for (int i = 0; i < 2; i++)
-        if (c->ev_landed[i]) CU(cudaStreamWaitEvent(q, c->ev_landed[i], 0));
-    return 0;
-}
-
 static int roll_pcm(mp3gpu_ctx *c, PcmStage &st, int n_streams, int n_frames, cudaStream_t q)
 {
     k_roll_history<<<(unsigned)(n_streams * c->cfg.n_ch), 256, 0, q>>>(st.buf, c->row, (long)n_streams * c->cfg.n_ch, n_frames * 1152);
@@ -690,7 +886,7 @@ static int pick_tile(int n_streams, int n_ch, int n_gran)
 }
 
 static int launch_front(mp3gpu_ctx *c, const short *pcm_rows, const PsyOut *psy, int n_streams, int n_frames, double *xr, double *sb,
-                        bool do_mdct, cudaStream_t q)
+                        bool do_mdct, cudaStream_t q, const int *nfr = nullptr)
 {
     const int n_gran = 2 * n_frames, n_ch = c->cfg.n_ch;
     if (do_mdct && !sb) {  // production path: tiled kernel (front_tile.cuh)
@@ -698,7 +894,7 @@ static int launch_front(mp3gpu_ctx *c, const short *pcm_rows, const PsyOut *psy,
         const long ctas = (long)n_streams * n_ch * n_tiles;
         prof_begin(c, MP3GPU_K_FRONT, q);
         const long grid = (FT_PERSISTENT && ctas > 2L * c->sm_count) ? 2L * c->sm_count : ctas;
-        k_front_tile<<<(unsigned)grid, FT_THREADS, sizeof(FrontTileSmem), q>>>(pcm_rows, c->row * n_ch, c->row, HIST, n_streams, n_ch, n_gran, ctas, psy, xr);
+        k_front_tile<<<(unsigned)grid, FT_THREADS, sizeof(FrontTileSmem), q>>>(pcm_rows, c->row * n_ch, c->row, HIST, n_streams, n_ch, n_gran, ctas, nfr, psy, xr);
         prof_end(c, q);
         c->launches++;
         CU(cudaGetLastError());
@@ -717,33 +913,47 @@ static int launch_front(mp3gpu_ctx *c, const short *pcm_rows, const PsyOut *psy,
     return 0;
 }
 
-static int launch_psy(mp3gpu_ctx *c, const short *pcm_rows, int n_streams, int n_frames, PsyOut *psy, cudaStream_t q)
+static int launch_psy(mp3gpu_ctx *c, const short *pcm_rows, int n_streams, int n_frames, PsyOut *psy, cudaStream_t q, const int *nfr = nullptr)
 {
     const int n_gran = 2 * n_frames, n_ch = c->cfg.n_ch;
     const long gcs = (long)n_streams * n_gran * n_ch;
     prof_begin(c, MP3GPU_K_PSY_FRONT, q);
     k_psy_front<<<(unsigned)((gcs + PSYF_WARPS - 1) / PSYF_WARPS), PSYF_WARPS * 32, PSYF_WARPS * sizeof(PsyFrontSmem), q>>>(
-        c->psy_dev, pcm_rows, c->row * n_ch, c->row, n_streams, n_ch, n_gran, c->d_mid);
+        c->psy_dev, pcm_rows, c->row * n_ch, c->row, n_streams, n_ch, n_gran, nfr, c->d_mid);
     prof_end(c, q);
     c->launches++;
     CU(cudaGetLastError());
     const long chans = (long)n_streams * n_ch;
     prof_begin(c, MP3GPU_K_PSY_SCAN, q);
     k_psy_scan<<<(unsigned)((chans + PSYS_WARPS - 1) / PSYS_WARPS), PSYS_WARPS * 32, PSYS_WARPS * sizeof(PsyScanSmem), q>>>(
-        c->d_psy_tab, c->d_mid, c->d_psy_state, n_streams, n_ch, n_gran, psy);
+        c->d_psy_tab, c->d_mid, c->d_psy_state, n_streams, n_ch, n_gran, nfr, psy);
     prof_end(c, q);
     c->launches++;
     CU(cudaGetLastError());
     return 0;
 }
 
-static int launch_rate_loop(mp3gpu_ctx *c, const double *xr, const PsyOut *psy, int n_streams, int n_frames, short *ix, GrInfoOut *gi,
-                            unsigned char *sf, FrameOut *fo, cudaStream_t q)
+// warps per CTA of the persistent rate loop: the streams are spread over all SMs, at most RL_WARPS per SM
+static int rate_loop_warps(const mp3gpu_ctx *c, int n_streams, unsigned *grid)
 {
-    const unsigned grid = (unsigned)((n_streams + RL_WARPS - 1) / RL_WARPS);
+    int wpc = (n_streams + c->sm_count - 1) / c->sm_count;
+    if (wpc > RL_WARPS) wpc = RL_WARPS;
+    if (wpc < 1) wpc = 1;
+    long ctas = ((long)n_streams + wpc - 1) / wpc;
+    if (ctas > c->sm_count) ctas = c->sm_count;
+    *grid = (unsigned)ctas;
+    return wpc;
+}
+
+static int launch_rate_loop(mp3gpu_ctx *c, const double *xr, const PsyOut *psy, int n_streams, int n_frames, short *ix, GrInfoOut *gi,
+                            unsigned char *sf, FrameOut *fo, cudaStream_t q, const int *nfr = nullptr)
+{
+    unsigned grid;
+    const int wpc = rate_loop_warps(c, n_streams, &grid);
+    CU(cudaMemsetAsync(c->d_sched, 0, ((size_t)n_streams + 1) * sizeof(int), q));
     prof_begin(c, MP3GPU_K_RATE_LOOP, q);
-    k_rate_loop<<<grid, RL_WARPS * 32, RL_SMEM_BYTES, q>>>(c->d_rate_tab, c->geom, c->d_loop_state, c->d_lane_state,
-                                                                                n_streams, n_frames, xr, psy, ix, gi, sf, fo);
+    k_rate_loop<<<grid, wpc * 32, RL_HOT_BYTES + wpc * sizeof(RateWarpSmem), q>>>(c->d_rate_tab, c->geom, c->d_loop_state, c->d_lane_state,
+                                                                                  n_streams, n_frames, nfr, c->d_sched, xr, psy, ix, gi, sf, fo);
     prof_end(c, q);
     c->launches++;
     CU(cudaGetLastError());
@@ -751,7 +961,7 @@ static int launch_rate_loop(mp3gpu_ctx *c, const double *xr, const PsyOut *psy, 
 }
 
 static int encode_common(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, int16_t *ix, mp3gpu_gr_info *gi, uint8_t *sf,
-                         mp3gpu_frame_out *fo, void *stream, bool host)
+                         mp3gpu_frame_out *fo, void *stream, bool host, const int **nfr_out = nullptr)
 {
     int rc = check_shape(c, n_streams, n_frames);
     if (rc) return rc;
@@ -761,15 +971,19 @@ static int encode_common(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n
     if (host) rc = stage_pcm_host_overlapped(c, pcm, n_streams, n_frames, q);
     else rc = stage_pcm_dev(c, pcm, n_streams, n_frames, q);
     if (rc) return rc;
+    const int *nfr = nullptr;
+    if ((rc = call_frames(c, c->frames_done_loop, n_streams, n_frames, q, &nfr))) return rc;
+    if (nfr_out) *nfr_out = nfr;
     // musicin.c:751-779 order: psy first (it decides block_type), then filterbank + MDCT, then the rate loop
-    if ((rc = launch_psy(c, c->pcm_main.buf, n_streams, n_frames, c->d_psyout, q))) return rc;
-    if ((rc = launch_front(c, c->pcm_main.buf, c->d_psyout, n_streams, n_frames, c->d_xr, nullptr, true, q))) return rc;
+    if ((rc = launch_psy(c, c->pcm_main.buf, n_streams, n_frames, c->d_psyout, q, nfr))) return rc;
+    if ((rc = launch_front(c, c->pcm_main.buf, c->d_psyout, n_streams, n_frames, c->d_xr, nullptr, true, q, nfr))) return rc;
     short *o_ix = host ? c->d_ix : (ix ? ix : c->d_ix);
     GrInfoOut *o_gi = host ? c->d_gi : (gi ? (GrInfoOut *)gi : c->d_gi);
     unsigned char *o_sf = host ? c->d_sf : (sf ? sf : c->d_sf);
     FrameOut *o_fo = host ? c->d_fo : (fo ? (FrameOut *)fo : c->d_fo);
-    if ((rc = launch_rate_loop(c, c->d_xr, c->d_psyout, n_streams, n_frames, o_ix, o_gi, o_sf, o_fo, q))) return rc;
+    if ((rc = launch_rate_loop(c, c->d_xr, c->d_psyout, n_streams, n_frames, o_ix, o_gi, o_sf, o_fo, q, nfr))) return rc;
     if ((rc = roll_pcm(c, c->pcm_main, n_streams, n_frames, q))) return rc;
+    c->frames_done_loop += n_frames;
     if (host) {
         if (ix) CU(cudaMemcpyAsync(ix, c->d_ix, gcs * 576 * sizeof(short), cudaMemcpyDeviceToHost, q));
         if (gi) CU(cudaMemcpyAsync(gi, c->d_gi, gcs * sizeof(GrInfoOut), cudaMemcpyDeviceToHost, q));
@@ -784,7 +998,7 @@ static int encode_common(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n
 // buffer (absolute file positions), then slides the window.  After the call window byte 0 corresponds to
 // absolute byte (frames_done - tail_frames) * FB.
 static int format_common(mp3gpu_ctx *c, const short *ix, const GrInfoOut *gi, const unsigned char *sf, const FrameOut *fo, int n_streams,
-                         int n_frames, uint8_t *mp3, long stride, bool host, cudaStream_t q)
+                         int n_frames, uint8_t *mp3, long stride, bool host, cudaStream_t q, const int *nfr)
 {
     const long FB = c->frame_bytes, T = c->tail_frames;
     if (mp3 && stride < (c->frames_done + n_frames) * FB) return fail(MP3GPU_EINVAL, "mp3 stride too small for the frames encoded so far");
@@ -795,9 +1009,9 @@ static int format_common(mp3gpu_ctx *c, const short *ix, const GrInfoOut *gi, co
     CU(cudaMemset2DAsync(c->d_win + T * FB, c->wstride, 0, (size_t)n_frames * FB, n_streams, q));
     prof_begin(c, MP3GPU_K_BITSTREAM, q);
     const long frames = (long)n_streams * n_frames;
-    k_bits_headers<<<(unsigned)((frames + 127) / 128), 128, 0, q>>>(c->d_bit_tab, G, gi, fo, c->d_win, c->d_next_begin);
+    k_bits_headers<<<(unsigned)((frames + 127) / 128), 128, 0, q>>>(c->d_bit_tab, G, nfr, gi, fo, c->d_win, c->d_next_begin);
     const long gcs = frames * 2 * c->cfg.n_ch;
-    k_bits_emit<<<(unsigned)((gcs + BITS_WARPS - 1) / BITS_WARPS), BITS_WARPS * 32, 0, q>>>(c->d_bit_tab, G, ix, gi, sf, fo, c->d_win);
+    k_bits_emit<<<(unsigned)((gcs + BITS_WARPS - 1) / BITS_WARPS), BITS_WARPS * 32, 0, q>>>(c->d_bit_tab, G, nfr, ix, gi, sf, fo, c->d_win);
     prof_end(c, q);
     c->launches += 2;
     CU(cudaGetLastError());
@@ -816,9 +1030,10 @@ static int format_common(mp3gpu_ctx *c, const short *ix, const GrInfoOut *gi, co
             }
             const int t = c->d2h_turn;
             c->d2h_turn ^= 1;
-            // q waits for the copy that last used this staging buffer (two calls ago: long done) — which is also what makes
-            // the bytes of call i-2 ordered before anything enqueued on q from here on; call i-1 is joined by the next call
-            CU(cudaStreamWaitEvent(q, c->ev_landed[t], 0));
+            // q waits for BOTH copies still in flight: the one that last used this staging buffer (call i-2) and the one of
+            // call i-1 — the contract in mp3gpu.h: the bytes of a call have landed once the next call's work on its stream has
+            // completed.  The wait sits behind this call's kernels, so the copy of call i-1 still overlaps them.
+            { int rcj = join_deliveries(c, q); if (rcj) return rcj; }
             CU(cudaMemcpy2DAsync(c->d2h_stage[t], (size_t)width, c->d_win + skip, (size_t)c->wstride, (size_t)width, n_streams,
                                  cudaMemcpyDeviceToDevice, q));
             CU(cudaEventRecord(c->ev_staged[t], q));
@@ -841,6 +1056,7 @@ static int flush_common(mp3gpu_ctx *c, int n_streams, uint8_t *mp3, long stride,
 {
     if (!c) return fail(MP3GPU_EINVAL, "null ctx");
     if (n_streams < 1 || n_streams > c->cfg.max_streams) return fail(MP3GPU_EINVAL, "bad n_streams");
+    DEV_GUARD(c);
     const long FB = c->frame_bytes, T = c->tail_frames;
     const long origin = (c->frames_done - T) * FB, skip = origin < 0 ? -origin : 0, width = T * FB - skip;
     if (mp3 && stride < c->frames_done * FB) return fail(MP3GPU_EINVAL, "mp3 stride too small");
@@ -855,7 +1071,10 @@ static int flush_common(mp3gpu_ctx *c, int n_streams, uint8_t *mp3, long stride,
         // BF_FlushBitstream (formatBitstream.c:87-125) zero-fills main data for every header still queued, i.e. whole
         // frame capacities: the write position keeps its offset inside the frame, so the last frame ends up short by
         // (bytes still in the reservoir) mod (main-data bytes per frame)
-        for (int s = 0; s < n_streams; s++) lengths[s] = c->frames_done * FB - nb[s] % (FB - c->si_bytes);
+        for (int s = 0; s < n_streams; s++) {
+            const long fr = c->h_total[s] < c->frames_done ? (long)c->h_total[s] : c->frames_done;     // the stream's own frame count
+            lengths[s] = fr * FB - nb[s] % (FB - c->si_bytes);
+        }
     }
     return 0;
 }
@@ -865,12 +1084,15 @@ static int flush_common(mp3gpu_ctx *c, int n_streams, uint8_t *mp3, long stride,
 extern "C" int mp3gpu_begin_segment(mp3gpu_ctx *c, void *stream)
 {
     if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    DEV_GUARD(c);
     cudaStream_t q = (cudaStream_t)stream;
+    { int rcj = join_deliveries(c, q); if (rcj) return rcj; }     // the window is about to be cleared: pipelined copies of it must have landed
     static_assert(offsetof(LoopStreamState, resv_size) == 0, "resv_size must lead LoopStreamState");
     CU(cudaMemset2DAsync(c->d_loop_state, sizeof(LoopStreamState), 0, sizeof(int), (size_t)c->cfg.max_streams, q));
     CU(cudaMemsetAsync(c->d_win, 0, (size_t)c->cfg.max_streams * c->wstride, q));
     CU(cudaMemsetAsync(c->d_next_begin, 0, (size_t)c->cfg.max_streams * sizeof(int), q));
     c->frames_done = 0;
+    c->frames_done_loop = 0;          // stream lengths (mp3gpu_set_stream_frames) count from the segment start
     return 0;
 }
 
@@ -879,7 +1101,8 @@ extern "C" int mp3gpu_begin_segment(mp3gpu_ctx *c, void *stream)
 extern "C" int mp3gpu_stream_wave(int device)
 {
     int sms = 0, ctas = 0;
-    if (cudaSetDevice(device) != cudaSuccess) return fail(MP3GPU_ECUDA, "cudaSetDevice failed");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(MP3GPU_ECUDA, "cudaSetDevice failed");
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return fail(MP3GPU_ECUDA, "no device attribute");
     cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_rate_loop, RL_WARPS * 32, RL_SMEM_BYTES) != cudaSuccess || ctas < 1)
@@ -901,7 +1124,10 @@ extern "C" int mp3gpu_format_bitstream_batch(mp3gpu_ctx *c, const int16_t *ix, c
     int rc = check_shape(c, n_streams, n_frames);
     if (rc) return rc;
     if (!ix || !gi || !sf || !fo) return fail(MP3GPU_EINVAL, "null pointer");
-    return format_common(c, ix, (const GrInfoOut *)gi, sf, (const FrameOut *)fo, n_streams, n_frames, mp3, mp3_stride, false, (cudaStream_t)stream);
+    DEV_GUARD(c);
+    const int *nfr = nullptr;
+    if ((rc = call_frames(c, c->frames_done, n_streams, n_frames, (cudaStream_t)stream, &nfr))) return rc;
+    return format_common(c, ix, (const GrInfoOut *)gi, sf, (const FrameOut *)fo, n_streams, n_frames, mp3, mp3_stride, false, (cudaStream_t)stream, nfr);
 }
 
 static int encode_mp3_common(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, uint8_t *mp3, long stride, void *stream, bool host)
@@ -911,9 +1137,12 @@ static int encode_mp3_common(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, i
     // validate before any stream state advances
     if (mp3 && stride < (c->frames_done + n_frames) * (long)c->frame_bytes)
         return fail(MP3GPU_EINVAL, "mp3 stride too small for the frames encoded so far");
-    rc = encode_common(c, pcm, n_streams, n_frames, nullptr, nullptr, nullptr, nullptr, stream, host);
+    DEV_GUARD(c);
+    if (c->frames_done_loop != c->frames_done) return fail(MP3GPU_ESTATE, "mp3 and non-mp3 encode calls mixed on one ctx without a reset");
+    const int *nfr = nullptr;
+    rc = encode_common(c, pcm, n_streams, n_frames, nullptr, nullptr, nullptr, nullptr, stream, host, &nfr);
     if (rc) return rc;
-    return format_common(c, c->d_ix, c->d_gi, c->d_sf, c->d_fo, n_streams, n_frames, mp3, stride, host, (cudaStream_t)stream);
+    return format_common(c, c->d_ix, c->d_gi, c->d_sf, c->d_fo, n_streams, n_frames, mp3, stride, host, (cudaStream_t)stream, nfr);
 }
 
 extern "C" int mp3gpu_encode_frames_mp3(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, uint8_t *mp3, long mp3_stride, void *stream)
@@ -940,12 +1169,16 @@ extern "C" int mp3gpu_flush_mp3_dev(mp3gpu_ctx *c, int n_streams, uint8_t *mp3, 
 extern "C" int mp3gpu_encode_frames(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, int16_t *ix, mp3gpu_gr_info *gi,
                                     uint8_t *sf, mp3gpu_frame_out *fo, void *stream)
 {
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    DEV_GUARD(c);
     return encode_common(c, pcm, n_streams, n_frames, ix, gi, sf, fo, stream, true);
 }
 
 extern "C" int mp3gpu_encode_frames_dev(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, int16_t *ix, mp3gpu_gr_info *gi,
                                         uint8_t *sf, mp3gpu_frame_out *fo, void *stream)
 {
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    DEV_GUARD(c);
     return encode_common(c, pcm, n_streams, n_frames, ix, gi, sf, fo, stream, false);
 }
 
@@ -954,6 +1187,7 @@ extern "C" int mp3gpu_filter_subband_batch(mp3gpu_ctx *c, const int16_t *pcm, in
     int rc = check_shape(c, n_streams, n_frames);
     if (rc) return rc;
     if (!pcm || !sb) return fail(MP3GPU_EINVAL, "null pointer");
+    DEV_GUARD(c);
     cudaStream_t q = (cudaStream_t)stream;
     if ((rc = stage_pcm(c, c->pcm_fb, pcm, n_streams, n_frames, cudaMemcpyDeviceToDevice, q))) return rc;
     if ((rc = launch_front(c, c->pcm_fb.buf, nullptr, n_streams, n_frames, nullptr, sb, false, q))) return rc;
@@ -966,6 +1200,7 @@ extern "C" int mp3gpu_subband_mdct_batch(mp3gpu_ctx *c, const int16_t *pcm, cons
     int rc = check_shape(c, n_streams, n_frames);
     if (rc) return rc;
     if (!pcm || !psy || !xr) return fail(MP3GPU_EINVAL, "null pointer");
+    DEV_GUARD(c);
     cudaStream_t q = (cudaStream_t)stream;
     if ((rc = stage_pcm(c, c->pcm_fb, pcm, n_streams, n_frames, cudaMemcpyDeviceToDevice, q))) return rc;
     if ((rc = launch_front(c, c->pcm_fb.buf, (const PsyOut *)psy, n_streams, n_frames, xr, nullptr, true, q))) return rc;
@@ -978,6 +1213,7 @@ extern "C" int mp3gpu_mdct_sub_batch(mp3gpu_ctx *c, const double *sb, const mp3g
     int rc = check_shape(c, n_streams, n_frames);
     if (rc) return rc;
     if (!sb || !psy || !xr) return fail(MP3GPU_EINVAL, "null pointer");
+    DEV_GUARD(c);
     cudaStream_t q = (cudaStream_t)stream;
     if (!c->d_sb_prev) {
         const size_t n = (size_t)c->cfg.max_streams * c->cfg.n_ch * 576;
@@ -997,6 +1233,7 @@ extern "C" int mp3gpu_L3psycho_anal_batch(mp3gpu_ctx *c, const int16_t *pcm, int
     int rc = check_shape(c, n_streams, n_frames);
     if (rc) return rc;
     if (!pcm || !psy) return fail(MP3GPU_EINVAL, "null pointer");
+    DEV_GUARD(c);
     cudaStream_t q = (cudaStream_t)stream;
     if ((rc = stage_pcm(c, c->pcm_psy, pcm, n_streams, n_frames, cudaMemcpyDeviceToDevice, q))) return rc;
     if ((rc = launch_psy(c, c->pcm_psy.buf, n_streams, n_frames, (PsyOut *)psy, q))) return rc;
@@ -1009,6 +1246,7 @@ extern "C" int mp3gpu_iteration_loop_batch(mp3gpu_ctx *c, const double *xr, cons
     int rc = check_shape(c, n_streams, n_frames);
     if (rc) return rc;
     if (!xr || !psy || !ix || !gi || !sf || !fo) return fail(MP3GPU_EINVAL, "null pointer");
+    DEV_GUARD(c);
     return launch_rate_loop(c, xr, (const PsyOut *)psy, n_streams, n_frames, ix, (GrInfoOut *)gi, sf, (FrameOut *)fo, (cudaStream_t)stream);
 }
 
@@ -1017,6 +1255,7 @@ extern "C" int mp3gpu_quantize_count_batch(mp3gpu_ctx *c, const double *xr_abs, 
 {
     if (!c) return fail(MP3GPU_EINVAL, "null ctx");
     if (n < 1 || !xr_abs || !q || !block_type || !ix || !gi || !bits) return fail(MP3GPU_EINVAL, "bad argument");
+    DEV_GUARD(c);
     k_quantize_count<<<(unsigned)((n + RL_WARPS - 1) / RL_WARPS), RL_WARPS * 32, RL_SMEM_BYTES, (cudaStream_t)stream>>>(
         c->d_rate_tab, xr_abs, q, block_type, n, ix, (GrInfoOut *)gi, bits, 0);
     c->launches++;
@@ -1029,6 +1268,7 @@ extern "C" int mp3gpu_count_bits_batch(mp3gpu_ctx *c, const int16_t *ix, const i
 {
     if (!c) return fail(MP3GPU_EINVAL, "null ctx");
     if (n < 1 || !ix || !block_type || !gi || !bits) return fail(MP3GPU_EINVAL, "bad argument");
+    DEV_GUARD(c);
     k_quantize_count<<<(unsigned)((n + RL_WARPS - 1) / RL_WARPS), RL_WARPS * 32, RL_SMEM_BYTES, (cudaStream_t)stream>>>(
         c->d_rate_tab, nullptr, nullptr, block_type, n, const_cast<int16_t *>(ix), (GrInfoOut *)gi, bits, 1);
     c->launches++;

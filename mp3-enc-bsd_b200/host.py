@@ -36,7 +36,8 @@ EXPORTS = ["mp3gpu_last_error", "mp3gpu_version", "mp3gpu_create", "mp3gpu_destr
            "mp3gpu_L3psycho_anal_batch", "mp3gpu_iteration_loop_batch", "mp3gpu_quantize_count_batch",
            "mp3gpu_kernel_launches", "mp3gpu_profile_enable", "mp3gpu_profile_collect",
            "mp3gpu_encode_frames_mp3", "mp3gpu_encode_frames_mp3_dev", "mp3gpu_flush_mp3", "mp3gpu_flush_mp3_dev",
-           "mp3gpu_frame_bytes", "mp3gpu_format_bitstream_batch", "mp3gpu_begin_segment", "mp3gpu_stream_wave", "mp3gpu_set_pcm_layout", "mp3gpu_count_bits_batch", "mp3gpu_set_host_delivery"]
+           "mp3gpu_frame_bytes", "mp3gpu_format_bitstream_batch", "mp3gpu_begin_segment", "mp3gpu_stream_wave", "mp3gpu_set_pcm_layout", "mp3gpu_count_bits_batch", "mp3gpu_set_host_delivery",
+           "mp3gpu_reset_async", "mp3gpu_set_stream_frames", "mp3gpu_reset_streams"]
 LEGACY_EXPORTS = ["window_subband", "filter_subband", "mdct_sub", "L3psycho_anal", "iteration_loop", "quantize", "count_bits",
                   "mp3gpu_legacy_reset", "mp3gpu_legacy_kernel_launches"]
 KERNEL_NAMES = ["psy_front", "psy_scan", "front_polyphase_mdct", "rate_loop", "bitstream"]
@@ -71,6 +72,9 @@ def load_library():
         lib.mp3gpu_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
         lib.mp3gpu_destroy.argtypes = [C.c_void_p]
         lib.mp3gpu_reset.argtypes = [C.c_void_p]
+        lib.mp3gpu_reset_async.argtypes = [C.c_void_p, C.c_void_p]
+        lib.mp3gpu_set_stream_frames.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_long), C.c_void_p]
+        lib.mp3gpu_reset_streams.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.mp3gpu_sync.argtypes = [C.c_void_p, C.c_void_p]
         lib.mp3gpu_frame_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         vp = C.c_void_p
@@ -142,8 +146,26 @@ class Encoder:
         if rc != 0:
             raise Mp3GpuError(f"{what} failed ({rc}): {self.lib.mp3gpu_last_error().decode()}")
 
-    def reset(self):
-        self._check(self.lib.mp3gpu_reset(self.ctx), "mp3gpu_reset")
+    def reset(self, stream=None):
+        """forget all per-stream state.  Without `stream`: synchronous (waits for the device, mp3gpu_reset); with a stream:
+        ordered on that stream without blocking the host (mp3gpu_reset_async)."""
+        if stream is None:
+            self._check(self.lib.mp3gpu_reset(self.ctx), "mp3gpu_reset")
+        else:
+            self._check(self.lib.mp3gpu_reset_async(self.ctx, C.c_void_p(stream or 0)), "mp3gpu_reset_async")
+
+    def reset_streams(self, first, count, stream=None):
+        """restart streams [first, first+count) as new streams; the others keep their state (mp3gpu.h)"""
+        self._check(self.lib.mp3gpu_reset_streams(self.ctx, int(first), int(count), C.c_void_p(stream or 0)), "mp3gpu_reset_streams")
+
+    def set_stream_frames(self, frames, stream=None):
+        """per-stream lengths in frames, counted from the last reset (None: no limits); see mp3gpu.h"""
+        if frames is None:
+            rc = self.lib.mp3gpu_set_stream_frames(self.ctx, 1, None, C.c_void_p(stream or 0))
+        else:
+            arr = (C.c_long * len(frames))(*[int(f) for f in frames])
+            rc = self.lib.mp3gpu_set_stream_frames(self.ctx, len(frames), arr, C.c_void_p(stream or 0))
+        self._check(rc, "mp3gpu_set_stream_frames")
 
     @property
     def kernel_launches(self):
@@ -264,10 +286,11 @@ class Encoder:
         """segment seam: keep the signal history, empty the bit reservoir, restart the byte stream (mp3gpu.h)"""
         self._check(self.lib.mp3gpu_begin_segment(self.ctx, C.c_void_p(stream or 0)), "mp3gpu_begin_segment")
 
-    def encode_streams(self, pcm, chunk_frames=None):
+    def encode_streams(self, pcm, chunk_frames=None, n_samples=None):
         """Whole streams in one go (HOST numpy): pcm int16 [S][n_ch][n] (zero-padded to whole frames like
         get_audio(), encode.c:162-166) -> list of S `bytes`, each what the reference CLI writes for that stream
-        except the one spurious byte close_bit_stream_w() appends."""
+        except the one spurious byte close_bit_stream_w() appends.  n_samples: per-stream sample counts (streams of
+        different lengths in one batch, mp3gpu_set_stream_frames); the rows of pcm are zero beyond them."""
         pcm = np.ascontiguousarray(pcm, dtype=np.int16)
         S, n_ch, n = pcm.shape
         F = (n + 1151) // 1152
@@ -278,6 +301,8 @@ class Encoder:
         chunk = min(chunk_frames or self.cfg.max_frames, self.cfg.max_frames)
         mp3 = np.zeros((S, F * self.frame_bytes), np.uint8)
         self.reset()
+        if n_samples is not None:
+            self.set_stream_frames([(int(k) + 1151) // 1152 for k in n_samples])
         for f0 in range(0, F, chunk):
             f1 = min(F, f0 + chunk)
             self.encode_frames_mp3(np.ascontiguousarray(pcm[:, :, f0 * 1152:f1 * 1152]), mp3)
@@ -364,36 +389,36 @@ def read_pcm_file(path, samples_per_read=2304):
 def encode_files(paths, sfreq=44100, n_ch=2, bitrate=128, device=0, chunk_frames=32):
     """Batch-encode PCM files of one format (WAV or raw, see read_pcm_file) to MPEG-1 Layer III byte streams on one
     GPU: the batched equivalent of running the reference CLI once per file (minus the spurious last byte of
-    close_bit_stream_w, see mp3gpu.h).  Shorter files are zero-padded to the longest one for the lock-step batch and
-    cut back to their own frame count afterwards (trailing silence never influences earlier frames; the cut follows
-    BF_FlushBitstream like the reference: mp3gpu_flush semantics applied per file)."""
+    close_bit_stream_w, see mp3gpu.h).  Files of any mix of lengths share ONE ctx: every stream gets its own frame
+    count (mp3gpu_set_stream_frames; the last frame is zero-filled as in encode.c:162-166), ends there, and is cut by
+    mp3gpu_flush_mp3 exactly as BF_FlushBitstream cuts a stream encoded alone."""
     pcms = [read_pcm_file(p, 1152 * n_ch) for p in paths]
-    frames = [(len(x) + 1152 * n_ch - 1) // (1152 * n_ch) for x in pcms]   # the last frame is zero-filled (encode.c:162-166)
-    out = [None] * len(paths)
-    # files with equal frame counts share a batch (the reservoir cut at the end of a stream needs the true last frame)
-    groups = {}
-    for i, f in enumerate(frames):
-        groups.setdefault(f, []).append(i)
-    for F, idx in sorted(groups.items()):
-        if F == 0:
-            for i in idx:
-                out[i] = b""
-            continue
-        batch = np.zeros((len(idx), F * 1152 * n_ch), np.int16)
-        for k, i in enumerate(idx):
-            batch[k, :len(pcms[i])] = pcms[i]
-        batch = batch.reshape(len(idx), F * 1152, n_ch)
-        enc = Encoder(sfreq, n_ch, bitrate, max_streams=len(idx), max_frames=min(chunk_frames, F), device=device)
-        enc.set_pcm_layout(True)
-        mp3 = np.zeros((len(idx), F * enc.frame_bytes), np.uint8)
-        step = enc.cfg.max_frames
-        for f0 in range(0, F, step):
-            f1 = min(F, f0 + step)
-            enc.encode_frames_mp3(np.ascontiguousarray(batch[:, f0 * 1152:f1 * 1152]), mp3)
-        lengths = enc.flush_mp3(mp3, len(idx))
-        for k, i in enumerate(idx):
-            out[i] = mp3[k, :lengths[k]].tobytes()
-        enc.close()
+    frames = [(len(x) + 1152 * n_ch - 1) // (1152 * n_ch) for x in pcms]
+    if not paths:
+        return []
+    F = max(frames)
+    if F == 0:
+        return [b""] * len(paths)
+    S = len(paths)
+    step = min(chunk_frames, F)
+    enc = Encoder(sfreq, n_ch, bitrate, max_streams=S, max_frames=step, device=device)
+    enc.set_pcm_layout(True)
+    enc.set_stream_frames(frames)
+    mp3 = np.zeros((S, F * enc.frame_bytes), np.uint8)
+    chunk = np.zeros((S, step * 1152 * n_ch), np.int16)
+    for f0 in range(0, F, step):
+        f1 = min(F, f0 + step)
+        lo, hi = f0 * 1152 * n_ch, f1 * 1152 * n_ch
+        chunk[:] = 0
+        for k, x in enumerate(pcms):
+            if len(x) > lo:
+                m = min(len(x), hi) - lo
+                chunk[k, :m] = x[lo:lo + m]
+        enc.encode_frames_mp3(np.ascontiguousarray(chunk[:, :hi - lo]).reshape(S, (f1 - f0) * 1152, n_ch), mp3)
+        enc.sync()      # the staging array is reused by the next iteration
+    lengths = enc.flush_mp3(mp3, S)
+    out = [mp3[k, :lengths[k]].tobytes() for k in range(S)]
+    enc.close()
     return out
 
 

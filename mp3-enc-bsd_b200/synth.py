@@ -91,3 +91,86 @@ def full_scale_tone(seconds=1.0, fs=44100, freq=1000.0, n_ch=2):
     n = int(round(seconds * fs))
     t = np.arange(n, dtype=np.float64) / fs
     return _to_i16(np.stack([np.sin(2 * np.pi * freq * t)] * n_ch))
+
+
+# ---- heterogeneous clip batch for the throughput bench (BASELINE configs[3]) --------------------------------------
+# torch ops only, so the same code generates the batch on the GPU (bench) and single clips on the CPU (reference arm,
+# tests).  Every clip is a pure function of its GLOBAL index (counter-based noise, per-clip parameters from a hash), so a
+# rank's shard holds the same clips whatever the world size is.
+HETERO_CLASSES = ["tone+fm+noise", "tone+fm+noise", "partials", "transients", "loud-noise", "silence-then-music", "quiet-partials",
+                  "am-tone"]
+
+
+def _hash_u01(torch, a, b):
+    """counter-based uniform [0,1): murmur-style finaliser of two int64 tensors (broadcast)"""
+    x = (a * 0x9E3779B1 + b * 0x85EBCA6B + 0x165667B1) & 0xFFFFFFFF
+    x = ((x ^ (x >> 16)) * 0x85EBCA6B) & 0xFFFFFFFF
+    x = ((x ^ (x >> 13)) * 0xC2B2AE35) & 0xFFFFFFFF
+    x = x ^ (x >> 16)
+    return x.to(torch.float32) * (1.0 / 4294967296.0)
+
+
+def hetero_batch(torch, first, count, n_samples, fs=44100, n_ch=2, device="cpu", sub=32, out=None, force_class=None, start=0):
+    """int16 [count][n_ch][n_samples]: clips first .. first+count-1 of the heterogeneous bench batch.
+    Class = index % 8 (HETERO_CLASSES): the config-1 recipe at levels spread over 30 dB and detuned, sums of partials
+    (config-3 like), decaying noise / tone bursts on near silence (config-2 like, drives short blocks), loud white noise
+    (bit pressure), digital silence followed by music, a -40 dB clip, an amplitude-modulated tone (configs[4] recipe).
+    force_class: every clip takes that class (the per-clip parameters still come from the clip index).
+    start: absolute index of the first sample (a clip is a pure function of the absolute sample index too, so a long clip
+    can be generated piecewise)."""
+    if out is None:
+        out = torch.empty((count, n_ch, n_samples), dtype=torch.int16, device=device)
+    two_pi = 6.283185307179586
+    idx = torch.arange(start, start + n_samples, dtype=torch.int64, device=device)
+    t = idx.to(torch.float64) / fs
+    t32 = t.to(torch.float32)
+    chs = torch.arange(n_ch, dtype=torch.int64, device=device).view(1, n_ch, 1)
+    fm_dev = ((500.0 / 0.3) * torch.cos(two_pi * 0.3 * t))                       # config-1 FM phase deviation
+    for s0 in range(0, count, sub):
+        b = min(sub, count - s0)
+        clip = torch.arange(first + s0, first + s0 + b, dtype=torch.int64, device=device).view(b, 1, 1)
+        cls = clip % 8 if force_class is None else torch.full_like(clip, int(force_class))
+        par = lambda k: _hash_u01(torch, clip, torch.full_like(clip, 1000003 + k))          # per-clip parameter k in [0,1)
+        # white noise ~ N(0,1): sum of four uniforms
+        key = clip * 4 + chs
+        u = sum(_hash_u01(torch, key * 7919 + j, idx.view(1, 1, -1)) for j in range(4))
+        noise = (u - 2.0) * 1.7320508
+        level = torch.pow(10.0, -1.5 * par(0))                                   # 0 .. -30 dB
+        f0 = 440.0 * torch.pow(2.0, 2.0 * par(1) - 1.0)                          # 220 .. 880 Hz
+        ph_tone = (two_pi * f0.to(torch.float64) * t.view(1, 1, -1))
+        tone = torch.sin(ph_tone).to(torch.float32)
+        fm = torch.sin(two_pi * 1000.0 * t - fm_dev).to(torch.float32).view(1, 1, -1)
+        x_c1 = (0.25 * tone + 0.15 * fm + 0.05 * noise) * level
+        # partials: 12 log-uniform frequencies 50 Hz .. 12 kHz, amplitude ~ 1 / sqrt(f), channel-dependent phases
+        part = torch.zeros((b, n_ch, n_samples), dtype=torch.float32, device=device)
+        norm = torch.zeros((b, 1, 1), dtype=torch.float32, device=device)
+        for k in range(12):
+            fk = 50.0 * torch.pow(240.0, par(10 + k))
+            ak = torch.rsqrt(fk / 50.0)
+            phk = two_pi * _hash_u01(torch, key, torch.full_like(key, 77 + k))
+            part += ak * torch.sin((two_pi * fk.to(torch.float64) * t.view(1, 1, -1)).to(torch.float32) + phk)
+            norm += ak
+        x_part = 0.7 * part / norm + 0.01 * noise
+        # transients: near silence + a 20 ms decaying burst every 250 ms (noise, every third one a 5 kHz tone)
+        tb = torch.remainder(t32 - 0.1, 0.25)
+        kb = torch.floor((t32 - 0.1) / 0.25)
+        env = torch.where((t32 >= 0.1) & (tb < 0.020), torch.exp(-tb / 0.004), torch.zeros_like(tb)).view(1, 1, -1)
+        tone5k = torch.sin(two_pi * 5000.0 * t).to(torch.float32).view(1, 1, -1)
+        is_tone = (torch.remainder(kb, 3.0) == 2.0).view(1, 1, -1)
+        x_tr = 1e-3 * noise + env * torch.where(is_tone, 0.8 * tone5k, 0.95 * 0.5773503 * noise)
+        x_loud = 0.28 * noise                                                     # clipped rarely, every band full
+        gate = (t32 >= 5.0).view(1, 1, -1)
+        x_sil = torch.where(gate, x_c1 / level * 0.7, torch.zeros_like(x_c1))     # digital silence, then the recipe at -3 dB
+        x_quiet = 0.01 * x_part
+        am = (0.6 + 0.4 * torch.sin(two_pi * 0.05 * t + two_pi * par(2).to(torch.float64))).to(torch.float32)
+        x_am = (0.25 * tone + 0.15 * fm + 0.05 * noise) * am
+        x = torch.where(cls <= 1, x_c1, torch.where(cls == 2, x_part, torch.where(cls == 3, x_tr, torch.where(
+            cls == 4, x_loud, torch.where(cls == 5, x_sil, torch.where(cls == 6, x_quiet, x_am))))))
+        out[s0:s0 + b] = torch.clamp(torch.round(x * 32767.0), -32768, 32767).to(torch.int16)
+    return out
+
+
+def hetero_stream(torch, start, count, fs=44100, n_ch=2, device="cpu"):
+    """samples [start, start+count) of THE long stream of BASELINE configs[4] (clip 0 as class "am-tone": the config-1
+    recipe under a slow amplitude envelope): int16 [n_ch][count]"""
+    return hetero_batch(torch, 0, 1, count, fs, n_ch, device, force_class=7, start=start)[0]
