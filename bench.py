@@ -86,7 +86,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.rows, self._halt = index, [], threading.Event()
         self.proc = None
 
     def run(self):
@@ -96,14 +96,14 @@ class ClockSampler(threading.Thread):
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
                                           "-lms", "200"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
-                if self._stop.is_set():
+                if self._halt.is_set():
                     break
                 self.rows.append([x.strip() for x in line.split(",")])
         except Exception:
             pass
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         if self.proc:
             self.proc.kill()
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
@@ -254,6 +254,7 @@ def main():
     ap.add_argument("--segment-frames", type=int, default=116, help="config 5: frames per segment")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the A/B pass over the front-end variants")
     ap.add_argument("--front", default=os.environ.get("MP3GPU_FRONT", ""), help="front-end variant (see mp3gpu.h); default: the library's")
     args = ap.parse_args()
 
@@ -385,6 +386,30 @@ def main():
         step_dev()
     prof = enc.profile_collect(reset=True)
     enc.profile_enable(False)
+    # A/B of the front-end variants (mp3gpu_set_front_variant): one warm-up step + one profiled step each; what changes in
+    # the produced byte streams is measured on the device against the default variant's output of the same batch
+    variants = {}
+    if not args.no_variants and not args.front:
+        base_out = mp3_dev.clone()
+        fbytes = enc.frame_bytes
+        for v in ("fma", "fma_tc", "fp32"):
+            enc.set_front_variant(v)
+            step_dev()
+            enc.profile_enable(True)
+            enc.profile_collect(reset=True)
+            step_dev()
+            pv = enc.profile_collect(reset=True)
+            enc.profile_enable(False)
+            same = (mp3_dev.view(S, n_frames, fbytes) == base_out.view(S, n_frames, fbytes)).all(dim=2)
+            info = enc.front_variant_info()
+            ms = pv["front_polyphase_mdct"][0]
+            variants[v] = {"front_ms_per_step": ms, "algorithmic_bytes_per_gc": info["bytes_per_gc"],
+                           "achieved_gbs": info["bytes_per_gc"] * S * n_frames * 2 * NCH / (ms * 1e-3) / 1e9 if ms > 0 else 0.0,
+                           "step_ms": sum(x[0] for x in pv.values()),
+                           "identical_frame_fraction_vs_exact": float(same.float().mean().item()),
+                           "identical_streams_vs_exact": int(same.all(dim=1).sum().item())}
+        enc.set_front_variant("exact")
+        del base_out
 
     audio_rank = S * n_samples / FS * args.steps
     t_dev_max, audio_total = reduce_timing(t_dev, audio_rank, device)
@@ -435,6 +460,11 @@ def main():
         "kernels": kernels,
         "clocks": clocks,
     }
+    if variants:
+        for v in variants.values():
+            v["frac_hbm"] = v["achieved_gbs"] / peak
+        out["front_variants"] = dict(variants, note="same batch, one profiled step each; exact = the default above; identical_* compare the "
+                                     "MP3 bytes of all %d clips of this rank with the default variant's" % S)
     if not args.no_parity and args.parity_clips > 0:
         # checker leg, outside every timed region: clips of this batch through the unmodified reference CLI
         k = min(args.parity_clips, S)

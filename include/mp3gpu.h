@@ -114,6 +114,25 @@ int mp3gpu_stream_wave(int device);
 /* frame geometry the reference derives in musicin.c:562-572,729-746 */
 int mp3gpu_frame_geometry(const mp3gpu_ctx *ctx, int *bits_per_frame, int *mean_bits);
 
+/* Arithmetic of the fused polyphase filterbank + MDCT kernel (window_subband / filter_subband encode.c:287-409,
+ * mdct_sub / mdct mdct.c:25-198).  BASELINE's north star allows <= 1e-12 relative error for an FP64 and <= 1e-5 for an FP32
+ * path; Huffman counts and table selection stay bit-exact given the quantised values in every variant.
+ *   EXACT (default)  every sum in the reference's order with unfused IEEE multiply / add: subband samples and xr
+ *                    bit-identical to the reference, the MP3 bytes identical to the reference CLI's file.
+ *   FMA              FP64 with fused multiply-add, the MDCT as time-domain-aliasing fold + 18-point DCT-IV, the matrixing
+ *                    direct-form on the reference's 9-decimal coefficients: ~1e-15 relative to the granule's largest value.
+ *   FMA_TC           as FMA, the matrixing as one 32 x 32 x 32 product per 32 slots on the FP64 tensor cores.
+ *   FP32             FP32 throughout, the matrixing as Lee's fast 32-point DCT-III, float spectra handed to the rate loop:
+ *                    ~1e-6.  The rate loop quantises what it is given, so frames are no longer byte-identical.
+ * Error is measured against the largest |value| of the granule (pointwise relative error is meaningless for
+ * near-zero lines).  Set before the first encode call of a batch. */
+#define MP3GPU_FRONT_EXACT 0
+#define MP3GPU_FRONT_FMA 1
+#define MP3GPU_FRONT_FP32 2
+#define MP3GPU_FRONT_FMA_TC 3   /* FMA with the 32 x 32 matrixing on the FP64 tensor cores (mma.sync m8n8k4, SASS DMMA): the A/B */
+int mp3gpu_set_front_variant(mp3gpu_ctx *ctx, int variant);
+int mp3gpu_get_front_variant(const mp3gpu_ctx *ctx, int *variant, int *algorithmic_bytes_per_gc);
+
 /* Layout of the `pcm` argument of the mp3gpu_encode_frames* family.  PLANAR (default): [n_streams][n_ch][n_frames*1152],
  * what get_audio() leaves in buffer[2][1152] (encode.c:181-269).  INTERLEAVED: [n_streams][n_frames*1152][n_ch], the
  * sample order of a WAV / raw PCM file as read_samples() delivers it (encode.c:107-167); the channel split of

@@ -21,6 +21,7 @@
 #include "../../include/mp3gpu.h"
 #include "front_core.h"
 #include "front_tile.cuh"
+#include "front_fast.cuh"
 #include "psy_core.h"
 #include "rate_loop_core.h"
 #include "tables.h"
@@ -216,7 +217,8 @@ k_rate_loop(const RateTables *__restrict__ gT, FrameGeom G, LoopStreamState *sta
 #pragma unroll
         for (int i = 0; i < 4; i++) { st_en[i].v = lane_states[s].en[i][lane]; st_xm[i].v = lane_states[s].xm[i][lane]; }
         const long g0 = (s * n_frames + f) * gpf;                // first granule-channel of the frame
-        rate_loop_stream(w, H, *gT, M, G, S, st_en, st_xm, 1, xr + g0 * 576, psy + g0, ix + g0 * 576, gi + g0, sf + g0 * 40,
+        const double *xf = G.xr_f32 ? reinterpret_cast<const double *>(reinterpret_cast<const float *>(xr) + g0 * 576) : xr + g0 * 576;
+        rate_loop_stream(w, H, *gT, M, G, S, st_en, st_xm, 1, xf, psy + g0, ix + g0 * 576, gi + g0, sf + g0 * 40,
                          fo + s * (long)n_frames + f, nullptr);
 #pragma unroll
         for (int i = 0; i < 4; i++) { lane_states[s].en[i][lane] = st_en[i].v; lane_states[s].xm[i][lane] = st_xm[i].v; }
@@ -391,6 +393,7 @@ struct mp3gpu_ctx {
     int *d_total = nullptr, *d_nfr = nullptr;
     std::vector<int> h_total;
     bool have_total = false;
+    int front_variant = MP3GPU_FRONT_EXACT;
     int *d_sched = nullptr;    // rate-loop work queue: [0] ticket counter, [1 + s] frames of stream s finished in this launch
     // host-PCM ingest: double-buffered dense staging filled on a private copy stream, so that the H2D copy of
     // call i+1 overlaps the kernels of call i (the caller only ever sees its own stream)
@@ -528,6 +531,22 @@ static int upload(T **dst, const T *src, size_t n = 1)
     return 0;
 }
 
+// FP32 copies of the front-end tables for the FP32 variant (front_fast.cuh)
+static cudaError_t upload_front_f(const FrontTables *F)
+{
+    FrontTablesF *f = new FrontTablesF;
+    memset(f, 0, sizeof(*f));
+    for (int w = 0; w < 4; w++) for (int k = 0; k < 36; k++) f->win[w][k] = (float)F->win[w][k];
+    for (int m = 0; m < 6; m++) for (int j = 0; j < 6; j++) f->dct4_s[m][j] = (float)F->dct4_s[m][j];
+    for (int k = 0; k < 8; k++) { f->ca[k] = (float)F->ca[k]; f->cs[k] = (float)F->cs[k]; }
+    for (int i = 0; i < 512; i++) f->window[i] = (float)F->window[i];
+    for (int m = 0; m < 18; m++) for (int j = 0; j < 18; j++) f->dct4_l[m][j] = (float)F->dct4_l[m][j];
+    cudaError_t e = cudaMemcpyToSymbol(c_front_f, f, sizeof(FrontTablesF));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_front_f, f, sizeof(FrontTablesF));
+    delete f;
+    return e;
+}
+
 static int create_body(mp3gpu_ctx *c)
 {
     const mp3gpu_config *cfg = &c->cfg;
@@ -539,6 +558,7 @@ static int create_body(mp3gpu_ctx *c)
         build_front_tables(F);
         cudaError_t e = cudaMemcpyToSymbol(c_front, F, sizeof(FrontTables));
         if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_front, F, sizeof(FrontTables));
+        if (e == cudaSuccess) e = upload_front_f(F);
         delete F;
         if (e != cudaSuccess) return fail(MP3GPU_ECUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString(e));
         PsyTables *P = new PsyTables;
@@ -598,6 +618,14 @@ static int create_body(mp3gpu_ctx *c)
     CU(cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_quantize_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_front_tile, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_front_fast<double, false, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontFastSmem<double, false>)));
+    CU(cudaFuncSetAttribute(k_front_fast<float, true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontFastSmem<float, true>)));
+    CU(cudaFuncSetAttribute(k_front_fast<float, true, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontFastSmem<float, true>)));
+    CU(cudaFuncSetAttribute(k_front_fast<double, false, double>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_front_fast<double, false, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontFastSmem<double, false>)));
+    CU(cudaFuncSetAttribute(k_front_fast<double, false, double, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_front_fast<float, true, float>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_front_fast<float, true, double>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_psy_front, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return mp3gpu_reset(c);
@@ -849,6 +877,24 @@ static int stage_pcm_dev(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n
     return 0;
 }
 
+extern "C" int mp3gpu_set_front_variant(mp3gpu_ctx *c, int variant)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    if (variant != MP3GPU_FRONT_EXACT && variant != MP3GPU_FRONT_FMA && variant != MP3GPU_FRONT_FP32 && variant != MP3GPU_FRONT_FMA_TC)
+        return fail(MP3GPU_EINVAL, "unknown front-end variant");
+    c->front_variant = variant;
+    return 0;
+}
+
+extern "C" int mp3gpu_get_front_variant(const mp3gpu_ctx *c, int *variant, int *xr_bytes_per_gc)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    if (variant) *variant = c->front_variant;
+    // algorithmic bytes per granule-channel of the fused kernel: PCM + block type + xr
+    if (xr_bytes_per_gc) *xr_bytes_per_gc = 1152 + 4 + (c->front_variant == MP3GPU_FRONT_FP32 ? 2304 : 4608);
+    return 0;
+}
+
 extern "C" int mp3gpu_set_pcm_layout(mp3gpu_ctx *c, int layout)
 {
     if (!c) return fail(MP3GPU_EINVAL, "null ctx");
@@ -886,15 +932,29 @@ static int pick_tile(int n_streams, int n_ch, int n_gran)
 }
 
 static int launch_front(mp3gpu_ctx *c, const short *pcm_rows, const PsyOut *psy, int n_streams, int n_frames, double *xr, double *sb,
-                        bool do_mdct, cudaStream_t q, const int *nfr = nullptr)
+                        bool do_mdct, cudaStream_t q, const int *nfr = nullptr, bool f32_out = false)
 {
     const int n_gran = 2 * n_frames, n_ch = c->cfg.n_ch;
-    if (do_mdct && !sb) {  // production path: tiled kernel (front_tile.cuh)
+    if (do_mdct && !sb) {  // production path: tiled kernel (front_tile.cuh / front_fast.cuh)
         const long n_tiles = (n_gran + FT_G - 1) / FT_G;
         const long ctas = (long)n_streams * n_ch * n_tiles;
         prof_begin(c, MP3GPU_K_FRONT, q);
+        if (c->front_variant == MP3GPU_FRONT_FMA_TC) {
+            k_front_fast<double, false, double, true><<<(unsigned)ctas, FT_THREADS, sizeof(FrontFastSmem<double, false>), q>>>(
+                pcm_rows, c->row * n_ch, c->row, HIST, n_streams, n_ch, n_gran, nfr, psy, xr);
+        } else if (c->front_variant == MP3GPU_FRONT_FMA) {
+            k_front_fast<double, false, double><<<(unsigned)ctas, FT_THREADS, sizeof(FrontFastSmem<double, false>), q>>>(
+                pcm_rows, c->row * n_ch, c->row, HIST, n_streams, n_ch, n_gran, nfr, psy, xr);
+        } else if (c->front_variant == MP3GPU_FRONT_FP32 && f32_out) {
+            k_front_fast<float, true, float><<<(unsigned)ctas, FT_THREADS, sizeof(FrontFastSmem<float, true>), q>>>(
+                pcm_rows, c->row * n_ch, c->row, HIST, n_streams, n_ch, n_gran, nfr, psy, reinterpret_cast<float *>(xr));
+        } else if (c->front_variant == MP3GPU_FRONT_FP32) {
+            k_front_fast<float, true, double><<<(unsigned)ctas, FT_THREADS, sizeof(FrontFastSmem<float, true>), q>>>(
+                pcm_rows, c->row * n_ch, c->row, HIST, n_streams, n_ch, n_gran, nfr, psy, xr);
+        } else {
         const long grid = (FT_PERSISTENT && ctas > 2L * c->sm_count) ? 2L * c->sm_count : ctas;
         k_front_tile<<<(unsigned)grid, FT_THREADS, sizeof(FrontTileSmem), q>>>(pcm_rows, c->row * n_ch, c->row, HIST, n_streams, n_ch, n_gran, ctas, nfr, psy, xr);
+        }
         prof_end(c, q);
         c->launches++;
         CU(cudaGetLastError());
@@ -946,13 +1006,15 @@ static int rate_loop_warps(const mp3gpu_ctx *c, int n_streams, unsigned *grid)
 }
 
 static int launch_rate_loop(mp3gpu_ctx *c, const double *xr, const PsyOut *psy, int n_streams, int n_frames, short *ix, GrInfoOut *gi,
-                            unsigned char *sf, FrameOut *fo, cudaStream_t q, const int *nfr = nullptr)
+                            unsigned char *sf, FrameOut *fo, cudaStream_t q, const int *nfr = nullptr, bool xr_f32 = false)
 {
     unsigned grid;
+    FrameGeom G = c->geom;
+    G.xr_f32 = xr_f32 ? 1 : 0;
     const int wpc = rate_loop_warps(c, n_streams, &grid);
     CU(cudaMemsetAsync(c->d_sched, 0, ((size_t)n_streams + 1) * sizeof(int), q));
     prof_begin(c, MP3GPU_K_RATE_LOOP, q);
-    k_rate_loop<<<grid, wpc * 32, RL_HOT_BYTES + wpc * sizeof(RateWarpSmem), q>>>(c->d_rate_tab, c->geom, c->d_loop_state, c->d_lane_state,
+    k_rate_loop<<<grid, wpc * 32, RL_HOT_BYTES + wpc * sizeof(RateWarpSmem), q>>>(c->d_rate_tab, G, c->d_loop_state, c->d_lane_state,
                                                                                   n_streams, n_frames, nfr, c->d_sched, xr, psy, ix, gi, sf, fo);
     prof_end(c, q);
     c->launches++;
@@ -976,12 +1038,13 @@ static int encode_common(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n
     if (nfr_out) *nfr_out = nfr;
     // musicin.c:751-779 order: psy first (it decides block_type), then filterbank + MDCT, then the rate loop
     if ((rc = launch_psy(c, c->pcm_main.buf, n_streams, n_frames, c->d_psyout, q, nfr))) return rc;
-    if ((rc = launch_front(c, c->pcm_main.buf, c->d_psyout, n_streams, n_frames, c->d_xr, nullptr, true, q, nfr))) return rc;
+    const bool f32 = c->front_variant == MP3GPU_FRONT_FP32;      // the FP32 front end hands float spectra to the rate loop
+    if ((rc = launch_front(c, c->pcm_main.buf, c->d_psyout, n_streams, n_frames, c->d_xr, nullptr, true, q, nfr, f32))) return rc;
     short *o_ix = host ? c->d_ix : (ix ? ix : c->d_ix);
     GrInfoOut *o_gi = host ? c->d_gi : (gi ? (GrInfoOut *)gi : c->d_gi);
     unsigned char *o_sf = host ? c->d_sf : (sf ? sf : c->d_sf);
     FrameOut *o_fo = host ? c->d_fo : (fo ? (FrameOut *)fo : c->d_fo);
-    if ((rc = launch_rate_loop(c, c->d_xr, c->d_psyout, n_streams, n_frames, o_ix, o_gi, o_sf, o_fo, q, nfr))) return rc;
+    if ((rc = launch_rate_loop(c, c->d_xr, c->d_psyout, n_streams, n_frames, o_ix, o_gi, o_sf, o_fo, q, nfr, f32))) return rc;
     if ((rc = roll_pcm(c, c->pcm_main, n_streams, n_frames, q))) return rc;
     c->frames_done_loop += n_frames;
     if (host) {

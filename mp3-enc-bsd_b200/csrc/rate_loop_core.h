@@ -96,9 +96,11 @@ struct FrameGeom {
     int n_ch, mean_bits, bits_per_frame;
     int mean_per_ch;   // mean_bits / n_ch           } derived once on the host (frame_geom_derive): a run-time integer division
     int resv_max;      // ResvFrameBegin's ResvMax   } is ~25 instructions, and this kernel pays for code size
+    int xr_f32;        // the spectra the rate loop reads are float[576] per granule-channel (FP32 front-end variant), not double
 };
 inline void frame_geom_derive(FrameGeom *G)
 {
+    G->xr_f32 = 0;
     G->mean_per_ch = G->mean_bits / G->n_ch;
     G->resv_max = (G->bits_per_frame > 7680) ? 0 : ((7680 - G->bits_per_frame > 4088) ? 4088 : 7680 - G->bits_per_frame);   // reservoir.c:62-84
 }
@@ -521,7 +523,9 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
         int s = lane + 32 * k;
         int e0 = slot_e0(is_short, s);
         int e1 = is_short ? e0 + 3 : e0 + 1;
-        double a = xr[e0], b = xr[e1];
+        double a, b;
+        if (G.xr_f32) { a = (double)reinterpret_cast<const float *>(xr)[e0]; b = (double)reinterpret_cast<const float *>(xr)[e1]; }
+        else { a = xr[e0]; b = xr[e1]; }
         if (a < 0) sg |= 1 << (2 * k);
         if (b < 0) sg |= 2 << (2 * k);
         a = fabs(a); b = fabs(b);
@@ -940,7 +944,9 @@ SIMT_FN void rate_loop_stream(const WarpCtx &w, const RateHot &H, const RateTabl
             for (int ch = 0; ch < G.n_ch; ch++) {
                 const int g = (f * 2 + gr) * G.n_ch + ch;
                 const PsyOut &po = psy[g];
-                p23[gr * 2 + ch] = encode_gc(w, H, T, M, G, S, st_en, st_xm, gr, ch, xr + (size_t)g * 576, po.ratio_l, po.ratio_s,
+                const double *xg = G.xr_f32 ? reinterpret_cast<const double *>(reinterpret_cast<const float *>(xr) + (size_t)g * 576)
+                                            : xr + (size_t)g * 576;
+                p23[gr * 2 + ch] = encode_gc(w, H, T, M, G, S, st_en, st_xm, gr, ch, xg, po.ratio_l, po.ratio_s,
                                              po.pe, po.block_type, scfsi[ch], g0[ch], ix + (size_t)g * 576, gi + g,
                                              sf + (size_t)g * 40, max_bits_dbg ? max_bits_dbg + g : nullptr);
             }

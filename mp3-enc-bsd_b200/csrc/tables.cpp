@@ -108,6 +108,10 @@ void build_front_tables(FrontTables *F)
     for (int m = 0; m < N / 2; m++)
         for (int k = 0; k < N; k++)
             F->cos_l[m][k] = cos((kRefPi / (2 * N)) * (2 * k + 1 + N / 2) * (2 * m + 1)) / (N / 4);
+    for (int m = 0; m < 18; m++)
+        for (int j = 0; j < 18; j++) F->dct4_l[m][j] = cos((kRefPi / 72) * (2 * j + 1) * (2 * m + 1)) / 9;
+    for (int m = 0; m < 6; m++)
+        for (int j = 0; j < 6; j++) F->dct4_s[m][j] = cos((kRefPi / 24) * (2 * j + 1) * (2 * m + 1)) / 3;
 }
 
 void build_rate_tables(int sr, RateTables *R)

@@ -19,6 +19,9 @@ struct FrontTables {
     double cos_l[18][36];
     double cos_s[6][12];
     double ca[8], cs[8];     // alias butterflies
+    // tolerance-path variants (front_fast.cuh): the 36 -> 18 / 12 -> 6 MDCT after the time-domain aliasing fold is a DCT-IV
+    double dct4_l[18][18];   // cos(pi/72 (2j+1)(2m+1)) / 9   = cos_l's kernel on the folded input
+    double dct4_s[6][6];     // cos(pi/24 (2j+1)(2m+1)) / 3
 };
 
 // ---- FFT as a levelised straight-line program (subs.c:185-534) ------------------------------------

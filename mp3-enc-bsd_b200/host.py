@@ -37,7 +37,9 @@ EXPORTS = ["mp3gpu_last_error", "mp3gpu_version", "mp3gpu_create", "mp3gpu_destr
            "mp3gpu_kernel_launches", "mp3gpu_profile_enable", "mp3gpu_profile_collect",
            "mp3gpu_encode_frames_mp3", "mp3gpu_encode_frames_mp3_dev", "mp3gpu_flush_mp3", "mp3gpu_flush_mp3_dev",
            "mp3gpu_frame_bytes", "mp3gpu_format_bitstream_batch", "mp3gpu_begin_segment", "mp3gpu_stream_wave", "mp3gpu_set_pcm_layout", "mp3gpu_count_bits_batch", "mp3gpu_set_host_delivery",
-           "mp3gpu_reset_async", "mp3gpu_set_stream_frames", "mp3gpu_reset_streams"]
+           "mp3gpu_reset_async", "mp3gpu_set_stream_frames", "mp3gpu_reset_streams",
+           "mp3gpu_set_front_variant", "mp3gpu_get_front_variant"]
+FRONT_VARIANTS = {"exact": 0, "fma": 1, "fp32": 2, "fma_tc": 3}
 LEGACY_EXPORTS = ["window_subband", "filter_subband", "mdct_sub", "L3psycho_anal", "iteration_loop", "quantize", "count_bits",
                   "mp3gpu_legacy_reset", "mp3gpu_legacy_kernel_launches"]
 KERNEL_NAMES = ["psy_front", "psy_scan", "front_polyphase_mdct", "rate_loop", "bitstream"]
@@ -75,6 +77,8 @@ def load_library():
         lib.mp3gpu_reset_async.argtypes = [C.c_void_p, C.c_void_p]
         lib.mp3gpu_set_stream_frames.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_long), C.c_void_p]
         lib.mp3gpu_reset_streams.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.mp3gpu_set_front_variant.argtypes = [C.c_void_p, C.c_int]
+        lib.mp3gpu_get_front_variant.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.mp3gpu_sync.argtypes = [C.c_void_p, C.c_void_p]
         lib.mp3gpu_frame_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         vp = C.c_void_p
@@ -153,6 +157,15 @@ class Encoder:
             self._check(self.lib.mp3gpu_reset(self.ctx), "mp3gpu_reset")
         else:
             self._check(self.lib.mp3gpu_reset_async(self.ctx, C.c_void_p(stream or 0)), "mp3gpu_reset_async")
+
+    def set_front_variant(self, name):
+        """arithmetic of the fused filterbank + MDCT kernel: "exact" (default), "fma" (FP64, <= 1e-12), "fp32" (<= 1e-5)"""
+        self._check(self.lib.mp3gpu_set_front_variant(self.ctx, FRONT_VARIANTS[name]), "mp3gpu_set_front_variant")
+
+    def front_variant_info(self):
+        v, b = C.c_int(), C.c_int()
+        self._check(self.lib.mp3gpu_get_front_variant(self.ctx, C.byref(v), C.byref(b)), "mp3gpu_get_front_variant")
+        return {"name": {n: k for k, n in FRONT_VARIANTS.items()}[v.value], "bytes_per_gc": b.value}
 
     def reset_streams(self, first, count, stream=None):
         """restart streams [first, first+count) as new streams; the others keep their state (mp3gpu.h)"""
