@@ -256,6 +256,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the A/B pass over the front-end variants")
     ap.add_argument("--front", default=os.environ.get("MP3GPU_FRONT", ""), help="front-end variant (see mp3gpu.h); default: the library's")
+    ap.add_argument("--pipeline", default=os.environ.get("MP3GPU_PIPELINE", "overlap"), choices=["serial", "overlap"],
+                    help="overlap: the front end of chunk i+1 runs beside the rate loop of chunk i (mp3gpu_set_pipeline)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -318,6 +320,7 @@ def main():
     enc = mod.Encoder(FS, NCH, KBPS, max_streams=S, max_frames=F, device=local_rank)
     if args.front:
         enc.set_front_variant(args.front)
+    enc.set_pipeline(args.pipeline == "overlap")
     # ---- synthetic PCM: generated on the device, kept (a) on the device chunk-major for `value`,
     #      (b) in pinned host memory chunk-major for `e2e`
     pcm_all = torch.zeros((S, NCH, n_frames * 1152), dtype=torch.int16, device=device)
@@ -444,6 +447,7 @@ def main():
         "config": dict(config_common, clips_total=cfg["clips"], clips_this_rank=S, chunk_frames=F, content=mod.synth.HETERO_CLASSES
                        if cfg["cls"] is None else mod.synth.HETERO_CLASSES[cfg["cls"]],
                        precision="fp64 filterbank/MDCT/rate loop, fp32 FFT (as the reference); front-end variant: " + front_info["name"],
+                       pipeline=args.pipeline,
                        l2="inputs larger than L2: %.1f GB PCM and %.1f GB of spectra per step and GPU" % (
                            S * n_frames * 1152 * NCH * 2 / 1e9, gc_per_step * 4608 / 1e9)),
         "e2e": {"value": audio_total / t_host_max, "unit": "audio-s/s",

@@ -133,6 +133,19 @@ int mp3gpu_frame_geometry(const mp3gpu_ctx *ctx, int *bits_per_frame, int *mean_
 int mp3gpu_set_front_variant(mp3gpu_ctx *ctx, int variant);
 int mp3gpu_get_front_variant(const mp3gpu_ctx *ctx, int *variant, int *algorithmic_bytes_per_gc);
 
+/* Pipelining of successive calls of the mp3gpu_encode_frames* family.  SERIAL (default): all work of a call is enqueued on
+ * `stream`.  OVERLAP: PCM staging, the psychoacoustic model and the filterbank + MDCT of a call run on a private
+ * low-priority stream, so that they execute beside the rate loop of the PREVIOUS call (the rate loop is bound by the
+ * per-stream dependency chain and leaves SM resources free whenever the batch is smaller than the device's warp slots:
+ * sharded batches, segmented streams); psy results and spectra are double-buffered.  The rate loop, the bitstream kernels and
+ * every copy of results stay on `stream`, which waits for the front end: results are ordered on `stream` exactly as in
+ * SERIAL mode.  One difference: the device-pointer variants read `pcm` on the private stream, so the buffer must be
+ * complete when the call is made (not produced by work still pending on `stream`); work enqueued on `stream` after the call
+ * is ordered behind that read.  Switch modes between batches (the call synchronises the device). */
+#define MP3GPU_PIPELINE_SERIAL 0
+#define MP3GPU_PIPELINE_OVERLAP 1
+int mp3gpu_set_pipeline(mp3gpu_ctx *ctx, int mode);
+
 /* Layout of the `pcm` argument of the mp3gpu_encode_frames* family.  PLANAR (default): [n_streams][n_ch][n_frames*1152],
  * what get_audio() leaves in buffer[2][1152] (encode.c:181-269).  INTERLEAVED: [n_streams][n_frames*1152][n_ch], the
  * sample order of a WAV / raw PCM file as read_samples() delivers it (encode.c:107-167); the channel split of

@@ -96,6 +96,18 @@ void iteration_loop(double pe[][2], double xr_org[2][2][576], III_psy_ratio *rat
  * scalefactor-band tables of the last iteration_loop() call (44.1 kHz before any). */
 void quantize(double xr[576], int ix[576], gr_info *cod_info);
 int count_bits(int *ix, gr_info *cod_info);
+/* the rest of the inner-loop boundary (loop-pvt.h:46-117, loop.c:51-53), each reading and writing exactly the gr_info fields the
+ * reference's function does: inner_loop (loop.c:569: steps from quantizerStepSize upwards until the granule fits max_bits),
+ * bin_search_StepSize (loop.c:2119), calc_runlen (:1488), count1_bitcount (:1531), subdivide (:1638), bigv_tab_select (:1717),
+ * new_choose_table (:1793), bigv_bitcount (:1954). */
+int inner_loop(double xr[2][2][576], int l3_enc[2][2][576], int max_bits, gr_info *cod_info, int gr, int ch);
+int bin_search_StepSize(int desired_rate, double start, int *ix, double xrs[576], gr_info *cod_info);
+void calc_runlen(int ix[576], gr_info *cod_info);
+int count1_bitcount(int ix[576], gr_info *cod_info);
+void subdivide(gr_info *cod_info);
+void bigv_tab_select(int ix[576], gr_info *cod_info);
+int new_choose_table(int ix[576], unsigned int begin, unsigned int end);
+int bigv_bitcount(int ix[576], gr_info *gi);
 #endif
 
 /* forget the hidden per-stream state of all five entry points */

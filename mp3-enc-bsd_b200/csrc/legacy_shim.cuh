@@ -440,3 +440,320 @@ extern "C" int count_bits(int *ix, gr_info *cod_info)
     legacy_count_result(g, cod_info);
     return bits;
 }
+
+
+// ---- the rest of the reference's inner-loop boundary (loop-pvt.h:46-117, loop.c:51-53), single-call legacy form -------------
+// inner_loop, bin_search_StepSize, calc_runlen, count1_bitcount, subdivide, bigv_tab_select, new_choose_table, bigv_bitcount.
+// Each reads and writes the fields of the caller's gr_info exactly as the reference's function does (no more, no fewer),
+// so a host program can replace any subset of them.  One warp runs the same building blocks as the batched rate loop
+// (quantize_all / count_all / count_regions, rate_loop_core.h); there is no host-side arithmetic.
+namespace mp3gpu {
+
+enum { LL_RUNLEN = 1, LL_COUNT1, LL_SUBDIVIDE, LL_TABSEL, LL_BIGV, LL_CHOOSE, LL_INNER, LL_BINSEARCH };
+
+struct LegacyLoopArgs {
+    int mode, bt, wsf;          // block type as the rate loop sees it: wsf ? block_type : 0
+    int a, b;                   // max_bits | desired_rate | begin ;  start step | end
+    GrInfoOut g;                // in / out: big_values, count1, count1table_select, region0/1_count, table_select, address1..3
+    int result, q;              // return value, final quantizerStepSize
+};
+
+// bits of the pairs of ix[start, end) in Huffman table t, count_bit() / HuffmanCode() in count mode (loop.c:172-225)
+__device__ __forceinline__ int ll_count_bit(const RateTables &T, const short *ix, int start, int end, int t, int lane)
+{
+    if (t == 0) return 0;
+    const int ylen = T.hxlen[t], lin = T.hlinbits[t];
+    const unsigned char *hl = T.hlen + T.hoff[t];
+    int sum = 0;
+    for (int i = start + 2 * lane; i < end; i += 64) {
+        int x = ix[i], y = (i + 1 < 576) ? ix[i + 1] : 0;
+        if (t > 15) {
+            if (x > 14) { x = 15; sum += lin; }
+            if (y > 14) { y = 15; sum += lin; }
+        }
+        sum += hl[x * ylen + y] + (x != 0) + (y != 0);
+    }
+    return __reduce_add_sync(0xffffffffu, sum);
+}
+
+__global__ void __launch_bounds__(32)
+k_legacy_loop(const RateTables *__restrict__ gT, LegacyLoopArgs *A, const double *xr_abs, short *ix)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const RateHot &H = load_rate_hot(gT, smem_raw);
+    RateWarpSmem &M = *reinterpret_cast<RateWarpSmem *>(smem_raw + RL_HOT_BYTES);
+    const RateTables &T = *gT;
+    WarpCtx w;
+    const int lane = w.lane;
+    LegacyLoopArgs a = *A;
+    const bool is_short = a.wsf && a.bt == 2, wsf = a.wsf != 0;
+    CountResult C;
+    memset(&C, 0, sizeof(C));
+    C.big_values = a.g.big_values; C.count1 = a.g.count1; C.count1table_select = a.g.count1table_select;
+    C.region0_count = a.g.region0_count; C.region1_count = a.g.region1_count;
+    C.table_select[0] = a.g.table_select[0]; C.table_select[1] = a.g.table_select[1]; C.table_select[2] = a.g.table_select[2];
+    C.address1 = a.g.address1; C.address2 = a.g.address2; C.address3 = a.g.address3;
+    int result = 0, q = a.b;
+    // quantised values -> slots (the layouts of rate_loop_core.h); LL_CHOOSE: slot s = elements (begin + 2 s, begin + 2 s + 1)
+    PerThread<int> nzmax, bigmax;
+    if (a.mode == LL_RUNLEN || a.mode == LL_COUNT1 || a.mode == LL_TABSEL || a.mode == LL_CHOOSE) {
+        int nz = -1, bg = -1;
+        for (int k = 0; k < 9; k++) {
+            const int s = lane + 32 * k;
+            int e0, e1;
+            if (a.mode == LL_CHOOSE) { e0 = a.a + 2 * s; e1 = e0 + 1; if (e0 >= a.b) e0 = e1 = 576; }
+            else { e0 = slot_e0(is_short, s); e1 = is_short ? e0 + 3 : e0 + 1; }
+            const int x = e0 < 576 ? ix[e0] : 0, y = e1 < 576 ? ix[e1] : 0;
+            U2 v; v.x = (unsigned short)x; v.y = (unsigned short)y;
+            M.ix[s] = v;
+            if ((x | y) != 0) nz = s;
+            if (x > 1 || y > 1) bg = s;
+        }
+        nzmax.v = nz; bigmax.v = bg;
+        __syncwarp();
+    }
+    switch (a.mode) {
+    case LL_RUNLEN:                                              // calc_runlen, loop.c:1488-1519
+        if (is_short) { C.count1 = 0; C.big_values = 288; }
+        else {
+            const int n = w.reduce_max(nzmax) + 1, B = w.reduce_max(bigmax);
+            C.count1 = (n - 1 - B) >> 1;
+            C.big_values = n - 2 * C.count1;
+        }
+        break;
+    case LL_COUNT1: {                                            // count1_bitcount, loop.c:1531-1590: the caller's big_values / count1
+        int acc = 0;
+        for (int t = lane; t < C.count1; t += 32) {
+            const int s0 = C.big_values + 2 * t;
+            if (s0 + 1 < 288) {
+                const U2 u = M.ix[s0], v = M.ix[s0 + 1];
+                acc += (int)H.c1lut[(u.x & 1) | ((u.y & 1) << 1) | ((v.x & 1) << 2) | ((v.y & 1) << 3)];
+            }
+        }
+        const int both = __reduce_add_sync(0xffffffffu, acc);
+        const int sum0 = both & 0xffff, sum1 = both >> 16;
+        if (sum0 < sum1) { result = sum0; C.count1table_select = 0; } else { result = sum1; C.count1table_select = 1; }
+        break;
+    }
+    case LL_SUBDIVIDE:                                           // subdivide, loop.c:1638-1704
+        if (C.big_values == 0) { C.region0_count = 0; C.region1_count = 0; }
+        else if (!wsf) {
+            const int bv = C.big_values > 288 ? 288 : C.big_values;
+            C.region0_count = H.subdiv[bv][0]; C.region1_count = H.subdiv[bv][1];
+            C.address1 = H.sfb_l[C.region0_count + 1];
+            C.address2 = H.sfb_l[C.region0_count + C.region1_count + 2];
+            C.address3 = 2 * C.big_values;
+        } else if (a.bt == 2) { C.region0_count = 8; C.region1_count = 36; C.address1 = 36; C.address2 = 2 * C.big_values; C.address3 = 0; }
+        else { C.region0_count = 7; C.region1_count = 13; C.address1 = H.sfb_l[8]; C.address2 = 2 * C.big_values; C.address3 = 0; }
+        break;
+    case LL_TABSEL: {                                            // bigv_tab_select, loop.c:1717-1775
+        CountResult D = C;
+        D.table_select[0] = D.table_select[1] = D.table_select[2] = 0;
+        if (is_short) { D.address1 = 36; D.address2 = 576; }     // the short branch partitions by line < 12, not by the addresses
+        count_regions(w, H, M, is_short, is_short ? 576 : 2 * C.big_values, 0, D);
+        C.table_select[0] = D.table_select[0]; C.table_select[1] = D.table_select[1]; C.table_select[2] = D.table_select[2];
+        break;
+    }
+    case LL_CHOOSE: {                                            // new_choose_table(ix, begin, end), loop.c:1793-1900
+        CountResult D;
+        memset(&D, 0, sizeof(D));
+        const int n = a.b > a.a ? (a.b - a.a + 1) / 2 : 0;
+        D.address1 = 2 * (n > 288 ? 288 : n); D.address2 = 0;
+        count_regions(w, H, M, false, 0, 0, D);
+        result = D.table_select[0];
+        break;
+    }
+    case LL_BIGV:                                                // bigv_bitcount, loop.c:1954-2016: the caller's tables and addresses
+        if (is_short) {
+            // lines < 12 of every window (elements < 36) with table_select[0], the rest with table_select[1]; a pair is
+            // (line, line + 1) of one window: elements (3 l + w, 3 l + 3 + w)
+            int sum = 0;
+            for (int p = lane; p < 288; p += 32) {
+                const int e0 = slot_e0(true, p), t = C.table_select[e0 < 36 ? 0 : 1];
+                if (t == 0) continue;
+                int x = ix[e0], y = ix[e0 + 3];
+                const int ylen = T.hxlen[t], lin = T.hlinbits[t];
+                if (t > 15) { if (x > 14) { x = 15; sum += lin; } if (y > 14) { y = 15; sum += lin; } }
+                sum += T.hlen[T.hoff[t] + x * ylen + y] + (x != 0) + (y != 0);
+            }
+            result = __reduce_add_sync(0xffffffffu, sum);
+        } else {
+            result = ll_count_bit(T, ix, 0, C.address1, C.table_select[0], lane) +
+                     ll_count_bit(T, ix, C.address1, C.address2, C.table_select[1], lane) +
+                     ll_count_bit(T, ix, C.address2, C.address3, C.table_select[2], lane);
+        }
+        break;
+    case LL_INNER:
+    case LL_BINSEARCH: {
+        for (int k = 0; k < 9; k++) {
+            const int s = lane + 32 * k;
+            const int e0 = slot_e0(is_short, s), e1 = is_short ? e0 + 3 : e0 + 1;
+            D2 x; x.x = xr_abs[e0]; x.y = xr_abs[e1];
+            M.xs[s] = x;
+        }
+        PerThread<float> rowmax;
+        refresh_pow34(w, M, rowmax);
+        C.kz = 9;
+        int bits;
+        if (a.mode == LL_INNER) {                                // inner_loop, loop.c:569-606 (max_bits = a.a, start step = a.b)
+            for (;;) {
+                bits = probe(w, H, T, M, is_short, wsf, q, rowmax, C);
+                if (!(bits > a.a && q < 1024)) break;
+                q += 1;
+            }
+        } else {                                                 // bin_search_StepSize, loop.c:2119-2140 (desired_rate = a.a, start = a.b)
+            int top = a.b, bot = 200, next = a.b, last;
+            do {
+                last = next;
+                next = (top + bot) / 2;                          // aint((top + bot) / 2.0)
+                bits = probe(w, H, T, M, is_short, wsf, next, rowmax, C);
+                if (bits > a.a) top = next; else bot = next;
+            } while (bits != a.a && (last - next > 1 || next - last > 1));
+            q = next;
+        }
+        result = bits;
+        __syncwarp();
+        for (int k = 0; k < 9; k++) {
+            const int s = lane + 32 * k;
+            const int e0 = slot_e0(is_short, s), e1 = is_short ? e0 + 3 : e0 + 1;
+            const U2 v = M.ix[s];
+            ix[e0] = (short)v.x; ix[e1] = (short)v.y;
+        }
+        break;
+    }
+    }
+    if (lane == 0) {
+        a.g.big_values = C.big_values; a.g.count1 = C.count1; a.g.count1table_select = C.count1table_select;
+        a.g.region0_count = C.region0_count; a.g.region1_count = C.region1_count;
+        a.g.table_select[0] = C.table_select[0]; a.g.table_select[1] = C.table_select[1]; a.g.table_select[2] = C.table_select[2];
+        a.g.address1 = C.address1; a.g.address2 = C.address2; a.g.address3 = C.address3;
+        a.result = result; a.q = q;
+        *A = a;
+    }
+}
+
+}  // namespace mp3gpu
+
+static LegacyLoopArgs *g_ll_args = nullptr;
+
+// run one mode of k_legacy_loop on the caller's gr_info; xr (576 doubles, any sign) and ix (576 ints, any sign) may be NULL
+static bool legacy_loop_call(int mode, gr_info *cod, int a, int b, const double *xr, int *ix, bool ix_in, bool ix_out, LegacyLoopArgs *res)
+{
+    if (!legacy_init()) return false;
+    LegacyState &L = g_legacy;
+    if (!legacy_rate_tables(L) || !legacy_probe_buffers()) return false;
+    if (!g_ll_args) {
+        if (cudaMalloc(&g_ll_args, sizeof(LegacyLoopArgs)) != cudaSuccess) legacy_fatal("out of device memory");
+        cudaFuncSetAttribute(k_legacy_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RL_HOT_BYTES + sizeof(RateWarpSmem)));
+    }
+    LegacyLoopArgs h;
+    memset(&h, 0, sizeof(h));
+    h.mode = mode; h.a = a; h.b = b;
+    if (cod) {
+        h.wsf = cod->window_switching_flag != 0; h.bt = h.wsf ? (int)cod->block_type : 0;
+        h.g.big_values = (int)cod->big_values; h.g.count1 = (int)cod->count1; h.g.count1table_select = (int)cod->count1table_select;
+        h.g.region0_count = (int)cod->region0_count; h.g.region1_count = (int)cod->region1_count;
+        h.g.table_select[0] = (int)cod->table_select[0]; h.g.table_select[1] = (int)cod->table_select[1]; h.g.table_select[2] = (int)cod->table_select[2];
+        h.g.address1 = (int)cod->address1; h.g.address2 = (int)cod->address2; h.g.address3 = (int)cod->address3;
+    }
+    cudaError_t e = cudaMemcpy(g_ll_args, &h, sizeof(h), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && xr) {
+        double ax[576];
+        for (int i = 0; i < 576; i++) ax[i] = fabs(xr[i]);
+        e = cudaMemcpy(g_probe.d_x, ax, sizeof(ax), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess && ix && ix_in) {
+        short in[576];
+        for (int i = 0; i < 576; i++) { int v = ix[i] < 0 ? -ix[i] : ix[i]; in[i] = (short)(v > 32767 ? 32767 : v); }
+        e = cudaMemcpy(L.d_ix, in, sizeof(in), cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) {
+        k_legacy_loop<<<1, 32, RL_HOT_BYTES + sizeof(RateWarpSmem)>>>(L.d_rate_tab, g_ll_args, g_probe.d_x, L.d_ix);
+        L.launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(res, g_ll_args, sizeof(*res), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && ix && ix_out) {
+        short out[576];
+        e = cudaMemcpy(out, L.d_ix, sizeof(out), cudaMemcpyDeviceToHost);
+        for (int i = 0; i < 576; i++) ix[i] = out[i];
+    }
+    if (e != cudaSuccess) { legacy_fail(MP3GPU_ECUDA, "loop function", e); return false; }
+    return true;
+}
+
+// loop.c:1488-1519: sets count1 and big_values
+extern "C" void calc_runlen(int ix[576], gr_info *cod_info)
+{
+    LegacyLoopArgs r;
+    if (!legacy_loop_call(LL_RUNLEN, cod_info, 0, 0, nullptr, ix, true, false, &r)) return;
+    cod_info->count1 = r.g.count1; cod_info->big_values = r.g.big_values;
+}
+
+// loop.c:1531-1590: bits of the count1 quads for the caller's big_values / count1; sets count1table_select
+extern "C" int count1_bitcount(int ix[576], gr_info *cod_info)
+{
+    LegacyLoopArgs r;
+    if (!legacy_loop_call(LL_COUNT1, cod_info, 0, 0, nullptr, ix, true, false, &r)) return 0;
+    cod_info->count1table_select = r.g.count1table_select;
+    return r.result;
+}
+
+// loop.c:1638-1704: region0/1_count and (unless big_values == 0) address1..3 from big_values and the block type
+extern "C" void subdivide(gr_info *cod_info)
+{
+    LegacyLoopArgs r;
+    if (!legacy_loop_call(LL_SUBDIVIDE, cod_info, 0, 0, nullptr, nullptr, false, false, &r)) return;
+    cod_info->region0_count = r.g.region0_count; cod_info->region1_count = r.g.region1_count;
+    cod_info->address1 = r.g.address1; cod_info->address2 = r.g.address2; cod_info->address3 = r.g.address3;
+}
+
+// loop.c:1717-1775: table_select[3] for the caller's addresses / big_values
+extern "C" void bigv_tab_select(int ix[576], gr_info *cod_info)
+{
+    LegacyLoopArgs r;
+    if (!legacy_loop_call(LL_TABSEL, cod_info, 0, 0, nullptr, ix, true, false, &r)) return;
+    cod_info->table_select[0] = r.g.table_select[0]; cod_info->table_select[1] = r.g.table_select[1]; cod_info->table_select[2] = r.g.table_select[2];
+}
+
+// loop.c:1793-1900: the cheapest table for ix[begin, end)
+extern "C" int new_choose_table(int ix[576], unsigned int begin, unsigned int end)
+{
+    LegacyLoopArgs r;
+    if (begin > 576) begin = 576;
+    if (end > 576) end = 576;
+    if (!legacy_loop_call(LL_CHOOSE, nullptr, (int)begin, (int)end, nullptr, ix, true, false, &r)) return 0;
+    return r.result;
+}
+
+// loop.c:1954-2016: bits of the big-value regions with the caller's tables and addresses
+extern "C" int bigv_bitcount(int ix[576], gr_info *gi)
+{
+    LegacyLoopArgs r;
+    if (!legacy_loop_call(LL_BIGV, gi, 0, 0, nullptr, ix, true, false, &r)) return 0;
+    return r.result;
+}
+
+static void legacy_loop_result(const LegacyLoopArgs &r, gr_info *c)
+{
+    legacy_count_result(r.g, c);
+    c->quantizerStepSize = (double)r.q;
+}
+
+// loop.c:569-606: from quantizerStepSize upwards until the granule fits max_bits; ix, the count fields and the step are updated
+extern "C" int inner_loop(double xr[2][2][576], int l3_enc[2][2][576], int max_bits, gr_info *cod_info, int gr, int ch)
+{
+    LegacyLoopArgs r;
+    if (!legacy_loop_call(LL_INNER, cod_info, max_bits, (int)cod_info->quantizerStepSize, xr[gr][ch], l3_enc[gr][ch], false, true, &r)) return 0;
+    legacy_loop_result(r, cod_info);
+    return r.result;
+}
+
+// loop.c:2119-2140: binary search of the step between `start` and 200; returns the last step probed
+extern "C" int bin_search_StepSize(int desired_rate, double start, int *ix, double xrs[576], gr_info *cod_info)
+{
+    LegacyLoopArgs r;
+    if (!legacy_loop_call(LL_BINSEARCH, cod_info, desired_rate, (int)start, xrs, ix, false, true, &r)) return 0;
+    legacy_loop_result(r, cod_info);
+    return r.q;
+}

@@ -394,6 +394,14 @@ struct mp3gpu_ctx {
     std::vector<int> h_total;
     bool have_total = false;
     int front_variant = MP3GPU_FRONT_EXACT;
+    // MP3GPU_PIPELINE_OVERLAP: the front end (PCM staging, psy, filterbank + MDCT) of call i + 1 runs on a private low-priority
+    // stream beside the rate loop of call i; psy results, spectra and per-call frame counts are double-buffered
+    int overlap = 0, ov_turn = 0;
+    cudaStream_t front_stream = nullptr;
+    PsyOut *d_psyout2 = nullptr;
+    double *d_xr2 = nullptr;
+    int *d_nfr2 = nullptr;
+    cudaEvent_t ev_front_done[2] = {nullptr, nullptr}, ev_bufs_free[2] = {nullptr, nullptr}, ev_sync = nullptr;
     int *d_sched = nullptr;    // rate-loop work queue: [0] ticket counter, [1 + s] frames of stream s finished in this launch
     // host-PCM ingest: double-buffered dense staging filled on a private copy stream, so that the H2D copy of
     // call i+1 overlaps the kernels of call i (the caller only ever sees its own stream)
@@ -638,7 +646,13 @@ extern "C" void mp3gpu_destroy(mp3gpu_ctx *c)
     cudaDeviceSynchronize();          // nothing of this ctx may still be in flight when its buffers go
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
-    void *ptrs[] = {c->d_total, c->d_nfr, c->d_sched,
+    for (int i = 0; i < 2; i++) {
+        if (c->ev_front_done[i]) cudaEventDestroy(c->ev_front_done[i]);
+        if (c->ev_bufs_free[i]) cudaEventDestroy(c->ev_bufs_free[i]);
+    }
+    if (c->ev_sync) cudaEventDestroy(c->ev_sync);
+    if (c->front_stream) cudaStreamDestroy(c->front_stream);
+    void *ptrs[] = {c->d_psyout2, c->d_xr2, c->d_nfr2, c->d_total, c->d_nfr, c->d_sched,
                     c->d_psy_tab, c->d_rate_tab, c->d_ops1024, c->d_ops256, c->d_lv1024, c->d_lv256, c->d_out1024, c->d_out256,
                     c->d_tw, c->pcm_main.buf, c->pcm_fb.buf, c->pcm_psy.buf, c->d_psy_state, c->d_loop_state, c->d_lane_state,
                     c->d_sb_prev, c->d_mid, c->d_psyout, c->d_xr, c->d_ix, c->d_gi, c->d_sf, c->d_fo,
@@ -667,12 +681,30 @@ static int join_deliveries(mp3gpu_ctx *c, cudaStream_t q)
     return 0;
 }
 
+// Overlap mode: state owned by the front stream (PCM rows, psy state) is about to be touched on q, or q's clears must be
+// visible to the front stream's next kernels.
+static int order_after_front(mp3gpu_ctx *c, cudaStream_t q)
+{
+    if (!c->front_stream) return 0;
+    CU(cudaEventRecord(c->ev_sync, c->front_stream));
+    CU(cudaStreamWaitEvent(q, c->ev_sync, 0));
+    return 0;
+}
+static int front_after(mp3gpu_ctx *c, cudaStream_t q)
+{
+    if (!c->front_stream) return 0;
+    CU(cudaEventRecord(c->ev_sync, q));
+    CU(cudaStreamWaitEvent(c->front_stream, c->ev_sync, 0));
+    return 0;
+}
+
 // forget all per-stream state, ordered on stream q behind everything the ctx has in flight on its private streams
 static int reset_on(mp3gpu_ctx *c, cudaStream_t q)
 {
     const size_t S = c->cfg.max_streams, NCH = c->cfg.n_ch;
     int rc = join_deliveries(c, q);
     if (rc) return rc;
+    if ((rc = order_after_front(c, q))) return rc;
     for (int i = 0; i < 2; i++)
         if (c->ev_ready[i]) CU(cudaStreamWaitEvent(q, c->ev_ready[i], 0));      // host-PCM staging copies
     CU(cudaMemsetAsync(c->pcm_main.buf, 0, S * NCH * c->row * sizeof(short), q));
@@ -688,7 +720,7 @@ static int reset_on(mp3gpu_ctx *c, cudaStream_t q)
     c->frames_done_loop = 0;
     c->have_total = false;
     c->h_total.assign(S, INT_MAX);
-    return 0;
+    return front_after(c, q);
 }
 
 // Synchronous reset: waits for everything in flight on the ctx's device (any stream), clears, returns when cleared.
@@ -720,6 +752,7 @@ extern "C" int mp3gpu_reset_streams(mp3gpu_ctx *c, int first, int count, void *s
     if (first < 0 || count < 1 || (long)first + count > c->cfg.max_streams) return fail(MP3GPU_EINVAL, "stream range out of bounds");
     DEV_GUARD(c);
     cudaStream_t q = (cudaStream_t)stream;
+    { int rco = order_after_front(c, q); if (rco) return rco; }
     const size_t NCH = c->cfg.n_ch, rows = (size_t)count * NCH, r0 = (size_t)first * NCH, pitch = (size_t)c->row * sizeof(short);
     short *bufs[3] = {c->pcm_main.buf, c->pcm_fb.buf, c->pcm_psy.buf};
     for (short *b : bufs)
@@ -730,7 +763,7 @@ extern "C" int mp3gpu_reset_streams(mp3gpu_ctx *c, int first, int count, void *s
     CU(cudaMemsetAsync(c->d_lane_state + first, 0, (size_t)count * sizeof(LoopLaneState), q));
     CU(cudaMemsetAsync(c->d_win + (size_t)first * c->wstride, 0, (size_t)count * c->wstride, q));
     CU(cudaMemsetAsync(c->d_next_begin + first, 0, (size_t)count * sizeof(int), q));
-    return 0;
+    return front_after(c, q);
 }
 
 // Per-stream lengths: stream s ends after frames[s] frames (counted from the last reset).  Calls keep the lockstep shape
@@ -756,14 +789,15 @@ extern "C" int mp3gpu_set_stream_frames(mp3gpu_ctx *c, int n_streams, const long
 }
 
 // the frames each stream contributes to a call starting at absolute frame `done` (nullptr: all of them, no limits set)
-static int call_frames(mp3gpu_ctx *c, long done, int n_streams, int n_frames, cudaStream_t q, const int **nfr)
+static int call_frames(mp3gpu_ctx *c, long done, int n_streams, int n_frames, cudaStream_t q, const int **nfr, int *buf = nullptr)
 {
     *nfr = nullptr;
     if (!c->have_total) return 0;
-    k_call_frames<<<(unsigned)((n_streams + 255) / 256), 256, 0, q>>>(c->d_total, done, n_frames, n_streams, c->d_nfr);
+    if (!buf) buf = c->d_nfr;
+    k_call_frames<<<(unsigned)((n_streams + 255) / 256), 256, 0, q>>>(c->d_total, done, n_frames, n_streams, buf);
     c->launches++;
     CU(cudaGetLastError());
-    *nfr = c->d_nfr;
+    *nfr = buf;
     return 0;
 }
 
@@ -874,6 +908,32 @@ static int stage_pcm_dev(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n
     k_deinterleave<<<(unsigned)((total + 255) / 256), 256, 0, q>>>(pcm, c->pcm_main.buf, c->row, n_streams, c->cfg.n_ch, n);
     c->launches++;
     CU(cudaGetLastError());
+    return 0;
+}
+
+// Pipelining of successive calls of the mp3gpu_encode_frames* family (see mp3gpu.h)
+extern "C" int mp3gpu_set_pipeline(mp3gpu_ctx *c, int mode)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    if (mode != MP3GPU_PIPELINE_SERIAL && mode != MP3GPU_PIPELINE_OVERLAP) return fail(MP3GPU_EINVAL, "unknown pipeline mode");
+    DEV_GUARD(c);
+    CU(cudaDeviceSynchronize());                       // mode switches happen between batches: nothing in flight
+    if (mode == MP3GPU_PIPELINE_OVERLAP && !c->front_stream) {
+        int least = 0, greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CU(cudaStreamCreateWithPriority(&c->front_stream, cudaStreamNonBlocking, least));
+        const size_t S = c->cfg.max_streams, GC = (size_t)c->cfg.max_frames * 2 * c->cfg.n_ch;
+        int rc;
+        if ((rc = dalloc(&c->d_psyout2, S * GC))) return rc;
+        if ((rc = dalloc(&c->d_xr2, S * GC * 576))) return rc;
+        if ((rc = dalloc(&c->d_nfr2, S))) return rc;
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventCreateWithFlags(&c->ev_front_done[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->ev_bufs_free[i], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming));
+    }
+    c->overlap = mode == MP3GPU_PIPELINE_OVERLAP;
     return 0;
 }
 
@@ -1030,22 +1090,35 @@ static int encode_common(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n
     if (!pcm) return fail(MP3GPU_EINVAL, "null pcm");
     cudaStream_t q = (cudaStream_t)stream;
     const size_t gcs = (size_t)n_streams * n_frames * 2 * c->cfg.n_ch;
-    if (host) rc = stage_pcm_host_overlapped(c, pcm, n_streams, n_frames, q);
-    else rc = stage_pcm_dev(c, pcm, n_streams, n_frames, q);
+    // Overlap mode: everything up to the spectra runs on the private front stream `f` into buffer set b, the rate loop
+    // and what follows on the caller's stream q; q waits for f, f waits for the rate loop that last read buffer set b.
+    const bool ov = c->overlap != 0;
+    cudaStream_t f = ov ? c->front_stream : q;
+    const int b = ov ? (c->ov_turn ^= 1) : 0;
+    PsyOut *psyout = b ? c->d_psyout2 : c->d_psyout;
+    double *xrb = b ? c->d_xr2 : c->d_xr;
+    if (ov) CU(cudaStreamWaitEvent(f, c->ev_bufs_free[b], 0));
+    if (host) rc = stage_pcm_host_overlapped(c, pcm, n_streams, n_frames, f);
+    else rc = stage_pcm_dev(c, pcm, n_streams, n_frames, f);
     if (rc) return rc;
     const int *nfr = nullptr;
-    if ((rc = call_frames(c, c->frames_done_loop, n_streams, n_frames, q, &nfr))) return rc;
+    if ((rc = call_frames(c, c->frames_done_loop, n_streams, n_frames, f, &nfr, b ? c->d_nfr2 : c->d_nfr))) return rc;
     if (nfr_out) *nfr_out = nfr;
     // musicin.c:751-779 order: psy first (it decides block_type), then filterbank + MDCT, then the rate loop
-    if ((rc = launch_psy(c, c->pcm_main.buf, n_streams, n_frames, c->d_psyout, q, nfr))) return rc;
+    if ((rc = launch_psy(c, c->pcm_main.buf, n_streams, n_frames, psyout, f, nfr))) return rc;
     const bool f32 = c->front_variant == MP3GPU_FRONT_FP32;      // the FP32 front end hands float spectra to the rate loop
-    if ((rc = launch_front(c, c->pcm_main.buf, c->d_psyout, n_streams, n_frames, c->d_xr, nullptr, true, q, nfr, f32))) return rc;
+    if ((rc = launch_front(c, c->pcm_main.buf, psyout, n_streams, n_frames, xrb, nullptr, true, f, nfr, f32))) return rc;
+    if ((rc = roll_pcm(c, c->pcm_main, n_streams, n_frames, f))) return rc;
+    if (ov) {
+        CU(cudaEventRecord(c->ev_front_done[b], f));
+        CU(cudaStreamWaitEvent(q, c->ev_front_done[b], 0));
+    }
     short *o_ix = host ? c->d_ix : (ix ? ix : c->d_ix);
     GrInfoOut *o_gi = host ? c->d_gi : (gi ? (GrInfoOut *)gi : c->d_gi);
     unsigned char *o_sf = host ? c->d_sf : (sf ? sf : c->d_sf);
     FrameOut *o_fo = host ? c->d_fo : (fo ? (FrameOut *)fo : c->d_fo);
-    if ((rc = launch_rate_loop(c, c->d_xr, c->d_psyout, n_streams, n_frames, o_ix, o_gi, o_sf, o_fo, q, nfr, f32))) return rc;
-    if ((rc = roll_pcm(c, c->pcm_main, n_streams, n_frames, q))) return rc;
+    if ((rc = launch_rate_loop(c, xrb, psyout, n_streams, n_frames, o_ix, o_gi, o_sf, o_fo, q, nfr, f32))) return rc;
+    if (ov) CU(cudaEventRecord(c->ev_bufs_free[b], q));          // re-recorded behind the formatter by the mp3 entry points
     c->frames_done_loop += n_frames;
     if (host) {
         if (ix) CU(cudaMemcpyAsync(ix, c->d_ix, gcs * 576 * sizeof(short), cudaMemcpyDeviceToHost, q));
@@ -1205,7 +1278,9 @@ static int encode_mp3_common(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, i
     const int *nfr = nullptr;
     rc = encode_common(c, pcm, n_streams, n_frames, nullptr, nullptr, nullptr, nullptr, stream, host, &nfr);
     if (rc) return rc;
-    return format_common(c, c->d_ix, c->d_gi, c->d_sf, c->d_fo, n_streams, n_frames, mp3, stride, host, (cudaStream_t)stream, nfr);
+    rc = format_common(c, c->d_ix, c->d_gi, c->d_sf, c->d_fo, n_streams, n_frames, mp3, stride, host, (cudaStream_t)stream, nfr);
+    if (!rc && c->overlap) CU(cudaEventRecord(c->ev_bufs_free[c->ov_turn], (cudaStream_t)stream));
+    return rc;
 }
 
 extern "C" int mp3gpu_encode_frames_mp3(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n_frames, uint8_t *mp3, long mp3_stride, void *stream)

@@ -283,6 +283,8 @@ SIMT_FN void refresh_pow34(const WarpCtx &w, RateWarpSmem &M, PerThread<float> &
     w.sync();
 }
 
+SIMT_FN int count_regions(const WarpCtx &w, const RateHot &H, const RateWarpSmem &M, bool is_short, int bvr, int c1bits, CountResult &C);
+
 // count_bits() = calc_runlen + count1_bitcount + subdivide + bigv_tab_select + bigv_bitcount
 // (loop.c:2099-2113 and 590-594) on the quantised values in shared memory.  `C` carries address1..3
 // across probes exactly like the reference's cod_info does (subdivide() leaves them untouched when
@@ -339,10 +341,16 @@ SIMT_FN int count_all(const WarpCtx &w, const RateHot &H, const RateWarpSmem &M,
             C.address1 = H.sfb_l[8]; C.address2 = bvr; C.address3 = 0;
         }
     }
-    // ---- bigv_tab_select + bigv_bitcount (loop.c:1717-1775, 1793-1943, 1954-2016) ----
-    // region of element e: R0 = [0,a1), R1 = [a1,a2) if a2 > a1, R2 = [a2,bvr) if bvr > a2.  (Region-2
-    // counting in the reference runs over [a2, a3): a3 == bvr for plain long blocks and 0 for
-    // start/stop/short blocks, where region 2 is never selected, so [a2,bvr) covers both.)
+    return count_regions(w, H, M, is_short, bvr, c1bits, C);
+}
+
+// bigv_tab_select + bigv_bitcount (loop.c:1717-1775, 1793-1943, 1954-2016) on the regions given by C.address1 / C.address2
+// and bvr = 2 * big_values; adds the bits to c1bits, sets C.table_select and C.bits.
+// region of element e: R0 = [0,a1), R1 = [a1,a2) if a2 > a1, R2 = [a2,bvr) if bvr > a2.  (Region-2
+// counting in the reference runs over [a2, a3): a3 == bvr for plain long blocks and 0 for
+// start/stop/short blocks, where region 2 is never selected, so [a2,bvr) covers both.)
+SIMT_FN int count_regions(const WarpCtx &w, const RateHot &H, const RateWarpSmem &M, bool is_short, int bvr, int c1bits, CountResult &C)
+{
     const int a1 = C.address1, a2 = C.address2;
     const bool has0 = a1 > 0, has1 = a2 > a1, has2 = !is_short && bvr > a2;
     // Slots s hold elements 2 s, 2 s + 1 and a1, a2, bvr are even, so region r is the slot range [lo[r], hi[r]) (empty when

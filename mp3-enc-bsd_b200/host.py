@@ -38,9 +38,11 @@ EXPORTS = ["mp3gpu_last_error", "mp3gpu_version", "mp3gpu_create", "mp3gpu_destr
            "mp3gpu_encode_frames_mp3", "mp3gpu_encode_frames_mp3_dev", "mp3gpu_flush_mp3", "mp3gpu_flush_mp3_dev",
            "mp3gpu_frame_bytes", "mp3gpu_format_bitstream_batch", "mp3gpu_begin_segment", "mp3gpu_stream_wave", "mp3gpu_set_pcm_layout", "mp3gpu_count_bits_batch", "mp3gpu_set_host_delivery",
            "mp3gpu_reset_async", "mp3gpu_set_stream_frames", "mp3gpu_reset_streams",
-           "mp3gpu_set_front_variant", "mp3gpu_get_front_variant"]
+           "mp3gpu_set_front_variant", "mp3gpu_get_front_variant", "mp3gpu_set_pipeline"]
 FRONT_VARIANTS = {"exact": 0, "fma": 1, "fp32": 2, "fma_tc": 3}
 LEGACY_EXPORTS = ["window_subband", "filter_subband", "mdct_sub", "L3psycho_anal", "iteration_loop", "quantize", "count_bits",
+                  "inner_loop", "bin_search_StepSize", "calc_runlen", "count1_bitcount", "subdivide", "bigv_tab_select",
+                  "new_choose_table", "bigv_bitcount",
                   "mp3gpu_legacy_reset", "mp3gpu_legacy_kernel_launches"]
 KERNEL_NAMES = ["psy_front", "psy_scan", "front_polyphase_mdct", "rate_loop", "bitstream"]
 
@@ -78,6 +80,7 @@ def load_library():
         lib.mp3gpu_set_stream_frames.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_long), C.c_void_p]
         lib.mp3gpu_reset_streams.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.mp3gpu_set_front_variant.argtypes = [C.c_void_p, C.c_int]
+        lib.mp3gpu_set_pipeline.argtypes = [C.c_void_p, C.c_int]
         lib.mp3gpu_get_front_variant.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.mp3gpu_sync.argtypes = [C.c_void_p, C.c_void_p]
         lib.mp3gpu_frame_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -157,6 +160,10 @@ class Encoder:
             self._check(self.lib.mp3gpu_reset(self.ctx), "mp3gpu_reset")
         else:
             self._check(self.lib.mp3gpu_reset_async(self.ctx, C.c_void_p(stream or 0)), "mp3gpu_reset_async")
+
+    def set_pipeline(self, overlap):
+        """False: all work of a call on the caller's stream; True: the front end of call i+1 beside the rate loop of call i (mp3gpu.h)"""
+        self._check(self.lib.mp3gpu_set_pipeline(self.ctx, 1 if overlap else 0), "mp3gpu_set_pipeline")
 
     def set_front_variant(self, name):
         """arithmetic of the fused filterbank + MDCT kernel: "exact" (default), "fma" (FP64, <= 1e-12), "fp32" (<= 1e-5)"""

@@ -135,3 +135,52 @@ def test_two_ctxs_on_one_device_interleaved(pkg):
     l1, l2 = e1.flush_mp3(m1, 1), e2.flush_mp3(m2, 1)
     assert m1[0, :l1[0]].tobytes() == oracle_bytes(a) and m2[0, :l2[0]].tobytes() == oracle_bytes(b, 44100, 64)
     assert torch.cuda.current_device() == 0
+
+
+@pytest.mark.parametrize("host", [True, False])
+def test_overlap_pipeline_gives_identical_bytes(pkg, host):
+    """MP3GPU_PIPELINE_OVERLAP: the front end of call i+1 runs beside the rate loop of call i on a private stream with
+    double-buffered spectra; ragged chunks, per-stream lengths, two batches with a stream-ordered reset between them"""
+    S, F = 9, 26
+    lens = [F * 1152, 20 * 1152 + 5, 3 * 1152, F * 1152, 1, 11 * 1152, F * 1152 - 1, 7 * 1152, 25 * 1152]
+    pcm = np.zeros((S, 2, F * 1152), np.int16)
+    clips = []
+    for s, n in enumerate(lens):
+        c = clip(pkg, n, 1200 + 3 * s)
+        clips.append(c)
+        pcm[s, :, :n] = c
+    want = [oracle_bytes(c) for c in clips]
+    enc = pkg.Encoder(44100, 2, 128, max_streams=S, max_frames=7)
+    enc.set_pipeline(True)
+    st = torch.cuda.Stream()
+    dev = torch.device("cuda", 0)
+    for batch in range(2):
+        enc.reset(stream=st.cuda_stream)
+        enc.set_stream_frames([(n + 1151) // 1152 for n in lens], stream=st.cuda_stream)
+        if host:
+            mp3 = torch.zeros((S, F * enc.frame_bytes), dtype=torch.uint8).pin_memory().numpy()
+            pin = torch.from_numpy(pcm).pin_memory().numpy()
+        else:
+            mp3 = torch.zeros((S, F * enc.frame_bytes), dtype=torch.uint8, device=dev)
+            pin = torch.from_numpy(pcm).to(dev)
+        # overlap mode reads the PCM on a private stream: the chunks must be complete when the call is made and stay alive
+        # until the batch is flushed (mp3gpu.h), so they are all prepared up front
+        sizes, f0, chunks = [7, 1, 5, 7, 2, 4], 0, []
+        for cfr in sizes:
+            ch = pin[:, :, f0 * 1152:(f0 + cfr) * 1152]
+            chunks.append(np.ascontiguousarray(ch) if host else ch.contiguous())
+            f0 += cfr
+        assert f0 == F
+        torch.cuda.synchronize()
+        for ch in chunks:
+            if host:
+                enc.encode_frames_mp3(ch, mp3, stream=st.cuda_stream)
+            else:
+                enc.encode_frames_mp3_dev(ch, mp3, stream=st.cuda_stream)
+        lengths = enc.flush_mp3(mp3, S, stream=st.cuda_stream)
+        out = mp3 if host else mp3.cpu().numpy()
+        for s in range(S):
+            assert out[s, :lengths[s]].tobytes() == want[s], (batch, s, lengths[s], len(want[s]))
+    enc.set_pipeline(False)
+    got = enc.encode_streams(pcm, chunk_frames=7, n_samples=lens)
+    assert got == want
