@@ -171,6 +171,11 @@ __device__ __forceinline__ const RateHot &load_rate_hot(const RateTables *gT, un
 // reached f, then loads the stream's state (LoopStreamState + LoopLaneState, 1.1 KB), encodes the frame and publishes
 // f + 1.  An awaited frame is always in the hands of a running warp (tickets are only drawn by running warps), so waiting
 // cannot deadlock whatever part of the grid is resident.
+// Hand-over without touching L1: the stream state is read and written with L2-coherent (.relaxed.gpu, SASS .STRONG.GPU)
+// accesses, the progress word is polled the same way, and the only fence is the MEMBAR of the releasing store.  The reader
+// issues its state loads after the polled value has come back (no speculation), the writer's state stores are at L2 before
+// the progress word is — so no acquire fence is needed, and with it no CCTL.IVALL: an acquire per poll, or even per item,
+// throws away the quantiser / noise tables that every warp of the SM keeps re-reading through L1.
 // Why: with one warp owning a stream for a whole call, 10 000 streams on 4144 warp slots ran as 3 rounds for 2.41 rounds of
 // work and every CTA waited for its slowest warp; below one wave the CTAs of 28 warps left most SMs empty (1250 streams =
 // 45 SMs).  Frame-granular items balance to within one frame (~0.7 ms of ~60 ms), and the launch spreads min(28, S / SMs)
@@ -180,6 +185,19 @@ __device__ __forceinline__ int ld_acquire_gpu(const int *p)
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+// polling load: served by L2, no ordering — an acquire load invalidates the SM's L1 every time it executes, and with it the
+// quantiser / noise tables every other warp of the SM is reading (ncu: 66 % of the long-scoreboard stalls of the first
+// persistent version were pow43[] gathers that kept missing L1 behind the pollers)
+__device__ __forceinline__ int ld_relaxed_gpu(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(int *p, int v)
+{
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_release_gpu(int *p, int v)
 {
@@ -199,33 +217,52 @@ k_rate_loop(const RateTables *__restrict__ gT, FrameGeom G, LoopStreamState *sta
     WarpCtx w{WarpCtx::Pinned()};
     const int lane = w.lane;
     const int gpf = 2 * G.n_ch;                                  // granule-channels per frame
+    const int wpc = blockDim.x >> 5;
+    // Every stream has a warp of its own (batch <= warps of the grid): static assignment, the warp walks the frames of its
+    // stream in order — no waiting, no fences, nothing that flushes L1.  Otherwise: the ticket queue.  (One frame per trip
+    // in both modes: the code of the item exists once, this kernel pays for code size.)
+    const bool fixed = (long)n_streams <= (long)gridDim.x * wpc;
     const long total = (long)n_streams * n_frames;
+    int next_f = 0;
     for (;;) {
-        long t = 0;
-        if (lane == 0) t = (long)atomicAdd(reinterpret_cast<unsigned int *>(sched), 1u);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= total) break;
-        const int f = (int)(t / n_streams);
-        const long s = t - (long)f * n_streams;
-        if (nfr && f >= nfr[s]) continue;                        // the stream ended before this frame
-        if (f > 0) {
-            if (lane == 0) while (ld_acquire_gpu(sched + 1 + s) < f) __nanosleep(200);
-            __syncwarp();
+        long s;
+        int f;
+        if (fixed) {
+            s = (long)blockIdx.x * wpc + warp;
+            f = next_f++;
+            if (s >= n_streams || f >= (nfr ? min(n_frames, nfr[s]) : n_frames)) break;
+        } else {
+            long t = 0;
+            if (lane == 0) t = (long)atomicAdd(reinterpret_cast<unsigned int *>(sched), 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= total) break;
+            f = (int)(t / n_streams);
+            s = t - (long)f * n_streams;
+            if (nfr && f >= nfr[s]) continue;                    // the stream ended before this frame
+            if (f > 0) {
+                if (lane == 0) while (ld_relaxed_gpu(sched + 1 + s) < f) __nanosleep(200);
+                __syncwarp();
+            }
         }
-        LoopStreamState S = states[s];
+        LoopStreamState S;
+        static_assert(sizeof(LoopStreamState) % 4 == 0, "LoopStreamState is copied word by word");
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(LoopStreamState) / 4); i++)
+            reinterpret_cast<int *>(&S)[i] = ld_relaxed_gpu(reinterpret_cast<const int *>(&states[s]) + i);
         PerThread<int> st_en[4], st_xm[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { st_en[i].v = lane_states[s].en[i][lane]; st_xm[i].v = lane_states[s].xm[i][lane]; }
-        const long g0 = (s * n_frames + f) * gpf;                // first granule-channel of the frame
+        for (int i = 0; i < 4; i++) { st_en[i].v = ld_relaxed_gpu(&lane_states[s].en[i][lane]); st_xm[i].v = ld_relaxed_gpu(&lane_states[s].xm[i][lane]); }
+        const long g0 = (s * n_frames + f) * gpf;                // first granule-channel of the item
         const double *xf = G.xr_f32 ? reinterpret_cast<const double *>(reinterpret_cast<const float *>(xr) + g0 * 576) : xr + g0 * 576;
         rate_loop_stream(w, H, *gT, M, G, S, st_en, st_xm, 1, xf, psy + g0, ix + g0 * 576, gi + g0, sf + g0 * 40,
                          fo + s * (long)n_frames + f, nullptr);
 #pragma unroll
-        for (int i = 0; i < 4; i++) { lane_states[s].en[i][lane] = st_en[i].v; lane_states[s].xm[i][lane] = st_xm[i].v; }
-        if (lane == 0) states[s] = S;
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) st_release_gpu(sched + 1 + s, f + 1);
+        for (int i = 0; i < 4; i++) { st_relaxed_gpu(&lane_states[s].en[i][lane], st_en[i].v); st_relaxed_gpu(&lane_states[s].xm[i][lane], st_xm[i].v); }
+        if (lane < (int)(sizeof(LoopStreamState) / 4)) st_relaxed_gpu(reinterpret_cast<int *>(&states[s]) + lane, reinterpret_cast<const int *>(&S)[lane]);
+        if (!fixed) {
+            __syncwarp();                                        // every lane's state stores are issued before lane 0's MEMBAR + store
+            if (lane == 0) st_release_gpu(sched + 1 + s, f + 1);
+        }
     }
 }
 
