@@ -380,8 +380,10 @@ def main():
     torch.cuda.synchronize(device)
     t_host = timed(step_host, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    # separate profiled pass: CUDA events around every launch of the hot kernels (per-kernel split + the roofline figure)
+    # separate profiled pass: CUDA events around every launch of the hot kernels (per-kernel split + the roofline figure);
+    # serial pipeline, so that a kernel's events bracket that kernel alone
     enc.set_host_delivery(False)
+    enc.set_pipeline(False)
     enc.profile_enable(True)
     enc.profile_collect(reset=True)
     prof_steps = max(1, min(args.steps, 2))
@@ -460,7 +462,7 @@ def main():
                      "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per granule-channel (%s) x "
                                        "granule-channels per launch" % FRONT_TRAFFIC_SOURCE,
                      "achieved_per_launch_bytes": front_info["bytes_per_gc"] * gc_per_launch,
-                     "measured_in": "separate profiled pass of %d step(s) (CUDA events around every launch)" % prof_steps},
+                     "measured_in": "separate profiled pass of %d step(s), serial pipeline (CUDA events around every launch)" % prof_steps},
         "kernels": kernels,
         "clocks": clocks,
     }

@@ -141,6 +141,30 @@ __device__ __forceinline__ void ft_mdct_short6(const double (&in)[36], double (&
     }
 }
 
+// ---- bulk asynchronous copy (TMA engine, SASS UBLKCP) of the contiguous PCM tile into shared memory -----------------------
+// One elected thread posts the copy and the byte count on an mbarrier; every thread waits on the barrier's phase.  The
+// tile is one contiguous, 16-byte aligned run of a PCM row, so the 1-D bulk form is enough (no tensor map).
+#ifndef FT_TMA
+#define FT_TMA 1      // A/B (profiles/r02_front_variants.md): 1 = cp.async.bulk, 0 = 16-byte loads by all threads
+#endif
+__device__ __forceinline__ unsigned ft_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ft_mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ft_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void ft_bulk_load(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ft_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(ft_smem_u32(dst)), "l"(src), "r"(bytes), "r"(ft_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ft_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}"
+                 ::"r"(ft_smem_u32(bar)), "r"(parity) : "memory");
+}
+
 __device__ __forceinline__ void ft_group_barrier(int group)   // the three warps of one granule
 {
     asm volatile("bar.sync %0, 96;" ::"r"(group + 1) : "memory");
@@ -159,6 +183,22 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_tiles = (n_gran + FT_G - 1) / FT_G;
     const double *tab = M.tab;
+#if FT_TMA && !FT_PERSISTENT
+    // the PCM tile is on its way (TMA engine) while the threads fetch the tables
+    __shared__ unsigned long long ft_bar;
+    {
+        const long bid0 = blockIdx.x;
+        const int t0 = (int)(bid0 % n_tiles), ch0 = (int)((bid0 / n_tiles) % n_ch);
+        const long s0 = bid0 / ((long)n_tiles * n_ch);
+        const int live0 = nfr ? min(n_gran, 2 * nfr[s0]) : n_gran, ng0 = min(FT_G, live0 - t0 * FT_G);
+        if (ng0 <= 0) return;                                       // CTA-uniform: the stream ended before this tile
+        if (tid == 0) {
+            ft_mbar_init(&ft_bar, 1);
+            const short *src0 = pcm_rows + s0 * stream_stride + ch0 * ch_stride + hist + 576L * (t0 * FT_G - 1) - 480;
+            ft_bulk_load(M.pcm, src0, (unsigned)((480 + 32 * 18 * (ng0 + 1)) * sizeof(short)), &ft_bar);
+        }
+    }
+#endif
     {
         if (tid < 256) reinterpret_cast<double2 *>(M.window)[tid] = reinterpret_cast<const double2 *>(g_front.window)[tid];
         double2 *t2 = reinterpret_cast<double2 *>(M.tab);
@@ -193,12 +233,21 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
     {
         const short *src = pcm_rows + s * stream_stride + ch * ch_stride + hist + 576L * (g_first - 1) - 480;
         const int n_valid = 480 + 32 * n_slots;           // multiple of 8
-        const uint4 *src4 = reinterpret_cast<const uint4 *>(src);
         uint4 *dst4 = reinterpret_cast<uint4 *>(M.pcm);
+#if FT_TMA && !FT_PERSISTENT
+        (void)src;
+        for (int i = n_valid / 8 + tid; i < FT_PCM / 8; i += FT_THREADS) dst4[i] = make_uint4(0, 0, 0, 0);   // a short last tile
+#else
+        const uint4 *src4 = reinterpret_cast<const uint4 *>(src);
         for (int i = tid; i < FT_PCM / 8; i += FT_THREADS)
             dst4[i] = (i < n_valid / 8) ? src4[i] : make_uint4(0, 0, 0, 0);
+#endif
         if (tid < ng) M.bt[tid] = psy[((s * n_gran + g_first + tid) * (long)n_ch + ch)].block_type;
     }
+#if FT_TMA && !FT_PERSISTENT
+    __syncthreads();                                      // thread 0's mbarrier.init is visible to every waiter
+    ft_mbar_wait(&ft_bar, 0);
+#endif
     __syncthreads();
 
     // ---- stage A: lane = tap i (and i+32); slots of one parity form a sliding 8-tap FIR -------------

@@ -546,11 +546,13 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
         scr[s] = simt::dadd(a2, b2);
         e2 = simt::dadd(e2, simt::dadd(a2, b2));
         // quantanf_init's sum of log(xr^2) over the non-zero lines (loop.c:380-386): one log per six lines on the product of
-        // their squares (|xr| of non-zero MDCT lines lies within 1e+-40, far from over / underflow); like the lane-wise order
-        // of the sum this moves sum1 by a few ulp, which nint(8 ln(sfm)) only sees on an exact rounding boundary
+        // their squares; like the lane-wise order of the sum this moves sum1 by a few ulp, which nint(8 ln(sfm)) only sees on
+        // an exact rounding boundary.  Six squares stay normal numbers for |xr| in 1e-25 .. 1e+25; rounding residue of a
+        // cancelling MDCT can be smaller, so the product is flushed early whenever it leaves 1e-200 .. 1e+200 (a square
+        // itself cannot underflow before |xr| < 1e-154, where the reference's own xr * xr is already denormal).
         pr = simt::dmul(pr, a != 0 ? a2 : 1.0);
         pr = simt::dmul(pr, b != 0 ? b2 : 1.0);
-        if (k % 3 == 2) { lg = simt::dadd(lg, ref_log(pr)); pr = 1.0; }
+        if (k % 3 == 2 || pr < 1e-200 || pr > 1e200) { lg = simt::dadd(lg, ref_log(pr)); pr = 1.0; }
     }
     sign() = sg; t0() = mx; t1() = e2;
     Bd.xfsf[0]() = lg;  // borrowed as scratch for the log sum

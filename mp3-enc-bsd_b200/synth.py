@@ -174,3 +174,65 @@ def hetero_stream(torch, start, count, fs=44100, n_ch=2, device="cpu"):
     """samples [start, start+count) of THE long stream of BASELINE configs[4] (clip 0 as class "am-tone": the config-1
     recipe under a slow amplitude envelope): int16 [n_ch][count]"""
     return hetero_batch(torch, 0, 1, count, fs, n_ch, device, force_class=7, start=start)[0]
+
+
+# ---- machine-independent clips (IEEE add / multiply and integer arithmetic only) -------------------------------------------
+# numpy's sin / exp may differ in the last bit between CPUs (SIMD code paths), which after rounding to int16 can change a
+# sample; fixtures that are stored as HASHES of the reference's output need PCM that is the same everywhere.
+def _lcg_noise(n, seed):
+    """uniform noise in [-1, 1): 64-bit LCG (Knuth's MMIX constants) evaluated by jumping, top 24 bits"""
+    a, c, m = 6364136223846793005, 1442695040888963407, (1 << 64) - 1
+    # x_k = a^k x_0 + c (a^k - 1) / (a - 1): evaluate blockwise with Python big ints for the block heads, numpy inside
+    out = np.empty(n, np.float64)
+    x = (seed * 2654435761 + 12345) & m
+    block = 1 << 16
+    ak, ck = np.uint64(a), np.uint64(c)
+    for b0 in range(0, n, block):
+        k = min(block, n - b0)
+        v = np.empty(k, np.uint64)
+        cur = np.uint64(x)
+        with np.errstate(over="ignore"):
+            for i in range(k):
+                cur = cur * ak + ck
+                v[i] = cur
+        x = int(cur)
+        out[b0:b0 + k] = (v >> np.uint64(40)).astype(np.float64) / float(1 << 23) - 1.0
+    return out
+
+
+def _parabolic_tone(n, fs, freq_mhz, phase0=0):
+    """sine-like wave from integer phase arithmetic: p = frac(f t) exactly (integers), s = 16 p (1 - p) on each half wave"""
+    t = np.arange(n, dtype=np.int64)
+    period_units = fs * 1000                                  # phase in units of 1 / (fs * 1000) cycles
+    ph = (t * freq_mhz + phase0) % period_units               # exact integers (freq in millihertz)
+    p = ph.astype(np.float64) / float(period_units)           # one correctly rounded division
+    half = p < 0.5
+    q = np.where(half, p, p - 0.5) * 2.0
+    s = 4.0 * q * (1.0 - q)
+    return np.where(half, s, -s)
+
+
+def exact_clip(kind, seconds, fs, n_ch, seed=1):
+    """int16 [n_ch][n], identical on every IEEE machine.  kind: "music" (three tones + noise), "transient" (decaying noise
+    bursts on near silence every 250 ms: drives short blocks), "loud" (full-band noise at -10 dB: bit pressure)"""
+    n = int(round(seconds * fs))
+    chans = []
+    for ch in range(n_ch):
+        noise = _lcg_noise(n, 1000 * seed + ch)
+        if kind == "music":
+            x = 0.25 * _parabolic_tone(n, fs, 440000 + 7000 * ch) + 0.15 * _parabolic_tone(n, fs, 1330500, 12345 * (ch + 1)) + \
+                0.1 * _parabolic_tone(n, fs, 5200250) + 0.04 * noise
+        elif kind == "transient":
+            t = np.arange(n, dtype=np.int64)
+            per, burst = fs // 4, fs // 50
+            k = (t - fs // 10) % per
+            on = (t >= fs // 10) & (k < burst)
+            env = np.where(on, (1.0 - k.astype(np.float64) / float(burst)) ** 2, 0.0)
+            env = env * env                                      # (1 - k / burst)^4: fast decay, arithmetic only
+            x = 1e-3 * noise + 0.9 * env * noise
+        elif kind == "loud":
+            x = 0.3 * noise
+        else:
+            raise ValueError(kind)
+        chans.append(x)
+    return _to_i16(np.stack(chans))
