@@ -37,7 +37,9 @@ def run(args, cfg, config_common, mod, rank, world, local_rank, device):
     enc = mod.Encoder(FS, NCH, KBPS, max_streams=max(S, 1), max_frames=max(L, P), device=local_rank)
     if args.front:
         enc.set_front_variant(args.front)
-    enc.set_pipeline(args.pipeline == "overlap")
+    # serial pipeline: the segment batch is produced on the caller's stream right before each call, and overlap mode reads
+    # the PCM on a private stream (mp3gpu.h: the buffer must be complete when the call is made)
+    enc.set_pipeline(False)
     FB = enc.frame_bytes
     # the rank's part of the stream: frames [klo*L - P, khi*L), zero-padded at both ends of the stream
     a, b = (klo * L - P) * 1152, khi * L * 1152
@@ -127,7 +129,6 @@ def run(args, cfg, config_common, mod, rank, world, local_rank, device):
         step(True)
     t_host = timed(True, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    enc.set_pipeline(False)
     enc.profile_enable(True)
     enc.profile_collect(reset=True)
     step(False)
