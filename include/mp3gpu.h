@@ -142,6 +142,18 @@ int mp3gpu_get_front_variant(const mp3gpu_ctx *ctx, int *variant, int *algorithm
  * SERIAL mode.  One difference: the device-pointer variants read `pcm` on the private stream, so the buffer must be
  * complete when the call is made (not produced by work still pending on `stream`); work enqueued on `stream` after the call
  * is ordered behind that read.  Switch modes between batches (the call synchronises the device). */
+/* Speculative segmentation of the rate loop (on by default).  When a call's batch leaves at least half of the device's
+ * warp slots empty, the frames of the call are cut into up to 8 segments per stream that are encoded concurrently: segment
+ * 0 from the stream's state, the others from a guessed reservoir; a segment whose predecessor ended elsewhere is encoded
+ * again from the true state until its state rejoins the recorded one.  The result is bit-identical to the sequential order
+ * (reservoir.c:101-145) by construction — only the latency of a stream's dependency chain changes.  Longer calls (more
+ * frames per call) give it more to cut.  0 switches it off (A/B, tests). */
+int mp3gpu_set_rate_loop_segments(mp3gpu_ctx *ctx, int enable);
+/* diagnostics since ctx creation (or the last reset = 1): for pass p = 0..7, out[4p .. 4p+3] = frames encoded, frames replayed
+ * (only the reservoir bookkeeping redone), segments left alone, segments that rejoined their previous run before their end.
+ * Synchronises the device. */
+int mp3gpu_rate_loop_segment_stats(mp3gpu_ctx *ctx, long out[32], int reset);
+
 #define MP3GPU_PIPELINE_SERIAL 0
 #define MP3GPU_PIPELINE_OVERLAP 1
 int mp3gpu_set_pipeline(mp3gpu_ctx *ctx, int mode);

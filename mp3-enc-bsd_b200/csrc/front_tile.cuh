@@ -231,13 +231,12 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
 
     // ---- stage 0: PCM tile.  smem sample j <-> stream time 576*(g_first-1) - 480 + j ---------------
     {
-        const short *src = pcm_rows + s * stream_stride + ch * ch_stride + hist + 576L * (g_first - 1) - 480;
         const int n_valid = 480 + 32 * n_slots;           // multiple of 8
         uint4 *dst4 = reinterpret_cast<uint4 *>(M.pcm);
 #if FT_TMA && !FT_PERSISTENT
-        (void)src;
         for (int i = n_valid / 8 + tid; i < FT_PCM / 8; i += FT_THREADS) dst4[i] = make_uint4(0, 0, 0, 0);   // a short last tile
 #else
+        const short *src = pcm_rows + s * stream_stride + ch * ch_stride + hist + 576L * (g_first - 1) - 480;
         const uint4 *src4 = reinterpret_cast<const uint4 *>(src);
         for (int i = tid; i < FT_PCM / 8; i += FT_THREADS)
             dst4[i] = (i < n_valid / 8) ? src4[i] : make_uint4(0, 0, 0, 0);

@@ -145,7 +145,7 @@ static bool legacy_init()
     if (e == cudaSuccess) e = cudaMalloc(&L.d_xr4, 4 * 576 * sizeof(double));
     if (e != cudaSuccess) { legacy_fail(MP3GPU_ECUDA, "init", e); return false; }
     cudaFuncSetAttribute(k_psy_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PSYF_WARPS * sizeof(PsyFrontSmem)));
-    cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES);
+    cudaFuncSetAttribute(k_rate_loop<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES);
     L.ready = true;
     mp3gpu_legacy_reset();
     return true;
@@ -310,8 +310,10 @@ extern "C" void iteration_loop(double pe[][2], double xr_org[2][2][576], III_psy
     G.n_ch = stereo; G.mean_bits = mean_bits; G.bits_per_frame = bitsPerFrame;
     frame_geom_derive(&G);
     LCU(cudaMemset(L.d_sched, 0, 2 * sizeof(int)));
-    k_rate_loop<<<1, 32, RL_HOT_BYTES + sizeof(RateWarpSmem)>>>(L.d_rate_tab, G, L.d_loop_state, L.d_lane_state, 1, 1, nullptr, L.d_sched, L.d_xr4,
-                                                                 L.d_psyout, L.d_ix, L.d_gi, L.d_sf, L.d_fo);
+    SegArgs no_seg;
+    memset(&no_seg, 0, sizeof(no_seg));
+    k_rate_loop<false><<<1, 32, RL_HOT_BYTES + sizeof(RateWarpSmem)>>>(L.d_rate_tab, G, L.d_loop_state, L.d_lane_state, 1, 1, nullptr, L.d_sched, no_seg,
+                                                                 L.d_xr4, L.d_psyout, L.d_ix, L.d_gi, L.d_sf, L.d_fo);
     L.launches++;
     LCU(cudaGetLastError());
     short ix[4][576];

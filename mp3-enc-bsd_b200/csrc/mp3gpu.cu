@@ -204,10 +204,106 @@ __device__ __forceinline__ void st_release_gpu(int *p, int v)
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// ---- speculative segmentation of the rate loop ------------------------------------------------------------------------------
+// Below one wave of streams the rate loop is bound by the dependency chain of a stream (frame f needs the reservoir frame
+// f - 1 left, reservoir.c:101-145), not by the device: 1250 streams keep 9 of 28 warp slots per SM busy for the same 200 ms
+// that 4144 streams take.  The chain is cut speculatively: the n_frames of a call are split into G segments per stream and
+// every (stream, segment) pair — a virtual stream — gets a warp.  Segment 0 starts from the stream's true state, the others
+// from a guess (the state the stream entered the call with).  A pass records the state after every frame (snapshots) and
+// the state each segment ends in; in the next pass a segment whose predecessor ended in a state other than the one it
+// started from runs again from the true state — and stops as soon as its state equals the snapshot of its previous run at
+// the same frame, because from there on everything it would produce is what is already there.  The reservoir recurrence is
+// contractive in practice (a wrong start is forgotten within a few frames), so the second pass re-encodes a few frames per
+// segment; but nothing relies on that: after pass g + 1 segment g is final by induction (segment 0 is exact after pass 1,
+// and a segment is re-run whenever its start differs from its predecessor's latest end), so G passes are always enough
+// and the result is identical, bit for bit, to the sequential order.  Passes with nothing to do cost one near-empty launch.
+struct SegArgs {
+    int G, seg_frames, pass;
+    LoopStreamState *fin_s;      // [2][n_streams * G]   state a segment ended in, double-buffered by pass parity
+    LoopLaneState *fin_l;
+    LoopStreamState *used_s;     // [n_streams * G]      state the latest run of a segment started from
+    LoopLaneState *used_l;
+    LoopStreamState *snap_s;     // [n_streams * n_frames] state after every frame of the latest run that reached it
+    LoopLaneState *snap_l;
+    int *snap_bits;              // [n_streams * n_frames][8] max_bits of the frame's granule-channels, their part2_3_length before stuffing
+    unsigned long long *stats;   // [8 passes][4]: frames encoded, frames replayed, segments left alone, segments merged early
+};
+
+struct WarpLoopState {           // the rate-loop state of one stream in the registers of a warp
+    LoopStreamState S;
+    PerThread<int> en[4], xm[4];
+};
+__device__ __forceinline__ void wls_load(WarpLoopState &W, const LoopStreamState *ps, const LoopLaneState *pl, int lane)
+{
+    static_assert(sizeof(LoopStreamState) % 4 == 0 && sizeof(LoopStreamState) / 4 <= 32, "LoopStreamState is moved word by word");
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(LoopStreamState) / 4); i++) reinterpret_cast<int *>(&W.S)[i] = ld_relaxed_gpu(reinterpret_cast<const int *>(ps) + i);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { W.en[i].v = ld_relaxed_gpu(&pl->en[i][lane]); W.xm[i].v = ld_relaxed_gpu(&pl->xm[i][lane]); }
+}
+__device__ __forceinline__ void wls_store(const WarpLoopState &W, LoopStreamState *ps, LoopLaneState *pl, int lane)
+{
+#pragma unroll
+    for (int i = 0; i < 4; i++) { st_relaxed_gpu(&pl->en[i][lane], W.en[i].v); st_relaxed_gpu(&pl->xm[i][lane], W.xm[i].v); }
+    if (lane < (int)(sizeof(LoopStreamState) / 4)) st_relaxed_gpu(reinterpret_cast<int *>(ps) + lane, reinterpret_cast<const int *>(&W.S)[lane]);
+}
+// 2: equal; 1: equal but for the reservoir level (word 0 of LoopStreamState); 0: different
+__device__ __forceinline__ int wls_compare(const WarpLoopState &W, const LoopStreamState *ps, const LoopLaneState *pl, int lane)
+{
+    static_assert(offsetof(LoopStreamState, resv_size) == 0, "resv_size must lead LoopStreamState");
+    bool ok = true, resv_ok = true;
+#pragma unroll
+    for (int i = 0; i < 4; i++) ok = ok && W.en[i].v == ld_relaxed_gpu(&pl->en[i][lane]) && W.xm[i].v == ld_relaxed_gpu(&pl->xm[i][lane]);
+    if (lane < (int)(sizeof(LoopStreamState) / 4)) {
+        const bool same = reinterpret_cast<const int *>(&W.S)[lane] == ld_relaxed_gpu(reinterpret_cast<const int *>(ps) + lane);
+        if (lane == 0) resv_ok = same; else ok = ok && same;
+    }
+    if (!__all_sync(0xffffffffu, ok)) return 0;
+    return __all_sync(0xffffffffu, resv_ok) ? 2 : 1;
+}
+__device__ __forceinline__ bool wls_equal(const WarpLoopState &W, const LoopStreamState *ps, const LoopLaneState *pl, int lane)
+{
+    return wls_compare(W, ps, pl, lane) == 2;
+}
+
+// Re-run of a frame whose incoming state differs from the previous run's only in the reservoir level: if every
+// granule-channel is still given the max_bits it was given then (ResvMaxBits is flat in the reservoir level over wide
+// ranges), the rate loop would retrace its steps — quantised values, side info and scalefactors stand, and only the
+// reservoir bookkeeping (ResvAdjust loop.c:355, ResvFrameEnd reservoir.c:155-226: stuffing into part2_3_length, resvDrain,
+// main_data_begin) is redone.  Returns false (nothing written) when some max_bits changed.
+__device__ __noinline__ bool seg_replay_frame(const FrameGeom &G, LoopStreamState &S, const PsyOut *psy_f, const int *bits_prev, GrInfoOut *gi_f,
+                                              FrameOut *fo_f, int lane)
+{
+    int resv = S.resv_size, p23[4] = {0, 0, 0, 0};
+    const int mdb = resv / 8;
+    for (int gr = 0; gr < 2; gr++)
+        for (int ch = 0; ch < G.n_ch; ch++) {
+            const int k = gr * G.n_ch + ch, i = gr * 2 + ch;
+            if (resv_max_bits(G, resv, psy_f[k].pe) != bits_prev[k]) return false;
+            p23[i] = bits_prev[4 + i];
+            resv += G.mean_per_ch - p23[i];
+        }
+    LoopStreamState T = S;
+    T.resv_size = resv;
+    int drain = 0;
+    resv_frame_end(G, T, p23, &drain);
+    S.resv_size = T.resv_size;
+    if (lane == 0) {
+        for (int gr = 0; gr < 2; gr++)
+            for (int ch = 0; ch < G.n_ch; ch++) gi_f[gr * G.n_ch + ch].part2_3_length = p23[gr * 2 + ch];
+        fo_f->resv_drain = drain;
+        fo_f->main_data_begin = mdb;                               // the scfsi bytes of the frame stand
+    }
+    return true;
+}
+
+// SEG: the instance with the segmented mode compiled in.  The plain instance is what full batches run: the segment
+// bookkeeping is cold code, but this kernel is instruction-fetch sensitive (+1250 instructions cost 4 % at 10 000 streams).
+template <bool SEG>
 __global__ void __launch_bounds__(RL_WARPS * 32, RL_MIN_CTAS)
 k_rate_loop(const RateTables *__restrict__ gT, FrameGeom G, LoopStreamState *states, LoopLaneState *lane_states, int n_streams, int n_frames,
-            const int *__restrict__ nfr, int *sched, const double *__restrict__ xr, const PsyOut *__restrict__ psy, short *ix, GrInfoOut *gi,
-            unsigned char *sf, FrameOut *fo)
+            const int *__restrict__ nfr, int *sched, SegArgs seg, const double *__restrict__ xr, const PsyOut *__restrict__ psy, short *ix,
+            GrInfoOut *gi, unsigned char *sf, FrameOut *fo)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RateHot &H0 = load_rate_hot(gT, smem_raw);
@@ -218,19 +314,57 @@ k_rate_loop(const RateTables *__restrict__ gT, FrameGeom G, LoopStreamState *sta
     const int lane = w.lane;
     const int gpf = 2 * G.n_ch;                                  // granule-channels per frame
     const int wpc = blockDim.x >> 5;
-    // Every stream has a warp of its own (batch <= warps of the grid): static assignment, the warp walks the frames of its
-    // stream in order — no waiting, no fences, nothing that flushes L1.  Otherwise: the ticket queue.  (One frame per trip
-    // in both modes: the code of the item exists once, this kernel pays for code size.)
-    const bool fixed = (long)n_streams <= (long)gridDim.x * wpc;
+    // Three ways to hand frames to warps, one copy of the frame's code (this kernel pays for code size):
+    //   segmented  a warp per (stream, segment), see above                      (batch x G <= warps of the grid)
+    //   fixed      a warp per stream walks the stream's frames in order         (batch <= warps of the grid)
+    //   queue      tickets, frame-major, state handed from warp to warp         (anything larger)
+    const bool segmented = SEG && seg.G > 1;
+    const bool fixed = !segmented && (long)n_streams <= (long)gridDim.x * wpc;
     const long total = (long)n_streams * n_frames;
-    int next_f = 0;
+    int next_f = 0, f_end = 0;
+    bool started = false, clean = false;                         // clean: the state differs from the previous run's at most in the reservoir level
+    long vs = (long)blockIdx.x * wpc + warp;                     // segmented: virtual stream index, advanced by the warps of the grid
+    const long vs_step = (long)gridDim.x * wpc;
+    WarpLoopState W;
     for (;;) {
         long s;
         int f;
-        if (fixed) {
+        if (segmented) {
+            if (!started) {                                      // first trip of a segment: find it and the state it starts from
+                started = true;
+                if (vs >= (long)n_streams * seg.G) break;
+                s = vs / seg.G;
+                const int g = (int)(vs - s * seg.G);
+                const int nf = nfr ? min(n_frames, nfr[s]) : n_frames;
+                const int f0 = min(g * seg.seg_frames, nf);
+                f_end = min(f0 + seg.seg_frames, nf);
+                const long rd = (long)((seg.pass - 1) & 1) * n_streams * seg.G, wr = (long)(seg.pass & 1) * n_streams * seg.G;
+                if (g == 0 || seg.pass == 1) wls_load(W, &states[s], &lane_states[s], lane);          // true state / the guess
+                else wls_load(W, &seg.fin_s[rd + vs - 1], &seg.fin_l[rd + vs - 1], lane);             // where the predecessor ended
+                if (seg.pass > 1) {
+                    const int cmp = wls_compare(W, &seg.used_s[vs], &seg.used_l[vs], lane);
+                    if (cmp == 2) {
+                        wls_load(W, &seg.fin_s[rd + vs], &seg.fin_l[rd + vs], lane);                  // nothing changed: carry the end state over
+                        wls_store(W, &seg.fin_s[wr + vs], &seg.fin_l[wr + vs], lane);
+                        if (lane == 0) atomicAdd(&seg.stats[4 * (seg.pass - 1) + 2], 1ull);
+                        vs += vs_step; started = false; continue;
+                    }
+                    clean = cmp == 1;
+                }
+                wls_store(W, &seg.used_s[vs], &seg.used_l[vs], lane);
+                if (f0 >= f_end) {                               // empty segment: pass the state through
+                    wls_store(W, &seg.fin_s[wr + vs], &seg.fin_l[wr + vs], lane);
+                    vs += vs_step; started = false; continue;
+                }
+                next_f = f0;
+            }
+            s = vs / seg.G;
+            f = next_f++;
+        } else if (fixed) {
             s = (long)blockIdx.x * wpc + warp;
             f = next_f++;
             if (s >= n_streams || f >= (nfr ? min(n_frames, nfr[s]) : n_frames)) break;
+            wls_load(W, &states[s], &lane_states[s], lane);
         } else {
             long t = 0;
             if (lane == 0) t = (long)atomicAdd(reinterpret_cast<unsigned int *>(sched), 1u);
@@ -243,27 +377,62 @@ k_rate_loop(const RateTables *__restrict__ gT, FrameGeom G, LoopStreamState *sta
                 if (lane == 0) while (ld_relaxed_gpu(sched + 1 + s) < f) __nanosleep(200);
                 __syncwarp();
             }
+            wls_load(W, &states[s], &lane_states[s], lane);
         }
-        LoopStreamState S;
-        static_assert(sizeof(LoopStreamState) % 4 == 0, "LoopStreamState is copied word by word");
-#pragma unroll
-        for (int i = 0; i < (int)(sizeof(LoopStreamState) / 4); i++)
-            reinterpret_cast<int *>(&S)[i] = ld_relaxed_gpu(reinterpret_cast<const int *>(&states[s]) + i);
-        PerThread<int> st_en[4], st_xm[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) { st_en[i].v = ld_relaxed_gpu(&lane_states[s].en[i][lane]); st_xm[i].v = ld_relaxed_gpu(&lane_states[s].xm[i][lane]); }
-        const long g0 = (s * n_frames + f) * gpf;                // first granule-channel of the item
-        const double *xf = G.xr_f32 ? reinterpret_cast<const double *>(reinterpret_cast<const float *>(xr) + g0 * 576) : xr + g0 * 576;
-        rate_loop_stream(w, H, *gT, M, G, S, st_en, st_xm, 1, xf, psy + g0, ix + g0 * 576, gi + g0, sf + g0 * 40,
-                         fo + s * (long)n_frames + f, nullptr);
-#pragma unroll
-        for (int i = 0; i < 4; i++) { st_relaxed_gpu(&lane_states[s].en[i][lane], st_en[i].v); st_relaxed_gpu(&lane_states[s].xm[i][lane], st_xm[i].v); }
-        if (lane < (int)(sizeof(LoopStreamState) / 4)) st_relaxed_gpu(reinterpret_cast<int *>(&states[s]) + lane, reinterpret_cast<const int *>(&S)[lane]);
-        if (!fixed) {
-            __syncwarp();                                        // every lane's state stores are issued before lane 0's MEMBAR + store
-            if (lane == 0) st_release_gpu(sched + 1 + s, f + 1);
+        const long g0 = (s * n_frames + f) * gpf;                // first granule-channel of the frame
+        const long sn = s * n_frames + f;
+        bool replayed = false;
+        if (segmented && clean) {
+            replayed = seg_replay_frame(G, W.S, psy + g0, seg.snap_bits + 8 * sn, gi + g0, fo + sn, lane);
+            if (replayed) {                                      // the rest of the state is what the previous run left after this frame
+                const int resv = W.S.resv_size;
+                wls_load(W, &seg.snap_s[sn], &seg.snap_l[sn], lane);
+                W.S.resv_size = resv;
+            }
+        }
+        if (!replayed) {
+            const double *xf = G.xr_f32 ? reinterpret_cast<const double *>(reinterpret_cast<const float *>(xr) + g0 * 576) : xr + g0 * 576;
+            rate_loop_stream(w, H, *gT, M, G, W.S, W.en, W.xm, 1, xf, psy + g0, ix + g0 * 576, gi + g0, sf + g0 * 40, fo + sn,
+                             segmented ? seg.snap_bits + 8 * sn : nullptr, segmented ? seg.snap_bits + 8 * sn + 4 : nullptr);
+        }
+        if (segmented) {
+            const long rd = (long)((seg.pass - 1) & 1) * n_streams * seg.G, wr = (long)(seg.pass & 1) * n_streams * seg.G;
+            const int cmp = seg.pass > 1 ? wls_compare(W, &seg.snap_s[sn], &seg.snap_l[sn], lane) : 0;
+            if (lane == 0) atomicAdd(&seg.stats[4 * (seg.pass - 1) + (replayed ? 1 : 0)], 1ull);
+            if (cmp == 2) {
+                if (lane == 0) atomicAdd(&seg.stats[4 * (seg.pass - 1) + 3], 1ull);
+                // merged with the previous run: the rest of the segment, and the state it ends in, stand
+                wls_load(W, &seg.fin_s[rd + vs], &seg.fin_l[rd + vs], lane);
+                wls_store(W, &seg.fin_s[wr + vs], &seg.fin_l[wr + vs], lane);
+                vs += vs_step; started = false; clean = false; continue;
+            }
+            clean = cmp == 1;
+            wls_store(W, &seg.snap_s[sn], &seg.snap_l[sn], lane);
+            if (next_f >= f_end) {
+                wls_store(W, &seg.fin_s[wr + vs], &seg.fin_l[wr + vs], lane);
+                vs += vs_step; started = false; clean = false;
+            }
+        } else {
+            wls_store(W, &states[s], &lane_states[s], lane);
+            if (!fixed) {
+                __syncwarp();                                    // every lane's state stores are issued before lane 0's MEMBAR + store
+                if (lane == 0) st_release_gpu(sched + 1 + s, f + 1);
+            }
         }
     }
+}
+
+// after the last pass: the state every stream leaves the call with is where its last segment ended
+__global__ void k_seg_commit(SegArgs seg, int n_streams, LoopStreamState *states, LoopLaneState *lane_states)
+{
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long s = t >> 5;
+    const int lane = (int)(t & 31);
+    if (s >= n_streams) return;
+    const long src = (long)(seg.pass & 1) * n_streams * seg.G + s * seg.G + seg.G - 1;
+    WarpLoopState W;
+    wls_load(W, &seg.fin_s[src], &seg.fin_l[src], lane);
+    wls_store(W, &states[s], &lane_states[s], lane);
 }
 
 // quantize + count_bits on n independent granules.  count_only: ix[] holds magnitudes already (count_bits(), loop.c:2099)
@@ -439,6 +608,13 @@ struct mp3gpu_ctx {
     double *d_xr2 = nullptr;
     int *d_nfr2 = nullptr;
     cudaEvent_t ev_front_done[2] = {nullptr, nullptr}, ev_bufs_free[2] = {nullptr, nullptr}, ev_sync = nullptr;
+    // speculative segmentation of the rate loop (k_rate_loop): end / start states per virtual stream, per-frame snapshots
+    int segment_rate_loop = 1;
+    LoopStreamState *d_seg_fin_s = nullptr, *d_seg_used_s = nullptr, *d_seg_snap_s = nullptr;
+    LoopLaneState *d_seg_fin_l = nullptr, *d_seg_used_l = nullptr, *d_seg_snap_l = nullptr;
+    int *d_seg_snap_bits = nullptr;
+    unsigned long long *d_seg_stats = nullptr;
+    size_t seg_vs_cap = 0, seg_snap_cap = 0;
     int *d_sched = nullptr;    // rate-loop work queue: [0] ticket counter, [1 + s] frames of stream s finished in this launch
     // host-PCM ingest: double-buffered dense staging filled on a private copy stream, so that the H2D copy of
     // call i+1 overlaps the kernels of call i (the caller only ever sees its own stream)
@@ -660,7 +836,8 @@ static int create_body(mp3gpu_ctx *c)
     CU(cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(512 * 8 + FRONT_WARPS * sizeof(FrontWarpSmem))));
     CU(cudaFuncSetAttribute(k_front_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontTileSmem)));
     CU(cudaFuncSetAttribute(k_mdct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FRONT_WARPS * sizeof(FrontWarpSmem))));
-    CU(cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_rate_loop<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(k_rate_loop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_quantize_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES));
     CU(cudaFuncSetAttribute(k_front_tile, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_front_fast<double, false, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontFastSmem<double, false>)));
@@ -671,7 +848,8 @@ static int create_body(mp3gpu_ctx *c)
     CU(cudaFuncSetAttribute(k_front_fast<double, false, double, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_front_fast<float, true, float>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_front_fast<float, true, double>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_rate_loop<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_rate_loop<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_psy_front, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return mp3gpu_reset(c);
 }
@@ -689,7 +867,8 @@ extern "C" void mp3gpu_destroy(mp3gpu_ctx *c)
     }
     if (c->ev_sync) cudaEventDestroy(c->ev_sync);
     if (c->front_stream) cudaStreamDestroy(c->front_stream);
-    void *ptrs[] = {c->d_psyout2, c->d_xr2, c->d_nfr2, c->d_total, c->d_nfr, c->d_sched,
+    void *ptrs[] = {c->d_seg_stats, c->d_seg_fin_s, c->d_seg_fin_l, c->d_seg_used_s, c->d_seg_used_l, c->d_seg_snap_s, c->d_seg_snap_l, c->d_seg_snap_bits,
+                    c->d_psyout2, c->d_xr2, c->d_nfr2, c->d_total, c->d_nfr, c->d_sched,
                     c->d_psy_tab, c->d_rate_tab, c->d_ops1024, c->d_ops256, c->d_lv1024, c->d_lv256, c->d_out1024, c->d_out256,
                     c->d_tw, c->pcm_main.buf, c->pcm_fb.buf, c->pcm_psy.buf, c->d_psy_state, c->d_loop_state, c->d_lane_state,
                     c->d_sb_prev, c->d_mid, c->d_psyout, c->d_xr, c->d_ix, c->d_gi, c->d_sf, c->d_fo,
@@ -948,6 +1127,29 @@ static int stage_pcm_dev(mp3gpu_ctx *c, const int16_t *pcm, int n_streams, int n
     return 0;
 }
 
+// diagnostics of the speculative segmentation since ctx creation: per pass p (0-based) out[4p .. 4p+3] = frames encoded,
+// frames replayed (reservoir bookkeeping only), segments left alone, segments that rejoined their previous run early
+extern "C" int mp3gpu_rate_loop_segment_stats(mp3gpu_ctx *c, long out[32], int reset)
+{
+    if (!c || !out) return fail(MP3GPU_EINVAL, "null argument");
+    DEV_GUARD(c);
+    for (int i = 0; i < 32; i++) out[i] = 0;
+    if (!c->d_seg_stats) return 0;
+    unsigned long long h[32];
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h, c->d_seg_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 32; i++) out[i] = (long)h[i];
+    if (reset) CU(cudaMemset(c->d_seg_stats, 0, sizeof(h)));
+    return 0;
+}
+
+extern "C" int mp3gpu_set_rate_loop_segments(mp3gpu_ctx *c, int enable)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    c->segment_rate_loop = enable ? 1 : 0;
+    return 0;
+}
+
 // Pipelining of successive calls of the mp3gpu_encode_frames* family (see mp3gpu.h)
 extern "C" int mp3gpu_set_pipeline(mp3gpu_ctx *c, int mode)
 {
@@ -1102,17 +1304,91 @@ static int rate_loop_warps(const mp3gpu_ctx *c, int n_streams, unsigned *grid)
     return wpc;
 }
 
+// Speculative segmentation (see k_rate_loop): how many segments per stream for this launch.  Only when the batch leaves
+// at least half of the device's warp slots empty and the call is long enough for segments of >= 16 frames.
+static int rate_loop_segments(const mp3gpu_ctx *c, int n_streams, int n_frames)
+{
+    if (!c->segment_rate_loop) return 1;
+    const long slots = (long)c->sm_count * RL_WARPS;
+    if (n_streams >= slots) return 1;                        // a full wave or more: the ticket queue keeps every warp busy
+    // frames on the critical path: rounds of segments over the warp slots x frames per segment, + what the later passes
+    // typically re-encode behind each seam
+    int best = 1;
+    long best_cost = n_frames;
+    for (int g = 2; g <= 8 && n_frames / g >= 16; g++) {
+        const long seg = (n_frames + g - 1) / g, rounds = ((long)n_streams * g + slots - 1) / slots;
+        const long cost = rounds * seg + 6L * (g - 1);
+        if (cost * 100 < best_cost * 85) { best = g; best_cost = cost; }
+    }
+    return best;
+}
+
 static int launch_rate_loop(mp3gpu_ctx *c, const double *xr, const PsyOut *psy, int n_streams, int n_frames, short *ix, GrInfoOut *gi,
                             unsigned char *sf, FrameOut *fo, cudaStream_t q, const int *nfr = nullptr, bool xr_f32 = false)
 {
     unsigned grid;
     FrameGeom G = c->geom;
     G.xr_f32 = xr_f32 ? 1 : 0;
+    SegArgs seg;
+    memset(&seg, 0, sizeof(seg));
+    seg.G = rate_loop_segments(c, n_streams, n_frames);
+    if (seg.G > 1) {
+        const size_t vs = (size_t)n_streams * seg.G, snaps = (size_t)n_streams * n_frames;
+        if (vs > c->seg_vs_cap) {
+            void *old[] = {c->d_seg_fin_s, c->d_seg_fin_l, c->d_seg_used_s, c->d_seg_used_l};
+            CU(cudaStreamSynchronize(q));
+            for (void *p : old) if (p) cudaFree(p);
+            c->d_seg_fin_s = nullptr; c->d_seg_fin_l = nullptr; c->d_seg_used_s = nullptr; c->d_seg_used_l = nullptr;
+            c->seg_vs_cap = 0;
+            int rc;
+            if ((rc = dalloc(&c->d_seg_fin_s, 2 * vs)) || (rc = dalloc(&c->d_seg_fin_l, 2 * vs)) || (rc = dalloc(&c->d_seg_used_s, vs)) ||
+                (rc = dalloc(&c->d_seg_used_l, vs))) return rc;
+            c->seg_vs_cap = vs;
+        }
+        if (snaps > c->seg_snap_cap) {
+            CU(cudaStreamSynchronize(q));
+            if (c->d_seg_snap_s) cudaFree(c->d_seg_snap_s);
+            if (c->d_seg_snap_l) cudaFree(c->d_seg_snap_l);
+            c->d_seg_snap_s = nullptr; c->d_seg_snap_l = nullptr; c->seg_snap_cap = 0;
+            int rc;
+            if (c->d_seg_snap_bits) cudaFree(c->d_seg_snap_bits);
+            c->d_seg_snap_bits = nullptr;
+            if ((rc = dalloc(&c->d_seg_snap_s, snaps)) || (rc = dalloc(&c->d_seg_snap_l, snaps)) || (rc = dalloc(&c->d_seg_snap_bits, 8 * snaps))) return rc;
+            c->seg_snap_cap = snaps;
+        }
+        seg.seg_frames = (n_frames + seg.G - 1) / seg.G;
+        seg.fin_s = c->d_seg_fin_s; seg.fin_l = c->d_seg_fin_l; seg.used_s = c->d_seg_used_s; seg.used_l = c->d_seg_used_l;
+        seg.snap_s = c->d_seg_snap_s; seg.snap_l = c->d_seg_snap_l; seg.snap_bits = c->d_seg_snap_bits;
+        if (!c->d_seg_stats) {
+            int rc = dalloc(&c->d_seg_stats, 32);
+            if (rc) return rc;
+            CU(cudaMemsetAsync(c->d_seg_stats, 0, 32 * sizeof(unsigned long long), q));
+        }
+        seg.stats = c->d_seg_stats;
+        const long vsl = (long)vs;
+        int wpc = (int)((vsl + c->sm_count - 1) / c->sm_count);
+        if (wpc > RL_WARPS) wpc = RL_WARPS;
+        long ctas = (vsl + wpc - 1) / wpc;
+        if (ctas > c->sm_count) ctas = c->sm_count;          // more virtual streams than warps: a warp takes several, one after the other
+        grid = (unsigned)ctas;
+        prof_begin(c, MP3GPU_K_RATE_LOOP, q);
+        for (seg.pass = 1; seg.pass <= seg.G; seg.pass++) {
+            k_rate_loop<true><<<grid, wpc * 32, RL_HOT_BYTES + wpc * sizeof(RateWarpSmem), q>>>(c->d_rate_tab, G, c->d_loop_state, c->d_lane_state,
+                                                                                                n_streams, n_frames, nfr, c->d_sched, seg, xr, psy, ix, gi, sf, fo);
+            c->launches++;
+        }
+        seg.pass = seg.G;
+        k_seg_commit<<<(unsigned)(((long)n_streams * 32 + 255) / 256), 256, 0, q>>>(seg, n_streams, c->d_loop_state, c->d_lane_state);
+        c->launches++;
+        prof_end(c, q);
+        CU(cudaGetLastError());
+        return 0;
+    }
     const int wpc = rate_loop_warps(c, n_streams, &grid);
     CU(cudaMemsetAsync(c->d_sched, 0, ((size_t)n_streams + 1) * sizeof(int), q));
     prof_begin(c, MP3GPU_K_RATE_LOOP, q);
-    k_rate_loop<<<grid, wpc * 32, RL_HOT_BYTES + wpc * sizeof(RateWarpSmem), q>>>(c->d_rate_tab, G, c->d_loop_state, c->d_lane_state,
-                                                                                  n_streams, n_frames, nfr, c->d_sched, xr, psy, ix, gi, sf, fo);
+    k_rate_loop<false><<<grid, wpc * 32, RL_HOT_BYTES + wpc * sizeof(RateWarpSmem), q>>>(c->d_rate_tab, G, c->d_loop_state, c->d_lane_state,
+                                                                                         n_streams, n_frames, nfr, c->d_sched, seg, xr, psy, ix, gi, sf, fo);
     prof_end(c, q);
     c->launches++;
     CU(cudaGetLastError());
@@ -1277,8 +1553,8 @@ extern "C" int mp3gpu_stream_wave(int device)
     DeviceGuard guard(device);
     if (!guard.ok) return fail(MP3GPU_ECUDA, "cudaSetDevice failed");
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return fail(MP3GPU_ECUDA, "no device attribute");
-    cudaFuncSetAttribute(k_rate_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_rate_loop, RL_WARPS * 32, RL_SMEM_BYTES) != cudaSuccess || ctas < 1)
+    cudaFuncSetAttribute(k_rate_loop<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RL_SMEM_BYTES);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_rate_loop<false>, RL_WARPS * 32, RL_SMEM_BYTES) != cudaSuccess || ctas < 1)
         return fail(MP3GPU_ECUDA, "occupancy query failed");
     return sms * ctas * RL_WARPS;
 }

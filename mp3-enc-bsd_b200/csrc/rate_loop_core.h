@@ -500,6 +500,26 @@ SIMT_FN int part2_length_of(bool is_short, int gr, int compress, const int scfsi
     return bits;
 }
 
+// ResvMaxBits, reservoir.c:101-134: the bits a granule-channel may use, from the reservoir level and its perceptual entropy
+SIMT_FN int resv_max_bits(const FrameGeom &G, int resv_size, double pe)
+{
+    const int mean = G.mean_per_ch;
+    const int resv_max = G.resv_max;
+    int max_bits = mean > 4095 ? 4095 : mean;
+    if (resv_max != 0) {
+        int more_bits = (int)(pe * 3.1 - mean), add_bits = 0;
+        if (more_bits > 100) {
+            int frac = (resv_size * 6) / 10;
+            add_bits = frac < more_bits ? frac : more_bits;
+        }
+        int over_bits = resv_size - ((resv_max * 8) / 10) - add_bits;
+        if (over_bits > 0) add_bits += over_bits;
+        max_bits += add_bits;
+        if (max_bits > 4095) max_bits = 4095;
+    }
+    return max_bits;
+}
+
 struct Gr0Carry {             // what granule 1 may need from granule 0 of the same channel
     PerThread<int> sf0;       // long scalefactors of gr 0 (band per lane)
     int preflag, scalefac_scale;
@@ -630,23 +650,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
     }
 
     // ---- ResvMaxBits, reservoir.c:101-134 -------------------------------------------------------
-    int max_bits;
-    {
-        const int mean = G.mean_per_ch;
-        const int resv_max = G.resv_max;
-        max_bits = mean > 4095 ? 4095 : mean;
-        if (resv_max != 0) {
-            int more_bits = (int)(pe * 3.1 - mean), add_bits = 0;
-            if (more_bits > 100) {
-                int frac = (S.resv_size * 6) / 10;
-                add_bits = frac < more_bits ? frac : more_bits;
-            }
-            int over_bits = S.resv_size - ((resv_max * 8) / 10) - add_bits;
-            if (over_bits > 0) add_bits += over_bits;
-            max_bits += add_bits;
-            if (max_bits > 4095) max_bits = 4095;
-        }
-    }
+    const int max_bits = resv_max_bits(G, S.resv_size, pe);
     if (max_bits_out) *max_bits_out = max_bits;
 
     // ---- iteration variables, loop.c:319-346 ------------------------------------------------------
@@ -941,7 +945,7 @@ struct FrameOut {
 SIMT_FN void rate_loop_stream(const WarpCtx &w, const RateHot &H, const RateTables &T, RateWarpSmem &M, const FrameGeom &G, LoopStreamState &S,
                               PerThread<int> st_en[4], PerThread<int> st_xm[4], int n_frames,
                               const double *xr, const PsyOut *psy, short *ix, GrInfoOut *gi, unsigned char *sf,
-                              FrameOut *fo, int *max_bits_dbg)
+                              FrameOut *fo, int *max_bits_dbg, int *p23_pre = nullptr)
 {
     for (int f = 0; f < n_frames; f++) {
         int scfsi[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
@@ -960,6 +964,11 @@ SIMT_FN void rate_loop_stream(const WarpCtx &w, const RateHot &H, const RateTabl
                                              po.pe, po.block_type, scfsi[ch], g0[ch], ix + (size_t)g * 576, gi + g,
                                              sf + (size_t)g * 40, max_bits_dbg ? max_bits_dbg + g : nullptr);
             }
+        if (p23_pre) {                 // part2_3_length of the frame's granule-channels before the stuffing bits of ResvFrameEnd
+            FOR_THREADS(w)
+            if (lane == 0) { p23_pre[4 * f] = p23[0]; p23_pre[4 * f + 1] = p23[1]; p23_pre[4 * f + 2] = p23[2]; p23_pre[4 * f + 3] = p23[3]; }
+            END_THREADS
+        }
         int drain = 0;
         resv_frame_end(G, S, p23, &drain);
         FOR_THREADS(w)

@@ -39,7 +39,10 @@ def test_encode_frames_vs_reference_golden(pkg, golden, name):
     frac = (ix_ok & gi_ok).mean()
     print(f"{name}: {100 * frac:.2f}% of granule-channels identical to the reference (ix + all side info)")
     assert frac >= 0.98
-    assert enc.kernel_launches == 5
+    # psy_front, psy_scan, front_tile, roll_history + the rate loop: one launch, or G passes + a commit when the call is
+    # cut into G speculative segments (one stream of nf frames: G = min(nf // 16, 8))
+    G = min(nf // 16, 8)
+    assert enc.kernel_launches == (5 if G < 2 else 4 + G + 1)
 
 
 def test_batch_and_chunked_streaming(pkg):

@@ -184,3 +184,29 @@ def test_overlap_pipeline_gives_identical_bytes(pkg, host):
     enc.set_pipeline(False)
     got = enc.encode_streams(pcm, chunk_frames=7, n_samples=lens)
     assert got == want
+
+
+@pytest.mark.parametrize("S,F,chunk", [(3, 40, 40), (12, 70, 35), (40, 48, 48)])
+def test_speculative_rate_loop_segments_are_bit_identical(pkg, S, F, chunk):
+    """under-filled batches cut every call into up to 8 concurrently encoded segments per stream with a guessed reservoir
+    and re-encode what started wrong (k_rate_loop): every byte, and the state carried into the next call, must equal the
+    sequential order — checked against the oracle and against the same ctx with segmentation switched off; streams differ
+    in level (the guess is wrong by different amounts), one goes silent mid-way, lengths are ragged"""
+    lens = [F * 1152 - 700 * s for s in range(S)]
+    lens[1] = 17 * 1152 + 3
+    pcm = np.zeros((S, 2, F * 1152), np.int16)
+    clips = []
+    for s, n in enumerate(lens):
+        c = clip(pkg, n, 1500 + 3 * s)
+        c = np.clip(c.astype(np.int32) * (1 + s % 5) // 2, -32768, 32767).astype(np.int16)
+        if s == 2:
+            c[:, n // 2:] = 0
+        clips.append(c)
+        pcm[s, :, :n] = c
+    enc = pkg.Encoder(44100, 2, 128, max_streams=S, max_frames=chunk)
+    got = enc.encode_streams(pcm, chunk_frames=chunk, n_samples=lens)
+    enc.set_rate_loop_segments(False)
+    plain = enc.encode_streams(pcm, chunk_frames=chunk, n_samples=lens)
+    assert got == plain
+    for s in (0, 1, 2, S - 1):
+        assert got[s] == oracle_bytes(clips[s]), s
