@@ -133,6 +133,15 @@ int mp3gpu_frame_geometry(const mp3gpu_ctx *ctx, int *bits_per_frame, int *mean_
 int mp3gpu_set_front_variant(mp3gpu_ctx *ctx, int variant);
 int mp3gpu_get_front_variant(const mp3gpu_ctx *ctx, int *variant, int *algorithmic_bytes_per_gc);
 
+/* Implementation of the psychoacoustic model's FFTs (subs.c:185-534) in k_psy_front — both bit-identical to the reference:
+ *   REGS (default)  the split-radix dataflow as straight-line register code of a warp (two layouts, shuffles between the
+ *                   real / imaginary lanes of a complex node)
+ *   PROGRAM         the levelised op program interpreted in shared memory (round 1); kept as the A/B and self-check.
+ * The environment variable MP3GPU_PSY_FFT=program selects PROGRAM at context creation. */
+#define MP3GPU_PSY_REGS 0
+#define MP3GPU_PSY_PROGRAM 1
+int mp3gpu_set_psy_variant(mp3gpu_ctx *ctx, int variant);
+
 /* Pipelining of successive calls of the mp3gpu_encode_frames* family.  SERIAL (default): all work of a call is enqueued on
  * `stream`.  OVERLAP: PCM staging, the psychoacoustic model and the filterbank + MDCT of a call run on a private
  * low-priority stream, so that they execute beside the rate loop of the PREVIOUS call (the rate loop is bound by the

@@ -112,6 +112,30 @@ k_psy_front(PsyDev D, const short *pcm, long stream_stride, long ch_stride, int 
     psy_front(w, D, simt::pin_smem(Ms[warp]), pcm + s * stream_stride + ch * ch_stride + HIST + 576L * g, &mid[gc]);
 }
 
+// The same with the transforms in registers (fft_regs.h): 8064 B of shared memory per warp, 3 CTAs of 8 warps per SM
+#ifndef PSYF2_WARPS
+#define PSYF2_WARPS 8
+#endif
+#ifndef PSYF2_MIN_CTAS
+#define PSYF2_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(PSYF2_WARPS * 32, PSYF2_MIN_CTAS)
+k_psy_front_regs(PsyDev D, const short *pcm, long stream_stride, long ch_stride, int n_streams, int n_ch, int n_gran, const int *nfr, PsyMid *mid)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const long gc = (long)blockIdx.x * PSYF2_WARPS + warp;
+    if (gc >= (long)n_streams * n_gran * n_ch) return;
+    const int ch = (int)(gc % n_ch);
+    const int g = (int)((gc / n_ch) % n_gran);
+    const long s = gc / ((long)n_ch * n_gran);
+    if (nfr && g >= 2 * nfr[s]) return;
+    WarpCtx w{WarpCtx::Pinned()};
+    float *X = reinterpret_cast<float *>(smem_raw) + (size_t)warp * FFTR_X_WORDS;
+    psy_front_regs(w, D, X, pcm + s * stream_stride + ch * ch_stride + HIST + 576L * g, &mid[gc]);
+}
+#define PSYF2_SMEM (PSYF2_WARPS * FFTR_X_WORDS * sizeof(float))
+
 #ifndef PSYS_WARPS
 #define PSYS_WARPS 4
 #endif
@@ -572,6 +596,9 @@ struct mp3gpu_ctx {
     int *d_lv1024 = nullptr, *d_lv256 = nullptr;
     uint32_t *d_out1024 = nullptr, *d_out256 = nullptr;
     FftTwiddle *d_tw = nullptr;
+    float *d_twA = nullptr;
+    uint32_t *d_out_long = nullptr, *d_out_short = nullptr;
+    int psy_variant = MP3GPU_PSY_REGS;
     PsyDev psy_dev;
     // state
     PcmStage pcm_main, pcm_fb, pcm_psy;
@@ -752,6 +779,22 @@ static int upload(T **dst, const T *src, size_t n = 1)
     return 0;
 }
 
+// tables of the register FFT (fft_regs.h): constants into c_fftr of the current device, twiddles and output maps into global memory
+static int upload_fft_regs(float **twA, uint32_t **out_long, uint32_t **out_short, PsyDev *dev)
+{
+    int rc;
+    FftRegsPlan *P = new FftRegsPlan;
+    build_fft_regs_plan(P);
+    cudaError_t e = cudaMemcpyToSymbol(c_fftr, &P->c, sizeof(P->c));
+    rc = (e == cudaSuccess) ? 0 : fail(MP3GPU_ECUDA, "cudaMemcpyToSymbol(c_fftr): %s", cudaGetErrorString(e));
+    if (!rc) rc = upload(twA, P->twA.data(), P->twA.size());
+    if (!rc) rc = upload(out_long, P->out_long.data(), P->out_long.size());
+    if (!rc) rc = upload(out_short, P->out_short.data(), P->out_short.size());
+    delete P;
+    dev->twA = *twA; dev->out_long = *out_long; dev->out_short = *out_short;
+    return rc;
+}
+
 // FP32 copies of the front-end tables for the FP32 variant (front_fast.cuh)
 static cudaError_t upload_front_f(const FrontTables *F)
 {
@@ -801,6 +844,7 @@ static int create_body(mp3gpu_ctx *c)
         if ((rc = upload_fft(P10, &c->d_ops1024, &c->d_lv1024, &c->d_out1024, &c->psy_dev.f1024))) return rc;
         if ((rc = upload_fft(P8, &c->d_ops256, &c->d_lv256, &c->d_out256, &c->psy_dev.f256))) return rc;
         c->psy_dev.T = c->d_psy_tab; c->psy_dev.tw = c->d_tw;
+        if ((rc = upload_fft_regs(&c->d_twA, &c->d_out_long, &c->d_out_short, &c->psy_dev))) return rc;
         BitTables *B = new BitTables;
         build_bit_tables(sr, cfg->sfreq_hz, cfg->n_ch, cfg->bitrate_kbps, B);
         c->frame_bytes = B->frame_bytes; c->si_bytes = B->si_bytes;
@@ -851,6 +895,9 @@ static int create_body(mp3gpu_ctx *c)
     CU(cudaFuncSetAttribute(k_rate_loop<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_rate_loop<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_psy_front, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_psy_front_regs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PSYF2_SMEM));
+    CU(cudaFuncSetAttribute(k_psy_front_regs, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (const char *v = getenv("MP3GPU_PSY_FFT")) c->psy_variant = strcmp(v, "program") == 0 ? MP3GPU_PSY_PROGRAM : MP3GPU_PSY_REGS;
     return mp3gpu_reset(c);
 }
 
@@ -870,7 +917,7 @@ extern "C" void mp3gpu_destroy(mp3gpu_ctx *c)
     void *ptrs[] = {c->d_seg_stats, c->d_seg_fin_s, c->d_seg_fin_l, c->d_seg_used_s, c->d_seg_used_l, c->d_seg_snap_s, c->d_seg_snap_l, c->d_seg_snap_bits,
                     c->d_psyout2, c->d_xr2, c->d_nfr2, c->d_total, c->d_nfr, c->d_sched,
                     c->d_psy_tab, c->d_rate_tab, c->d_ops1024, c->d_ops256, c->d_lv1024, c->d_lv256, c->d_out1024, c->d_out256,
-                    c->d_tw, c->pcm_main.buf, c->pcm_fb.buf, c->pcm_psy.buf, c->d_psy_state, c->d_loop_state, c->d_lane_state,
+                    c->d_tw, c->d_twA, c->d_out_long, c->d_out_short, c->pcm_main.buf, c->pcm_fb.buf, c->pcm_psy.buf, c->d_psy_state, c->d_loop_state, c->d_lane_state,
                     c->d_sb_prev, c->d_mid, c->d_psyout, c->d_xr, c->d_ix, c->d_gi, c->d_sf, c->d_fo,
                     c->d_bit_tab, c->d_win, c->d_win_tmp, c->d_next_begin};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -1185,6 +1232,14 @@ extern "C" int mp3gpu_set_front_variant(mp3gpu_ctx *c, int variant)
     return 0;
 }
 
+extern "C" int mp3gpu_set_psy_variant(mp3gpu_ctx *c, int variant)
+{
+    if (!c) return fail(MP3GPU_EINVAL, "null ctx");
+    if (variant != MP3GPU_PSY_REGS && variant != MP3GPU_PSY_PROGRAM) return fail(MP3GPU_EINVAL, "unknown psy variant");
+    c->psy_variant = variant;
+    return 0;
+}
+
 extern "C" int mp3gpu_get_front_variant(const mp3gpu_ctx *c, int *variant, int *xr_bytes_per_gc)
 {
     if (!c) return fail(MP3GPU_EINVAL, "null ctx");
@@ -1277,8 +1332,12 @@ static int launch_psy(mp3gpu_ctx *c, const short *pcm_rows, int n_streams, int n
     const int n_gran = 2 * n_frames, n_ch = c->cfg.n_ch;
     const long gcs = (long)n_streams * n_gran * n_ch;
     prof_begin(c, MP3GPU_K_PSY_FRONT, q);
-    k_psy_front<<<(unsigned)((gcs + PSYF_WARPS - 1) / PSYF_WARPS), PSYF_WARPS * 32, PSYF_WARPS * sizeof(PsyFrontSmem), q>>>(
-        c->psy_dev, pcm_rows, c->row * n_ch, c->row, n_streams, n_ch, n_gran, nfr, c->d_mid);
+    if (c->psy_variant == MP3GPU_PSY_REGS)
+        k_psy_front_regs<<<(unsigned)((gcs + PSYF2_WARPS - 1) / PSYF2_WARPS), PSYF2_WARPS * 32, PSYF2_SMEM, q>>>(
+            c->psy_dev, pcm_rows, c->row * n_ch, c->row, n_streams, n_ch, n_gran, nfr, c->d_mid);
+    else
+        k_psy_front<<<(unsigned)((gcs + PSYF_WARPS - 1) / PSYF_WARPS), PSYF_WARPS * 32, PSYF_WARPS * sizeof(PsyFrontSmem), q>>>(
+            c->psy_dev, pcm_rows, c->row * n_ch, c->row, n_streams, n_ch, n_gran, nfr, c->d_mid);
     prof_end(c, q);
     c->launches++;
     CU(cudaGetLastError());

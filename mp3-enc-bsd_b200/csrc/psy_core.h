@@ -18,6 +18,7 @@
 #include "rate_loop_core.h"  // PsyOut
 #include "simt.h"
 #include "tables.h"
+#include "fft_regs.h"
 
 namespace mp3gpu {
 
@@ -35,6 +36,9 @@ struct PsyDev {
     const PsyTables *T;
     const FftTwiddle *tw;
     FftDev f1024, f256;
+    // register FFT (fft_regs.h)
+    const float *twA;
+    const uint32_t *out_long, *out_short;   // [513], [3][132]
 };
 
 struct PsyMid {
@@ -291,6 +295,65 @@ SIMT_FN double unpredictability(double r_new, double phi_new, double r_prime, do
 }
 
 // ---------------------------------------------------------------------------------------------------
+// history-free tail of psy_front: partition energies, weighted unpredictability, energy spreading.
+// E[0..512]: energies of the long transform in line order; cwv[i]: unpredictability of lines 6 + 4 i .. 9 + 4 i (i < 50);
+// eb[64]: scratch (all three in the warp's shared memory)
+// ---------------------------------------------------------------------------------------------------
+SIMT_FN void psy_front_tail(const WarpCtx &w, const PsyTables &T, const float *E, const double *cwv, double *eb_s, PsyMid *out)
+{
+    FOR_THREADS(w)
+    for (int j = T.tail_l + lane; j <= 512; j += 32) out->tail[j - T.tail_l] = E[j];
+    END_THREADS
+    // partition energy / weighted unpredictability, l3psy.c:565-578
+    FOR_THREADS(w)
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int p = lane + 32 * h;
+        double eb = 0.0;
+        float cb = 0.0f;
+        if (p < T.n_l) {
+            for (int j = T.lo_l[p]; j < T.hi_l[p]; j++) {
+                eb = simt::dadd(eb, (double)E[j]);
+                if (p >= T.n_hist_part) {
+                    double cw = (j < 206) ? cwv[(j - 6) >> 2] : 0.4;
+                    cb = (float)simt::dadd((double)cb, simt::dmul(cw, (double)E[j]));
+                }
+            }
+            if (p == 0)
+                for (int j = T.tail_l; j <= 512; j++) eb = simt::dadd(eb, (double)E[j]);
+        }
+        eb_s[p] = eb;
+        out->eb[p] = eb;
+        out->cb[p] = cb;
+    }
+    END_THREADS
+    w.sync();
+    // energy spreading, l3psy.c:586-605 (ecb is a float accumulator)
+    FOR_THREADS(w)
+    {
+        // The two partitions of a lane (b and b + 32) advance together: two independent float <- double accumulation
+        // chains in flight.
+        const int b0 = lane, b1 = lane + 32;
+        const int lo0 = T.spr_lo[b0], n0 = T.spr_hi[b0] - lo0 + 1;
+        const int lo1 = (b1 < 63) ? T.spr_lo[b1] : 0, n1 = (b1 < 63) ? T.spr_hi[b1] - lo1 + 1 : 0;
+        float e0 = 0.0f, e1 = 0.0f;
+        for (int i = 0; i < T.spr_wmax; i++) {
+            // step i of each lane's own row range [lo, hi] (banded matrix layout: one coalesced request per step); the terms
+            // are added in the reference's order, k ascending
+            const bool in0 = i < n0, in1 = i < n1;
+            const double s0 = in0 ? T.s3_band[i * 64 + b0] : 1.0, s1 = in1 ? T.s3_band[i * 64 + b1] : 1.0;
+            const double eb0 = in0 ? eb_s[lo0 + i] : 0.0, eb1 = in1 ? eb_s[lo1 + i] : 0.0;
+            if (in0 && (T.sparse || s0 != 1.0)) e0 = (float)simt::dadd((double)e0, simt::dmul(s0, eb0));
+            if (in1 && (T.sparse || s1 != 1.0)) e1 = (float)simt::dadd((double)e1, simt::dmul(s1, eb1));
+        }
+        out->ecb[b0] = e0;
+        out->ecb[b1] = e1;
+    }
+    END_THREADS
+    w.sync();
+}
+
+// ---------------------------------------------------------------------------------------------------
 // psy_front: history-free part, one warp per granule-channel.
 // pcm points at the first NEW sample of the granule (sample 576 g); pcm[-768 ..  575] are read.
 // ---------------------------------------------------------------------------------------------------
@@ -357,57 +420,92 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
         double r2 = sqrt((double)short_energy(D.f256, M.x, 1, k));
         M.cwv[i] = unpredictability(r2, (double)short_phase(D.f256, M.x, 1, k), r_prime, phi_prime);
     }
-    for (int j = T.tail_l + lane; j <= 512; j += 32) out->tail[j - T.tail_l] = M.E[j];
     END_THREADS
     w.sync();
-    // partition energy / weighted unpredictability, l3psy.c:565-578
-    FOR_THREADS(w)
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int p = lane + 32 * h;
-        double eb = 0.0;
-        float cb = 0.0f;
-        if (p < T.n_l) {
-            for (int j = T.lo_l[p]; j < T.hi_l[p]; j++) {
-                eb = simt::dadd(eb, (double)M.E[j]);
-                if (p >= T.n_hist_part) {
-                    double cw = (j < 206) ? M.cwv[(j - 6) >> 2] : 0.4;
-                    cb = (float)simt::dadd((double)cb, simt::dmul(cw, (double)M.E[j]));
-                }
-            }
-            if (p == 0)
-                for (int j = T.tail_l; j <= 512; j++) eb = simt::dadd(eb, (double)M.E[j]);
-        }
-        M.eb[p] = eb;
-        out->eb[p] = eb;
-        out->cb[p] = cb;
-    }
-    END_THREADS
-    w.sync();
-    // energy spreading, l3psy.c:586-605 (ecb is a float accumulator)
-    FOR_THREADS(w)
-    {
-        // The two partitions of a lane (b and b + 32) advance together: two independent float <- double accumulation
-        // chains in flight.
-        const int b0 = lane, b1 = lane + 32;
-        const int lo0 = T.spr_lo[b0], n0 = T.spr_hi[b0] - lo0 + 1;
-        const int lo1 = (b1 < 63) ? T.spr_lo[b1] : 0, n1 = (b1 < 63) ? T.spr_hi[b1] - lo1 + 1 : 0;
-        float e0 = 0.0f, e1 = 0.0f;
-        for (int i = 0; i < T.spr_wmax; i++) {
-            // step i of each lane's own row range [lo, hi] (banded matrix layout: one coalesced request per step); the terms
-            // are added in the reference's order, k ascending
-            const bool in0 = i < n0, in1 = i < n1;
-            const double s0 = in0 ? T.s3_band[i * 64 + b0] : 1.0, s1 = in1 ? T.s3_band[i * 64 + b1] : 1.0;
-            const double eb0 = in0 ? M.eb[lo0 + i] : 0.0, eb1 = in1 ? M.eb[lo1 + i] : 0.0;
-            if (in0 && (T.sparse || s0 != 1.0)) e0 = (float)simt::dadd((double)e0, simt::dmul(s0, eb0));
-            if (in1 && (T.sparse || s1 != 1.0)) e1 = (float)simt::dadd((double)e1, simt::dmul(s1, eb1));
-        }
-        out->ecb[b0] = e0;
-        out->ecb[b1] = e1;
-    }
-    END_THREADS
-    w.sync();
+    psy_front_tail(w, T, M.E, M.cwv, M.eb, out);
 }
+
+#if SIMT_DEV
+// ---------------------------------------------------------------------------------------------------
+// psy_front with the transforms in registers (fft_regs.h): same results as psy_front, bit for bit.
+// X: the warp's FFTR_X_WORDS floats of shared memory.  Once the energies are formed the transform data is dead and X is
+// reused: E[0..512] at X, cwv[52] (double) at X + 520, eb[64] (double) at X + 624.
+// ---------------------------------------------------------------------------------------------------
+#define PSYF2_CWV_WORD 520
+#define PSYF2_EB_WORD 624
+static_assert(PSYF2_EB_WORD + 128 <= FFTR_X_WORDS && PSYF2_CWV_WORD + 104 <= PSYF2_EB_WORD, "overlays");
+SIMT_FN void psy_front_regs(const WarpCtx &w, const PsyDev &D, float *X, const short *pcm, PsyMid *out)
+{
+    const PsyTables &T = *D.T;
+    const int lane = w.lane;
+    {
+        float xl[32], xs[3][8];
+        // long window, l3psy.c:483-494; three short windows, l3psy.c:518-527
+#pragma unroll
+        for (int r = 0; r < 32; r++) xl[r] = simt::fmul(T.hann_l[lane + 32 * r], (float)(int)pcm[lane + 32 * r - 768]);
+#pragma unroll
+        for (int t = 0; t < 3; t++)
+#pragma unroll
+            for (int r = 0; r < 8; r++) xs[t][r] = simt::fmul(T.hann_s[lane + 32 * r], (float)(int)pcm[lane + 32 * r - 768 + 128 * (2 + t)]);
+        fft_regs_run(xl, xs, D.twA, X, lane);
+    }
+    // energies of the long transform: bins lane + 32 k (k < 16) and bin 512; phases of lines 0..5
+    float e[17];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        float ph;
+        bin_energy_phase(D.out_long[lane + 32 * k], X, 1024, lane + 32 * k, false, &e[k], &ph);
+    }
+    e[16] = 0.f;
+    if (lane == 0) { float ph; bin_energy_phase(D.out_long[512], X, 1024, 512, false, &e[16], &ph); }
+    if (lane < 6) {
+        float e6, ph = 0.f;
+        bin_energy_phase(D.out_long[lane], X, 1024, lane, true, &e6, &ph);
+        out->e6[lane] = e6; out->phi6[lane] = ph;
+    }
+    // short transforms: lines 2..51 with phase -> unpredictability of lines 6..205 in groups of four, l3psy.c:531-549
+    double cw[2] = {0.0, 0.0};
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const int i = lane + 32 * it;
+        if (i < 50) {
+            const int k = i + 2;
+            float es[3], ps[3];
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+                ps[t] = 0.f;
+                bin_energy_phase(D.out_short[132 * t + k], X, 256, k, true, &es[t], &ps[t]);
+                out->es[t][k] = es[t];
+            }
+            const double r_prime = simt::dsub(simt::dmul(2.0, sqrt((double)es[0])), sqrt((double)es[2]));
+            const double phi_prime = simt::dsub(simt::dmul(2.0, (double)ps[0]), (double)ps[2]);
+            cw[it] = unpredictability(sqrt((double)es[1]), (double)ps[1], r_prime, phi_prime);
+        }
+    }
+    // the other short lines (0, 1, 52..128): energies only
+#pragma unroll
+    for (int it = 0; it < 3; it++) {
+        const int idx = lane + 32 * it, k = idx < 2 ? idx : idx + 50;
+        if (k <= 128) {
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+                float es, ph;
+                bin_energy_phase(D.out_short[132 * t + k], X, 256, k, false, &es, &ph);
+                out->es[t][k] = es;
+            }
+        }
+    }
+    w.sync();                                           // every read of the transform data is done
+    double *cwv = reinterpret_cast<double *>(X + PSYF2_CWV_WORD), *eb = reinterpret_cast<double *>(X + PSYF2_EB_WORD);
+#pragma unroll
+    for (int k = 0; k < 16; k++) X[lane + 32 * k] = e[k];
+    if (lane == 0) X[512] = e[16];
+    cwv[lane] = cw[0];
+    if (lane < 18) cwv[lane + 32] = cw[1];
+    w.sync();
+    psy_front_tail(w, T, X, cwv, eb, out);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // psy_scan: history-dependent part, one warp per (stream, channel), granules in order.

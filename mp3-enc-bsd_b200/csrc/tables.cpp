@@ -585,6 +585,114 @@ void build_fft_program(int logm, const std::vector<int> &tw_base, FftProgram *P)
     for (int i = 0; i < n; i++) { P->out_slot[i] = (uint16_t)B.phys[i]; P->out_neg[i] = B.neg[i]; }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// FFT in registers: block kinds, lane / slot assignment, twiddle tables, output maps (see tables.h)
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct RegsBlock { int kind, partner, is_xi; };
+struct RegsWalker {
+    RegsBlock blk[32];
+    // real node on elements [base, base + 2^logm), rsrec subs.c:412-523: its lower half is a real node, its upper half a
+    // complex node of a quarter of the length (real array at base + m/2, imaginary array at base + 3m/4)
+    void rs(int base, int logm)
+    {
+        if (logm == 6) { blk[base / 32] = {FFTR_C, -1, 0}; blk[base / 32 + 1] = {FFTR_D, -1, 0}; return; }
+        const int m = 1 << logm;
+        rs(base, logm - 1);
+        sr(base + m / 2, base + 3 * m / 4, logm - 2);
+    }
+    // complex node, srrec subs.c:185-362
+    void sr(int xr, int xi, int logm)
+    {
+        if (logm == 5) { blk[xr / 32] = {FFTR_A, xi / 32, 0}; blk[xi / 32] = {FFTR_A, xr / 32, 1}; return; }
+        if (logm == 6) {
+            sr(xr, xi, 5);
+            blk[xr / 32 + 1] = {FFTR_B, xi / 32 + 1, 0}; blk[xi / 32 + 1] = {FFTR_B, xr / 32 + 1, 1};
+            return;
+        }
+        const int m = 1 << logm;
+        sr(xr, xi, logm - 1);
+        sr(xr + m / 2, xi + m / 2, logm - 2);
+        sr(xr + 3 * m / 4, xi + 3 * m / 4, logm - 2);
+    }
+};
+}  // namespace
+
+void build_fft_regs_plan(FftRegsPlan *P)
+{
+    memset(&P->c, 0, sizeof(P->c));
+    std::vector<FftTwiddle> tw; std::vector<int> base;
+    build_fft_twiddles(&tw, &base);
+    auto triple = [&](int L, int set, int n) -> FftTwC {
+        const int m4 = 1 << (L - 2), m8 = m4 / 2, nel = m4 - 2;
+        FftTwC t = {0.f, 0.f, 0.f};
+        if (n == 0 || n == m8) return t;
+        const FftTwiddle &w = tw[base[L] + set * nel + (n < m8 ? n - 1 : n - 2)];
+        t.cn = w.cn; t.spcn = w.spcn; t.smcn = w.smcn;
+        return t;
+    };
+    for (int set = 0; set < 2; set++) {
+        for (int n = 0; n < 4; n++) P->c.small.t4[set][n] = triple(4, set, n);
+        for (int n = 0; n < 8; n++) P->c.small.t5[set][n] = triple(5, set, n);
+        for (int n = 0; n < 16; n++) P->c.small.t6[set][n] = triple(6, set, n);
+    }
+    P->twA.assign((size_t)FFTR_TWA_ENTRIES * 4, 0.f);
+    for (int L = 7; L <= 10; L++)
+        for (int set = 0; set < 2; set++)
+            for (int n = 0; n < (1 << (L - 2)); n++) {
+                const FftTwC t = triple(L, set, n);
+                float *d = &P->twA[(size_t)(FFTR_TWA_OFF(L, set) + n) * 4];
+                d[0] = t.cn; d[1] = t.spcn; d[2] = t.smcn;
+            }
+    // block kinds; lanes of pass 0 = the kind-a blocks, lanes of pass 1 = kinds b (16), c (4), d (4); slot = 32 * pass + lane
+    RegsWalker WL, WS;
+    WL.rs(0, 10); WS.rs(0, 8);
+    int slot_l[32], slot_s[3][8];
+    int next[2] = {0, 0};
+    for (int kind = 0; kind < 4; kind++) {
+        const int pass = kind == FFTR_A ? 0 : 1;
+        for (int b = 0; b < 32; b++) if (WL.blk[b].kind == kind) slot_l[b] = 32 * pass + next[pass]++;
+        for (int t = 0; t < 3; t++)
+            for (int b = 0; b < 8; b++) if (WS.blk[b].kind == kind) slot_s[t][b] = 32 * pass + next[pass]++;
+    }
+    for (int b = 0; b < 32; b++) {
+        P->kind_long[b] = (uint8_t)WL.blk[b].kind;
+        P->c.long_word[b] = (uint16_t)(FFTR_SLOT_WORDS * slot_l[b]);
+        if (WL.blk[b].partner >= 0) {
+            const int s = slot_l[b], ps = slot_l[WL.blk[b].partner];
+            P->c.partner[s / 32][s % 32] = (uint8_t)(ps % 32);
+            P->c.is_xi[s / 32][s % 32] = (uint8_t)WL.blk[b].is_xi;
+        }
+    }
+    for (int b = 0; b < 8; b++) P->kind_short[b] = (uint8_t)WS.blk[b].kind;
+    for (int t = 0; t < 3; t++)
+        for (int b = 0; b < 8; b++) {
+            P->c.short_word[t][b] = (uint16_t)(FFTR_SLOT_WORDS * slot_s[t][b]);
+            if (WS.blk[b].partner >= 0) {
+                const int s = slot_s[t][b], ps = slot_s[t][WS.blk[b].partner];
+                P->c.partner[s / 32][s % 32] = (uint8_t)(ps % 32);
+                P->c.is_xi[s / 32][s % 32] = (uint8_t)WS.blk[b].is_xi;
+            }
+        }
+    // output maps: every op works in place at the reference's array positions; the permutations of rsrec step 5 and
+    // BR_permute and the sign changes that follow the last arithmetic on a slot are exactly what build_fft_program tracks
+    FftProgram P10, P8;
+    build_fft_program(10, base, &P10);
+    build_fft_program(8, base, &P8);
+    auto word_l = [&](int j) { return (uint32_t)(P->c.long_word[j >> 5] + (j & 31)); };
+    P->out_long.assign(513, 0u);
+    for (int i = 0; i <= 512; i++) {
+        auto one = [&](int k) { return word_l(P10.out_slot[k]) | (P10.out_neg[k] ? 0x8000u : 0u); };
+        P->out_long[i] = one(i) | ((i > 0 ? one(1024 - i) : 0u) << 16);
+    }
+    P->out_short.assign(3 * 132, 0u);
+    for (int t = 0; t < 3; t++)
+        for (int i = 0; i <= 128; i++) {
+            auto one = [&](int k) { const int j = P8.out_slot[k]; return (uint32_t)(P->c.short_word[t][j >> 5] + (j & 31)) | (P8.out_neg[k] ? 0x8000u : 0u); };
+            P->out_short[t * 132 + i] = one(i) | ((i > 0 ? one(256 - i) : 0u) << 16);
+        }
+}
+
 void run_fft_program_host(const FftProgram &P, const std::vector<FftTwiddle> &tw, float *x)
 {
     const double SQ = 0.707106781186547524401;  // subs.c:26

@@ -90,6 +90,45 @@ void build_fft_twiddles(std::vector<FftTwiddle> *tw, std::vector<int> *tw_base);
 // host interpreter (used by the emulation tests and to self-check the builder at context creation)
 void run_fft_program_host(const FftProgram &P, const std::vector<FftTwiddle> &tw, float *x);
 
+// ---- FFT in registers (fft_regs.h): the same dataflow graph, mapped on a warp without an interpreter ----------------
+// A transform runs in two phases.  Phase 1 holds element j of the array in register j / 32 of lane j % 32: every
+// butterfly / twiddle step of a split-radix node whose strides are >= 32 is straight-line register code, identical in
+// all lanes, with the twiddle triple of line n = lane + 32 k as one coalesced 16-byte load.  The arrays then go through
+// shared memory (one 36-word slot per 32-element block) and phase 2 gives every lane one whole 32-element block: the
+// remaining nodes (length <= 32, plus the stride-16 steps of the length-64 complex nodes) are register code with
+// compile-time twiddles; the real / imaginary arrays of a complex node sit in two lanes that exchange values by shuffle.
+// The 32 + 3 x 8 blocks of a granule's 1024-point and three 256-point transforms are of four kinds and are SORTED by
+// kind over the lanes of two passes (kind a: 20 + 12 blocks = one full pass of 32 lanes).
+#define FFTR_SLOT_WORDS 36             // 32 data words + 4 pad words: 16-byte aligned block rows, conflict-free
+#define FFTR_SLOTS 56
+#define FFTR_X_WORDS (FFTR_SLOTS * FFTR_SLOT_WORDS)
+enum FftBlockKind : uint8_t {
+    FFTR_A = 0,   // half (real or imaginary array) of a complex node of length 32
+    FFTR_B = 1,   // half of the upper half (elements 32..63) of a complex node of length 64
+    FFTR_C = 2,   // real node of length 32
+    FFTR_D = 3,   // elements 32..63 of a real node of length 64
+};
+struct FftTwC { float cn, spcn, smcn; };
+struct FftSmallTw { FftTwC t4[2][4], t5[2][8], t6[2][16]; };   // [set: cn / c3n][n], nodes of length 16 / 32 / 64
+// phase-1 twiddles: per node length 2^L (L = 7..10) and set, m/4 entries (cn, spcn, smcn, 0) indexed by n
+#define FFTR_TWA_OFF(L, set) (((1 << ((L) - 1)) - 64) + (set) * (1 << ((L) - 2)))
+#define FFTR_TWA_ENTRIES FFTR_TWA_OFF(11, 0)
+struct FftRegsConst {                  // -> __constant__ memory
+    FftSmallTw small;
+    uint16_t long_word[32];            // first word of the slot of block r of the 1024-point array
+    uint16_t short_word[3][8];         // ... of block r of short transform t
+    uint8_t partner[2][32];            // [pass][lane] lane that holds the other component array (kinds a, b)
+    uint8_t is_xi[2][32];              // [pass][lane] this lane holds the imaginary array
+};
+struct FftRegsPlan {
+    FftRegsConst c;
+    std::vector<float> twA;            // FFTR_TWA_ENTRIES x 4
+    std::vector<uint32_t> out_long;    // bin i (0..512) -> re word | neg << 15 | (im word | neg << 15) << 16  (words into the warp's X[])
+    std::vector<uint32_t> out_short;   // [3][132]
+    uint8_t kind_long[32], kind_short[8];
+};
+void build_fft_regs_plan(FftRegsPlan *P);
+
 // ---- psychoacoustic model tables (l3psy.c:770-994 + :194-195) -------------------------------------
 struct PsyTables {
     int sr_idx, n_l, n_s;

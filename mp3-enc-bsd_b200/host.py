@@ -38,7 +38,7 @@ EXPORTS = ["mp3gpu_last_error", "mp3gpu_version", "mp3gpu_create", "mp3gpu_destr
            "mp3gpu_encode_frames_mp3", "mp3gpu_encode_frames_mp3_dev", "mp3gpu_flush_mp3", "mp3gpu_flush_mp3_dev",
            "mp3gpu_frame_bytes", "mp3gpu_format_bitstream_batch", "mp3gpu_begin_segment", "mp3gpu_stream_wave", "mp3gpu_set_pcm_layout", "mp3gpu_count_bits_batch", "mp3gpu_set_host_delivery",
            "mp3gpu_reset_async", "mp3gpu_set_stream_frames", "mp3gpu_reset_streams",
-           "mp3gpu_set_front_variant", "mp3gpu_get_front_variant", "mp3gpu_set_pipeline",
+           "mp3gpu_set_front_variant", "mp3gpu_get_front_variant", "mp3gpu_set_pipeline", "mp3gpu_set_psy_variant",
            "mp3gpu_set_rate_loop_segments", "mp3gpu_rate_loop_segment_stats"]
 FRONT_VARIANTS = {"exact": 0, "fma": 1, "fp32": 2, "fma_tc": 3}
 LEGACY_EXPORTS = ["window_subband", "filter_subband", "mdct_sub", "L3psycho_anal", "iteration_loop", "quantize", "count_bits",
@@ -81,6 +81,7 @@ def load_library():
         lib.mp3gpu_set_stream_frames.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_long), C.c_void_p]
         lib.mp3gpu_reset_streams.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.mp3gpu_set_front_variant.argtypes = [C.c_void_p, C.c_int]
+        lib.mp3gpu_set_psy_variant.argtypes = [C.c_void_p, C.c_int]
         lib.mp3gpu_set_pipeline.argtypes = [C.c_void_p, C.c_int]
         lib.mp3gpu_set_rate_loop_segments.argtypes = [C.c_void_p, C.c_int]
         lib.mp3gpu_rate_loop_segment_stats.argtypes = [C.c_void_p, C.POINTER(C.c_long), C.c_int]
@@ -177,6 +178,10 @@ class Encoder:
         out = (C.c_long * 32)()
         self._check(self.lib.mp3gpu_rate_loop_segment_stats(self.ctx, out, 1 if reset else 0), "mp3gpu_rate_loop_segment_stats")
         return [tuple(out[4 * p:4 * p + 4]) for p in range(8) if any(out[4 * p:4 * p + 4])]
+
+    def set_psy_variant(self, name):
+        """'regs' (default): FFTs as register code; 'program': the interpreted op program (A/B, both bit-identical)"""
+        self._check(self.lib.mp3gpu_set_psy_variant(self.ctx, {"regs": 0, "program": 1}[name]), "mp3gpu_set_psy_variant")
 
     def set_front_variant(self, name):
         """arithmetic of the fused filterbank + MDCT kernel: "exact" (default), "fma" (FP64, <= 1e-12), "fp32" (<= 1e-5)"""

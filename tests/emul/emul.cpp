@@ -5,6 +5,11 @@
 
 #include <vector>
 
+#include <ucontext.h>
+
+#include <functional>
+
+#include "../../mp3-enc-bsd_b200/csrc/fft_regs.h"
 #include "../../mp3-enc-bsd_b200/csrc/front_core.h"
 #include "../../mp3-enc-bsd_b200/csrc/psy_core.h"
 #include "../../mp3-enc-bsd_b200/csrc/rate_loop_core.h"
@@ -12,6 +17,81 @@
 
 namespace simt { thread_local int g_tid = 0; }
 using namespace mp3gpu;
+
+
+// ---- the 32 lanes of a warp as fibers: per-lane device code (fft_regs.h) runs unchanged; lanes::shfl / lanes::sync are
+// rendezvous points of the lanes named in the mask (a divergent group waits for its own members only) ----------------
+namespace {
+struct WarpFibers {
+    enum { RUN = 0, WAIT = 1, DONE = 2 };
+    ucontext_t main_ctx, ctx[32];
+    std::vector<char> stack[32];
+    int state[32], src[32], cur = -1;
+    unsigned want[32];
+    float val[32], res[32];
+    std::function<void(int)> body;
+    bool deadlock = false;
+};
+thread_local WarpFibers *g_warp = nullptr;
+
+void fiber_entry(int lane)
+{
+    WarpFibers *W = g_warp;
+    W->body(lane);
+    W->state[lane] = WarpFibers::DONE;
+    swapcontext(&W->ctx[lane], &W->main_ctx);
+}
+
+bool run_warp(const std::function<void(int)> &body)
+{
+    WarpFibers W;
+    W.body = body;
+    g_warp = &W;
+    for (int l = 0; l < 32; l++) {
+        W.stack[l].resize(256 * 1024);
+        getcontext(&W.ctx[l]);
+        W.ctx[l].uc_stack.ss_sp = W.stack[l].data(); W.ctx[l].uc_stack.ss_size = W.stack[l].size(); W.ctx[l].uc_link = &W.main_ctx;
+        makecontext(&W.ctx[l], (void (*)())fiber_entry, 1, l);
+        W.state[l] = WarpFibers::RUN;
+    }
+    for (;;) {
+        bool any = false, all_done = true;
+        for (int l = 0; l < 32; l++)
+            if (W.state[l] == WarpFibers::RUN) { any = true; W.cur = l; swapcontext(&W.main_ctx, &W.ctx[l]); }
+        // release every group whose members have all arrived with the same mask
+        for (int l = 0; l < 32; l++) {
+            if (W.state[l] != WarpFibers::WAIT) continue;
+            const unsigned m = W.want[l];
+            bool ready = true;
+            for (int k = 0; k < 32; k++) if ((m >> k & 1) && !(W.state[k] == WarpFibers::WAIT && W.want[k] == m)) ready = false;
+            if (!ready) continue;
+            for (int k = 0; k < 32; k++) if (m >> k & 1) W.res[k] = W.val[W.src[k]];
+            for (int k = 0; k < 32; k++) if (m >> k & 1) W.state[k] = WarpFibers::RUN;
+            any = true;
+        }
+        for (int l = 0; l < 32; l++) if (W.state[l] != WarpFibers::DONE) all_done = false;
+        if (all_done) break;
+        if (!any) { W.deadlock = true; break; }
+    }
+    g_warp = nullptr;
+    return !W.deadlock;
+}
+}  // namespace
+
+namespace mp3gpu {
+FftRegsConst c_fftr;
+namespace lanes {
+float shfl(unsigned mask, float v, int src)
+{
+    WarpFibers *W = g_warp;
+    const int l = W->cur;
+    W->val[l] = v; W->src[l] = src; W->want[l] = mask; W->state[l] = WarpFibers::WAIT;
+    swapcontext(&W->ctx[l], &W->main_ctx);
+    return W->res[l];
+}
+void sync() { (void)shfl(0xffffffffu, 0.f, g_warp->cur); }
+}  // namespace lanes
+}  // namespace mp3gpu
 
 extern "C" {
 
@@ -48,6 +128,30 @@ int emul_fft(float *x, int n, int *n_ops, int *n_levels)
         }
     }
     for (size_t l = 0; l < P.level_start.size(); l++) if (P.level_start[l] % 32) return -3;
+    return 0;
+}
+
+// FFT in registers (fft_regs.h) under the fiber warp: one 1024-point and three 256-point transforms, outputs in LOGICAL order
+int emul_fft_regs(const float *in_long, const float *in_short, float *out_long, float *out_short)
+{
+    static FftRegsPlan P;
+    build_fft_regs_plan(&P);
+    c_fftr = P.c;
+    std::vector<float> X(FFTR_X_WORDS, 0.f);
+    const bool ok = run_warp([&](int lane) {
+        float xl[32], xs[3][8];
+        for (int r = 0; r < 32; r++) xl[r] = in_long[lane + 32 * r];
+        for (int t = 0; t < 3; t++) for (int r = 0; r < 8; r++) xs[t][r] = in_short[256 * t + lane + 32 * r];
+        fft_regs_run(xl, xs, P.twA.data(), X.data(), lane);
+    });
+    if (!ok) return -1;
+    auto val = [&](uint32_t w) { const float v = X[w & 0x7fffu]; return (w & 0x8000u) ? -v : v; };
+    for (int i = 0; i <= 512; i++) { out_long[i] = val(P.out_long[i]); if (i > 0 && i < 512) out_long[1024 - i] = val(P.out_long[i] >> 16); }
+    for (int t = 0; t < 3; t++)
+        for (int i = 0; i <= 128; i++) {
+            out_short[256 * t + i] = val(P.out_short[132 * t + i]);
+            if (i > 0 && i < 128) out_short[256 * t + 256 - i] = val(P.out_short[132 * t + i] >> 16);
+        }
     return 0;
 }
 

@@ -76,3 +76,27 @@ def test_pipeline_edge_inputs(emul):
         assert np.array_equal(r["psy"]["pe"], o["pe"]), name
         assert np.array_equal(np.abs(r["ix"].astype(np.int32)), o["ix"]), name
         assert np.array_equal(r["gi"], o["gi"]), name
+
+
+def test_fft_regs_bit_exact(emul):
+    """fft_regs.h (the per-lane register code that k_psy_front_regs runs, here under 32 fibers) against the op program and
+    the oracle: one 1024-point and three 256-point transforms, every output word bit-identical (signed zeros included)"""
+    import ctypes as C
+    rng = np.random.default_rng(7)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    for scale in (1.0, 3000.0, 1e-3, 0.0):
+        xl = (rng.standard_normal(1024) * scale).astype(np.float32)
+        xs = (rng.standard_normal(768) * scale).astype(np.float32)
+        ol, osh = np.zeros(1024, np.float32), np.zeros(768, np.float32)
+        assert emul.lib.emul_fft_regs(vp(xl), vp(xs), vp(ol), vp(osh)) == 0, "lanes deadlocked"
+        _, yl, _, _ = emul.fft(xl)
+        assert np.array_equal(yl.view(np.uint32), ol.view(np.uint32))
+        for t in range(3):
+            _, ys, _, _ = emul.fft(xs[256 * t:256 * t + 256])
+            assert np.array_equal(ys.view(np.uint32), osh[256 * t:256 * t + 256].view(np.uint32))
+        e_ref, _ = oracle.fft(xl.copy())
+        e = np.empty(513, np.float32)
+        e[0], e[512] = ol[0] * ol[0], ol[512] * ol[512]
+        e[1:512] = ol[1:512] * ol[1:512] + ol[1023:512:-1] * ol[1023:512:-1]
+        e[1:512] = np.where(e[1:512].astype(np.float64) < 0.0005, np.float32(0.0005), e[1:512])
+        assert np.array_equal(e, e_ref)

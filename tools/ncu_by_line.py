@@ -59,7 +59,7 @@ def main():
     tot = [sum(v[k] for v in agg.values()) for k in range(len(col))]
     print("%-28s %9s %12s %12s %12s %12s %12s" % ("file:line", "samples", "inst", "smem_wave", "smem_excess", "gl_tag_req", "l2_sectors"))
     print("%-28s %9d %12d %12d %12d %12d %12d" % (("TOTAL",) + tuple(tot)))
-    for key, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:45]:
+    for key, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(__import__("os").environ.get("TOPN","45"))]:
         print("%-28s %9d %12d %12d %12d %12d %12d" % (("%s:%d" % key,) + tuple(v)))
 
 
