@@ -112,9 +112,10 @@ k_psy_front(PsyDev D, const short *pcm, long stream_stride, long ch_stride, int 
     psy_front(w, D, simt::pin_smem(Ms[warp]), pcm + s * stream_stride + ch * ch_stride + HIST + 576L * g, &mid[gc]);
 }
 
-// The same with the transforms in registers (fft_regs.h): 8064 B of shared memory per warp, 3 CTAs of 8 warps per SM
+// The same with the transforms in registers (fft_regs.h): 8064 B of shared memory per warp, 3 CTAs of 9 warps per SM (72
+// registers; A/B gpurun_out/r2x: 8 x 3 at 80 registers 67.6 ms, 9 x 3 62.3 ms, 6 x 4 66.9, 12 x 2 70.2: the kernel is latency bound)
 #ifndef PSYF2_WARPS
-#define PSYF2_WARPS 8
+#define PSYF2_WARPS 9
 #endif
 #ifndef PSYF2_MIN_CTAS
 #define PSYF2_MIN_CTAS 3

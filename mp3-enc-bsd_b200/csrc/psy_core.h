@@ -59,14 +59,16 @@ struct PsyMid {
 struct PsyFrontSmem {
     float x[FFT_X_ALLOC];
     float E[520];
+    double prod[516];   // cw * e per line (psy_front_tail)
 };
 struct PsyFrontView {
     float *x, *E;
     double *cwv;        // [52]  at x + 264
     double *eb;         // [64]  at x + 656
     double *thr;        // [64]  at E + 0   (after the long partition energies)
+    double *prod;
     SIMT_FN explicit PsyFrontView(PsyFrontSmem &S)
-        : x(S.x), E(S.E), cwv(reinterpret_cast<double *>(S.x + 264)), eb(reinterpret_cast<double *>(S.x + 656)), thr(reinterpret_cast<double *>(S.E)) {}
+        : x(S.x), E(S.E), cwv(reinterpret_cast<double *>(S.x + 264)), eb(reinterpret_cast<double *>(S.x + 656)), thr(reinterpret_cast<double *>(S.E)), prod(S.prod) {}
 };
 static_assert(264 + 2 * 52 <= FFT_BATCH_BYTES / 4 && 656 >= FFT_BATCH_BYTES / 4 + 264 && 656 + 2 * 64 <= 2 * (FFT_BATCH_BYTES / 4), "overlays must sit in dummy words");
 
@@ -297,34 +299,47 @@ SIMT_FN double unpredictability(double r_new, double phi_new, double r_prime, do
 // ---------------------------------------------------------------------------------------------------
 // history-free tail of psy_front: partition energies, weighted unpredictability, energy spreading.
 // E[0..512]: energies of the long transform in line order; cwv[i]: unpredictability of lines 6 + 4 i .. 9 + 4 i (i < 50);
-// eb[64]: scratch (all three in the warp's shared memory)
+// eb_s[64], prod[513]: scratch (all in the warp's shared memory)
 // ---------------------------------------------------------------------------------------------------
-SIMT_FN void psy_front_tail(const WarpCtx &w, const PsyTables &T, const float *E, const double *cwv, double *eb_s, PsyMid *out)
+SIMT_FN void psy_front_tail(const WarpCtx &w, const PsyTables &T, const float *E, const double *cwv, double *eb_s, double *prod, PsyMid *out)
 {
     FOR_THREADS(w)
     for (int j = T.tail_l + lane; j <= 512; j += 32) out->tail[j - T.tail_l] = E[j];
+    // cw[j] * e[j] of every line, l3psy.c:574-577 (lines 0..5 belong to the partitions whose cb psy_scan forms from history;
+    // lines >= 206 have cw = 0.4): the partition chains below are then three conversions and two additions per line
+#pragma unroll 1
+    for (int j = lane; j <= 512; j += 32) {
+        const double cw = (j < 6) ? 0.0 : (j < 206) ? cwv[(j - 6) >> 2] : 0.4;
+        prod[j] = simt::dmul(cw, (double)E[j]);
+    }
     END_THREADS
-    // partition energy / weighted unpredictability, l3psy.c:565-578
+    w.sync();
+    // partition energy / weighted unpredictability, l3psy.c:565-578: eb is a double, cb a FLOAT accumulator, so both are
+    // sequential chains in line order; a lane runs two chains at a time (slot 0: partition lane, slot 1: partition lane + 32).
+    // Partition 0 also takes the lines >= tail_l (zero-initialised partition map, l3psy.c:93): that chain runs in the idle
+    // slot 1 of lane 31, started from the sum of partition 0's own lines, beside the wide partitions instead of after them.
     FOR_THREADS(w)
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int p = lane + 32 * h;
-        double eb = 0.0;
-        float cb = 0.0f;
-        if (p < T.n_l) {
-            for (int j = T.lo_l[p]; j < T.hi_l[p]; j++) {
-                eb = simt::dadd(eb, (double)E[j]);
-                if (p >= T.n_hist_part) {
-                    double cw = (j < 206) ? cwv[(j - 6) >> 2] : 0.4;
-                    cb = (float)simt::dadd((double)cb, simt::dmul(cw, (double)E[j]));
-                }
-            }
-            if (p == 0)
-                for (int j = T.tail_l; j <= 512; j++) eb = simt::dadd(eb, (double)E[j]);
+    {
+        int j0 = T.ch_lo[0][lane], j1 = T.ch_lo[1][lane];
+        const int h0 = T.ch_hi[0][lane], h1 = T.ch_hi[1][lane];
+        double eb0 = 0.0, eb1 = 0.0;
+        float cb0 = 0.0f, cb1 = 0.0f;
+        if (lane == 31) for (int j = T.lo_l[0]; j < T.hi_l[0]; j++) eb1 = simt::dadd(eb1, (double)E[j]);
+        const int wa = T.ch_wmax[0], wb = T.ch_wmax[1];
+#pragma unroll 1
+        for (int i = 0; i < wa; i++) {
+            if (j0 < h0) { eb0 = simt::dadd(eb0, (double)E[j0]); cb0 = (float)simt::dadd((double)cb0, prod[j0]); j0++; }
+            if (j1 < h1) { eb1 = simt::dadd(eb1, (double)E[j1]); cb1 = (float)simt::dadd((double)cb1, prod[j1]); j1++; }
         }
-        eb_s[p] = eb;
-        out->eb[p] = eb;
-        out->cb[p] = cb;
+#pragma unroll 4
+        for (int i = wa; i < wb; i++)
+            if (j1 < h1) { eb1 = simt::dadd(eb1, (double)E[j1]); cb1 = (float)simt::dadd((double)cb1, prod[j1]); j1++; }
+        if (lane > 0) { eb_s[lane] = eb0; out->eb[lane] = eb0; }
+        const int p1 = (lane == 31) ? 0 : lane + 32;
+        eb_s[p1] = eb1; out->eb[p1] = eb1;
+        out->cb[lane] = cb0;
+        out->cb[lane + 32] = (lane == 31) ? 0.0f : cb1;
+        if (lane == 31) { eb_s[63] = 0.0; out->eb[63] = 0.0; }
     }
     END_THREADS
     w.sync();
@@ -336,15 +351,16 @@ SIMT_FN void psy_front_tail(const WarpCtx &w, const PsyTables &T, const float *E
         const int b0 = lane, b1 = lane + 32;
         const int lo0 = T.spr_lo[b0], n0 = T.spr_hi[b0] - lo0 + 1;
         const int lo1 = (b1 < 63) ? T.spr_lo[b1] : 0, n1 = (b1 < 63) ? T.spr_hi[b1] - lo1 + 1 : 0;
+        const bool sparse = T.sparse != 0;
+        const double *s0p = T.s3_band + b0, *s1p = T.s3_band + b1, *e0p = eb_s + lo0, *e1p = eb_s + lo1;
         float e0 = 0.0f, e1 = 0.0f;
-        for (int i = 0; i < T.spr_wmax; i++) {
+        const int wmax = T.spr_wmax;
+#pragma unroll 4
+        for (int i = 0; i < wmax; i++) {
             // step i of each lane's own row range [lo, hi] (banded matrix layout: one coalesced request per step); the terms
             // are added in the reference's order, k ascending
-            const bool in0 = i < n0, in1 = i < n1;
-            const double s0 = in0 ? T.s3_band[i * 64 + b0] : 1.0, s1 = in1 ? T.s3_band[i * 64 + b1] : 1.0;
-            const double eb0 = in0 ? eb_s[lo0 + i] : 0.0, eb1 = in1 ? eb_s[lo1 + i] : 0.0;
-            if (in0 && (T.sparse || s0 != 1.0)) e0 = (float)simt::dadd((double)e0, simt::dmul(s0, eb0));
-            if (in1 && (T.sparse || s1 != 1.0)) e1 = (float)simt::dadd((double)e1, simt::dmul(s1, eb1));
+            if (i < n0) { const double s = s0p[i * 64]; if (sparse || s != 1.0) e0 = (float)simt::dadd((double)e0, simt::dmul(s, e0p[i])); }
+            if (i < n1) { const double s = s1p[i * 64]; if (sparse || s != 1.0) e1 = (float)simt::dadd((double)e1, simt::dmul(s, e1p[i])); }
         }
         out->ecb[b0] = e0;
         out->ecb[b1] = e1;
@@ -422,7 +438,7 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
     }
     END_THREADS
     w.sync();
-    psy_front_tail(w, T, M.E, M.cwv, M.eb, out);
+    psy_front_tail(w, T, M.E, M.cwv, M.eb, M.prod, out);
 }
 
 #if SIMT_DEV
@@ -433,7 +449,8 @@ SIMT_FN void psy_front(const WarpCtx &w, const PsyDev &D, PsyFrontSmem &S, const
 // ---------------------------------------------------------------------------------------------------
 #define PSYF2_CWV_WORD 520
 #define PSYF2_EB_WORD 624
-static_assert(PSYF2_EB_WORD + 128 <= FFTR_X_WORDS && PSYF2_CWV_WORD + 104 <= PSYF2_EB_WORD, "overlays");
+#define PSYF2_PROD_WORD 752
+static_assert(PSYF2_PROD_WORD + 2 * 516 <= FFTR_X_WORDS && PSYF2_EB_WORD + 128 <= PSYF2_PROD_WORD && PSYF2_CWV_WORD + 104 <= PSYF2_EB_WORD, "overlays");
 SIMT_FN void psy_front_regs(const WarpCtx &w, const PsyDev &D, float *X, const short *pcm, PsyMid *out)
 {
     const PsyTables &T = *D.T;
@@ -458,12 +475,24 @@ SIMT_FN void psy_front_regs(const WarpCtx &w, const PsyDev &D, float *X, const s
     }
     e[16] = 0.f;
     if (lane == 0) { float ph; bin_energy_phase(D.out_long[512], X, 1024, 512, false, &e[16], &ph); }
-    if (lane < 6) {
-        float e6, ph = 0.f;
-        bin_energy_phase(D.out_long[lane], X, 1024, lane, true, &e6, &ph);
-        out->e6[lane] = e6; out->phi6[lane] = ph;
+    // Phases (double-precision atan2, the most expensive single operation of the kernel): lines 2..51 of the three short
+    // transforms and lines 0..5 of the long one = 156 bins, spread over five passes of the 32 lanes (one copy of the code).
+    // The short phases go to the pad words of the transform slots (item q -> pad word q % 4 of slot q / 4).
+#pragma unroll 1
+    for (int c = 0; c < 5; c++) {
+        const int q = lane + 32 * c;
+        if (q < 156) {
+            const bool is_long = q >= 150;
+            const int i3 = (q * 171) >> 9, t = q - 3 * i3;                 // q / 3, q % 3 (q < 256)
+            const int k = is_long ? q - 150 : i3 + 2;
+            float en, ph = 0.f;
+            bin_energy_phase(is_long ? D.out_long[k] : D.out_short[132 * t + k], X, is_long ? 1024 : 256, k, true, &en, &ph);
+            if (is_long) { out->e6[k] = en; out->phi6[k] = ph; }
+            else { out->es[t][k] = en; X[FFTR_SLOT_WORDS * (q >> 2) + 32 + (q & 3)] = ph; }
+        }
     }
-    // short transforms: lines 2..51 with phase -> unpredictability of lines 6..205 in groups of four, l3psy.c:531-549
+    w.sync();
+    // unpredictability of lines 6..205 in groups of four, l3psy.c:531-549
     double cw[2] = {0.0, 0.0};
 #pragma unroll
     for (int it = 0; it < 2; it++) {
@@ -473,9 +502,10 @@ SIMT_FN void psy_front_regs(const WarpCtx &w, const PsyDev &D, float *X, const s
             float es[3], ps[3];
 #pragma unroll
             for (int t = 0; t < 3; t++) {
-                ps[t] = 0.f;
-                bin_energy_phase(D.out_short[132 * t + k], X, 256, k, true, &es[t], &ps[t]);
-                out->es[t][k] = es[t];
+                float ph;
+                bin_energy_phase(D.out_short[132 * t + k], X, 256, k, false, &es[t], &ph);      // the energy again: 3 flops
+                const int q = 3 * i + t;
+                ps[t] = X[FFTR_SLOT_WORDS * (q >> 2) + 32 + (q & 3)];
             }
             const double r_prime = simt::dsub(simt::dmul(2.0, sqrt((double)es[0])), sqrt((double)es[2]));
             const double phi_prime = simt::dsub(simt::dmul(2.0, (double)ps[0]), (double)ps[2]);
@@ -503,7 +533,7 @@ SIMT_FN void psy_front_regs(const WarpCtx &w, const PsyDev &D, float *X, const s
     cwv[lane] = cw[0];
     if (lane < 18) cwv[lane + 32] = cw[1];
     w.sync();
-    psy_front_tail(w, T, X, cwv, eb, out);
+    psy_front_tail(w, T, X, cwv, eb, reinterpret_cast<double *>(X + PSYF2_PROD_WORD), out);
 }
 #endif
 

@@ -26,6 +26,15 @@ namespace mp3gpu {
 using simt::PerThread;
 using simt::WarpCtx;
 
+// work statistics of the host emulation (tests / tools only): granule-channels, outer iterations, probes, quantiser rows,
+// amplified bands, refreshed rows
+#if !SIMT_DEV && defined(MP3GPU_RL_STATS)
+extern long g_rl_stats[16];
+#define RL_STAT(i, n) (g_rl_stats[i] += (n))
+#else
+#define RL_STAT(i, n) ((void)0)
+#endif
+
 // ---- constant tables (host-built with the reference's libm expressions; see tables.cpp) ---------
 // Hot part: copied to shared memory by every CTA.
 // glut[g][16 x + y]: code length + sign bits of the pair (x, y) in every candidate table of group g,
@@ -225,6 +234,7 @@ SIMT_FN void quantize_all(const WarpCtx &w, const RateTables &T, RateWarpSmem &M
     END_THREADS
     const unsigned lm = w.ballot(live);
     const int k_lim = 32 - simt::clz(lm);
+    RL_STAT(2, 1); RL_STAT(3, k_lim);
     FOR_THREADS(w)
     const F2 *ys = reinterpret_cast<const F2 *>(M.scr);
     unsigned *ixw = reinterpret_cast<unsigned *>(M.ix);
@@ -534,6 +544,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
                       int block_type, int scfsi[4], Gr0Carry &g0, short *ix_out, GrInfoOut *gi_out, unsigned char *sf_out,
                       int *max_bits_out)
 {
+    RL_STAT(0, 1);
     const bool is_short = (block_type == 2);
     const bool wsf = (block_type != 0);
     const int nb_l = is_short ? 0 : 21;   // sfb_lmax (gr_deco, loop.c:2063-2081)
@@ -679,6 +690,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
         PerThread<int> save_sf[2];
         do {
             iteration++;
+            RL_STAT(1, 1);
             refresh_pow34(w, M, rowmax);
             part2 = part2_length_of(is_short, gr, compress, scfsi);
             const int huff_bits = max_bits - part2;
@@ -784,6 +796,7 @@ SIMT_FN int encode_gc(const WarpCtx &w, const RateHot &H, const RateTables &T, R
                 }
                 const unsigned amp0 = m0 & ~skip, amp1 = m1;
                 over = simt::popc(amp0) + simt::popc(amp1);
+                RL_STAT(4, over);
                 const unsigned long long amp = (unsigned long long)amp0 | ((unsigned long long)amp1 << 32);
                 FOR_THREADS(w)
                 if (copySF && !is_short && ((skip >> lane) & 1)) Bd.sf[0]() = g0.sf0();

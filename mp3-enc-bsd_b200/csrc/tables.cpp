@@ -263,6 +263,15 @@ void build_psy_tables(int sr, PsyTables *P)
     for (int i = 0; i < 21; i++) { P->bu_l[i] = ML.bu[i]; P->bo_l[i] = ML.bo[i]; P->w1_l[i] = ML.w1[i]; P->w2_l[i] = ML.w2[i]; }
     for (int i = 0; i < 12; i++) { P->bu_s[i] = MS.bu[i]; P->bo_s[i] = MS.bo[i]; P->w1_s[i] = MS.w1[i]; P->w2_s[i] = MS.w2[i]; }
     P->n_hist_part = P->part_l[5] + 1;
+    P->ch_wmax[0] = P->ch_wmax[1] = 0;
+    for (int h = 0; h < 2; h++)
+        for (int l = 0; l < 32; l++) {
+            const int p = l + 32 * h;
+            int lo = p < P->n_l ? P->lo_l[p] : 0, hi = p < P->n_l ? P->hi_l[p] : 0;
+            if (p == 63) { lo = P->tail_l; hi = 513; }       // n_l <= 63 for all three sampling rates
+            P->ch_lo[h][l] = (short)lo; P->ch_hi[h][l] = (short)hi;
+            P->ch_wmax[h] = std::max(P->ch_wmax[h], hi - lo);
+        }
 }
 
 // ---------------------------------------------------------------------------------------------------

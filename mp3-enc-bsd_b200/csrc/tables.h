@@ -152,6 +152,10 @@ struct PsyTables {
     short bu_l[24], bo_l[24], bu_s[12], bo_s[12];
     double w1_l[24], w2_l[24], w1_s[12], w2_s[12];
     int n_hist_part;              // partitions that contain FFT lines 0..5 (history-dependent cw)
+    // partition chains of psy_front_tail: lane l runs partition l (slot 0) and partition l + 32 (slot 1); lane 31's slot 1
+    // (partition 63 does not exist) runs the lines >= tail_l that fold into partition 0
+    short ch_lo[2][32], ch_hi[2][32];
+    int ch_wmax[2];               // longest chain of slot 0 / slot 1
 };
 
 void build_front_tables(FrontTables *F);

@@ -5,6 +5,7 @@
 
 #include <vector>
 
+#define MP3GPU_RL_STATS 1
 #include <ucontext.h>
 
 #include <functional>
@@ -16,6 +17,8 @@
 #include "../../mp3-enc-bsd_b200/csrc/tables.h"
 
 namespace simt { thread_local int g_tid = 0; }
+namespace mp3gpu { long g_rl_stats[16]; }
+extern "C" long *emul_rl_stats() { return mp3gpu::g_rl_stats; }
 using namespace mp3gpu;
 
 
