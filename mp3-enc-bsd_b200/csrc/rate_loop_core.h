@@ -60,6 +60,13 @@ struct alignas(16) RateHot {
     unsigned char subdiv[290][2];   // region0/1_count for big_values (long blocks, loop.c:1596-1690)
     unsigned char pretab[24];
     unsigned char pad1[8];
+    // band sums of long blocks (band_sums): the 21 scalefactor bands are cut into 32 runs of slots of near-equal length, one per
+    // lane (bands wider than the run limit take 2..4 adjacent lanes); lane l sums slots [bs_start[l], bs_start[l] + bs_count[l])
+    unsigned short bs_start[32];
+    unsigned char bs_count[32];
+    unsigned char bs_more[32];      // runs of the same band that follow this lane's run (the band's first lane adds them up)
+    unsigned char bs_first[24];     // lane of the first run of band b
+    unsigned char pad2[8];
 };
 
 // Cold part: stays in global memory (L1/L2 resident; touched rarely or with warp-uniform addresses)
@@ -483,9 +490,46 @@ SIMT_FN double band_sum_one(const RateHot &T, const double *scr, bool is_short, 
 
 SIMT_FN void band_sums(const WarpCtx &w, const RateHot &T, const double *scr, bool is_short, PerThread<double> out[2])
 {
+    if (is_short) {
+        FOR_THREADS(w)
+        out[0]() = band_sum_one(T, scr, true, lane);
+        out[1]() = band_sum_one(T, scr, true, lane + 32);
+        END_THREADS
+        return;
+    }
+    // long blocks: 21 bands of 2..38 slots.  One band per lane would leave a third of the lanes idle and the warp waiting for
+    // the widest band; the bands are cut into 32 runs of at most ~11 slots instead (RateHot::bs_*), the partial sums of a band
+    // meet in its first lane (in run order) and are handed to lane b.
+    PerThread<double> part, d1, d2, d3, tot;
+    PerThread<int> src;
     FOR_THREADS(w)
-    out[0]() = band_sum_one(T, scr, is_short, lane);
-    out[1]() = is_short ? band_sum_one(T, scr, true, lane + 32) : 0.0;
+    {
+        const double *p = scr + T.bs_start[lane];
+        const int n = T.bs_count[lane];
+        double a0 = 0.0, a1 = 0.0;
+        int i = 0;
+#pragma unroll 1
+        for (; i + 1 < n; i += 2) { a0 = simt::dadd(a0, p[0]); a1 = simt::dadd(a1, p[1]); p += 2; }
+        if (i < n) a0 = simt::dadd(a0, p[0]);
+        part() = simt::dadd(a0, a1);
+    }
+    END_THREADS
+    w.shfl_down(d1, part, 1); w.shfl_down(d2, part, 2); w.shfl_down(d3, part, 3);
+    FOR_THREADS(w)
+    {
+        const int more = T.bs_more[lane];
+        double v = part();
+        if (more >= 1) v = simt::dadd(v, d1());
+        if (more >= 2) v = simt::dadd(v, d2());
+        if (more >= 3) v = simt::dadd(v, d3());
+        tot() = v;
+        src() = lane < 21 ? T.bs_first[lane] : 0;
+    }
+    END_THREADS
+    w.shfl_idx(out[0], tot, src);
+    FOR_THREADS(w)
+    if (lane >= 21) out[0]() = 0.0;
+    out[1]() = 0.0;
     END_THREADS
 }
 

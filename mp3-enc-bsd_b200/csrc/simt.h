@@ -74,6 +74,9 @@ struct WarpCtx {  // one warp == one group
     }
     template <class T>
     SIMT_FN T broadcast(const PerThread<T> &x, int src_lane) const { return __shfl_sync(0xffffffffu, x.v, src_lane); }
+    // dst(lane) = src(lane + d) (lanes past the end keep their own value); dst(lane) = src(idx(lane))
+    SIMT_FN void shfl_down(PerThread<double> &dst, const PerThread<double> &src, int d) const { dst.v = __shfl_down_sync(0xffffffffu, src.v, d); }
+    SIMT_FN void shfl_idx(PerThread<double> &dst, const PerThread<double> &src, const PerThread<int> &idx) const { dst.v = __shfl_sync(0xffffffffu, src.v, idx.v); }
 };
 
 // Reference to a per-warp shared-memory object whose address is opaque to the optimiser.  Under register pressure
@@ -157,6 +160,8 @@ struct WarpCtx {
     }
     template <class T>
     T broadcast(const PerThread<T> &x, int src_lane) const { return x.v[src_lane]; }
+    void shfl_down(PerThread<double> &dst, const PerThread<double> &src, int d) const { double t[32]; for (int i = 0; i < 32; i++) t[i] = src.v[i + d < 32 ? i + d : i]; std::memcpy(dst.v, t, sizeof(t)); }
+    void shfl_idx(PerThread<double> &dst, const PerThread<double> &src, const PerThread<int> &idx) const { double t[32]; for (int i = 0; i < 32; i++) t[i] = src.v[idx.v[i] & 31]; std::memcpy(dst.v, t, sizeof(t)); }
 };
 
 #define FOR_THREADS(ctx) for (int lane = 0; lane < 32; ++lane) { simt::g_tid = lane;

@@ -179,6 +179,27 @@ void build_rate_tables(int sr, RateTables *R)
             if (line >= H.sfb_s[sfb] && line < H.sfb_s[sfb + 1]) b = 3 * sfb + w;
         H.band_short[s] = (unsigned char)b;
     }
+    {   // runs of band_sums (long blocks): the smallest run limit m with sum_b ceil(width_b / m) <= 32
+        int wdt[21], m = 1;
+        for (int b = 0; b < 21; b++) wdt[b] = (H.sfb_l[b + 1] >> 1) - (H.sfb_l[b] >> 1);
+        for (;; m++) {
+            int lanes = 0;
+            for (int b = 0; b < 21; b++) lanes += (wdt[b] + m - 1) / m;
+            if (lanes <= 32) break;
+        }
+        int l = 0;
+        for (int b = 0; b < 21; b++) {
+            const int k = (wdt[b] + m - 1) / m;          // runs of this band (<= 4 for Table B.8), lengths as equal as possible
+            int st = H.sfb_l[b] >> 1;
+            H.bs_first[b] = (unsigned char)l;
+            for (int r = 0; r < k; r++, l++) {
+                const int len = wdt[b] / k + (r < wdt[b] % k ? 1 : 0);
+                H.bs_start[l] = (unsigned short)st; H.bs_count[l] = (unsigned char)len; H.bs_more[l] = (unsigned char)(r == 0 ? k - 1 : 0);
+                st += len;
+            }
+        }
+        for (; l < 32; l++) { H.bs_start[l] = 0; H.bs_count[l] = 0; H.bs_more[l] = 0; }
+    }
     // subdivide() for plain long blocks, loop.c:1596-1690, tabulated over big_values
     static const unsigned char subdv[23][2] = {{0,0},{0,0},{0,0},{0,0},{0,0},{0,1},{1,1},{1,1},{1,2},{2,2},{2,3},{2,3},
         {3,4},{3,4},{3,4},{4,5},{4,5},{4,6},{5,6},{5,6},{5,7},{6,7},{6,7}};
