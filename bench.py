@@ -249,7 +249,7 @@ def main():
     ap.add_argument("--config", type=int, default=4, choices=[1, 2, 3, 4, 5], help="BASELINE.json configs[config - 1]; default 4 = configs[3]")
     ap.add_argument("--clips", type=int, default=int(os.environ.get("MP3GPU_BENCH_CLIPS", 0)), help="total clips of the batch (all ranks)")
     ap.add_argument("--seconds", type=float, default=0.0, help="clip (or stream) length; default: the config's")
-    ap.add_argument("--chunk-frames", type=int, default=0, help="frames per stream per library call (default: 32 for full batches, 192 below one wave)")
+    ap.add_argument("--chunk-frames", type=int, default=0, help="frames per stream per library call (default: 30 = two full 15-granule tiles of the filterbank kernel per channel for full batches, 192 below one wave)")
     ap.add_argument("--parity-clips", type=int, default=32, help="clips checked against the reference CLI after the timed region")
     ap.add_argument("--segment-frames", type=int, default=116, help="config 5: frames per segment")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -314,7 +314,7 @@ def main():
     S = hi - lo
     # frames per library call: 32 for a batch that fills the device; a shard below one wave of streams gets longer calls so
     # that the library can cut them into speculative rate-loop segments (mp3gpu_set_rate_loop_segments)
-    chunk = args.chunk_frames or (32 if S >= mod.host.stream_wave(local_rank) else 192)
+    chunk = args.chunk_frames or (30 if S >= mod.host.stream_wave(local_rank) else 192)
     F = min(chunk, n_frames)
     chunks = []
     f0 = 0

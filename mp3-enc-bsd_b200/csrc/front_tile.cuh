@@ -253,7 +253,10 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
     for (int c = warp; c < n_chunks; c += FT_WARPS) {
         double w0[8], w1[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) { w0[j] = M.window[lane + 64 * j]; w1[j] = M.window[lane + 32 + 64 * j]; }
+        // encode.c:306 divides the sample by SCALE = 32768 before the window multiply (encode.c:310); a power of two moves through
+        // the rounding of the product unchanged, so the taps carry it: (x / 32768) * w == x * (w / 32768) bit for bit (no
+        // product comes near the denormal range: |w| >= 4.77e-7 where it is not zero)
+        for (int j = 0; j < 8; j++) { w0[j] = __dmul_rn(M.window[lane + 64 * j], 1.0 / 32768); w1[j] = __dmul_rn(M.window[lane + 32 + 64 * j], 1.0 / 32768); }
         const int src_lane = (32 - lane) & 31;
 #pragma unroll 1
         for (int p = 0; p < 2; p++) {
@@ -262,13 +265,13 @@ k_front_tile(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
             double h0[8], h1[8];                                         // h[j] = sample for tap j of the CURRENT slot
 #pragma unroll
             for (int j = 1; j < 8; j++) {
-                h0[j] = __dmul_rn((double)M.pcm[base0 - 64 * j], 1.0 / 32768);       // encode.c:306 (/SCALE, exact)
-                h1[j] = __dmul_rn((double)M.pcm[base0 - 32 - 64 * j], 1.0 / 32768);
+                h0[j] = (double)M.pcm[base0 - 64 * j];
+                h1[j] = (double)M.pcm[base0 - 32 - 64 * j];
             }
 #pragma unroll
             for (int k = 0; k < 16; k++) {
-                h0[0] = __dmul_rn((double)M.pcm[base0 + 64 * k], 1.0 / 32768);
-                h1[0] = __dmul_rn((double)M.pcm[base0 - 32 + 64 * k], 1.0 / 32768);
+                h0[0] = (double)M.pcm[base0 + 64 * k];
+                h1[0] = (double)M.pcm[base0 - 32 + 64 * k];
                 double y0 = __dmul_rn(h0[0], w0[0]), y1 = __dmul_rn(h1[0], w1[0]);   // encode.c:310-311,392-396
 #pragma unroll
                 for (int j = 1; j < 8; j++) {
