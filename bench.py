@@ -41,8 +41,8 @@ sys.path.insert(0, ROOT)
 BYTES_PER_GC = {"front_polyphase_mdct": 5764, "psy_front": 1152 + 2864, "psy_scan": 1280 + 472,
                 "rate_loop": 4608 + 472 + 1152 + 80 + 40, "bitstream": 1152 + 80 + 40 + 417 // 4}
 # DRAM bytes per granule-channel of the front-end kernel from the ncu --set full capture (dram__bytes_read + write)
-FRONT_TRAFFIC_PER_GC = (0.697168e9 + 2.390813e9) / 530432
-FRONT_TRAFFIC_SOURCE = "profiles/r01_h_capture.md"
+FRONT_TRAFFIC_PER_GC = (0.654215936e9 + 2.239402e9) / 497280
+FRONT_TRAFFIC_SOURCE = "profiles/r02_final_ncu_metrics.txt"
 
 CONFIGS = {
     1: dict(fs=44100, n_ch=2, kbps=128, seconds=30.0, clips=2048, cls=0,
@@ -249,7 +249,7 @@ def main():
     ap.add_argument("--config", type=int, default=4, choices=[1, 2, 3, 4, 5], help="BASELINE.json configs[config - 1]; default 4 = configs[3]")
     ap.add_argument("--clips", type=int, default=int(os.environ.get("MP3GPU_BENCH_CLIPS", 0)), help="total clips of the batch (all ranks)")
     ap.add_argument("--seconds", type=float, default=0.0, help="clip (or stream) length; default: the config's")
-    ap.add_argument("--chunk-frames", type=int, default=0, help="frames per stream per library call (default: 30 = two full 15-granule tiles of the filterbank kernel per channel for full batches, 192 below one wave)")
+    ap.add_argument("--chunk-frames", type=int, default=0, help="frames per stream per library call (default: 30 = whole 15-granule tiles of the filterbank kernel for full batches, 192 or 64 below one wave)")
     ap.add_argument("--parity-clips", type=int, default=32, help="clips checked against the reference CLI after the timed region")
     ap.add_argument("--segment-frames", type=int, default=116, help="config 5: frames per segment")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -314,7 +314,10 @@ def main():
     S = hi - lo
     # frames per library call: 32 for a batch that fills the device; a shard below one wave of streams gets longer calls so
     # that the library can cut them into speculative rate-loop segments (mp3gpu_set_rate_loop_segments)
-    chunk = args.chunk_frames or (30 if S >= mod.host.stream_wave(local_rank) else 192)
+    wave = mod.host.stream_wave(local_rank)
+    # full batches: whole filterbank tiles; below one wave: long calls so that the rate loop can cut a stream into segments
+    # (needs 2 S <= wave), else medium calls (better copy / compute overlap of the host path)
+    chunk = args.chunk_frames or (30 if S >= wave else 192 if 2 * S <= wave else 64)
     F = min(chunk, n_frames)
     chunks = []
     f0 = 0

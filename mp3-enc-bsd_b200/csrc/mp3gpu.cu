@@ -1371,13 +1371,15 @@ static int rate_loop_segments(const mp3gpu_ctx *c, int n_streams, int n_frames)
     if (!c->segment_rate_loop) return 1;
     const long slots = (long)c->sm_count * RL_WARPS;
     if (n_streams >= slots) return 1;                        // a full wave or more: the ticket queue keeps every warp busy
-    // frames on the critical path: rounds of segments over the warp slots x frames per segment, + what the later passes
-    // typically re-encode behind each seam
+    // frames on the critical path: frames per segment + what the later passes typically re-encode behind each seam.  Only
+    // while every (stream, segment) pair gets its own warp: with two rounds of segments per warp the static assignment waits
+    // for the slowest pair twice and loses to the unsegmented walk (2500 heterogeneous clips, 96-frame calls: 279 ms against
+    // 214 ms per step, gpurun_out/r3d)
     int best = 1;
     long best_cost = n_frames;
-    for (int g = 2; g <= 8 && n_frames / g >= 16; g++) {
-        const long seg = (n_frames + g - 1) / g, rounds = ((long)n_streams * g + slots - 1) / slots;
-        const long cost = rounds * seg + 6L * (g - 1);
+    for (int g = 2; g <= 8 && n_frames / g >= 16 && (long)n_streams * g <= slots; g++) {
+        const long seg = (n_frames + g - 1) / g;
+        const long cost = seg + 6L * (g - 1);
         if (cost * 100 < best_cost * 85) { best = g; best_cost = cost; }
     }
     return best;
