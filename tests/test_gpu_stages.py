@@ -67,8 +67,27 @@ def test_L3psycho_anal_batch(pkg, golden, name):
     assert rel_err(psy["ratio_l"], o["ratio_l"]) <= 1e-5
     assert rel_err(psy["ratio_s"], o["ratio_s"]) <= 1e-5
     exact = (psy["pe"] == o["pe"]).mean()
-    print(f"{name}: pe bit-identical in {100 * exact:.1f}% of granules, max |dpe| {np.abs(psy['pe'] - o['pe']).max():.3e}")
-    assert exact >= 0.5
+    exact_r = (psy["ratio_l"] == o["ratio_l"]).mean()
+    print(f"{name}: pe bit-identical in {100 * exact:.2f}% of granules, ratio_l in {100 * exact_r:.2f}% of values, "
+          f"max |dpe| {np.abs(psy['pe'] - o['pe']).max():.3e}")
+    # measured on B200 (CUDA 12.9 libm against glibc): every value of every golden is bit-identical.  The FFTs are identical by
+    # construction; the double-precision libm calls are not (1-2 ulp), but each result is rounded to float before it is used
+    # (DESIGN.md section 2), so a difference is a ~2^-29 event per value
+    assert exact == 1.0 and exact_r == 1.0
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_psy_fft_variants_identical(pkg, golden, name):
+    """mp3gpu_set_psy_variant: the register FFTs (fft_regs.h, default) and the interpreted op program (round 1) must give the
+    same L3psycho_anal outputs bit for bit"""
+    g, o, enc, pcm, nf, n_ch, dev = setup_case(pkg, golden, name)
+    enc.set_psy_variant("regs")
+    a = pkg.host.psy_to_numpy(enc.L3psycho_anal_batch(pcm))[0]
+    enc.reset()
+    enc.set_psy_variant("program")
+    b = pkg.host.psy_to_numpy(enc.L3psycho_anal_batch(pcm))[0]
+    for f in ("pe", "ratio_l", "ratio_s", "block_type"):
+        assert np.array_equal(a[f], b[f]), f
 
 
 @pytest.mark.parametrize("name", CASES)
