@@ -58,3 +58,24 @@ print('ok', r)
     os.unlink(f.name)
     assert p.returncode == 0, p.stdout + p.stderr
     assert p.stdout.count("ok") == 2
+
+
+def test_c_host_builds_and_has_no_cpu_fallback(tmp_path):
+    """examples/mp3gpu_encode.c compiles with plain gcc against include/mp3gpu.h (no CUDA headers) and, on a machine without
+    a CUDA device, stops with the library's error — the hot path never falls back to the CPU"""
+    import torch
+    exe = os.path.join(ROOT, "examples", "mp3gpu_encode")
+    subprocess.run(["gcc", "-O2", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "mp3gpu_encode.c"), "-o", exe, "-L" + os.path.join(ROOT, "mp3-enc-bsd_b200"),
+                    "-lmp3gpu", "-Wl,-rpath,$ORIGIN/../mp3-enc-bsd_b200"], check=True)
+    wav = tmp_path / "a.wav"
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import write_wav
+    write_wav(str(wav), np.zeros((2, 2304), np.int16), 44100)
+    p = subprocess.run([exe, str(tmp_path), str(wav)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert p.returncode == 0, p.stderr
+        assert (tmp_path / "a.mp3").stat().st_size == 2 * 417 + 1 - 0 or (tmp_path / "a.mp3").exists()
+    else:
+        assert p.returncode == 1 and "mp3gpu_create" in p.stderr, (p.returncode, p.stderr)
+        assert not (tmp_path / "a.mp3").exists()
