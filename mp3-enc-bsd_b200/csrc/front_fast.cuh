@@ -476,4 +476,174 @@ k_front_fast(const short *__restrict__ pcm_rows, long stream_stride, long ch_str
     }
 }
 
+// ---- FP32 variant, second version (round 2): same dataflow and arithmetic as k_front_fast<float, true, float>, restructured
+// around what ncu showed (profiles/r02_front_variants.md): the PCM tile arrives by one bulk copy (TMA) while the threads
+// fetch their window taps straight from global memory (no table staging, no barrier for it); the 1/32768 scale rides on
+// the taps; the fold writes ONE value per lane (lanes 1..15 the sums, 17..31 the differences, one shuffle); the MDCT of a
+// granule is ONE warp's work (window products and the aliasing fold once instead of three times, a third of the input
+// loads, no barriers among warps of a granule), its 18 x 18 DCT-IV entirely on constant-bank operands.
+struct FrontF32Smem {
+    float rows[FT_SLOTS * FT_ROW];
+    short pcm[FT_PCM];
+    int bt[FT_G + 1];
+    unsigned long long bar;
+};
+
+// 18-point DCT-IV on the folded input, direct form: X[m] = sum_j u[j] dct4_l[m][j]; the coefficients as 16-byte uniform
+// constant loads (one LDCU.128 feeds four FFMA)
+__device__ __forceinline__ void ff_dct4_18(const float (&u)[18], float (&out)[18])
+{
+    using A = FastArith<float>;
+#pragma unroll
+    for (int m = 0; m < 18; m++) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const float4 c = *reinterpret_cast<const float4 *>(&c_front_f.dct4_l[m][j]);
+            acc = A::fma(u[j], c.x, acc); acc = A::fma(u[j + 1], c.y, acc);
+            acc = A::fma(u[j + 2], c.z, acc); acc = A::fma(u[j + 3], c.w, acc);
+        }
+        const float2 c2 = *reinterpret_cast<const float2 *>(&c_front_f.dct4_l[m][16]);
+        acc = A::fma(u[16], c2.x, acc); acc = A::fma(u[17], c2.y, acc);
+        out[m] = acc;
+    }
+}
+
+// A persistent version (3 CTAs per SM walking the tiles, the next tile's PCM fetched into the same buffer behind the MDCT
+// stage) was measured slower: 16.3 against 12.9 ms per 4144-clip step (the loop state spills under the 72-register cap and
+// costs two more CTA barriers per tile) — as FT_PERSISTENT was for the exact kernel.
+__global__ void __launch_bounds__(FT_THREADS, 3)
+k_front_f32(const short *__restrict__ pcm_rows, long stream_stride, long ch_stride, int hist, int n_streams, int n_ch, int n_gran,
+            const int *__restrict__ nfr, const PsyOut *__restrict__ psy, float *__restrict__ xr)
+{
+    using A = FastArith<float>;
+    extern __shared__ __align__(16) unsigned char ft_smem_raw[];
+    FrontF32Smem &M = *reinterpret_cast<FrontF32Smem *>(ft_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_tiles = (n_gran + FT_G - 1) / FT_G;
+    const long bid = blockIdx.x;
+    const int t = (int)(bid % n_tiles);
+    const int ch = (int)((bid / n_tiles) % n_ch);
+    const long s = bid / ((long)n_tiles * n_ch);
+    const int g_first = t * FT_G;
+    const int n_live = nfr ? min(n_gran, 2 * nfr[s]) : n_gran;
+    const int ng = min(FT_G, n_live - g_first);
+    if (ng <= 0) return;
+    const int n_slots = 18 * (ng + 1);
+    const int n_chunks = (n_slots + 31) >> 5;
+    const int n_valid = 480 + 32 * n_slots;               // multiple of 8 samples = 16 bytes
+    // ---- stage 0 ----------------------------------------------------------------------------------------------------------
+    if (tid == 0) {
+        ft_mbar_init(&M.bar, 1);
+        const short *src = pcm_rows + s * stream_stride + ch * ch_stride + hist + 576L * (g_first - 1) - 480;
+        ft_bulk_load(M.pcm, src, (unsigned)(n_valid * sizeof(short)), &M.bar);
+    }
+    {
+        uint4 *dst4 = reinterpret_cast<uint4 *>(M.pcm);
+        for (int i = n_valid / 8 + tid; i < FT_PCM / 8; i += FT_THREADS) dst4[i] = make_uint4(0, 0, 0, 0);   // a short last tile
+        if (tid < ng) M.bt[tid] = psy[((s * n_gran + g_first + tid) * (long)n_ch + ch)].block_type;
+    }
+    float w0[8], w1[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {       // encode.c:306: /SCALE, a power of two, moved onto the taps
+        w0[j] = A::mul(g_front_f.window[lane + 64 * j], 1.0f / 32768);
+        w1[j] = A::mul(g_front_f.window[lane + 32 + 64 * j], 1.0f / 32768);
+    }
+    // the fold as one fused expression per lane: v = f0 y0 + f1 y1 + fo o  (lane 0: y0 + y1; 1..15: y0 + o; 16: y0; 17..31: o - y1)
+    const float f0 = lane <= 16 ? 1.f : 0.f, f1 = lane == 0 ? 1.f : lane > 16 ? -1.f : 0.f, fo = (lane == 0 || lane == 16) ? 0.f : 1.f;
+    const int src_lane = (32 - lane) & 31;
+    // Lee's DCT-III input order: t[0] = y[16], t[n] = ysum[16 - n] (n = 1..16), t[n] = ysub[n - 17] (n = 17..31)
+    const int idx = lane == 0 ? 16 : lane <= 16 ? 16 - lane : 48 - lane;
+    __syncthreads();                                      // the mbarrier is initialised; bt[] and the zero fill are visible
+    ft_mbar_wait(&M.bar, 0);
+    // ---- stage A: lane = tap i (and i + 32); slots of one parity form a sliding 8-tap FIR (encode.c:306-311, 392-398) -----
+    for (int c = warp; c < n_chunks; c += FT_WARPS) {
+#pragma unroll 1
+        for (int p = 0; p < 2; p++) {
+            const int base0 = 480 + 32 * (32 * c + p) + 31 - lane;
+            float h0[8], h1[8];
+#pragma unroll
+            for (int j = 1; j < 8; j++) { h0[j] = (float)M.pcm[base0 - 64 * j]; h1[j] = (float)M.pcm[base0 - 32 - 64 * j]; }
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                h0[0] = (float)M.pcm[base0 + 64 * k];
+                h1[0] = (float)M.pcm[base0 - 32 + 64 * k];
+                float y0 = A::mul(h0[0], w0[0]), y1 = A::mul(h1[0], w1[0]);
+#pragma unroll
+                for (int j = 1; j < 8; j++) { y0 = A::fma(h0[j], w0[j], y0); y1 = A::fma(h1[j], w1[j], y1); }
+#pragma unroll
+                for (int j = 7; j > 0; j--) { h0[j] = h0[j - 1]; h1[j] = h1[j - 1]; }
+                // lanes 1..15 need y[32 - i] (y0 of lane 32 - i), lanes 17..31 need y[32 + (32 - lane)] (y1 of lane 32 - lane)
+                const float o = __shfl_sync(0xffffffffu, lane < 16 ? y1 : y0, src_lane);
+                M.rows[(size_t)(32 * c + 2 * k + p) * FT_ROW + idx] = A::fma(fo, o, A::fma(f1, y1, A::mul(f0, y0)));
+            }
+        }
+    }
+    __syncwarp();
+    // ---- stage B: thread = slot, Lee's DCT-III in registers ----------------------------------------------------------------
+    if (tid < n_chunks * 32) {
+        float *row = M.rows + (size_t)tid * FT_ROW;
+        float ys[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) ys[j] = row[j];
+        const bool odd_slot = ((tid % 18) & 1) != 0;
+        lee_dct3<32, float>(ys);
+#pragma unroll
+        for (int j = 0; j < 32; j++) row[j] = ((j & 1) && odd_slot) ? -ys[j] : ys[j];   // mdct.c:57-60
+    }
+    __syncthreads();
+    // ---- stage C + D: one warp per granule, lane = band --------------------------------------------------------------------
+    for (int r = 0; FT_WARPS * r < ng; r++) {
+        const int gl = 1 + FT_WARPS * r + warp;
+        const bool active = gl <= ng;
+        float in[36];
+        int bt = 0;
+        if (active) {
+            const float *p = M.rows + (size_t)(18 * (gl - 1)) * FT_ROW + lane;
+#pragma unroll
+            for (int k = 0; k < 36; k++) in[k] = p[k * FT_ROW];
+            bt = M.bt[gl - 1];
+        }
+        __syncthreads();                                  // every warp has its inputs: the rows of the previous granules are free
+        if (active) {
+            float *st = M.rows + (size_t)(18 * (gl - 1)) * FT_ROW;
+            if (bt == 2) {
+                float out[6];
+                ff_mdct_short6<0, float>(in, out);
+#pragma unroll
+                for (int m = 0; m < 6; m++) st[lane * 18 + 3 * m] = out[m];
+                ff_mdct_short6<1, float>(in, out);
+#pragma unroll
+                for (int m = 0; m < 6; m++) st[lane * 18 + 3 * m + 1] = out[m];
+                ff_mdct_short6<2, float>(in, out);
+#pragma unroll
+                for (int m = 0; m < 6; m++) st[lane * 18 + 3 * m + 2] = out[m];
+            } else {
+                float u[18], out[18];
+                if (bt == 0) ff_fold_long<0, float>(in, u); else if (bt == 1) ff_fold_long<1, float>(in, u); else ff_fold_long<3, float>(in, u);
+                ff_dct4_18(u, out);
+#pragma unroll
+                for (int m = 0; m < 18; m++) st[lane * 18 + m] = out[m];
+            }
+            __syncwarp();
+            if (bt != 2 && lane < 31) {                                                   // mdct.c:83-91
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const float a = st[lane * 18 + 17 - k], b = st[(lane + 1) * 18 + k];
+                    const float cs = FastTab<float>::cs(k), ca = FastTab<float>::ca(k);
+                    st[lane * 18 + 17 - k] = A::fma(b, ca, A::mul(a, cs));
+                    st[(lane + 1) * 18 + k] = A::fma(-a, ca, A::mul(b, cs));
+                }
+            }
+            __syncwarp();
+            float2 *d2 = reinterpret_cast<float2 *>(xr + ((s * n_gran + g_first + gl - 1) * (long)n_ch + ch) * 576);
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                const int e = lane + 32 * i;
+                d2[e] = make_float2(st[2 * e], st[2 * e + 1]);
+            }
+        }
+    }
+}
+
 }  // namespace mp3gpu

@@ -600,6 +600,7 @@ struct mp3gpu_ctx {
     float *d_twA = nullptr;
     uint32_t *d_out_long = nullptr, *d_out_short = nullptr;
     int psy_variant = MP3GPU_PSY_REGS;
+    bool fp32_v1 = false;
     PsyDev psy_dev;
     // state
     PcmStage pcm_main, pcm_fb, pcm_psy;
@@ -898,6 +899,9 @@ static int create_body(mp3gpu_ctx *c)
     CU(cudaFuncSetAttribute(k_psy_front, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(k_psy_front_regs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PSYF2_SMEM));
     CU(cudaFuncSetAttribute(k_psy_front_regs, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(k_front_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FrontF32Smem)));
+    CU(cudaFuncSetAttribute(k_front_f32, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (const char *v = getenv("MP3GPU_FRONT_FP32_V1")) c->fp32_v1 = atoi(v) != 0;
     if (const char *v = getenv("MP3GPU_PSY_FFT")) c->psy_variant = strcmp(v, "program") == 0 ? MP3GPU_PSY_PROGRAM : MP3GPU_PSY_REGS;
     return mp3gpu_reset(c);
 }
@@ -1301,8 +1305,12 @@ static int launch_front(mp3gpu_ctx *c, const short *pcm_rows, const PsyOut *psy,
             k_front_fast<double, false, double><<<(unsigned)ctas, FT_THREADS, sizeof(FrontFastSmem<double, false>), q>>>(
                 pcm_rows, c->row * n_ch, c->row, HIST, n_streams, n_ch, n_gran, nfr, psy, xr);
         } else if (c->front_variant == MP3GPU_FRONT_FP32 && f32_out) {
-            k_front_fast<float, true, float><<<(unsigned)ctas, FT_THREADS, sizeof(FrontFastSmem<float, true>), q>>>(
-                pcm_rows, c->row * n_ch, c->row, HIST, n_streams, n_ch, n_gran, nfr, psy, reinterpret_cast<float *>(xr));
+            if (c->fp32_v1)      // A/B: the first version of the FP32 kernel (MP3GPU_FRONT_FP32_V1=1)
+                k_front_fast<float, true, float><<<(unsigned)ctas, FT_THREADS, sizeof(FrontFastSmem<float, true>), q>>>(
+                    pcm_rows, c->row * n_ch, c->row, HIST, n_streams, n_ch, n_gran, nfr, psy, reinterpret_cast<float *>(xr));
+            else
+                k_front_f32<<<(unsigned)ctas, FT_THREADS, sizeof(FrontF32Smem), q>>>(
+                    pcm_rows, c->row * n_ch, c->row, HIST, n_streams, n_ch, n_gran, nfr, psy, reinterpret_cast<float *>(xr));
         } else if (c->front_variant == MP3GPU_FRONT_FP32) {
             k_front_fast<float, true, double><<<(unsigned)ctas, FT_THREADS, sizeof(FrontFastSmem<float, true>), q>>>(
                 pcm_rows, c->row * n_ch, c->row, HIST, n_streams, n_ch, n_gran, nfr, psy, xr);
