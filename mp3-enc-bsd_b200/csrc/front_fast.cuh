@@ -489,24 +489,57 @@ struct FrontF32Smem {
     unsigned long long bar;
 };
 
-// 18-point DCT-IV on the folded input, direct form: X[m] = sum_j u[j] dct4_l[m][j]; the coefficients as 16-byte uniform
-// constant loads (one LDCU.128 feeds four FFMA)
+// 18-point DCT-IV on the folded input, X[m] = sum_j u[j] cos(pi/72 (2j+1)(2m+1)) / 9, through ONE 9-point complex DFT:
+//   z[n] = u[2n] + i u[17 - 2n];  t[n] = z[n] e^{-i pi n / 18};  T = DFT9(t);  c[k] = T[k] e^{-i pi (4k+1) / 72} / 9;
+//   X[2k] = Re c[k],  X[17 - 2k] = -Im c[k]
+// (split the sum over even j and over j = 17 - 2n: the cosine of the second half is the sine of the first half's angle), the
+// DFT9 as 3 x 3 (two rounds of 3-point transforms, four twiddles between them).  156 fused operations on immediates instead of
+// 324 on loaded coefficients; the arithmetic differs from the direct form by FP32 rounding only (a few 1e-7 of the largest
+// value: the tolerance of this path is 1e-5).
+struct FfC { float r, i; };
+__device__ __forceinline__ void ff_dft3(FfC &x0, FfC &x1, FfC &x2)
+{
+    const float h = 0.866025404f;
+    const float sr = x1.r + x2.r, si = x1.i + x2.i, dr = x1.r - x2.r, di = x1.i - x2.i;
+    const float mr = __fmaf_rn(-0.5f, sr, x0.r), mi = __fmaf_rn(-0.5f, si, x0.i);
+    x0.r += sr; x0.i += si;
+    x1.r = __fmaf_rn(h, di, mr); x1.i = __fmaf_rn(-h, dr, mi);
+    x2.r = __fmaf_rn(-h, di, mr); x2.i = __fmaf_rn(h, dr, mi);
+}
+__device__ __forceinline__ FfC ff_rot(FfC x, float c, float s)     // x * (c - i s)
+{
+    FfC y;
+    y.r = __fmaf_rn(x.i, s, x.r * c); y.i = __fmaf_rn(-x.r, s, x.i * c);
+    return y;
+}
 __device__ __forceinline__ void ff_dct4_18(const float (&u)[18], float (&out)[18])
 {
-    using A = FastArith<float>;
+    constexpr float pre_c[9] = {1.f, 0.984807753f, 0.939692621f, 0.866025404f, 0.766044443f, 0.64278761f, 0.5f, 0.342020143f, 0.173648178f};
+    constexpr float pre_s[9] = {0.f, 0.173648178f, 0.342020143f, 0.5f, 0.64278761f, 0.766044443f, 0.866025404f, 0.939692621f, 0.984807753f};
+    constexpr float post_c[9] = {0.111005358f, 0.108477334f, 0.102653281f, 0.0937101606f, 0.0819197041f, 0.0676401588f, 0.0513054015f, 0.0334117555f, 0.0145029102f};
+    constexpr float post_s[9] = {0.0048465986f, 0.024048846f, 0.0425203814f, 0.0596999565f, 0.0750655786f, 0.0881503711f, 0.0985567592f, 0.10596855f, 0.11016054f};
+    FfC t[9];
+    t[0].r = u[0]; t[0].i = u[17];
 #pragma unroll
-    for (int m = 0; m < 18; m++) {
-        float acc = 0.f;
+    for (int n = 1; n < 9; n++) { FfC z; z.r = u[2 * n]; z.i = u[17 - 2 * n]; t[n] = ff_rot(z, pre_c[n], pre_s[n]); }
+    // DFT9, n = 3a + b, k = k1 + 3 k2: three DFT3 over a, twiddles W9^(b k1), three DFT3 over b
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-            const float4 c = *reinterpret_cast<const float4 *>(&c_front_f.dct4_l[m][j]);
-            acc = A::fma(u[j], c.x, acc); acc = A::fma(u[j + 1], c.y, acc);
-            acc = A::fma(u[j + 2], c.z, acc); acc = A::fma(u[j + 3], c.w, acc);
+    for (int b = 0; b < 3; b++) ff_dft3(t[b], t[3 + b], t[6 + b]);            // t[3 k1 + b] = A[b][k1]
+    t[4] = ff_rot(t[4], 0.766044443f, 0.64278761f);                           // b = 1, k1 = 1: W9^1
+    t[7] = ff_rot(t[7], 0.173648178f, 0.984807753f);                          // b = 1, k1 = 2: W9^2
+    t[5] = ff_rot(t[5], 0.173648178f, 0.984807753f);                          // b = 2, k1 = 1: W9^2
+    t[8] = ff_rot(t[8], -0.939692621f, 0.342020143f);                         // b = 2, k1 = 2: W9^4
+#pragma unroll
+    for (int k1 = 0; k1 < 3; k1++) ff_dft3(t[3 * k1], t[3 * k1 + 1], t[3 * k1 + 2]);   // t[3 k1 + k2] = T[k1 + 3 k2]
+#pragma unroll
+    for (int k1 = 0; k1 < 3; k1++)
+#pragma unroll
+        for (int k2 = 0; k2 < 3; k2++) {
+            const int k = k1 + 3 * k2;
+            const FfC T = t[3 * k1 + k2];
+            out[2 * k] = __fmaf_rn(T.i, post_s[k], T.r * post_c[k]);
+            out[17 - 2 * k] = __fmaf_rn(-T.i, post_c[k], T.r * post_s[k]);
         }
-        const float2 c2 = *reinterpret_cast<const float2 *>(&c_front_f.dct4_l[m][16]);
-        acc = A::fma(u[16], c2.x, acc); acc = A::fma(u[17], c2.y, acc);
-        out[m] = acc;
-    }
 }
 
 // A persistent version (3 CTAs per SM walking the tiles, the next tile's PCM fetched into the same buffer behind the MDCT
