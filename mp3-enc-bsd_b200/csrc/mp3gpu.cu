@@ -348,15 +348,16 @@ k_rate_loop(const RateTables *__restrict__ gT, FrameGeom G, LoopStreamState *sta
     const long total = (long)n_streams * n_frames;
     int next_f = 0, f_end = 0;
     bool started = false, clean = false;                         // clean: the state differs from the previous run's at most in the reservoir level
-    long vs = (long)blockIdx.x * wpc + warp;                     // segmented: virtual stream index, advanced by the warps of the grid
-    const long vs_step = (long)gridDim.x * wpc;
+    long vs = 0;                                                 // segmented: virtual stream index = a ticket (segments differ widely in cost)
     WarpLoopState W;
     for (;;) {
         long s;
         int f;
         if (segmented) {
-            if (!started) {                                      // first trip of a segment: find it and the state it starts from
+            if (!started) {                                      // first trip of a segment: draw it, find the state it starts from
                 started = true;
+                if (lane == 0) vs = (long)atomicAdd(reinterpret_cast<unsigned int *>(sched), 1u);
+                vs = __shfl_sync(0xffffffffu, vs, 0);
                 if (vs >= (long)n_streams * seg.G) break;
                 s = vs / seg.G;
                 const int g = (int)(vs - s * seg.G);
@@ -372,14 +373,14 @@ k_rate_loop(const RateTables *__restrict__ gT, FrameGeom G, LoopStreamState *sta
                         wls_load(W, &seg.fin_s[rd + vs], &seg.fin_l[rd + vs], lane);                  // nothing changed: carry the end state over
                         wls_store(W, &seg.fin_s[wr + vs], &seg.fin_l[wr + vs], lane);
                         if (lane == 0) atomicAdd(&seg.stats[4 * (seg.pass - 1) + 2], 1ull);
-                        vs += vs_step; started = false; continue;
+                        started = false; continue;
                     }
                     clean = cmp == 1;
                 }
                 wls_store(W, &seg.used_s[vs], &seg.used_l[vs], lane);
                 if (f0 >= f_end) {                               // empty segment: pass the state through
                     wls_store(W, &seg.fin_s[wr + vs], &seg.fin_l[wr + vs], lane);
-                    vs += vs_step; started = false; continue;
+                    started = false; continue;
                 }
                 next_f = f0;
             }
@@ -429,13 +430,13 @@ k_rate_loop(const RateTables *__restrict__ gT, FrameGeom G, LoopStreamState *sta
                 // merged with the previous run: the rest of the segment, and the state it ends in, stand
                 wls_load(W, &seg.fin_s[rd + vs], &seg.fin_l[rd + vs], lane);
                 wls_store(W, &seg.fin_s[wr + vs], &seg.fin_l[wr + vs], lane);
-                vs += vs_step; started = false; clean = false; continue;
+                started = false; clean = false; continue;
             }
             clean = cmp == 1;
             wls_store(W, &seg.snap_s[sn], &seg.snap_l[sn], lane);
             if (next_f >= f_end) {
                 wls_store(W, &seg.fin_s[wr + vs], &seg.fin_l[wr + vs], lane);
-                vs += vs_step; started = false; clean = false;
+                started = false; clean = false;
             }
         } else {
             wls_store(W, &states[s], &lane_states[s], lane);
@@ -1383,6 +1384,10 @@ static int rate_loop_segments(const mp3gpu_ctx *c, int n_streams, int n_frames)
     // while every (stream, segment) pair gets its own warp: with two rounds of segments per warp the static assignment waits
     // for the slowest pair twice and loses to the unsegmented walk (2500 heterogeneous clips, 96-frame calls: 279 ms against
     // 214 ms per step, gpurun_out/r3d)
+    if (const char *v = getenv("MP3GPU_RL_SEGMENTS")) {              // A/B: force the number of segments
+        const int g = atoi(v);
+        return (g >= 1 && g <= 8 && n_frames / g >= 8) ? g : 1;
+    }
     int best = 1;
     long best_cost = n_frames;
     for (int g = 2; g <= 8 && n_frames / g >= 16 && (long)n_streams * g <= slots; g++) {
@@ -1443,6 +1448,7 @@ static int launch_rate_loop(mp3gpu_ctx *c, const double *xr, const PsyOut *psy, 
         grid = (unsigned)ctas;
         prof_begin(c, MP3GPU_K_RATE_LOOP, q);
         for (seg.pass = 1; seg.pass <= seg.G; seg.pass++) {
+            CU(cudaMemsetAsync(c->d_sched, 0, sizeof(int), q));      // the pass's ticket counter
             k_rate_loop<true><<<grid, wpc * 32, RL_HOT_BYTES + wpc * sizeof(RateWarpSmem), q>>>(c->d_rate_tab, G, c->d_loop_state, c->d_lane_state,
                                                                                                 n_streams, n_frames, nfr, c->d_sched, seg, xr, psy, ix, gi, sf, fo);
             c->launches++;
