@@ -13,4 +13,5 @@ for k in k_psy_front_regs k_psy_scan k_front_tile k_rate_loop k_bits_emit; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$k" -s 4 -c 1 -o $out/full_$k -f \
     python bench.py --clips 4144 --seconds 2 --steps 1 --warmup 1 --no-cpu-baseline --no-parity --no-variants --pipeline serial > $out/ncu_$k.log 2>&1
 done
+timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-variants --parity-clips 1000 > $out/bench_parity1000.json 2> $out/bench_parity1000.err
 tail -3 $out/pytest.log; cat $out/bench.json | head -c 1500; tail -2 $out/bench.err

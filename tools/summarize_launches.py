@@ -6,7 +6,7 @@ def main(path):
     rows = [r for r in csv.reader(open(path, errors="ignore")) if len(r) > 14 and r[0].isdigit()]
     tot = collections.OrderedDict()
     for r in rows:
-        name = r[4].split("(")[0].split("::")[-1]
+        name = r[4].split("(")[0].split("::")[-1].replace("void ", "")
         if not name.startswith("k_"):
             continue
         t = tot.setdefault(name, [0, 0.0])
