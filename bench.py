@@ -315,17 +315,13 @@ def main():
     # frames per library call: 32 for a batch that fills the device; a shard below one wave of streams gets longer calls so
     # that the library can cut them into speculative rate-loop segments (mp3gpu_set_rate_loop_segments)
     wave = mod.host.stream_wave(local_rank)
-    # full batches: whole filterbank tiles; below one wave: long calls so that the rate loop can cut a stream into segments
-    # (needs 2 S <= wave), else medium calls (better copy / compute overlap of the host path)
-    chunk = args.chunk_frames or (30 if S >= wave else 192 if 2 * S <= wave else 64)
+    # full batches: whole filterbank tiles per call.  Below one wave: when the rate loop can cut a stream into segments (needs
+    # 2 S <= wave) the calls are as long as the clip (up to 400 frames: the segments get longer, and the library pipelines
+    # the upload of a long call with its front end over groups of streams); else medium calls
+    chunk = args.chunk_frames or (30 if S >= wave else min(n_frames, 400) if 2 * S <= wave else 64)
     F = min(chunk, n_frames)
     chunks = []
     f0 = 0
-    ramp = int(os.environ.get("MP3GPU_BENCH_RAMP", 64))
-    if not args.chunk_frames and F == 192 and n_frames > ramp > 0:
-        # long calls start with a short one: the host path cannot hide the upload of a step's first call behind anything
-        chunks.append((0, ramp))
-        f0 = ramp
     while f0 < n_frames:
         chunks.append((f0, min(F, n_frames - f0)))
         f0 += F
@@ -355,11 +351,50 @@ def main():
             enc.encode_frames_mp3_dev(dev_chunks[i], mp3_dev, stream=sptr)
         return enc.flush_mp3(mp3_dev, S, stream=sptr)
 
-    def step_host():
-        enc.reset(stream=sptr)
-        for i in range(len(chunks)):
-            enc.encode_frames_mp3(host_chunks[i].numpy(), mp3_host.numpy(), stream=sptr)
-        lengths_last[0] = enc.flush_mp3(mp3_host.numpy(), S, stream=sptr)
+    # e2e: TWO contexts on two streams take the steps in turn (what a host that encodes batch after batch does): the upload
+    # and front end of step i + 1 are enqueued before the flush of step i blocks the host, so a step's first upload is not
+    # exposed and the device never idles at a step boundary.  Every copy of every step is inside the timed region.
+    enc_b = mod.Encoder(FS, NCH, KBPS, max_streams=S, max_frames=F, device=local_rank)
+    if args.front:
+        enc_b.set_front_variant(args.front)
+    enc_b.set_pipeline(args.pipeline == "overlap")
+    stream_b = torch.cuda.Stream(device)
+    mp3_host_b = torch.zeros((S, mp3_bytes), dtype=torch.uint8, pin_memory=True)
+    host_ctx = [(enc, sptr, mp3_host), (enc_b, stream_b.cuda_stream, mp3_host_b)]
+    last_host = [0]
+
+    def host_enqueue(i):
+        e, sp, out = host_ctx[i % 2]
+        e.reset(stream=sp)
+        for ch in host_chunks:
+            e.encode_frames_mp3(ch.numpy(), out.numpy(), stream=sp)
+
+    def host_finish(i):
+        e, sp, out = host_ctx[i % 2]
+        lengths_last[0] = e.flush_mp3(out.numpy(), S, stream=sp)
+        last_host[0] = i % 2
+
+    def steps_host(k):
+        for i in range(k):
+            host_enqueue(i)
+            if i > 0:
+                host_finish(i - 1)
+        host_finish(k - 1)
+
+    def timed_host(k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        stream_b.wait_event(e0)
+        steps_host(k)
+        stream.wait_stream(stream_b)
+        e1.record(stream)
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        return e0.elapsed_time(e1) * 1e-3
 
     def timed(fn, k):
         if world > 1:
@@ -387,10 +422,11 @@ def main():
     t_dev = timed(step_dev, args.steps)                  # `value`: profiling off
     launches = enc.kernel_launches - l0
     enc.set_host_delivery(True)     # the D2H of a chunk's bytes overlaps the next chunk's kernels; flush_mp3 joins (mp3gpu.h)
-    for _ in range(2):
-        step_host()
+    for e_, _, _ in host_ctx:
+        e_.set_host_delivery(True)
+    steps_host(2)
     torch.cuda.synchronize(device)
-    t_host = timed(step_host, args.steps)
+    t_host = timed_host(args.steps)
     clocks = sampler.stop() if rank == 0 else None
     # separate profiled pass: CUDA events around every launch of the hot kernels (per-kernel split + the roofline figure);
     # serial pipeline, so that a kernel's events bracket that kernel alone
@@ -466,7 +502,9 @@ def main():
                            S * n_frames * 1152 * NCH * 2 / 1e9, gc_per_step * 4608 / 1e9)),
         "e2e": {"value": audio_total / t_host_max, "unit": "audio-s/s",
                 "h2d_bytes_per_step": int(S * n_frames * 1152 * NCH * 2), "d2h_bytes_per_step": int(S * mp3_bytes + 4 * S),
-                "output": "finished MPEG-1 Layer III byte streams (device bitstream formatter), %d bytes per clip" % mp3_bytes},
+                "output": "finished MPEG-1 Layer III byte streams (device bitstream formatter), %d bytes per clip" % mp3_bytes,
+                "host_pipeline": "two mp3gpu contexts on two streams take the steps in turn: step i + 1 is enqueued before the flush "
+                                 "of step i blocks the host; every H2D / D2H copy of every step is inside the timed region"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_front_tile (fused polyphase filterbank + MDCT + alias reduction), variant " + front_info["name"],
                      "achieved": fk["achieved_gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": fk["frac_hbm"],
@@ -497,7 +535,8 @@ def main():
             if c not in pick and len(pick) < k + 8:
                 pick.append(c)
         pcms = [np.concatenate([h[i].numpy() for h in host_chunks], axis=1)[:, :n_samples] for i in pick]
-        ours = [mp3_host[i, :int(lengths_last[0][i])].numpy().tobytes() for i in pick]
+        mp3_last = host_ctx[last_host[0]][2]
+        ours = [mp3_last[i, :int(lengths_last[0][i])].numpy().tobytes() for i in pick]
         out["parity"] = parity_report(cfg, pcms, ours, enc.frame_bytes)
         out["parity"]["clip_indices"] = [lo + i for i in pick]
     if not args.no_cpu_baseline:
