@@ -5,6 +5,8 @@
 #include "tables.h"
 
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -684,6 +686,16 @@ void build_fft_regs_plan(FftRegsPlan *P)
         for (int b = 0; b < 32; b++) if (WL.blk[b].kind == kind) slot_l[b] = 32 * pass + next[pass]++;
         for (int t = 0; t < 3; t++)
             for (int b = 0; b < 8; b++) if (WS.blk[b].kind == kind) slot_s[t][b] = 32 * pass + next[pass]++;
+    }
+    // fft_regs.h hard-codes the lane ranges of the two passes: 32 lanes of kind a; kinds b / c / d in lanes 0..15 / 16..19 / 20..23
+    {
+        int cnt[4] = {0, 0, 0, 0};
+        for (int b = 0; b < 32; b++) cnt[WL.blk[b].kind]++;
+        for (int b = 0; b < 8; b++) cnt[WS.blk[b].kind] += 3;
+        if (cnt[FFTR_A] != 32 || cnt[FFTR_B] != 16 || cnt[FFTR_C] != 4 || cnt[FFTR_D] != 4 || next[0] != 32 || next[1] != 24) {
+            fprintf(stderr, "mp3gpu: FFT block plan does not match the kernel's lane layout\n");
+            abort();
+        }
     }
     for (int b = 0; b < 32; b++) {
         P->kind_long[b] = (uint8_t)WL.blk[b].kind;
