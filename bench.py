@@ -61,6 +61,28 @@ CONFIGS = {
 }
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """Run this rank (and first-touch its pinned buffers) on the CPUs of the NUMA node its GPU hangs off: with one rank per
+    GPU the uploads of 8 ranks otherwise cross the socket interconnect at random.  Returns the node or None (no-op)."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def shard_range(n, rank, world):
     """contiguous, balanced partition of n units over `world` ranks"""
     base, rem = divmod(n, world)
@@ -304,6 +326,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     if args.config == 5:
@@ -504,7 +527,8 @@ def main():
                 "h2d_bytes_per_step": int(S * n_frames * 1152 * NCH * 2), "d2h_bytes_per_step": int(S * mp3_bytes + 4 * S),
                 "output": "finished MPEG-1 Layer III byte streams (device bitstream formatter), %d bytes per clip" % mp3_bytes,
                 "host_pipeline": "two mp3gpu contexts on two streams take the steps in turn: step i + 1 is enqueued before the flush "
-                                 "of step i blocks the host; every H2D / D2H copy of every step is inside the timed region"},
+                                 "of step i blocks the host; every H2D / D2H copy of every step is inside the timed region",
+                "numa_node": numa_node},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_front_tile (fused polyphase filterbank + MDCT + alias reduction), variant " + front_info["name"],
                      "achieved": fk["achieved_gbs"], "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": fk["frac_hbm"],
