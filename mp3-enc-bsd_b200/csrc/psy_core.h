@@ -646,6 +646,9 @@ SIMT_FN void psy_scan_step(const WarpCtx &w, const PsyTables &T, PsyScanSmem &M,
         R.r2() = R.r1(); R.r1() = rn;
         R.p2() = R.p1(); R.p1() = pn;
     }
+    // 0.4 * e of the lines that fold into partition 0 (l3psy.c:574-577 with cw = 0.4), formed by all lanes into M.prod: the
+    // sequential float accumulation below then reads shared memory instead of one dependent global load per line
+    for (int j = T.tail_l + lane; j <= 512; j += 32) M.prod[j - T.tail_l] = simt::dmul(0.4, (double)mid.tail[j - T.tail_l]);
     END_THREADS
     w.sync();
     // cb of the partitions that hold lines 0..5 (+ the partition-0 tail), l3psy.c:570-578
@@ -658,7 +661,7 @@ SIMT_FN void psy_scan_step(const WarpCtx &w, const PsyTables &T, PsyScanSmem &M,
             cb = 0.0f;
             for (int j = T.lo_l[p]; j < T.hi_l[p]; j++) cb = (float)simt::dadd((double)cb, simt::dmul(M.cw6[j], (double)mid.e6[j]));
             if (p == 0)
-                for (int j = T.tail_l; j <= 512; j++) cb = (float)simt::dadd((double)cb, simt::dmul(0.4, (double)mid.tail[j - T.tail_l]));
+                for (int j = 0; j <= 512 - T.tail_l; j++) cb = (float)simt::dadd((double)cb, M.prod[j]);
         }
         M.cb[p] = cb;
     }
@@ -672,6 +675,7 @@ SIMT_FN void psy_scan_step(const WarpCtx &w, const PsyTables &T, PsyScanSmem &M,
         if (b < 63) {
             double ctb = 0.0;
             const int klo = T.spr_lo[b];
+#pragma unroll 4
             for (int k = klo; k <= T.spr_hi[b]; k++) {   // latency-bound scan over the lane's own row range (banded layout)
                 const double s = T.s3_band[(k - klo) * 64 + b];
                 if (T.sparse || s != 1.0) ctb = simt::dadd(ctb, simt::dmul(s, (double)M.cb[k]));
