@@ -241,6 +241,9 @@ SIMT_FN void quantize_all(const WarpCtx &w, const RateTables &T, RateWarpSmem &M
     END_THREADS
     const unsigned lm = w.ballot(live);
     const int k_lim = 32 - simt::clz(lm);
+    // the previous probe's count loops READ ix[] of other lanes' slots; their results went through warp reductions that every
+    // lane waited for, so those reads are done — the barrier states the write-after-read order in the memory model's terms
+    w.sync();
     RL_STAT(2, 1); RL_STAT(3, k_lim);
     FOR_THREADS(w)
     const F2 *ys = reinterpret_cast<const F2 *>(M.scr);
